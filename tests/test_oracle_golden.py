@@ -1,0 +1,38 @@
+"""The oracle restatement must reproduce the golden vectors made by the
+reference's own code (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pileup_oracle
+from tests.golden import cases as golden_cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def oracle_run(name):
+    case = golden_cases.CASES[name]
+    batch, ref_bytes, contig = golden_cases.build(name)
+    ref_seq = ref_bytes.decode("ascii")
+    n = len(ref_seq)
+    # one chunk covering the contig: reads [max(1, 0-33), n+33], reference from 1
+    return pileup_oracle.run_region(batch, ref_seq, 1, 1, n + 33, snp_min_af=case["snp_af"],
+                                    indel_min_af=case["indel_af"], min_coverage=case["min_cov"],
+                                    min_mq=case["min_mq"], padding=case["padding"], phased=case["phased"])
+
+
+@pytest.mark.parametrize("name", sorted(golden_cases.CASES))
+def test_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    o = oracle_run(name)
+    assert o["pos"].tolist() == g["pos"].tolist()
+    assert o["depth"].tolist() == g["depth"].tolist()
+    assert list(o["alt_info"]) == [str(s).rstrip("\n") for s in g["alt_info"]]
+    assert list(o["ref33"]) == [str(s) for s in g["ref33"]]
+    assert np.array_equal(o["tensor"], g["tensor"])
