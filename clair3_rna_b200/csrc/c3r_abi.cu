@@ -1,0 +1,676 @@
+// libc3r_b200.so — C ABI (include/c3r_b200.h) and host orchestration of the kernels in
+// pileup.cuh (integer half) and nn_fp32.cuh / nn_tc.cuh (network forward).
+//
+// One context = one GPU.  A ticket owns a slot: device input buffers, scratch, pinned
+// result buffers and a stream.  submit() copies the flat records to HBM, runs the
+// position/row-space stages, reads back two scalars (rows, candidates) to size the
+// candidate-space buffers, then queues windows, alt_info, the network and the D2H
+// copies; wait() synchronises the slot's stream.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include <cuda_runtime.h>
+
+#include "../../include/c3r_b200.h"
+#include "pileup.cuh"
+#include "nn_fp32.cuh"
+#include "nn_tc.cuh"
+
+using namespace c3r;
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+struct Pin {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+constexpr int N_SLOTS = 2;
+constexpr int N_EV = 9;
+
+struct Slot {
+    bool in_use = false;
+    bool has_result = false;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[N_EV] = {};
+    cudaEvent_t ev_alt = nullptr;
+    // inputs
+    Buf pos, flag, mapq, hp, cigar_off, cigar, seq_off, seq, ref;
+    // per read/op
+    Buf admit, read_end, op_head, op_x, op_y, op_rid;
+    // position space
+    Buf covA, covE, rowR, wdiff, word_base;
+    // row space
+    Buf row_pos, counts, row_depth, row_flag, head_cnt, tail_cnt, skipdiff, max_skip, row_ins, row_del;
+    Buf binc, bin_cur, entries, events;
+    Buf cand_row, cand_pos, cand_depth, tensor, alt_off, alt_n, alt, cur_ref, deleted, probs;
+    Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32)
+    Buf scan_scratch;
+    // pinned results
+    Pin h_scalars, h_pos, h_depth, h_probs, h_alt_off, h_alt_n, h_alt, h_tensor, h_row_pos, h_counts, h_row_depth;
+    Dev d;
+    int64_t n_rows = 0, n_cand = 0, alt_total = 0;
+    int launches = 0;
+    c3r_result res;
+};
+
+}  // namespace
+
+struct c3r_ctx {
+    int device = 0;
+    c3r_params prm;
+    std::string err;
+    Slot slots[N_SLOTS];
+    int sm_count = 148;
+    // weights
+    bool have_weights = false;
+    Buf wbuf;                 // all fp32 weights, Keras-derived layouts
+    NetF32 net;
+    Buf nn_scratch;
+    NetF32Scratch nscr;
+    TcNet tc;                 // tensor-core path state (nn_tc.cuh)
+    Buf fwd_in, fwd_out;      // c3r_forward staging
+    cudaStream_t fwd_stream = nullptr;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            ctx->err = b__;                                                                        \
+            return C3R_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+int fail(c3r_ctx* ctx, int code, const std::string& msg) {
+    ctx->err = msg;
+    return code;
+}
+
+int ensure(c3r_ctx* ctx, Buf& b, size_t bytes) {
+    if (bytes < 256) bytes = 256;
+    if (b.cap >= bytes) return 0;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+int ensure_pin(c3r_ctx* ctx, Pin& b, size_t bytes) {
+    if (bytes < 256) bytes = 256;
+    if (b.cap >= bytes) return 0;
+    if (b.p) CK(cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    CK(cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+void release(Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+void release(Pin& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+
+template <class T> T* P(Buf& b) { return (T*)b.p; }
+
+// ------------------------------------------------------------ device stages
+// Stage A: everything up to the candidate list.  Needs only the resident inputs.
+int run_stage_a(c3r_ctx* ctx, Slot& s) {
+    Dev& d = s.d;
+    cudaStream_t st = s.st;
+    int& L = s.launches;
+    // clear accumulators
+    CK(cudaMemsetAsync(s.op_head.p, 0xff, (size_t)(d.n_ops + 1) * 4, st));
+    CK(cudaMemsetAsync(s.covA.p, 0, (size_t)(d.NW + 4) * 4, st));
+    CK(cudaMemsetAsync(s.covE.p, 0, (size_t)(d.NW + 4) * 4, st));
+    CK(cudaMemsetAsync(s.wdiff.p, 0, (size_t)(d.NW + 4) * 8, st));
+    CK(cudaMemsetAsync(s.binc.p, 0, (size_t)(d.NT_ub + d.L_ub + 4) * 4, st));
+    CK(cudaMemsetAsync(s.bin_cur.p, 0, (size_t)(d.NT_ub + d.L_ub + 4) * 4, st));
+    CK(cudaMemsetAsync(s.scalars.p, 0, 64, st));
+    if (d.padding) {
+        CK(cudaMemsetAsync(s.head_cnt.p, 0, (size_t)(d.L_ub + 2) * 4, st));
+        CK(cudaMemsetAsync(s.tail_cnt.p, 0, (size_t)(d.L_ub + 2) * 4, st));
+        CK(cudaMemsetAsync(s.skipdiff.p, 0, (size_t)(d.L_ub + 2) * 8, st));
+        CK(cudaMemsetAsync(s.deleted.p, 0, (size_t)(d.L_ub + 2), st));
+    }
+    CK(cudaEventRecord(s.ev[1], st));
+    if (d.n_reads > 0) {
+        k_read_prepare<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, st>>>(d);
+        ++L;
+    }
+    { OpCigar op; op.d = d; if (d.n_ops > 0) L += device_scan(op, d.n_ops, (ScanElem*)s.scan_scratch.p, (ScanElem*)nullptr, st); }
+    { OpWords op; op.d = d; L += device_scan(op, d.NW, (Int2*)s.scan_scratch.p, (Int2*)nullptr, st); }
+    { OpRows op; op.d = d; L += device_scan(op, d.NW, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
+    CK(cudaEventRecord(s.ev[2], st));
+    if (d.n_ops > 0) { k_bin<false><<<(unsigned)((d.n_ops + 255) / 256), 256, 0, st>>>(d); ++L; }
+    if (d.padding) { OpSkip op; op.d = d; L += device_scan(op, d.L_ub, (Int2*)s.scan_scratch.p, (Int2*)nullptr, st); }
+    { OpBins op; op.d = d; L += device_scan(op, d.NT_ub + d.L_ub + 2, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
+    if (d.n_ops > 0) { k_bin<true><<<(unsigned)((d.n_ops + 255) / 256), 256, 0, st>>>(d); ++L; }
+    CK(cudaEventRecord(s.ev[3], st));
+    {
+        const unsigned grid = (unsigned)(ctx->sm_count * 4);
+        if (d.C == 18) k_count<18><<<grid, 256, 0, st>>>(d); else k_count<30><<<grid, 256, 0, st>>>(d);
+        ++L;
+    }
+    CK(cudaEventRecord(s.ev[4], st));
+    { OpCand op; op.d = d; L += device_scan(op, d.L_ub, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
+    CK(cudaEventRecord(s.ev[5], st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int read_scalars(c3r_ctx* ctx, Slot& s) {
+    CK(cudaMemcpyAsync(s.h_scalars.p, s.scalars.p, 64, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaStreamSynchronize(s.st));
+    const int64_t* hs = (const int64_t*)s.h_scalars.p;
+    s.n_rows = hs[0];
+    s.n_cand = hs[1];
+    const int32_t err = ((const int32_t*)s.h_scalars.p)[6];
+    if (err) {
+        char b[128];
+        snprintf(b, sizeof b, "device capacity check failed (code %d): rows=%lld cand=%lld", err, (long long)s.n_rows, (long long)s.n_cand);
+        return fail(ctx, C3R_ERR_CAPACITY, b);
+    }
+    if (s.n_cand > s.d.cand_cap) return fail(ctx, C3R_ERR_CAPACITY, "candidate capacity exceeded");
+    return 0;
+}
+
+int ensure_stage_b(c3r_ctx* ctx, Slot& s) {
+    Dev& d = s.d;
+    const int64_t n = s.n_cand > 0 ? s.n_cand : 1;
+    const int per = WIN * d.C;
+    if (ensure(ctx, s.tensor, (size_t)n * per * 4)) return C3R_ERR_CUDA;
+    if (ensure(ctx, s.alt_off, (size_t)(n + 1) * 8)) return C3R_ERR_CUDA;
+    if (ensure(ctx, s.alt_n, (size_t)n * 4)) return C3R_ERR_CUDA;
+    d.alt_cap = 4 * n + d.events_ub + 8;
+    if (ensure(ctx, s.alt, (size_t)d.alt_cap * sizeof(AltEntry))) return C3R_ERR_CUDA;
+    if (ensure(ctx, s.probs, (size_t)n * 24 * 4)) return C3R_ERR_CUDA;
+    d.tensor = P<int32_t>(s.tensor);
+    d.alt_off = P<int64_t>(s.alt_off);
+    d.alt_n = P<int32_t>(s.alt_n);
+    d.alt = P<AltEntry>(s.alt);
+    return 0;
+}
+
+int nn_forward(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches);
+
+// Stage B: windows, padding, alt_info, network.  Needs n_cand on the host.
+int run_stage_b(c3r_ctx* ctx, Slot& s) {
+    Dev& d = s.d;
+    cudaStream_t st = s.st;
+    int& L = s.launches;
+    const int64_t n = s.n_cand;
+    if (n > 0) {
+        const unsigned grid = (unsigned)(n < ctx->sm_count * 16 ? n : ctx->sm_count * 16);
+        k_window<<<grid, 128, 0, st>>>(d, d.padding ? 0 : 1);
+        ++L;
+        if (d.padding) {
+            k_padding<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d); ++L;
+            k_rescale<<<grid, 128, 0, st>>>(d); ++L;
+        }
+        { OpAltOff op; op.d = d; L += device_scan(op, n, (long long*)s.scan_scratch.p, ((long long*)s.scalars.p) + 2, st); }
+        k_altinfo<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d); ++L;
+    }
+    CK(cudaEventRecord(s.ev[6], st));
+    CK(cudaEventRecord(s.ev_alt, st));
+    if (n > 0) {
+        int nl = 0;
+        int rc = nn_forward(ctx, d.tensor, n, P<float>(s.probs), st, &nl);
+        if (rc) return rc;
+        L += nl;
+    }
+    CK(cudaEventRecord(s.ev[7], st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int queue_d2h(c3r_ctx* ctx, Slot& s) {
+    Dev& d = s.d;
+    cudaStream_t st = s.st;
+    const int64_t n = s.n_cand;
+    const int per = WIN * d.C;
+    // alt total: a second tiny readback, taken before the network so it overlaps it
+    CK(cudaMemcpyAsync(s.h_scalars.p, s.scalars.p, 64, cudaMemcpyDeviceToHost, st));
+    if (n > 0) {
+        if (ensure_pin(ctx, s.h_pos, n * 4) || ensure_pin(ctx, s.h_depth, n * 4) || ensure_pin(ctx, s.h_probs, n * 96) ||
+            ensure_pin(ctx, s.h_alt_off, n * 8) || ensure_pin(ctx, s.h_alt_n, n * 4)) return C3R_ERR_CUDA;
+        CK(cudaMemcpyAsync(s.h_pos.p, s.cand_pos.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.h_depth.p, s.cand_depth.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.h_probs.p, s.probs.p, n * 96, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.h_alt_off.p, s.alt_off.p, n * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.h_alt_n.p, s.alt_n.p, n * 4, cudaMemcpyDeviceToHost, st));
+        if (ctx->prm.keep_tensor) {
+            if (ensure_pin(ctx, s.h_tensor, (size_t)n * per * 4)) return C3R_ERR_CUDA;
+            CK(cudaMemcpyAsync(s.h_tensor.p, s.tensor.p, (size_t)n * per * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (ctx->prm.keep_rows && s.n_rows > 0) {
+        const int64_t L = s.n_rows;
+        if (ensure_pin(ctx, s.h_row_pos, L * 4) || ensure_pin(ctx, s.h_counts, (size_t)L * d.C * 4) ||
+            ensure_pin(ctx, s.h_row_depth, L * 4)) return C3R_ERR_CUDA;
+        CK(cudaMemcpyAsync(s.h_row_pos.p, s.row_pos.p, L * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.h_counts.p, s.counts.p, (size_t)L * d.C * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s.h_row_depth.p, s.row_depth.p, L * 4, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
+int build_net(c3r_ctx* ctx, const std::map<std::string, std::pair<const float*, int64_t>>& w);
+
+}  // namespace
+
+// =============================================================== C ABI
+extern "C" {
+
+int c3r_abi_version(void) { return C3R_ABI_VERSION; }
+
+void c3r_default_params(c3r_params* p) {
+    memset(p, 0, sizeof *p);
+    p->channels = 18;
+    p->min_coverage = 4;
+    p->min_mq = 5;
+    p->excl_flags = 2316;
+    p->snp_min_af = 0.08;
+    p->indel_min_af = 0.15;
+    p->enable_padding = 0;
+    p->max_depth = 144;
+    p->skip_proportion = 0.2;
+    p->nn_impl = 1;
+    p->keep_tensor = 0;
+    p->keep_rows = 0;
+}
+
+int c3r_create(c3r_ctx** out, int device_ordinal, const c3r_params* params) {
+    if (!out || !params) return C3R_ERR_ARG;
+    *out = nullptr;
+    if (params->channels != 18 && params->channels != 30) return C3R_ERR_ARG;
+    c3r_ctx* ctx = new c3r_ctx();
+    ctx->device = device_ordinal;
+    ctx->prm = *params;
+    *out = ctx;                       // returned even on failure so the caller can read last_error
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev <= 0)
+        return fail(ctx, C3R_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+    if (device_ordinal < 0 || device_ordinal >= n_dev) return fail(ctx, C3R_ERR_ARG, "device ordinal out of range");
+    CK(cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major != 10)
+        return fail(ctx, C3R_ERR_CUDA, std::string("built for sm_100a only, device is ") + prop.name);
+    ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < N_SLOTS; ++i) {
+        Slot& s = ctx->slots[i];
+        CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        for (int k = 0; k < N_EV; ++k) CK(cudaEventCreate(&s.ev[k]));
+        CK(cudaEventCreateWithFlags(&s.ev_alt, cudaEventDisableTiming));
+        if (ensure(ctx, s.scalars, 256)) return C3R_ERR_CUDA;
+        if (ensure_pin(ctx, s.h_scalars, 256)) return C3R_ERR_CUDA;
+    }
+    CK(cudaStreamCreateWithFlags(&ctx->fwd_stream, cudaStreamNonBlocking));
+    return C3R_OK;
+}
+
+void c3r_destroy(c3r_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < N_SLOTS; ++i) {
+        Slot& s = ctx->slots[i];
+        Buf* bs[] = {&s.pos, &s.flag, &s.mapq, &s.hp, &s.cigar_off, &s.cigar, &s.seq_off, &s.seq, &s.ref, &s.admit,
+                     &s.read_end, &s.op_head, &s.op_x, &s.op_y, &s.op_rid, &s.covA, &s.covE, &s.rowR, &s.wdiff,
+                     &s.word_base, &s.row_pos, &s.counts, &s.row_depth, &s.row_flag, &s.head_cnt, &s.tail_cnt,
+                     &s.skipdiff, &s.max_skip, &s.row_ins, &s.row_del, &s.binc, &s.bin_cur, &s.entries, &s.events,
+                     &s.cand_row, &s.cand_pos, &s.cand_depth, &s.tensor, &s.alt_off, &s.alt_n, &s.alt, &s.cur_ref,
+                     &s.deleted, &s.probs, &s.scalars, &s.scan_scratch};
+        for (Buf* b : bs) release(*b);
+        Pin* ps[] = {&s.h_scalars, &s.h_pos, &s.h_depth, &s.h_probs, &s.h_alt_off, &s.h_alt_n, &s.h_alt, &s.h_tensor,
+                     &s.h_row_pos, &s.h_counts, &s.h_row_depth};
+        for (Pin* b : ps) release(*b);
+        for (int k = 0; k < N_EV; ++k) if (s.ev[k]) cudaEventDestroy(s.ev[k]);
+        if (s.ev_alt) cudaEventDestroy(s.ev_alt);
+        if (s.st) cudaStreamDestroy(s.st);
+    }
+    release(ctx->wbuf);
+    release(ctx->nn_scratch);
+    release(ctx->fwd_in);
+    release(ctx->fwd_out);
+    tc_release(ctx->tc);
+    if (ctx->fwd_stream) cudaStreamDestroy(ctx->fwd_stream);
+    delete ctx;
+}
+
+const char* c3r_last_error(c3r_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int c3r_set_weights(c3r_ctx* ctx, const c3r_weight_view* views, int n_views) {
+    if (!ctx || !views) return C3R_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    std::map<std::string, std::pair<const float*, int64_t>> w;
+    for (int i = 0; i < n_views; ++i) w[views[i].name] = std::make_pair(views[i].data, views[i].n_elem);
+    return build_net(ctx, w);
+}
+
+int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
+                     int64_t region_start1, int64_t region_end1, c3r_ticket* ticket) {
+    if (!ctx || !rd || !ticket) return C3R_ERR_ARG;
+    if (!ctx->have_weights) return fail(ctx, C3R_ERR_STATE, "c3r_set_weights must be called before c3r_submit_chunk");
+    if (region_end1 < region_start1 || region_start1 < 1) return fail(ctx, C3R_ERR_ARG, "bad region");
+    if (region_end1 > 0x7fff0000LL) return fail(ctx, C3R_ERR_CAPACITY, "positions must fit int32");
+    if (rd->n_seq_bytes * 2 >= 0xffffffffLL) return fail(ctx, C3R_ERR_CAPACITY, "more than 4G bases in one chunk");
+    if (rd->n_reads >= (1LL << 28)) return fail(ctx, C3R_ERR_CAPACITY, "more than 2^28 reads in one chunk");
+    CK(cudaSetDevice(ctx->device));
+    int si = -1;
+    for (int i = 0; i < N_SLOTS; ++i) if (!ctx->slots[i].in_use) { si = i; break; }
+    if (si < 0) return fail(ctx, C3R_ERR_STATE, "all tickets in flight; c3r_release one first");
+    Slot& s = ctx->slots[si];
+    s.launches = 0;
+    s.has_result = false;
+    Dev& d = s.d;
+    memset(&d, 0, sizeof d);
+    const c3r_params& pr = ctx->prm;
+    d.n_reads = rd->n_reads; d.n_ops = rd->n_ops;
+    d.R0 = (int32_t)(region_start1 - 1); d.R1 = (int32_t)region_end1;
+    d.W = (int64_t)d.R1 - d.R0; d.NW = (d.W + 31) / 32;
+    d.C = pr.channels; d.min_cov = pr.min_coverage; d.min_mq = pr.min_mq; d.excl = pr.excl_flags;
+    d.snp_af = pr.snp_min_af; d.indel_af = pr.indel_min_af; d.padding = pr.enable_padding;
+    d.max_depth = pr.max_depth; d.skip_prop = pr.skip_proportion;
+    d.ref_start0 = ref_start1 - 1; d.ref_len = ref_len;
+    // host-side upper bounds from the CIGARs
+    int64_t md_len = 0, md_ops = 0, ent_ub = 0, ev_ub = 0;
+    for (int64_t k = 0; k < rd->n_ops; ++k) {
+        const uint32_t c = rd->cigar[k], op = c & 15u;
+        const int64_t len = c >> 4;
+        if (op == 0 || op == 2 || op == 7 || op == 8) { md_len += len; ++md_ops; ent_ub += len / 32 + 2; }
+        if (op == 1 || op == 2) ++ev_ub;
+    }
+    int64_t L_ub = md_len + 32 * md_ops + 64;
+    if (L_ub > d.W) L_ub = d.W;
+    if (L_ub < 64) L_ub = 64;
+    d.L_ub = L_ub; d.NT_ub = (L_ub + 31) / 32 + 1;
+    d.entries_ub = ent_ub + 8; d.events_ub = ev_ub + 8;
+    d.cand_cap = L_ub;
+    const int64_t R = rd->n_reads > 0 ? rd->n_reads : 1, O = rd->n_ops > 0 ? rd->n_ops : 1;
+#define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
+    EN(pos, R * 4); EN(flag, R * 2); EN(mapq, R); EN(hp, R); EN(cigar_off, (R + 1) * 4); EN(cigar, O * 4);
+    EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 16); EN(ref, ref_len + 16);
+    EN(admit, R); EN(read_end, R * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_rid, O * 4);
+    EN(covA, (d.NW + 4) * 4); EN(covE, (d.NW + 4) * 4); EN(rowR, (d.NW + 4) * 4); EN(wdiff, (d.NW + 4) * 8);
+    EN(word_base, (d.NW + 4) * 4);
+    EN(row_pos, (L_ub + 2) * 4); EN(counts, ((L_ub + 32) * d.C) * 4); EN(row_depth, (L_ub + 2) * 4); EN(row_flag, L_ub + 2);
+    EN(head_cnt, (L_ub + 2) * 4); EN(tail_cnt, (L_ub + 2) * 4); EN(skipdiff, (L_ub + 2) * 8); EN(max_skip, (L_ub + 2) * 4);
+    EN(row_ins, (L_ub + 2) * 4); EN(row_del, (L_ub + 2) * 4);
+    EN(binc, (d.NT_ub + L_ub + 4) * 4); EN(bin_cur, (d.NT_ub + L_ub + 4) * 4);
+    EN(entries, d.entries_ub * sizeof(SegEntry)); EN(events, d.events_ub * sizeof(IndelEvent));
+    EN(cand_row, (L_ub + 2) * 4); EN(cand_pos, (L_ub + 2) * 4); EN(cand_depth, (L_ub + 2) * 4);
+    EN(cur_ref, (L_ub + 2) * 8); EN(deleted, L_ub + 2);
+    {
+        int64_t mx = d.n_ops > d.NW ? d.n_ops : d.NW;
+        if (d.NT_ub + L_ub + 4 > mx) mx = d.NT_ub + L_ub + 4;
+        EN(scan_scratch, (mx / SCAN_TILE + 2) * sizeof(ScanElem));
+    }
+#undef EN
+    d.pos = P<int32_t>(s.pos); d.flag = P<uint16_t>(s.flag); d.mapq = P<uint8_t>(s.mapq); d.hp = P<uint8_t>(s.hp);
+    d.cigar_off = P<int32_t>(s.cigar_off); d.cigar = P<uint32_t>(s.cigar); d.seq_off = P<int64_t>(s.seq_off);
+    d.seq = P<uint8_t>(s.seq); d.ref = P<uint8_t>(s.ref);
+    d.admit = P<uint8_t>(s.admit); d.read_end = P<int32_t>(s.read_end); d.op_head = P<int32_t>(s.op_head);
+    d.op_x = P<int32_t>(s.op_x); d.op_y = P<uint32_t>(s.op_y); d.op_rid = P<int32_t>(s.op_rid);
+    d.covA = P<uint32_t>(s.covA); d.covE = P<uint32_t>(s.covE); d.rowR = P<uint32_t>(s.rowR); d.wdiff = P<Int2>(s.wdiff);
+    d.word_base = P<int32_t>(s.word_base);
+    d.n_rows = P<int64_t>(s.scalars); d.n_cand = P<int64_t>(s.scalars) + 1; d.err = P<int32_t>(s.scalars) + 6;
+    d.row_pos = P<int32_t>(s.row_pos); d.counts = P<int32_t>(s.counts); d.row_depth = P<int32_t>(s.row_depth);
+    d.row_flag = P<uint8_t>(s.row_flag); d.head_cnt = P<int32_t>(s.head_cnt); d.tail_cnt = P<int32_t>(s.tail_cnt);
+    d.skipdiff = P<Int2>(s.skipdiff); d.max_skip = P<int32_t>(s.max_skip);
+    d.row_inscnt = P<int32_t>(s.row_ins); d.row_delcnt = P<int32_t>(s.row_del);
+    d.binc = P<int32_t>(s.binc); d.bin_cur = P<int32_t>(s.bin_cur); d.entries = P<SegEntry>(s.entries);
+    d.events = P<IndelEvent>(s.events);
+    d.cand_row = P<int32_t>(s.cand_row); d.cand_pos = P<int32_t>(s.cand_pos); d.cand_depth = P<int32_t>(s.cand_depth);
+    d.cur_ref = P<Int2>(s.cur_ref); d.deleted = P<uint8_t>(s.deleted);
+
+    cudaStream_t st = s.st;
+    CK(cudaEventRecord(s.ev[0], st));
+    if (rd->n_reads > 0) {
+        CK(cudaMemcpyAsync(s.pos.p, rd->pos, rd->n_reads * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.flag.p, rd->flag, rd->n_reads * 2, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.mapq.p, rd->mapq, rd->n_reads, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.hp.p, rd->hp, rd->n_reads, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.cigar_off.p, rd->cigar_off, (rd->n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(s.seq_off.p, rd->seq_off, (rd->n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (rd->n_ops > 0) CK(cudaMemcpyAsync(s.cigar.p, rd->cigar, rd->n_ops * 4, cudaMemcpyHostToDevice, st));
+    if (rd->n_seq_bytes > 0) CK(cudaMemcpyAsync(s.seq.p, rd->seq, rd->n_seq_bytes, cudaMemcpyHostToDevice, st));
+    if (ref_len > 0) CK(cudaMemcpyAsync(s.ref.p, ref, ref_len, cudaMemcpyHostToDevice, st));
+    s.in_use = true;
+    int rc = run_stage_a(ctx, s);
+    if (!rc) rc = read_scalars(ctx, s);
+    if (!rc) rc = ensure_stage_b(ctx, s);
+    if (!rc) rc = run_stage_b(ctx, s);
+    if (!rc) rc = queue_d2h(ctx, s);
+    if (!rc) { cudaError_t e = cudaEventRecord(s.ev[8], st); if (e != cudaSuccess) rc = fail(ctx, C3R_ERR_CUDA, cudaGetErrorString(e)); }
+    if (rc) { cudaStreamSynchronize(st); s.in_use = false; return rc; }
+    *ticket = si;
+    return C3R_OK;
+}
+
+int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* res) {
+    if (!ctx || !res || ticket < 0 || ticket >= N_SLOTS) return C3R_ERR_ARG;
+    Slot& s = ctx->slots[ticket];
+    if (!s.in_use) return fail(ctx, C3R_ERR_STATE, "ticket not in flight");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(s.st));
+    Dev& d = s.d;
+    const int32_t err = ((const int32_t*)s.h_scalars.p)[6];
+    if (err) return fail(ctx, C3R_ERR_CAPACITY, "device capacity check failed in the candidate stages");
+    s.alt_total = ((const int64_t*)s.h_scalars.p)[2];
+    if (!s.has_result) {
+        // alt entries: sized by the device-side total, copied after the first sync
+        const int64_t n = s.n_cand;
+        if (n > 0 && s.alt_total > 0) {
+            if (ensure_pin(ctx, s.h_alt, (size_t)s.alt_total * sizeof(AltEntry))) return C3R_ERR_CUDA;
+            CK(cudaMemcpyAsync(s.h_alt.p, s.alt.p, (size_t)s.alt_total * sizeof(AltEntry), cudaMemcpyDeviceToHost, s.st));
+            CK(cudaStreamSynchronize(s.st));
+        }
+        s.has_result = true;
+    }
+    c3r_result& r = s.res;
+    memset(&r, 0, sizeof r);
+    r.n_rows = s.n_rows;
+    r.n_cand = s.n_cand;
+    r.pos = (const int32_t*)s.h_pos.p; r.depth = (const int32_t*)s.h_depth.p; r.probs = (const float*)s.h_probs.p;
+    r.alt_off = (const int64_t*)s.h_alt_off.p; r.alt_n = (const int32_t*)s.h_alt_n.p; r.alt = (const c3r_alt_entry*)s.h_alt.p;
+    r.tensor = ctx->prm.keep_tensor ? (const int32_t*)s.h_tensor.p : nullptr;
+    if (ctx->prm.keep_rows) {
+        r.row_pos = (const int32_t*)s.h_row_pos.p; r.row_counts = (const int32_t*)s.h_counts.p;
+        r.row_depth = (const int32_t*)s.h_row_depth.p;
+    }
+    for (int k = 0; k < 8; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.ev[k], s.ev[k + 1]);
+        r.stage_ms[k] = ms;
+    }
+    r.kernel_launches = s.launches;
+    *res = r;
+    (void)d;
+    return C3R_OK;
+}
+
+int c3r_release(c3r_ctx* ctx, c3r_ticket ticket) {
+    if (!ctx || ticket < 0 || ticket >= N_SLOTS) return C3R_ERR_ARG;
+    Slot& s = ctx->slots[ticket];
+    if (s.in_use) { cudaSetDevice(ctx->device); cudaStreamSynchronize(s.st); }
+    s.in_use = false;
+    s.has_result = false;
+    return C3R_OK;
+}
+
+int c3r_rerun_resident(c3r_ctx* ctx, c3r_ticket ticket, float* total_ms, float* stage_ms8) {
+    if (!ctx || ticket < 0 || ticket >= N_SLOTS) return C3R_ERR_ARG;
+    Slot& s = ctx->slots[ticket];
+    if (!s.in_use) return fail(ctx, C3R_ERR_STATE, "ticket not in flight");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(s.st));
+    s.launches = 0;
+    CK(cudaEventRecord(s.ev[0], s.st));
+    int rc = run_stage_a(ctx, s);
+    if (!rc) rc = read_scalars(ctx, s);
+    if (!rc) rc = ensure_stage_b(ctx, s);
+    if (!rc) rc = run_stage_b(ctx, s);
+    if (rc) return rc;
+    CK(cudaEventRecord(s.ev[8], s.st));
+    CK(cudaStreamSynchronize(s.st));
+    if (total_ms) CK(cudaEventElapsedTime(total_ms, s.ev[0], s.ev[8]));
+    if (stage_ms8) {
+        for (int k = 0; k < 8; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s.ev[k], s.ev[k + 1]);
+            stage_ms8[k] = ms;
+        }
+    }
+    return s.launches;
+}
+
+int c3r_forward(c3r_ctx* ctx, const int32_t* tensor, int64_t n, float* probs, float* device_ms) {
+    if (!ctx || !tensor || !probs || n < 0) return C3R_ERR_ARG;
+    if (!ctx->have_weights) return fail(ctx, C3R_ERR_STATE, "c3r_set_weights must be called first");
+    if (n == 0) return C3R_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t per = (size_t)WIN * ctx->prm.channels * 4;
+    if (ensure(ctx, ctx->fwd_in, n * per) || ensure(ctx, ctx->fwd_out, n * 96)) return C3R_ERR_CUDA;
+    cudaStream_t st = ctx->fwd_stream;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaMemcpyAsync(ctx->fwd_in.p, tensor, n * per, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(e0, st));
+    int nl = 0;
+    int rc = nn_forward(ctx, (const int32_t*)ctx->fwd_in.p, n, (float*)ctx->fwd_out.p, st, &nl);
+    if (rc) return rc;
+    CK(cudaEventRecord(e1, st));
+    CK(cudaMemcpyAsync(probs, ctx->fwd_out.p, n * 96, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (device_ms) CK(cudaEventElapsedTime(device_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return nl;
+}
+
+}  // extern "C"
+
+// =============================================================== network glue
+namespace {
+
+constexpr int64_t NN_SUB = 4096;      // sites per fp32 sub-batch (bounds the fp32 scratch)
+
+int build_net(c3r_ctx* ctx, const std::map<std::string, std::pair<const float*, int64_t>>& w) {
+    const int C = ctx->prm.channels;
+    struct Need { const char* name; int64_t n; };
+    const Need needs[] = {
+        {"LSTM1/forward/kernel", (int64_t)C * G1}, {"LSTM1/forward/recurrent_kernel", (int64_t)U1 * G1}, {"LSTM1/forward/bias", G1},
+        {"LSTM1/backward/kernel", (int64_t)C * G1}, {"LSTM1/backward/recurrent_kernel", (int64_t)U1 * G1}, {"LSTM1/backward/bias", G1},
+        {"LSTM2/forward/kernel", (int64_t)H1W * G2}, {"LSTM2/forward/recurrent_kernel", (int64_t)U2 * G2}, {"LSTM2/forward/bias", G2},
+        {"LSTM2/backward/kernel", (int64_t)H1W * G2}, {"LSTM2/backward/recurrent_kernel", (int64_t)U2 * G2}, {"LSTM2/backward/bias", G2},
+        {"L4/kernel", (int64_t)L4_IN * DENSE}, {"L4/bias", DENSE},
+        {"L5_1/kernel", DENSE * DENSE}, {"L5_1/bias", DENSE}, {"L5_2/kernel", DENSE * DENSE}, {"L5_2/bias", DENSE},
+        {"Y_gt21_logits/kernel", DENSE * 21}, {"Y_gt21_logits/bias", 21},
+        {"Y_genotype_logits/kernel", DENSE * 3}, {"Y_genotype_logits/bias", 3}};
+    for (const Need& nd : needs) {
+        auto it = w.find(nd.name);
+        if (it == w.end()) return fail(ctx, C3R_ERR_ARG, std::string("missing weight ") + nd.name);
+        if (it->second.second != nd.n) return fail(ctx, C3R_ERR_ARG, std::string("wrong size for weight ") + nd.name);
+    }
+    auto W = [&](const char* n) { return w.find(n)->second.first; };
+    // host staging in the fp32 kernels' layouts
+    std::vector<float> h;
+    auto push = [&](size_t n) { size_t o = h.size(); h.resize(o + ((n + 63) / 64) * 64, 0.f); return o; };
+    const size_t o_w1 = push((size_t)C * 2 * G1), o_b1 = push(2 * G1), o_u1 = push((size_t)2 * U1 * G1);
+    const size_t o_w2 = push((size_t)H1W * 2 * G2), o_b2 = push(2 * G2), o_u2 = push((size_t)2 * U2 * G2);
+    const size_t o_k4 = push((size_t)L4_IN * DENSE), o_b4 = push(DENSE);
+    const size_t o_k51 = push(DENSE * DENSE), o_b51 = push(DENSE), o_k52 = push(DENSE * DENSE), o_b52 = push(DENSE);
+    const size_t o_ky1 = push(DENSE * 21), o_by1 = push(21), o_ky2 = push(DENSE * 3), o_by2 = push(3);
+    for (int c = 0; c < C; ++c) {
+        memcpy(&h[o_w1 + (size_t)c * 2 * G1], W("LSTM1/forward/kernel") + (size_t)c * G1, G1 * 4);
+        memcpy(&h[o_w1 + (size_t)c * 2 * G1 + G1], W("LSTM1/backward/kernel") + (size_t)c * G1, G1 * 4);
+    }
+    memcpy(&h[o_b1], W("LSTM1/forward/bias"), G1 * 4);
+    memcpy(&h[o_b1 + G1], W("LSTM1/backward/bias"), G1 * 4);
+    memcpy(&h[o_u1], W("LSTM1/forward/recurrent_kernel"), (size_t)U1 * G1 * 4);
+    memcpy(&h[o_u1 + (size_t)U1 * G1], W("LSTM1/backward/recurrent_kernel"), (size_t)U1 * G1 * 4);
+    for (int c = 0; c < H1W; ++c) {
+        memcpy(&h[o_w2 + (size_t)c * 2 * G2], W("LSTM2/forward/kernel") + (size_t)c * G2, G2 * 4);
+        memcpy(&h[o_w2 + (size_t)c * 2 * G2 + G2], W("LSTM2/backward/kernel") + (size_t)c * G2, G2 * 4);
+    }
+    memcpy(&h[o_b2], W("LSTM2/forward/bias"), G2 * 4);
+    memcpy(&h[o_b2 + G2], W("LSTM2/backward/bias"), G2 * 4);
+    memcpy(&h[o_u2], W("LSTM2/forward/recurrent_kernel"), (size_t)U2 * G2 * 4);
+    memcpy(&h[o_u2 + (size_t)U2 * G2], W("LSTM2/backward/recurrent_kernel"), (size_t)U2 * G2 * 4);
+    memcpy(&h[o_k4], W("L4/kernel"), (size_t)L4_IN * DENSE * 4);
+    memcpy(&h[o_b4], W("L4/bias"), DENSE * 4);
+    memcpy(&h[o_k51], W("L5_1/kernel"), DENSE * DENSE * 4);
+    memcpy(&h[o_b51], W("L5_1/bias"), DENSE * 4);
+    memcpy(&h[o_k52], W("L5_2/kernel"), DENSE * DENSE * 4);
+    memcpy(&h[o_b52], W("L5_2/bias"), DENSE * 4);
+    memcpy(&h[o_ky1], W("Y_gt21_logits/kernel"), DENSE * 21 * 4);
+    memcpy(&h[o_by1], W("Y_gt21_logits/bias"), 21 * 4);
+    memcpy(&h[o_ky2], W("Y_genotype_logits/kernel"), DENSE * 3 * 4);
+    memcpy(&h[o_by2], W("Y_genotype_logits/bias"), 3 * 4);
+    if (ensure(ctx, ctx->wbuf, h.size() * 4)) return C3R_ERR_CUDA;
+    CK(cudaMemcpy(ctx->wbuf.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    const float* b = (const float*)ctx->wbuf.p;
+    NetF32& n = ctx->net;
+    n.C = C;
+    n.w1 = b + o_w1; n.b1 = b + o_b1; n.u1 = b + o_u1; n.w2 = b + o_w2; n.b2 = b + o_b2; n.u2 = b + o_u2;
+    n.k4 = b + o_k4; n.b4 = b + o_b4; n.k51 = b + o_k51; n.b51 = b + o_b51; n.k52 = b + o_k52; n.b52 = b + o_b52;
+    n.ky1 = b + o_ky1; n.by1 = b + o_by1; n.ky2 = b + o_ky2; n.by2 = b + o_by2;
+    // tensor-core path: repack into fp16 operand images
+    std::string terr;
+    if (tc_build(ctx->tc, n, h.data(), o_w1, o_b1, o_u1, o_w2, o_b2, o_u2, o_k4, o_b4, ctx->sm_count, &terr))
+        return fail(ctx, C3R_ERR_CUDA, "tensor-core weight repack failed: " + terr);
+    ctx->have_weights = true;
+    return C3R_OK;
+}
+
+int nn_forward(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches) {
+    *launches = 0;
+    if (ctx->prm.nn_impl == 1) {
+        std::string terr;
+        int nl = tc_forward(ctx->tc, ctx->net, tensor_dev, n, probs_dev, st, &terr);
+        if (nl < 0) return fail(ctx, C3R_ERR_CUDA, "tensor-core forward failed: " + terr);
+        *launches = nl;
+        return 0;
+    }
+    const int C = ctx->prm.channels;
+    const int64_t cap = n < NN_SUB ? n : NN_SUB;
+    if (ctx->nscr.cap < cap) {
+        if (ensure(ctx, ctx->nn_scratch, netf32_scratch_bytes(cap, C))) return C3R_ERR_CUDA;
+        float* p = (float*)ctx->nn_scratch.p;
+        NetF32Scratch& s = ctx->nscr;
+        s.cap = cap;
+        s.x = p; p += (size_t)cap * NT * C;
+        s.zx1 = p; p += (size_t)cap * NT * 2 * G1;
+        s.h1 = p; p += (size_t)cap * NT * H1W;
+        s.zx2 = p; p += (size_t)cap * NT * 2 * G2;
+        s.h2 = p; p += (size_t)cap * NT * H2W;
+        s.l4 = p; p += (size_t)cap * DENSE;
+        s.hbuf = p; p += (size_t)cap * 2 * U2 * 2;
+        s.cbuf = p;
+    }
+    for (int64_t o = 0; o < n; o += ctx->nscr.cap) {
+        const int64_t m = n - o < ctx->nscr.cap ? n - o : ctx->nscr.cap;
+        *launches += netf32_forward(ctx->net, ctx->nscr, tensor_dev + o * WIN * C, m, probs_dev + o * 24, st);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace

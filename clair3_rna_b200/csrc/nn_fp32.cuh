@@ -1,0 +1,248 @@
+// Pileup network forward, fp32 on CUDA cores ("nn_impl = 0").
+//
+// Exact-arithmetic companion of the tensor-core path in nn_tc.cuh: same layer
+// decomposition, plain FFMA.  It exists so probabilities can be checked at fp32
+// precision on the device itself and so the integer half can be brought up
+// independently; the tcgen05 path is the one the bench measures.
+//
+// Math restated from /root/reference/clair3_rna/model.py:126-216 (Keras LSTM,
+// gate order i,f,c,o, sigmoid/tanh; Bidirectional concat; Flatten; Dense+SELU;
+// SELU-then-softmax heads) — SURVEY.md Appendix D.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace c3r {
+
+constexpr int U1 = 128, U2 = 160, NT = 33;
+constexpr int G1 = 4 * U1, G2 = 4 * U2;          // gate widths 512 / 640
+constexpr int H1W = 2 * U1, H2W = 2 * U2;        // 256 / 320
+constexpr int L4_IN = NT * H2W;                  // 10560
+constexpr int DENSE = 128;
+
+struct NetF32 {                                  // device pointers, Keras layouts
+    int C;
+    const float* w1;    // [C, 1024]   = [fwd kernel | bwd kernel]
+    const float* b1;    // [1024]
+    const float* u1;    // [2][128, 512]
+    const float* w2;    // [256, 1280]
+    const float* b2;    // [1280]
+    const float* u2;    // [2][160, 640]
+    const float* k4; const float* b4;            // [10560,128]
+    const float* k51; const float* b51;          // [128,128]
+    const float* k52; const float* b52;
+    const float* ky1; const float* by1;          // [128,21]
+    const float* ky2; const float* by2;          // [128,3]
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float seluf_(float x) {
+    return 1.0507009873554805f * (x > 0.0f ? x : 1.6732632423543772f * expm1f(x));
+}
+
+__global__ void k_i32_to_f32(const int32_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (float)in[i];
+}
+
+// C[M,N] = act(A[M,K] * B[K,N] + bias[N]);  64x64 tile, 256 threads, 4x4 per thread
+template <int ACT>
+__global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ A, const float* __restrict__ B,
+                                               const float* __restrict__ bias, float* __restrict__ Cm,
+                                               int64_t M, int N, int K) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t m0 = (int64_t)blockIdx.y * 64;
+    const int n0 = blockIdx.x * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        // A tile: 64 rows x 16 k  (thread loads 4 elements)
+        for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+            const int r = e >> 4, kk = e & 15;
+            const int64_t m = m0 + r;
+            As[kk][r] = (m < M && k0 + kk < K) ? A[m * K + k0 + kk] : 0.0f;
+        }
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int kk = e >> 6, c = e & 63;
+            Bs[kk][c] = (k0 + kk < K && n0 + c < N) ? B[(int64_t)(k0 + kk) * N + n0 + c] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.0f);
+            if (ACT == 1) v = seluf_(v);
+            Cm[m * N + n] = v;
+        }
+    }
+}
+
+// One LSTM time step for both directions.
+//   zx  [n, 33, 2*4u]   input projection + bias, (dir, gate, unit) along the last axis
+//   U   [2][u, 4u]      recurrent kernels
+//   hprev/hnext [2][n, u], c [2][n, u]
+//   hout [n, 33, 2u]    layer output, forward time order
+// block = 32 units x 8 site-groups, each thread 4 sites; grid (ceil(n/32), u/32, 2)
+template <int U>
+__global__ void __launch_bounds__(256) k_lstm_step(const float* __restrict__ zx, const float* __restrict__ Uk,
+                                                   const float* __restrict__ hprev, float* __restrict__ hnext,
+                                                   float* __restrict__ c, float* __restrict__ hout,
+                                                   int64_t n, int step) {
+    __shared__ float hs[32][U + 1];
+    const int dir = blockIdx.z;
+    const int t = dir == 0 ? step : NT - 1 - step;
+    const int unit = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int sg = threadIdx.x >> 5;                         // 0..7
+    const int64_t s0 = (int64_t)blockIdx.x * 32;
+    const float* Ud = Uk + (int64_t)dir * U * 4 * U;
+    const float* hp = hprev + (int64_t)dir * n * U;
+    for (int e = threadIdx.x; e < 32 * U; e += 256) {
+        const int r = e / U, k = e % U;
+        hs[r][k] = (step > 0 && s0 + r < n) ? hp[(s0 + r) * U + k] : 0.0f;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[i][g] = 0.0f;
+    if (step > 0) {
+        for (int k = 0; k < U; ++k) {
+            float w[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) w[g] = Ud[(int64_t)k * 4 * U + g * U + unit];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float h = hs[sg * 4 + i][k];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) acc[i][g] = fmaf(h, w[g], acc[i][g]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t s = s0 + sg * 4 + i;
+        if (s >= n) continue;
+        const float* z = zx + (s * NT + t) * (8 * U) + dir * 4 * U;
+        const float zi = acc[i][0] + z[unit], zf = acc[i][1] + z[U + unit];
+        const float zg = acc[i][2] + z[2 * U + unit], zo = acc[i][3] + z[3 * U + unit];
+        const int64_t ci = (int64_t)dir * n * U + s * U + unit;
+        const float cp = step > 0 ? c[ci] : 0.0f;
+        const float cn = sigmoidf_(zf) * cp + sigmoidf_(zi) * tanhf(zg);
+        const float h = sigmoidf_(zo) * tanhf(cn);
+        c[ci] = cn;
+        hnext[ci] = h;
+        hout[(s * NT + t) * (2 * U) + dir * U + unit] = h;
+    }
+}
+
+// L5_1/L5_2 + the two SELU heads + softmax; one block of 128 threads per site
+__global__ void __launch_bounds__(128) k_heads(NetF32 w, const float* __restrict__ l4, float* __restrict__ probs, int64_t n) {
+    __shared__ float x[DENSE], a1[DENSE], a2[DENSE], y[24];
+    for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
+        const int j = threadIdx.x;
+        x[j] = l4[s * DENSE + j];
+        __syncthreads();
+        float s1 = w.b51[j], s2 = w.b52[j];
+        for (int k = 0; k < DENSE; ++k) {
+            s1 = fmaf(x[k], w.k51[k * DENSE + j], s1);
+            s2 = fmaf(x[k], w.k52[k * DENSE + j], s2);
+        }
+        a1[j] = seluf_(s1);
+        a2[j] = seluf_(s2);
+        __syncthreads();
+        if (j < 21) {
+            float v = w.by1[j];
+            for (int k = 0; k < DENSE; ++k) v = fmaf(a1[k], w.ky1[k * 21 + j], v);
+            y[j] = seluf_(v);
+        } else if (j < 24) {
+            float v = w.by2[j - 21];
+            for (int k = 0; k < DENSE; ++k) v = fmaf(a2[k], w.ky2[k * 3 + (j - 21)], v);
+            y[j] = seluf_(v);
+        }
+        __syncthreads();
+        if (j < 24) {
+            const int lo = j < 21 ? 0 : 21, hi = j < 21 ? 21 : 24;
+            float mx = y[lo];
+            for (int k = lo + 1; k < hi; ++k) mx = fmaxf(mx, y[k]);
+            float sum = 0.0f;
+            for (int k = lo; k < hi; ++k) sum += expf(y[k] - mx);
+            probs[s * 24 + j] = expf(y[j] - mx) / sum;
+        }
+        __syncthreads();
+    }
+}
+
+struct NetF32Scratch {
+    float *x, *zx1, *h1, *zx2, *h2, *l4, *hbuf, *cbuf;      // sized for `cap` sites
+    int64_t cap;
+};
+
+inline size_t netf32_scratch_bytes(int64_t cap, int C) {
+    size_t f = (size_t)cap * NT * C + (size_t)cap * NT * 2 * G1 + (size_t)cap * NT * H1W + (size_t)cap * NT * 2 * G2 +
+               (size_t)cap * NT * H2W + (size_t)cap * DENSE + (size_t)cap * 2 * U2 * 2 + (size_t)cap * 2 * U2;
+    return f * sizeof(float) + 4096;
+}
+
+// forward of n <= scratch.cap sites; tensor int32 [n,33,C] on the device -> probs [n,24].  returns launches.
+inline int netf32_forward(const NetF32& w, const NetF32Scratch& s, const int32_t* tensor, int64_t n, float* probs,
+                          cudaStream_t st) {
+    if (n <= 0) return 0;
+    int launches = 0;
+    const int C = w.C;
+    const int64_t rows = n * NT;
+    k_i32_to_f32<<<(unsigned)((rows * C + 1023) / 1024 < 4096 ? (rows * C + 1023) / 1024 : 4096), 256, 0, st>>>(tensor, s.x, rows * C);
+    ++launches;
+    dim3 g1((2 * G1 + 63) / 64, (unsigned)((rows + 63) / 64));
+    k_sgemm<0><<<g1, 256, 0, st>>>(s.x, w.w1, w.b1, s.zx1, rows, 2 * G1, C);
+    ++launches;
+    float* hA = s.hbuf;
+    float* hB = s.hbuf + (size_t)s.cap * 2 * U2;
+    for (int step = 0; step < NT; ++step) {
+        dim3 g((unsigned)((n + 31) / 32), U1 / 32, 2);
+        k_lstm_step<U1><<<g, 256, 0, st>>>(s.zx1, w.u1, hA, hB, s.cbuf, s.h1, n, step);
+        ++launches;
+        float* tmp = hA; hA = hB; hB = tmp;
+    }
+    dim3 g2((2 * G2 + 63) / 64, (unsigned)((rows + 63) / 64));
+    k_sgemm<0><<<g2, 256, 0, st>>>(s.h1, w.w2, w.b2, s.zx2, rows, 2 * G2, H1W);
+    ++launches;
+    for (int step = 0; step < NT; ++step) {
+        dim3 g((unsigned)((n + 31) / 32), U2 / 32, 2);
+        k_lstm_step<U2><<<g, 256, 0, st>>>(s.zx2, w.u2, hA, hB, s.cbuf, s.h2, n, step);
+        ++launches;
+        float* tmp = hA; hA = hB; hB = tmp;
+    }
+    dim3 g4((DENSE + 63) / 64, (unsigned)((n + 63) / 64));
+    k_sgemm<1><<<g4, 256, 0, st>>>(s.h2, w.k4, w.b4, s.l4, n, DENSE, L4_IN);
+    ++launches;
+    k_heads<<<(unsigned)(n < 2048 ? n : 2048), 128, 0, st>>>(w, s.l4, probs, n);
+    ++launches;
+    return launches;
+}
+
+}  // namespace c3r

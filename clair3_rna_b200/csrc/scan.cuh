@@ -1,0 +1,135 @@
+// Device-wide inclusive scan, three passes (tile reduce / aggregate scan / tile apply).
+//
+// The pileup path needs a handful of small scans (CIGAR ops, bitmap words, rows,
+// bins, candidates); each is expressed as an `Op` functor so the load (e.g. decode
+// a CIGAR word) and the store (e.g. emit op geometry, mark coverage) are fused into
+// the scan passes instead of being separate kernels.
+//
+//   struct Op {
+//       typedef ... T;                                   // POD
+//       __device__ T identity() const;
+//       __device__ T combine(const T& a, const T& b) const;   // associative, a before b
+//       __device__ T load(int64_t i) const;
+//       __device__ void store(int64_t i, const T& inclusive, const T& own) const;
+//       __device__ int64_t size() const;                 // element count (may read device memory)
+//   };
+//
+// Grids are sized from a host-side upper bound; tiles beyond size() exit.  A three
+// pass scan reads the input twice; it is used because every scan here is far smaller
+// than the count/tensor traffic and a look-back scan can spin forever if a
+// predecessor tile is not resident.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace c3r {
+
+constexpr int SCAN_BT = 256;      // threads per block
+constexpr int SCAN_IPT = 8;       // items per thread
+constexpr int SCAN_TILE = SCAN_BT * SCAN_IPT;
+
+template <class Op>
+__device__ __forceinline__ typename Op::T block_scan_exclusive(const Op& op, typename Op::T v,
+                                                               typename Op::T* smem, typename Op::T* total) {
+    // Hillis-Steele over SCAN_BT thread aggregates in shared memory.
+    typedef typename Op::T T;
+    const int t = threadIdx.x;
+    smem[t] = v;
+    __syncthreads();
+#pragma unroll
+    for (int d = 1; d < SCAN_BT; d <<= 1) {
+        T x = smem[t];
+        if (t >= d) x = op.combine(smem[t - d], x);
+        __syncthreads();
+        smem[t] = x;
+        __syncthreads();
+    }
+    T excl = t ? smem[t - 1] : op.identity();
+    if (total) *total = smem[SCAN_BT - 1];
+    return excl;
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SCAN_BT) scan_reduce_kernel(Op op, typename Op::T* tile_aggr) {
+    typedef typename Op::T T;
+    __shared__ T smem[SCAN_BT];
+    const int64_t n = op.size();
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
+    const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_IPT;
+    T acc = op.identity();
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k)
+        if (i0 + k < n) acc = op.combine(acc, op.load(i0 + k));
+    __shared__ T tot;
+    block_scan_exclusive(op, acc, smem, threadIdx.x == 0 ? &tot : (T*)nullptr);
+    // thread SCAN_BT-1's inclusive value is the tile aggregate
+    if (threadIdx.x == SCAN_BT - 1) tile_aggr[blockIdx.x] = smem[SCAN_BT - 1];
+}
+
+// single block: tile_aggr[0..nb) -> exclusive prefix in place; total to *total_out
+template <class Op>
+__global__ void __launch_bounds__(SCAN_BT) scan_aggr_kernel(Op op, typename Op::T* tile_aggr, typename Op::T* total_out) {
+    typedef typename Op::T T;
+    __shared__ T smem[SCAN_BT];
+    __shared__ T carry_s;
+    const int64_t n = op.size();
+    const int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (threadIdx.x == 0) carry_s = op.identity();
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < nb; b0 += SCAN_BT) {
+        const int64_t i = b0 + threadIdx.x;
+        T v = i < nb ? tile_aggr[i] : op.identity();
+        T excl = block_scan_exclusive(op, v, smem, (T*)nullptr);
+        T carry = carry_s;
+        T chunk_total = smem[SCAN_BT - 1];
+        __syncthreads();
+        if (i < nb) tile_aggr[i] = op.combine(carry, excl);
+        if (threadIdx.x == 0) carry_s = op.combine(carry, chunk_total);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SCAN_BT) scan_apply_kernel(Op op, const typename Op::T* tile_excl) {
+    typedef typename Op::T T;
+    __shared__ T smem[SCAN_BT];
+    const int64_t n = op.size();
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
+    const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_IPT;
+    T own[SCAN_IPT];
+    T acc = op.identity();
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        if (i0 + k < n) {
+            own[k] = op.load(i0 + k);
+            acc = op.combine(acc, own[k]);
+        }
+    }
+    T excl = block_scan_exclusive(op, acc, smem, (T*)nullptr);
+    T run = op.combine(tile_excl[blockIdx.x], excl);
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        if (i0 + k < n) {
+            run = op.combine(run, own[k]);
+            op.store(i0 + k, run, own[k]);
+        }
+    }
+}
+
+// Host helper.  `n_upper` bounds op.size(); scratch must hold ceil(n_upper/SCAN_TILE) T's.
+// Returns the number of kernels launched.
+template <class Op>
+inline int device_scan(const Op& op, int64_t n_upper, typename Op::T* scratch, typename Op::T* total_out,
+                       cudaStream_t stream) {
+    if (n_upper <= 0) n_upper = 1;
+    const unsigned nb = (unsigned)((n_upper + SCAN_TILE - 1) / SCAN_TILE);
+    scan_reduce_kernel<Op><<<nb, SCAN_BT, 0, stream>>>(op, scratch);
+    scan_aggr_kernel<Op><<<1, SCAN_BT, 0, stream>>>(op, scratch, total_out);
+    scan_apply_kernel<Op><<<nb, SCAN_BT, 0, stream>>>(op, scratch);
+    return 3;
+}
+
+}  // namespace c3r

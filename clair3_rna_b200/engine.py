@@ -1,0 +1,219 @@
+"""Host side of the C ABI: one `Engine` per GPU.
+
+`Engine.call_chunk()` is the in-process replacement of one reference
+`call_var_bam` producer|consumer pipeline up to the 24 probabilities
+(/root/reference/clair3_rna/call_var_bam.py:278-295): it packs nothing itself,
+it hands the flat records of `reads.ReadBatch` to libc3r_b200.so and copies the
+library-owned result buffers into numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+import numpy as np
+
+from . import lib as L
+from . import params as P
+from .reads import ReadBatch, NT16
+
+
+class C3RError(RuntimeError):
+    pass
+
+
+@dataclass
+class ChunkResult:
+    n_rows: int
+    pos: np.ndarray            # int32 [n] 1-based
+    depth: np.ndarray          # int32 [n]
+    probs: np.ndarray          # float32 [n,24]
+    alt_off: np.ndarray        # int64 [n]
+    alt_n: np.ndarray          # int32 [n]
+    alt: np.ndarray            # structured [total]
+    tensor: np.ndarray | None  # int32 [n,33,C]
+    row_pos: np.ndarray | None
+    row_counts: np.ndarray | None
+    row_depth: np.ndarray | None
+    stage_ms: list = field(default_factory=list)
+    launches: int = 0
+
+    @property
+    def n_cand(self) -> int:
+        return int(self.pos.size)
+
+
+ALT_DTYPE = np.dtype([("kind", "u1"), ("base", "u1"), ("len", "<u2"), ("count", "<i4"),
+                      ("seq_off", "<u4"), ("order", "<u4")])
+
+
+def _view(ptr, n, dtype):
+    if not ptr or n <= 0:
+        return np.zeros(0, dtype)
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    buf = (C.c_char * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(n)).copy()
+
+
+class Engine:
+    def __init__(self, device: int = 0, channels: int = 18, *, snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF,
+                 min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ, enable_padding=False, nn_impl=1,
+                 keep_tensor=False, keep_rows=False):
+        self.lib = L.load()
+        if self.lib.c3r_abi_version() != 1:
+            raise C3RError("ABI version mismatch")
+        prm = L.Params()
+        self.lib.c3r_default_params(C.byref(prm))
+        prm.channels = channels
+        prm.snp_min_af = snp_min_af
+        prm.indel_min_af = indel_min_af
+        prm.min_coverage = min_coverage
+        prm.min_mq = min_mq
+        prm.enable_padding = int(enable_padding)
+        prm.nn_impl = nn_impl
+        prm.keep_tensor = int(keep_tensor)
+        prm.keep_rows = int(keep_rows)
+        self.params = prm
+        self.channels = channels
+        self.ctx = C.c_void_p()
+        rc = self.lib.c3r_create(C.byref(self.ctx), device, C.byref(prm))
+        if rc != 0:
+            msg = self.lib.c3r_last_error(self.ctx).decode() if self.ctx else "c3r_create failed"
+            if self.ctx:
+                self.lib.c3r_destroy(self.ctx)
+                self.ctx = C.c_void_p()
+            raise C3RError("c3r_create: %s (rc=%d)" % (msg, rc))
+        self._keep = {}
+
+    # ------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc < 0:
+            raise C3RError("%s: %s (rc=%d)" % (what, self.lib.c3r_last_error(self.ctx).decode(), rc))
+        return rc
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.c3r_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, weights: dict):
+        arrs = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()}
+        views = (L.WeightView * len(arrs))()
+        for i, (k, v) in enumerate(arrs.items()):
+            views[i].name = k.encode()
+            views[i].data = v.ctypes.data
+            views[i].n_elem = v.size
+        self._check(self.lib.c3r_set_weights(self.ctx, views, len(arrs)), "c3r_set_weights")
+
+    # ------------------------------------------------------------------
+    def submit(self, batch: ReadBatch, ref: np.ndarray, ref_start1: int, region_start1: int, region_end1: int) -> int:
+        rd = L.Reads()
+        rd.n_reads, rd.n_ops, rd.n_seq_bytes = batch.n_reads, batch.n_ops, int(batch.seq.size)
+        arrs = dict(pos=np.ascontiguousarray(batch.pos, np.int32), flag=np.ascontiguousarray(batch.flag, np.uint16),
+                    mapq=np.ascontiguousarray(batch.mapq, np.uint8), hp=np.ascontiguousarray(batch.hp, np.uint8),
+                    cigar_off=np.ascontiguousarray(batch.cigar_off, np.int32),
+                    cigar=np.ascontiguousarray(batch.cigar, np.uint32),
+                    seq_off=np.ascontiguousarray(batch.seq_off, np.int64), seq=np.ascontiguousarray(batch.seq, np.uint8))
+        for k, v in arrs.items():
+            setattr(rd, k, v.ctypes.data)
+        ref = np.ascontiguousarray(ref, np.uint8)
+        t = C.c_int64(-1)
+        self._check(self.lib.c3r_submit_chunk(self.ctx, C.byref(rd), ref.ctypes.data, ref_start1, int(ref.size),
+                                              region_start1, region_end1, C.byref(t)), "c3r_submit_chunk")
+        return int(t.value)
+
+    def wait(self, ticket: int, release: bool = True) -> ChunkResult:
+        r = L.Result()
+        self._check(self.lib.c3r_wait(self.ctx, ticket, C.byref(r)), "c3r_wait")
+        n, Ct = int(r.n_cand), self.channels
+        alt_off = _view(r.alt_off, n, np.int64)
+        alt_n = _view(r.alt_n, n, np.int32)
+        total = int((alt_off + alt_n).max()) if n else 0
+        out = ChunkResult(
+            n_rows=int(r.n_rows), pos=_view(r.pos, n, np.int32), depth=_view(r.depth, n, np.int32),
+            probs=_view(r.probs, n * 24, np.float32).reshape(n, 24), alt_off=alt_off, alt_n=alt_n,
+            alt=_view(r.alt, total, ALT_DTYPE),
+            tensor=_view(r.tensor, n * 33 * Ct, np.int32).reshape(n, 33, Ct) if r.tensor else None,
+            row_pos=_view(r.row_pos, r.n_rows, np.int32) if r.row_pos else None,
+            row_counts=_view(r.row_counts, r.n_rows * Ct, np.int32).reshape(-1, Ct) if r.row_counts else None,
+            row_depth=_view(r.row_depth, r.n_rows, np.int32) if r.row_depth else None,
+            stage_ms=[float(x) for x in r.stage_ms], launches=int(r.kernel_launches))
+        if release:
+            self.lib.c3r_release(self.ctx, ticket)
+        return out
+
+    def release(self, ticket: int):
+        self.lib.c3r_release(self.ctx, ticket)
+
+    def call_chunk(self, batch, ref, ref_start1, region_start1, region_end1) -> ChunkResult:
+        return self.wait(self.submit(batch, ref, ref_start1, region_start1, region_end1))
+
+    def rerun_resident(self, ticket: int):
+        """-> (total_ms, [8 stage ms], kernel launches) of one device-resident pass."""
+        tot = C.c_float(0)
+        st = (C.c_float * 8)()
+        n = self._check(self.lib.c3r_rerun_resident(self.ctx, ticket, C.byref(tot), st), "c3r_rerun_resident")
+        return float(tot.value), [float(x) for x in st], n
+
+    def forward(self, tensor: np.ndarray):
+        """network alone: int32 [n,33,C] -> (float32 [n,24], device ms)"""
+        t = np.ascontiguousarray(tensor, np.int32)
+        n = t.shape[0]
+        out = np.empty((n, 24), np.float32)
+        ms = C.c_float(0)
+        self._check(self.lib.c3r_forward(self.ctx, t.ctypes.data, n, out.ctypes.data, C.byref(ms)), "c3r_forward")
+        return out, float(ms.value)
+
+
+# ---------------------------------------------------------------------- host formatting
+def alt_info_strings(res: ChunkResult, batch: ReadBatch, ref: np.ndarray, ref_start1: int) -> list:
+    """alt_info text of each candidate exactly as the reference's producer prints it
+    (/root/reference/src/create_tensor_pileup.py:595-596): "<depth>-KEY n KEY n ..."."""
+    out = []
+    seq = batch.seq
+    refb = ref.tobytes() if isinstance(ref, np.ndarray) else bytes(ref)
+    for i in range(res.n_cand):
+        a, n = int(res.alt_off[i]), int(res.alt_n[i])
+        items = []
+        p0 = int(res.pos[i]) - ref_start1           # offset of the candidate in ref
+        for e in res.alt[a:a + n]:
+            kind = chr(int(e["kind"]))
+            if kind == 'X' or kind == 'R':
+                key = kind + chr(int(e["base"]))
+            elif kind == 'I':
+                q, ln = int(e["seq_off"]), int(e["len"])
+                by = seq[q // 2: (q + ln + 1) // 2 + 1]
+                codes = np.empty(by.size * 2, np.uint8)
+                codes[0::2] = by >> 4
+                codes[1::2] = by & 15
+                s = codes[q & 1: (q & 1) + ln]
+                key = 'I' + chr(int(e["base"])) + "".join(NT16[c] for c in s)
+            else:
+                ln = int(e["len"])
+                key = 'D' + refb[p0 + 1: p0 + 1 + ln].decode("ascii")
+            items.append("%s %d" % (key, int(e["count"])))
+        out.append("%d-%s" % (int(res.depth[i]), " ".join(items)))
+    return out
+
+
+def flank_strings(res: ChunkResult, ref: np.ndarray, ref_start1: int) -> list:
+    """33-base reference context, padded with 'A' off the loaded reference
+    (get_flanked_sequence, create_tensor_pileup.py:313-331)."""
+    refs = ref.tobytes().decode("ascii")
+    out = []
+    for p in res.pos:
+        lo = int(p) - P.FLANK - ref_start1
+        hi = int(p) + P.FLANK + 1 - ref_start1
+        if lo >= 0 and hi <= len(refs):
+            out.append(refs[lo:hi])
+        else:
+            s = 'A' * max(0, -lo) + refs[max(0, lo):hi]
+            if hi > len(refs):
+                s += 'A' * (hi - len(refs))
+            out.append(s)
+    return out

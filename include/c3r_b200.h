@@ -1,0 +1,150 @@
+/*
+ * c3r_b200.h — C ABI of libc3r_b200.so: the B200-native pileup calling hot path
+ * of Clair3-RNA (candidate tensor generation + pileup-network inference).
+ *
+ * The reference has no in-process plugin API for this path: it sits behind a
+ * process boundary, `python clair3_rna.py call_var_bam ...` per (contig, chunk)
+ * (/root/reference/run_clair3_rna:681-706, clair3_rna/call_var_bam.py:88-333),
+ * which pipes `create_tensor_pileup` text rows into `call_variants`.  The entry
+ * points below are what a binding for that unit of work needs; each one cites
+ * the reference code it replaces.  See INTEGRATION.md for the ctypes stub.
+ *
+ * Conventions: every call returns 0 on success and a negative c3r_status on
+ * failure; c3r_last_error(ctx) returns a message for the last failure on that
+ * context (valid until the next call on it).  No exceptions cross the boundary.
+ * A context is bound to one GPU and is single-producer (not thread safe);
+ * distinct contexts are independent.  Inputs are borrowed for the duration of
+ * the call only (they are copied to the device before the call returns).
+ * Result buffers are owned by the library (pinned host memory) and stay valid
+ * until c3r_release() for that ticket or c3r_destroy().
+ */
+#ifndef C3R_B200_H
+#define C3R_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C3R_ABI_VERSION 1
+#define C3R_WINDOW 33        /* shared/param_p.py:34-35  no_of_positions */
+#define C3R_N_OUT 24         /* 21 gt21 + 3 genotype, shared/param_p.py:37 */
+
+typedef enum {
+    C3R_OK = 0,
+    C3R_ERR_ARG = -1,        /* bad argument / unsupported value            */
+    C3R_ERR_CUDA = -2,       /* CUDA runtime error, see c3r_last_error      */
+    C3R_ERR_STATE = -3,      /* call order violated (no weights, bad ticket)*/
+    C3R_ERR_CAPACITY = -4    /* input exceeds a documented limit            */
+} c3r_status;
+
+typedef struct c3r_ctx c3r_ctx;
+
+/* Options of the path.  Defaults mirror shared/param_p.py and the argv
+ * call_var_bam forwards (clair3_rna/call_var_bam.py:205-245). */
+typedef struct {
+    int32_t channels;        /* 18, or 30 with --enable_phasing_model (create_tensor_pileup.py:466) */
+    int32_t min_coverage;    /* --minCoverage, param_p.py:90 (4)           */
+    int32_t min_mq;          /* --minMQ, param_p.py:20 (5)                 */
+    uint32_t excl_flags;     /* samtools --excl-flags, param_p.py:41 (2316)*/
+    double snp_min_af;       /* --snp_min_af, param_p.py:88 (0.08)         */
+    double indel_min_af;     /* --indel_min_af, param_p.py:89 (0.15)       */
+    int32_t enable_padding;  /* --enable_padding_in_splice_junction_regions (create_tensor_pileup.py:573-593) */
+    int32_t max_depth;       /* param_p.py:14 (144): depth > 1.5*max_depth rescales the window (clair3_rna/utils.py:85-92) */
+    double skip_proportion;  /* param_p.py:46 (0.2)                        */
+    int32_t nn_impl;         /* 0 = fp32 CUDA-core network, 1 = tcgen05 fp16/fp32-accumulate network */
+    int32_t keep_tensor;     /* also return the int32 windows (parity / debug) */
+    int32_t keep_rows;       /* also return the per-position count matrix (parity / debug) */
+} c3r_params;
+
+/* Flat alignment records of one region, BAM record order (coordinate sorted).
+ * This is what `samtools mpileup BAM -r ctg:s-e` reads from the BAM
+ * (create_tensor_pileup.py:446-451); layout in clair3_rna_b200/reads.py. */
+typedef struct {
+    int64_t n_reads;
+    int64_t n_ops;
+    int64_t n_seq_bytes;
+    const int32_t* pos;        /* [n_reads]   0-based leftmost position          */
+    const uint16_t* flag;      /* [n_reads]   SAM flag                           */
+    const uint8_t* mapq;       /* [n_reads]                                      */
+    const uint8_t* hp;         /* [n_reads]   HP:i tag, 0 = absent               */
+    const int32_t* cigar_off;  /* [n_reads+1] CSR into cigar                     */
+    const uint32_t* cigar;     /* [n_ops]     BAM encoding len<<4|op             */
+    const int64_t* seq_off;    /* [n_reads+1] base offsets, each even            */
+    const uint8_t* seq;        /* [n_seq_bytes] nt16 nibbles, high nibble first  */
+} c3r_reads;
+
+/* Network weights in Keras layout, fp32 (clair3_rna/model.py:126-156):
+ *   LSTM{1,2}/{forward,backward}/{kernel[in,4u], recurrent_kernel[u,4u], bias[4u]}   gate order i,f,c,o
+ *   L4, L5_1, L5_2, Y_gt21_logits, Y_genotype_logits: {kernel[in,out], bias[out]}
+ * Replaces m.load_weights(chkpnt_fn) at clair3_rna/call_variants.py:1472. */
+typedef struct {
+    const char* name;          /* e.g. "LSTM1/forward/kernel" */
+    const float* data;
+    int64_t n_elem;
+} c3r_weight_view;
+
+/* One allele of a candidate's alt_info (create_tensor_pileup.py:595-596),
+ * in the reference's dict insertion order. */
+typedef struct {
+    uint8_t kind;              /* 'X' base, 'I' insertion, 'D' deletion, 'R' reference */
+    uint8_t base;              /* X: alt base letter; R/I: reference base letter       */
+    uint16_t len;              /* I: inserted length; D: deleted length                */
+    int32_t count;
+    uint32_t seq_off;          /* I: base offset of the inserted bases in c3r_reads.seq */
+    uint32_t order;            /* first-occurrence key (read ordinal*2 + is_indel)     */
+} c3r_alt_entry;
+
+typedef struct {
+    int64_t n_rows;            /* pileup rows (covered positions kept on the device)   */
+    int64_t n_cand;            /* emitted candidates                                   */
+    const int32_t* pos;        /* [n_cand] 1-based candidate position                  */
+    const int32_t* depth;      /* [n_cand] depth as in alt_info                        */
+    const float* probs;        /* [n_cand*24] network output                           */
+    const int64_t* alt_off;    /* [n_cand]   start of each candidate's alleles         */
+    const int32_t* alt_n;      /* [n_cand]   number of alleles                         */
+    const c3r_alt_entry* alt;
+    const int32_t* tensor;     /* [n_cand*33*channels] or NULL (keep_tensor)           */
+    const int32_t* row_pos;    /* [n_rows] 1-based, or NULL (keep_rows)                */
+    const int32_t* row_counts; /* [n_rows*channels] or NULL (keep_rows)                */
+    const int32_t* row_depth;  /* [n_rows] or NULL (keep_rows)                         */
+    float stage_ms[8];         /* device time of: 0 H2D, 1 K1 scan+rows, 2 bin, 3 K2 count, 4 K3 filter,
+                                  5 K4 window+alt, 6 K5 network, 7 D2H                  */
+    int32_t kernel_launches;   /* kernels launched for this ticket                     */
+} c3r_result;
+
+typedef int64_t c3r_ticket;
+
+int c3r_abi_version(void);
+void c3r_default_params(c3r_params* p);
+
+int c3r_create(c3r_ctx** out, int device_ordinal, const c3r_params* params);
+void c3r_destroy(c3r_ctx* ctx);
+const char* c3r_last_error(c3r_ctx* ctx);
+
+int c3r_set_weights(c3r_ctx* ctx, const c3r_weight_view* views, int n_views);
+
+/* One (contig, chunk): replaces one `call_var_bam` producer|consumer pipeline up
+ * to the 24 probabilities (clair3_rna/call_var_bam.py:278-295).
+ *   ref / ref_start1 / ref_len: upper-case reference bytes of [ref_start1, ref_start1+ref_len)
+ *                               (create_tensor_pileup.py:416-428, expandReferenceRegion)
+ *   region_start1..region_end1: the 1-based inclusive mpileup region (:412-415)          */
+int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* reads, const uint8_t* ref, int64_t ref_start1,
+                     int64_t ref_len, int64_t region_start1, int64_t region_end1, c3r_ticket* ticket);
+int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* result);
+int c3r_release(c3r_ctx* ctx, c3r_ticket ticket);
+
+/* Re-run the device stages of a ticket on the inputs already resident in HBM
+ * (no H2D, no D2H).  Used by bench.py for the device-resident throughput and
+ * by ncu captures.  total_ms receives the CUDA-event time of the pass. */
+int c3r_rerun_resident(c3r_ctx* ctx, c3r_ticket ticket, float* total_ms, float* stage_ms8);
+
+/* Network forward alone on host int32 windows [n,33,channels] -> probs [n,24]
+ * (clair3_rna/model.py:175-216 via predict_on_batch, call_variants.py:1505). */
+int c3r_forward(c3r_ctx* ctx, const int32_t* tensor, int64_t n, float* probs, float* device_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C3R_B200_H */

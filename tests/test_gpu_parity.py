@@ -1,0 +1,129 @@
+"""GPU parity: the CUDA path through the C ABI against (a) the golden vectors the
+reference's own code produced and (b) the oracle on the same inputs.  Integer
+results are bit exact; probabilities within 1e-3 absolute (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden import cases as golden_cases
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+PROB_TOL = 1e-3          # north_star: network probabilities within 1e-3 absolute
+
+
+def load_golden(name):
+    z = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+_cache = {}
+
+
+def run_case(name, nn_impl):
+    key = (name, nn_impl)
+    if key in _cache:
+        return _cache[key]
+    from clair3_rna_b200 import weights
+    from clair3_rna_b200.engine import Engine
+    case = golden_cases.CASES[name]
+    batch, ref_bytes, contig = golden_cases.build(name)
+    ref = np.frombuffer(ref_bytes, np.uint8)
+    C = 30 if case["phased"] else 18
+    eng = Engine(0, C, snp_min_af=case["snp_af"], indel_min_af=case["indel_af"], min_coverage=case["min_cov"],
+                 min_mq=case["min_mq"], enable_padding=case["padding"], nn_impl=nn_impl,
+                 keep_tensor=True, keep_rows=True)
+    w = weights.synthetic(C, sharpen=8.0)
+    eng.set_weights(w)
+    res = eng.call_chunk(batch, ref, 1, 1, len(ref_bytes) + 33)
+    eng.close()
+    _cache[key] = (res, batch, ref, w)
+    return _cache[key]
+
+
+@pytest.mark.parametrize("name", sorted(golden_cases.CASES))
+def test_candidates_and_tensors_match_reference_golden(name):
+    from clair3_rna_b200.engine import alt_info_strings, flank_strings
+    g = load_golden(name)
+    res, batch, ref, _ = run_case(name, 0)
+    assert res.pos.tolist() == g["pos"].tolist()
+    assert res.depth.tolist() == g["depth"].tolist()
+    assert np.array_equal(res.tensor, g["tensor"])
+    assert alt_info_strings(res, batch, ref, 1) == [str(s).rstrip("\n") for s in g["alt_info"]]
+    assert flank_strings(res, ref, 1) == [str(s) for s in g["ref33"]]
+
+
+@pytest.mark.parametrize("name", ["cfg1_ont_drna", "phased_noisy", "pad_dense"])
+def test_rows_match_oracle_columns(name):
+    """every count row against the oracle's per-column vector (not only candidate windows)"""
+    from oracle import mpileup, pileup_oracle
+    case = golden_cases.CASES[name]
+    res, batch, ref, _ = run_case(name, 0)
+    ref_seq = ref.tobytes().decode("ascii")
+    rows = {int(p): i for i, p in enumerate(res.row_pos)}
+    n_checked = 0
+    for pos1, depth_col, bases, hps in mpileup.mpileup_rows(batch, 1, len(ref_seq) + 33, 2316, case["min_mq"]):
+        vec, _alt, depth, _pass, _ms = pileup_oracle.column_vector(
+            pos1, bases, ref_seq, 1, hps.split(",") if case["phased"] else None, case["snp_af"], case["indel_af"])
+        if pos1 in rows:
+            i = rows[pos1]
+            assert res.row_counts[i].tolist() == vec, pos1
+            assert int(res.row_depth[i]) == depth
+            n_checked += 1
+        else:
+            assert depth == 0 and not any(vec), "covered column %d has no row" % pos1
+    assert n_checked == len(rows)
+
+
+@pytest.mark.parametrize("nn_impl", [0, 1])
+@pytest.mark.parametrize("name", ["cfg1_ont_drna", "cfg4_hifi_phased", "pad_dense", "phased_noisy"])
+def test_probabilities_match_oracle(name, nn_impl):
+    from oracle import model
+    g = load_golden(name)
+    res, _, _, w = run_case(name, nn_impl)
+    assert np.array_equal(res.tensor, g["tensor"])
+    p = model.forward(w, g["tensor"])
+    assert res.probs.shape == p.shape
+    err = np.abs(res.probs - p).max() if p.size else 0.0
+    assert err <= (1e-4 if nn_impl == 0 else PROB_TOL), err
+    # calls identical except where the top two probabilities are within the tolerance
+    for lo, hi in ((0, 21), (21, 24)):
+        a, b = res.probs[:, lo:hi], p[:, lo:hi]
+        differ = a.argmax(1) != b.argmax(1)
+        if differ.any():
+            srt = np.sort(b[differ], axis=1)
+            assert np.all(srt[:, -1] - srt[:, -2] <= 2 * PROB_TOL)
+
+
+def test_forward_entry_point_matches_chunk_path():
+    g = load_golden("cfg1_ont_drna")
+    res, _, _, w = run_case("cfg1_ont_drna", 0)
+    from clair3_rna_b200.engine import Engine
+    eng = Engine(0, 18, nn_impl=0)
+    eng.set_weights(w)
+    p, ms = eng.forward(g["tensor"])
+    eng.close()
+    assert np.allclose(p, res.probs, atol=1e-6)
+
+
+def test_empty_and_ragged_inputs():
+    from clair3_rna_b200 import weights
+    from clair3_rna_b200.engine import Engine
+    from clair3_rna_b200.reads import ReadBatch
+    eng = Engine(0, 18, nn_impl=0, keep_tensor=True)
+    eng.set_weights(weights.synthetic(18))
+    ref = np.frombuffer(b"ACGT" * 200, np.uint8)
+    empty = ReadBatch.from_records("chr1", [])
+    r = eng.call_chunk(empty, ref, 1, 1, 800)
+    assert r.n_cand == 0 and r.n_rows == 0
+    # a single short read: rows but no candidate can have a full flank on both sides of a 20 bp read
+    codes = np.array([1, 2, 4, 8] * 5, np.uint8)
+    one = ReadBatch.from_records("chr1", [(100, 0, 60, 0, [(20, 0)], codes)])
+    r = eng.call_chunk(one, ref, 1, 1, 800)
+    assert r.n_rows == 20 and r.n_cand == 0
+    # all reads filtered
+    filt = ReadBatch.from_records("chr1", [(100, 256, 60, 0, [(20, 0)], codes), (105, 0, 3, 0, [(20, 0)], codes)])
+    r = eng.call_chunk(filt, ref, 1, 1, 800)
+    assert r.n_rows == 0 and r.n_cand == 0
+    eng.close()
