@@ -32,7 +32,7 @@ struct Pin {
     size_t cap = 0;
 };
 
-constexpr int N_SLOTS = 2;
+constexpr int N_SLOTS = 4;
 constexpr int N_EV = 9;
 
 struct Slot {
@@ -76,6 +76,7 @@ struct c3r_ctx {
     Buf nn_scratch;
     NetF32Scratch nscr;
     TcNet tc;                 // tensor-core path state (nn_tc.cuh)
+    bool tc_dirty = false;    // a tensor-core forward ran since the last device error check
     Buf fwd_in, fwd_out;      // c3r_forward staging
     cudaStream_t fwd_stream = nullptr;
 };
@@ -268,6 +269,20 @@ int queue_d2h(c3r_ctx* ctx, Slot& s) {
 }
 
 int build_net(c3r_ctx* ctx, const std::map<std::string, std::pair<const float*, int64_t>>& w);
+
+// bounded mbarrier waits in the tensor-core kernels report protocol failures here
+int check_tc(c3r_ctx* ctx, cudaStream_t st) {
+    if (!ctx->tc_dirty) return 0;
+    ctx->tc_dirty = false;
+    int code = 0;
+    if (tc_check_error(ctx->tc, st, &code)) return fail(ctx, C3R_ERR_CUDA, "could not read the tensor-core error word");
+    if (code) {
+        char b[96];
+        snprintf(b, sizeof b, "tensor-core kernel synchronisation timed out (wait site %d)", code);
+        return fail(ctx, C3R_ERR_CUDA, b);
+    }
+    return 0;
+}
 
 }  // namespace
 
@@ -472,6 +487,7 @@ int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* res) {
     Dev& d = s.d;
     const int32_t err = ((const int32_t*)s.h_scalars.p)[6];
     if (err) return fail(ctx, C3R_ERR_CAPACITY, "device capacity check failed in the candidate stages");
+    if (int rc = check_tc(ctx, s.st)) return rc;
     s.alt_total = ((const int64_t*)s.h_scalars.p)[2];
     if (!s.has_result) {
         // alt entries: sized by the device-side total, copied after the first sync
@@ -480,6 +496,10 @@ int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* res) {
             if (ensure_pin(ctx, s.h_alt, (size_t)s.alt_total * sizeof(AltEntry))) return C3R_ERR_CUDA;
             CK(cudaMemcpyAsync(s.h_alt.p, s.alt.p, (size_t)s.alt_total * sizeof(AltEntry), cudaMemcpyDeviceToHost, s.st));
             CK(cudaStreamSynchronize(s.st));
+        }
+        if (ctx->prm.keep_rows) {                    // header: row_pos is 1-based
+            int32_t* rp = (int32_t*)s.h_row_pos.p;
+            for (int64_t i = 0; i < s.n_rows; ++i) rp[i] += 1;
         }
         s.has_result = true;
     }
@@ -529,6 +549,7 @@ int c3r_rerun_resident(c3r_ctx* ctx, c3r_ticket ticket, float* total_ms, float* 
     if (rc) return rc;
     CK(cudaEventRecord(s.ev[8], s.st));
     CK(cudaStreamSynchronize(s.st));
+    if (int rc3 = check_tc(ctx, s.st)) return rc3;
     if (total_ms) CK(cudaEventElapsedTime(total_ms, s.ev[0], s.ev[8]));
     if (stage_ms8) {
         for (int k = 0; k < 8; ++k) {
@@ -559,10 +580,33 @@ int c3r_forward(c3r_ctx* ctx, const int32_t* tensor, int64_t n, float* probs, fl
     CK(cudaEventRecord(e1, st));
     CK(cudaMemcpyAsync(probs, ctx->fwd_out.p, n * 96, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (int rc2 = check_tc(ctx, st)) return rc2;
     if (device_ms) CK(cudaEventElapsedTime(device_ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return nl;
+}
+
+int c3r_debug_fetch(c3r_ctx* ctx, int which, void* dst, int64_t max_bytes, int64_t* n_bytes) {
+    if (!ctx || !dst || !n_bytes) return C3R_ERR_ARG;
+    TcNet& t = ctx->tc;
+    if (!t.cap_tiles) return fail(ctx, C3R_ERR_STATE, "no tensor-core forward has run");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    const size_t tiles = (size_t)t.cap_tiles;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    switch (which) {
+        case 0: src = t.h1; bytes = tiles * NT * 4 * TC_IMG * 2; break;
+        case 1: src = t.zx2; bytes = tiles * NT * 10 * 128 * 128 * 4; break;
+        case 2: src = t.h2; bytes = tiles * NT * 5 * TC_IMG * 2; break;
+        case 3: src = t.l4; bytes = tiles * 128 * DENSE * 4; break;
+        default: return fail(ctx, C3R_ERR_ARG, "unknown buffer");
+    }
+    if ((int64_t)bytes > max_bytes) bytes = (size_t)max_bytes;
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    *n_bytes = (int64_t)bytes;
+    return C3R_OK;
 }
 
 }  // extern "C"
@@ -647,6 +691,7 @@ int nn_forward(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_
         int nl = tc_forward(ctx->tc, ctx->net, tensor_dev, n, probs_dev, st, &terr);
         if (nl < 0) return fail(ctx, C3R_ERR_CUDA, "tensor-core forward failed: " + terr);
         *launches = nl;
+        ctx->tc_dirty = true;
         return 0;
     }
     const int C = ctx->prm.channels;

@@ -1,10 +1,665 @@
-// placeholder replaced below by the tcgen05 implementation
+// Pileup network forward on the 5th-gen tensor cores ("nn_impl = 1").
+//
+//   fp16 operands, fp32 accumulation in TMEM, fp32 gate math and cell state.
+//   LSTM1's input kernel is split W = W_hi + W_lo (two fp16 terms) because its operand is
+//   raw read counts (|x| up to hundreds), everything else is single fp16.
+//
+// Kernels
+//   k_gemm_tc   tcgen05 GEMM, cta_group::1, 128x128 tiles, bulk-async-copy (TMA unit) operand
+//               pipeline.  Used for LSTM2's hoisted input projection (K=256, N=1280) and L4
+//               (K=10560, N=128, +SELU).
+//   k_lstm_tc   persistent recurrent layer, cta_group::2: a CTA pair owns 256 sites of one
+//               direction; the recurrent (and, for LSTM1, input) weights stay resident in
+//               shared memory split across the pair; per step tcgen05.mma -> TMEM -> gates in
+//               registers -> h back to shared memory as the next step's A operand.
+//
+// Operand layout everywhere: K-major, no swizzle, 8x(16 B) core matrices; element (r, k) of a
+// tile with R rows sits at  (k/8)*R*8 + r*8 + k%8  halfs  (LBO = R*16 B, SBO = 128 B).
+// Activations are written by their producer kernel already in this layout, so every operand
+// tile is one contiguous bulk copy.
+//
+// Math restated from /root/reference/clair3_rna/model.py:126-216.
 #pragma once
+#include <cstdint>
 #include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include "nn_fp32.cuh"
+#include "tc_ptx.cuh"
+
 namespace c3r {
-struct TcNet { int ready = 0; };
-inline int tc_build(TcNet&, const NetF32&, const float*, size_t, size_t, size_t, size_t, size_t, size_t, size_t, size_t, int, std::string*) { return 0; }
-inline int tc_forward(TcNet&, const NetF32&, const int32_t*, int64_t, float*, cudaStream_t, std::string* err) { *err = "tensor-core path not built yet"; return -1; }
-inline void tc_release(TcNet&) {}
+
+constexpr int TC_TILE = 128;                 // sites per CTA tile
+constexpr int TC_KB = 64;                    // K per pipeline stage
+constexpr int TC_IMG = TC_TILE * TC_KB;      // halfs in one 128x64 operand image (16 KB)
+
+// ================================================================== GEMM
+struct GemmArgs {
+    const __half* A;      // [m_tiles][n_kb][TC_IMG]
+    const __half* B;      // [n_tiles][n_kb][TC_IMG]
+    const float* bias;    // [n_tiles*128], GEMM column order
+    float* out;
+    int m_tiles, n_tiles, n_kb;
+    int mode;             // 0: ZX layout [m][n][32 col-groups][128 rows][4]   1: row-major [m*128+r][n_tiles*128] + SELU
+    int* err;
+};
+
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM = GEMM_STAGES * 2 * TC_IMG * 2 + 1024;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * 2 * TC_IMG * 2);
+    // bars: full[4] empty[4] acc_full[2] acc_empty[2], then tmem ptr
+    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 12);
+    const uint32_t s_base = ptx::smem_u32(smem);
+    const uint32_t b_full = ptx::smem_u32(bars), b_empty = b_full + 32, b_accf = b_full + 64, b_acce = b_full + 80;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < GEMM_STAGES; ++i) { ptx::mbar_init(b_full + 8 * i, 1); ptx::mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(b_accf + 8 * i, 1); ptx::mbar_init(b_acce + 8 * i, 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_ptr_s), 256);
+        ptx::tmem_relinquish<1>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_s;
+    const int n_tiles_total = g.m_tiles * g.n_tiles;
+    const uint32_t idesc = ptx::make_idesc_f16(128, 128);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+                const int m = tile / g.n_tiles, n = tile % g.n_tiles;
+                const __half* a = g.A + (size_t)m * g.n_kb * TC_IMG;
+                const __half* b = g.B + (size_t)n * g.n_kb * TC_IMG;
+                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
+                    const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
+                    ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 101);
+                    ptx::mbar_arrive_expect_tx(b_full + 8 * s, 2 * TC_IMG * 2);
+                    ptx::bulk_g2s(s_base + s * (2 * TC_IMG * 2), a + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
+                    ptx::bulk_g2s(s_base + s * (2 * TC_IMG * 2) + TC_IMG * 2, b + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, tc = 0;
+            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
+                const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
+                ptx::mbar_wait(b_acce + 8 * slot, aph ^ 1, g.err, 102);
+                ptx::tc_fence_after();
+                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
+                    const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
+                    ptx::mbar_wait(b_full + 8 * s, ph, g.err, 103);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = s_base + s * (2 * TC_IMG * 2), sb = sa + TC_IMG * 2;
+#pragma unroll
+                    for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
+                        const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                        const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                        ptx::mma_f16<1>(tmem + slot * 128, da, db, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
+                    }
+                    ptx::mma_commit_1(b_empty + 8 * s);
+                }
+                ptx::mma_commit_1(b_accf + 8 * slot);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        uint32_t tc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
+            const int m = tile / g.n_tiles, n = tile % g.n_tiles;
+            const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
+            ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 104);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 128;
+            const float* bias = g.bias + (size_t)n * 128;
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                uint32_t v[16];
+                ptx::tmem_ld16(taddr + j * 16, v);
+                ptx::tmem_wait_ld();
+                if (g.mode == 0) {
+                    float4* o = (float4*)g.out + (((size_t)m * g.n_tiles + n) * 32 + j * 4) * 128 + row;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        float4 f;
+                        f.x = __uint_as_float(v[c4 * 4 + 0]) + bias[j * 16 + c4 * 4 + 0];
+                        f.y = __uint_as_float(v[c4 * 4 + 1]) + bias[j * 16 + c4 * 4 + 1];
+                        f.z = __uint_as_float(v[c4 * 4 + 2]) + bias[j * 16 + c4 * 4 + 2];
+                        f.w = __uint_as_float(v[c4 * 4 + 3]) + bias[j * 16 + c4 * 4 + 3];
+                        o[(size_t)c4 * 128] = f;
+                    }
+                } else {
+                    float* o = g.out + ((size_t)m * 128 + row) * ((size_t)g.n_tiles * 128) + (size_t)n * 128 + j * 16;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) o[c] = seluf_(__uint_as_float(v[c]) + bias[j * 16 + c]);
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc<1>(tmem, 256);
 }
+
+// ================================================================== LSTM layer
+// One CTA pair (cluster of 2, tcgen05 cta_group::2) = 256 sites x one direction.
+//   CH      gate-column chunks per step; a chunk = 32 units x 4 gates = 128 accumulator columns
+//   KX      K of the input part fused into the step MMA (LSTM1: [x | x | 1 | 1 | 0..] against
+//           [W_hi ; W_lo ; b_hi ; b_lo ; 0]); 0 for LSTM2 whose input projection is hoisted
+//   U       units (K of the recurrent part) = CH*32
+template <int CH, int KX>
+struct LstmCfg {
+    static constexpr int U = CH * 32;
+    static constexpr int KT = KX + U;                       // K per step
+    static constexpr int B_BYTES = CH * 64 * KT * 2;        // this CTA's half of the weights
+    static constexpr int AH_BYTES = TC_TILE * U * 2;        // h operand, one buffer
+    static constexpr int AX_BYTES = TC_TILE * KX * 2;       // x operand, one buffer
+    static constexpr int BAR_OFF = B_BYTES + 2 * AH_BYTES + 2 * AX_BYTES;
+    static constexpr int SMEM = BAR_OFF + 256;
+    static constexpr int TMEM_COLS = 512;                   // 2 accumulator slots (256) + cell state (U <= 160)
+    static constexpr int C_COL = 256;
+};
+
+struct LstmArgs {
+    const __half* Wimg;     // [2 dirs][2 ranks][B_BYTES/2] operand images
+    const int32_t* tensor;  // LSTM1: int32 windows [n][33][C]
+    int C;
+    const float* zx;        // LSTM2: hoisted projection, ZX layout [tile][33][2*CH][32][128][4]
+    __half* hout;           // packed output [tile][33][KB_OUT][TC_IMG]
+    int kb_out;             // 64-column blocks per time step in hout (LSTM1: 4, LSTM2: 5)
+    int64_t n_sites;        // valid sites (tensor rows); tiles beyond are zero
+    int n_tiles;            // 128-site tiles (even)
+    int* err;
+};
+
+constexpr int LSTM_THREADS = 320;            // warp 0: MMA issue, warp 1: x loader, warps 2-9: gates
+
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    // 1 / (1 + 2^(-x*log2e)); ex2.approx + rcp.approx are ~1-2 ulp
+    return __frcp_rn(1.0f + exp2f(-1.4426950408889634f * x));
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float xc = fminf(fmaxf(x, -15.0f), 15.0f);
+    return 1.0f - 2.0f * __frcp_rn(1.0f + exp2f(2.8853900817779268f * xc));
+}
+
+template <int CH, int KX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_lstm_tc(LstmArgs a) {
+    typedef LstmCfg<CH, KX> Cfg;
+    constexpr int U = Cfg::U, KT = Cfg::KT;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t s_base = ptx::smem_u32(smem);
+    const uint32_t s_B = s_base, s_AH = s_base + Cfg::B_BYTES, s_AX = s_AH + 2 * Cfg::AH_BYTES;
+    uint64_t* bars = (uint64_t*)(smem + Cfg::BAR_OFF);
+    // barriers: 0 w_full | 1,2 acc_full[2] | 3,4 acc_empty[2] | 5,6 x_ready[2] | 7,8 step_done[2] ; then tmem ptr
+    // Every wait below targets the current or the immediately preceding phase of its barrier
+    // (mbarrier parity waits cannot tell phases further apart).
+    const uint32_t b0 = ptx::smem_u32(bars);
+    const uint32_t b_w = b0, b_accf = b0 + 8, b_acce = b0 + 24, b_xr = b0 + 40, b_step = b0 + 56;
+    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 10);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    // clusters come in (forward, backward) pairs so a cluster keeps one direction's weights resident
+    const int cluster_id = blockIdx.x >> 1, n_cpairs = gridDim.x >> 2;
+    const int dir = cluster_id & 1;
+    const int n_tile_pairs = a.n_tiles / 2;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(b_w, 1);
+        ptx::mbar_init(b_accf, 1); ptx::mbar_init(b_accf + 8, 1);
+        ptx::mbar_init(b_acce, 16); ptx::mbar_init(b_acce + 8, 16);      // 8 gate warps x 2 CTAs
+        ptx::mbar_init(b_xr, 2); ptx::mbar_init(b_xr + 8, 2);            // loader warp x 2 CTAs
+        ptx::mbar_init(b_step, 1); ptx::mbar_init(b_step + 8, 1);
+        ptx::fence_barrier_init();
+        // this CTA's half of the direction's weights: resident for the whole kernel
+        ptx::mbar_arrive_expect_tx(b_w, Cfg::B_BYTES);
+        const __half* wsrc = a.Wimg + ((size_t)dir * 2 + rank) * (Cfg::B_BYTES / 2);
+        constexpr uint32_t PIECE = 32768;
+        for (uint32_t o = 0; o < (uint32_t)Cfg::B_BYTES; o += PIECE) {
+            const uint32_t nb = (uint32_t)Cfg::B_BYTES - o < PIECE ? (uint32_t)Cfg::B_BYTES - o : PIECE;
+            ptx::bulk_g2s(s_B + o, (const uint8_t*)wsrc + o, nb, b_w);
+        }
+    }
+    if (warp == 0) {
+        ptx::tmem_alloc<2>(ptx::smem_u32(tmem_ptr_s), Cfg::TMEM_COLS);
+        ptx::tmem_relinquish<2>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::mbar_wait(b_w, 0, a.err, 201);                      // weights landed in this CTA ...
+    ptx::cluster_sync();                                     // ... and in the peer
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_s;
+    constexpr uint32_t IDESC = ptx::make_idesc_f16(256, 128);
+
+    uint32_t work_it = 0;                                    // work items done by this cluster
+    for (int tile_pair = cluster_id >> 1; tile_pair < n_tile_pairs; tile_pair += n_cpairs, ++work_it) {
+        const int tile = tile_pair * 2 + (int)rank;          // this CTA's 128 sites
+        const uint32_t base_use = work_it * (uint32_t)(NT * CH);     // accumulator uses before this work item
+        const uint32_t base_step = work_it * (uint32_t)NT;
+
+        if (warp == 0) {
+            // ------------------------------------------------ MMA issue (leader CTA, one thread)
+            if (rank == 0 && lane == 0) {
+                for (int step = 0; step < NT; ++step) {
+                    const uint32_t gstep = base_step + step;
+                    const uint32_t buf = gstep & 1;
+                    if (KX > 0) ptx::mbar_wait_cluster(b_xr + 8 * buf, (gstep >> 1) & 1, a.err, 202);
+                    for (int c = 0; c < CH; ++c) {
+                        const uint32_t use = base_use + step * CH + c;
+                        const uint32_t slot = use & 1;
+                        // slot free (its previous use drained by both CTAs) ...
+                        ptx::mbar_wait_cluster(b_acce + 8 * slot, ((use >> 1) & 1) ^ 1, a.err, 203);
+                        // ... and, at the start of a step, every chunk of the previous step finished
+                        // (h complete): the other slot's latest use is use-1.
+                        if (c == 0 && use > 0) {
+                            const uint32_t prev = use - 1;
+                            ptx::mbar_wait_cluster(b_acce + 8 * (prev & 1), (prev >> 1) & 1, a.err, 204);
+                        }
+                        ptx::tc_fence_after();
+                        const uint32_t sb = s_B + c * (64 * KT * 2);
+                        bool first = true;
+                        if (KX > 0) {
+                            const uint32_t sx = s_AX + buf * Cfg::AX_BYTES;
+#pragma unroll
+                            for (int k = 0; k < KX / 16; ++k) {
+                                const uint64_t da = ptx::make_smem_desc(sx + k * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                const uint64_t db = ptx::make_smem_desc(sb + k * 2 * (64 * 16), 64 * 16, 128);
+                                ptx::mma_f16<2>(tmem + slot * 128, da, db, IDESC, first ? 0u : 1u);
+                                first = false;
+                            }
+                        }
+                        if (step > 0) {
+                            const uint32_t sh = s_AH + buf * Cfg::AH_BYTES;
+#pragma unroll
+                            for (int k = 0; k < U / 16; ++k) {
+                                const uint64_t da = ptx::make_smem_desc(sh + k * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                const uint64_t db = ptx::make_smem_desc(sb + (KX / 8 + k * 2) * (64 * 16), 64 * 16, 128);
+                                ptx::mma_f16<2>(tmem + slot * 128, da, db, IDESC, first ? 0u : 1u);
+                                first = false;
+                            }
+                        }
+                        // (LSTM2, step 0: no MMA at all; the commit below still fires the barrier)
+                        ptx::mma_commit_2_mcast(b_accf + 8 * slot, 3);
+                    }
+                    ptx::mma_commit_2_mcast(b_step + 8 * buf, 3);
+                }
+            }
+        } else if (warp == 1) {
+            // ------------------------------------------------ LSTM1: x_t -> fp16 operand tile
+            if (KX > 0) {
+                const int C = a.C;
+                for (int step = 0; step < NT; ++step) {
+                    const uint32_t gstep = base_step + step;
+                    const uint32_t buf = gstep & 1;
+                    // buffer `buf` was last read by the MMAs of global step gstep-2
+                    if (gstep >= 2) ptx::mbar_wait(b_step + 8 * buf, ((gstep >> 1) - 1) & 1, a.err, 205);
+                    const int t = dir == 0 ? step : NT - 1 - step;
+                    uint8_t* ax = smem + (Cfg::B_BYTES + 2 * Cfg::AH_BYTES) + buf * Cfg::AX_BYTES;
+                    for (int r = lane; r < TC_TILE; r += 32) {
+                        const int64_t site = (int64_t)tile * TC_TILE + r;
+                        __align__(16) __half hv[KX > 0 ? KX : 8];
+#pragma unroll
+                        for (int k = 0; k < KX; ++k) hv[k] = __float2half(0.0f);
+                        if (site < a.n_sites) {
+                            const int32_t* src = a.tensor + (site * NT + t) * C;
+                            for (int cch = 0; cch < C; ++cch) {
+                                const __half h = __float2half((float)src[cch]);
+                                hv[cch] = h;
+                                hv[C + cch] = h;
+                            }
+                        }
+                        hv[2 * C] = __float2half(1.0f);
+                        hv[2 * C + 1] = __float2half(1.0f);
+#pragma unroll
+                        for (int k8 = 0; k8 < KX / 8; ++k8)
+                            *(uint4*)(ax + (size_t)k8 * (TC_TILE * 16) + r * 16) = *(const uint4*)(&hv[k8 * 8]);
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(b_xr + 8 * buf, 0);
+                }
+            }
+        } else {
+            // ------------------------------------------------ gates: TMEM -> c, h
+            const int gw = warp - 2;                         // 0..7
+            const int q = warp & 3;                          // TMEM lane quarter this warp may access
+            const int half = gw >> 2;                        // which 16 units of the chunk
+            const int row = q * 32 + lane;
+            const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+            for (int step = 0; step < NT; ++step) {
+                const uint32_t gstep = base_step + step;
+                const uint32_t nbuf = (gstep + 1) & 1;       // h_t goes to the buffer step+1 reads
+                const int t = dir == 0 ? step : NT - 1 - step;
+                uint8_t* ah = smem + Cfg::B_BYTES + nbuf * Cfg::AH_BYTES;
+                __half* hout_t = a.hout + ((size_t)tile * NT + t) * a.kb_out * TC_IMG;
+                const bool has_acc = (KX > 0) || step > 0;
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const uint32_t use = base_use + step * CH + c;
+                    const uint32_t slot = use & 1;
+                    float z[4][16];
+                    if (KX == 0) {
+                        // hoisted projection: [tile][t][dir*CH + c][gate*8 + ug][row][4]
+                        const float4* zp = (const float4*)a.zx +
+                            ((((size_t)tile * NT + t) * (2 * CH) + dir * CH + c) * 32) * 128 + row;
+#pragma unroll
+                        for (int gte = 0; gte < 4; ++gte)
+#pragma unroll
+                            for (int ug = 0; ug < 4; ++ug) {
+                                const float4 f = zp[(size_t)(gte * 8 + half * 4 + ug) * 128];
+                                z[gte][ug * 4 + 0] = f.x; z[gte][ug * 4 + 1] = f.y;
+                                z[gte][ug * 4 + 2] = f.z; z[gte][ug * 4 + 3] = f.w;
+                            }
+                    } else {
+#pragma unroll
+                        for (int gte = 0; gte < 4; ++gte)
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) z[gte][u] = 0.0f;
+                    }
+                    ptx::mbar_wait(b_accf + 8 * slot, (use >> 1) & 1, a.err, 208);
+                    ptx::tc_fence_after();
+                    uint32_t cprev[16];
+                    if (has_acc) {
+#pragma unroll
+                        for (int gte = 0; gte < 4; ++gte) {
+                            uint32_t v[16];
+                            ptx::tmem_ld16(tmem + lane_addr + slot * 128 + gte * 32 + half * 16, v);
+                            ptx::tmem_wait_ld();
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) z[gte][u] += __uint_as_float(v[u]);
+                        }
+                    }
+                    if (step > 0) {
+                        ptx::tmem_ld16(tmem + lane_addr + Cfg::C_COL + c * 32 + half * 16, cprev);
+                        ptx::tmem_wait_ld();
+                    }
+                    uint32_t cnew[16];
+                    __align__(16) __half hh[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const float cp = step > 0 ? __uint_as_float(cprev[u]) : 0.0f;
+                        const float ig = sigmoid_fast(z[0][u]), fg = sigmoid_fast(z[1][u]);
+                        const float gg = tanh_fast(z[2][u]), og = sigmoid_fast(z[3][u]);
+                        const float cn = fg * cp + ig * gg;
+                        cnew[u] = __float_as_uint(cn);
+                        hh[u] = __float2half(og * tanh_fast(cn));
+                    }
+                    ptx::tmem_st16(tmem + lane_addr + Cfg::C_COL + c * 32 + half * 16, cnew);
+                    // h_t: next step's A operand (k index = unit) and the layer output
+                    const int unit0 = c * 32 + half * 16;
+#pragma unroll
+                    for (int g8 = 0; g8 < 2; ++g8) {
+                        const uint4 pk = *(const uint4*)(&hh[g8 * 8]);
+                        const int k8 = unit0 / 8 + g8;
+                        *(uint4*)(ah + (size_t)k8 * (TC_TILE * 16) + row * 16) = pk;
+                        const int col8 = (dir * U) / 8 + k8;                 // 8-column group in the concat [fwd | bwd]
+                        __half* o = hout_t + (size_t)(col8 / 8) * TC_IMG + (size_t)(col8 % 8) * (TC_TILE * 8) + row * 8;
+                        *(uint4*)o = pk;
+                    }
+                    ptx::tmem_wait_st();
+                    ptx::tc_fence_before();
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(b_acce + 8 * slot, 0);
+                }
+            }
+            // the step_done commits multicast to this CTA have landed before it may exit
+            if (gw == 0) {
+                const uint32_t g_last = base_step + NT - 1;
+                ptx::mbar_wait(b_step + 8 * (g_last & 1), (g_last >> 1) & 1, a.err, 209);
+                ptx::mbar_wait(b_step + 8 * ((g_last - 1) & 1), ((g_last - 1) >> 1) & 1, a.err, 210);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 0) ptx::tmem_dealloc<2>(tmem, Cfg::TMEM_COLS);
+}
+
+// ================================================================== host side
+struct TcNet {
+    int ready = 0;
+    int C = 18, KX = 48, sm_count = 148;
+    void* wbuf = nullptr;          // all fp16 images + fp32 biases
+    size_t wbytes = 0;
+    const __half *img1 = nullptr, *img2 = nullptr, *w2p = nullptr, *k4p = nullptr;
+    const float *b2p = nullptr, *b4 = nullptr;
+    // activation scratch (sized for cap_tiles 128-site tiles)
+    void* abuf = nullptr;
+    size_t abytes = 0;
+    int cap_tiles = 0;
+    __half *h1 = nullptr, *h2 = nullptr;
+    float *zx2 = nullptr, *l4 = nullptr;
+    int* err = nullptr;
+    bool attr_set = false;
+};
+
+inline void tc_release(TcNet& t) {
+    if (t.wbuf) cudaFree(t.wbuf);
+    if (t.abuf) cudaFree(t.abuf);
+    if (t.err) cudaFree(t.err);
+    t = TcNet();
+}
+
+// element (r, k) of an R-row K-major no-swizzle image
+inline size_t img_index(int R, int r, int k) { return (size_t)(k / 8) * R * 8 + (size_t)r * 8 + (k % 8); }
+
+inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, size_t o_b1, size_t o_u1, size_t o_w2,
+                    size_t o_b2, size_t o_u2, size_t o_k4, size_t o_b4, int sm_count, std::string* err) {
+    tc_release(t);
+    const int C = net.C;
+    t.C = C;
+    t.KX = C == 18 ? 48 : 64;
+    t.sm_count = sm_count;
+    const int KX = t.KX;
+    const int KT1 = KX + U1, KT2 = U2;
+    const size_t n_img1 = (size_t)2 * 2 * 4 * 64 * KT1;          // [dir][rank][chunk][64 x KT1]
+    const size_t n_img2 = (size_t)2 * 2 * 5 * 64 * KT2;
+    const size_t n_w2p = (size_t)10 * 4 * TC_IMG;                 // [n_tile][kb][128x64]
+    const size_t n_k4p = (size_t)(L4_IN / TC_KB) * TC_IMG;
+    std::vector<__half> hb(n_img1 + n_img2 + n_w2p + n_k4p);
+    std::vector<float> fb(2 * G2 + DENSE);
+    __half* img1 = hb.data();
+    __half* img2 = img1 + n_img1;
+    __half* w2p = img2 + n_img2;
+    __half* k4p = w2p + n_w2p;
+    auto split = [](float w, __half& hi, __half& lo) {
+        hi = __float2half(w);
+        lo = __float2half(w - __half2float(hi));
+    };
+    // Keras gate column of chunk column j (gate-major inside a chunk: j = gate*32 + unit_local)
+    for (int dir = 0; dir < 2; ++dir)
+        for (int rank = 0; rank < 2; ++rank) {
+            // LSTM1
+            for (int c = 0; c < 4; ++c) {
+                __half* im = img1 + ((((size_t)dir * 2 + rank) * 4 + c) * 64) * KT1;
+                for (int j = 0; j < 64; ++j) {
+                    const int col = rank * 64 + j, gate = col / 32, ul = col % 32;
+                    const int kc = gate * U1 + c * 32 + ul;                     // column in [.., 4u]
+                    for (int k = 0; k < KT1; ++k) {
+                        __half v = __float2half(0.0f);
+                        if (k < C || (k >= C && k < 2 * C)) {
+                            const int ch = k < C ? k : k - C;
+                            __half hi, lo;
+                            split(h[o_w1 + (size_t)ch * 2 * G1 + dir * G1 + kc], hi, lo);
+                            v = k < C ? hi : lo;
+                        } else if (k == 2 * C || k == 2 * C + 1) {
+                            __half hi, lo;
+                            split(h[o_b1 + dir * G1 + kc], hi, lo);
+                            v = k == 2 * C ? hi : lo;
+                        } else if (k >= KX) {
+                            v = __float2half(h[o_u1 + (size_t)dir * U1 * G1 + (size_t)(k - KX) * G1 + kc]);
+                        }
+                        im[img_index(64, j, k)] = v;
+                    }
+                }
+            }
+            // LSTM2 (recurrent part only)
+            for (int c = 0; c < 5; ++c) {
+                __half* im = img2 + ((((size_t)dir * 2 + rank) * 5 + c) * 64) * KT2;
+                for (int j = 0; j < 64; ++j) {
+                    const int col = rank * 64 + j, gate = col / 32, ul = col % 32;
+                    const int kc = gate * U2 + c * 32 + ul;
+                    for (int k = 0; k < KT2; ++k)
+                        im[img_index(64, j, k)] = __float2half(h[o_u2 + (size_t)dir * U2 * G2 + (size_t)k * G2 + kc]);
+                }
+            }
+        }
+    // hoisted LSTM2 input projection: B[n_tile = dir*5 + chunk][kb][128 x 64], bias in the same column order
+    for (int dir = 0; dir < 2; ++dir)
+        for (int c = 0; c < 5; ++c) {
+            const int nt = dir * 5 + c;
+            for (int j = 0; j < 128; ++j) {
+                const int gate = j / 32, ul = j % 32;
+                const int kc = gate * U2 + c * 32 + ul;
+                fb[(size_t)nt * 128 + j] = h[o_b2 + dir * G2 + kc];
+                for (int k = 0; k < H1W; ++k)
+                    w2p[((size_t)nt * 4 + k / TC_KB) * TC_IMG + img_index(128, j, k % TC_KB)] =
+                        __float2half(h[o_w2 + (size_t)k * 2 * G2 + dir * G2 + kc]);
+            }
+        }
+    for (int k = 0; k < L4_IN; ++k)
+        for (int j = 0; j < DENSE; ++j)
+            k4p[(size_t)(k / TC_KB) * TC_IMG + img_index(128, j, k % TC_KB)] = __float2half(h[o_k4 + (size_t)k * DENSE + j]);
+    for (int j = 0; j < DENSE; ++j) fb[2 * G2 + j] = h[o_b4 + j];
+
+    t.wbytes = hb.size() * 2 + fb.size() * 4 + 256;
+    cudaError_t e = cudaMalloc(&t.wbuf, t.wbytes);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    uint8_t* d = (uint8_t*)t.wbuf;
+    cudaMemcpy(d, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
+    const size_t foff = ((hb.size() * 2 + 255) / 256) * 256;
+    e = cudaMemcpy(d + foff, fb.data(), fb.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    t.img1 = (const __half*)d;
+    t.img2 = t.img1 + n_img1;
+    t.w2p = t.img2 + n_img2;
+    t.k4p = t.w2p + n_w2p;
+    t.b2p = (const float*)(d + foff);
+    t.b4 = t.b2p + 2 * G2;
+    e = cudaMalloc((void**)&t.err, 64);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    cudaMemset(t.err, 0, 64);
+    t.ready = 1;
+    return 0;
+}
+
+inline int tc_ensure(TcNet& t, int tiles, std::string* err) {
+    if (tiles <= t.cap_tiles) return 0;
+    if (t.abuf) cudaFree(t.abuf);
+    t.abuf = nullptr;
+    const size_t n_h1 = (size_t)tiles * NT * 4 * TC_IMG, n_h2 = (size_t)tiles * NT * 5 * TC_IMG;
+    const size_t n_zx = (size_t)tiles * NT * 10 * 128 * 128, n_l4 = (size_t)tiles * 128 * DENSE;
+    t.abytes = (n_h1 + n_h2) * 2 + (n_zx + n_l4) * 4 + 1024;
+    cudaError_t e = cudaMalloc(&t.abuf, t.abytes);
+    if (e != cudaSuccess) { *err = std::string("activation scratch: ") + cudaGetErrorString(e); t.cap_tiles = 0; return -1; }
+    uint8_t* p = (uint8_t*)t.abuf;
+    t.zx2 = (float*)p; p += n_zx * 4;
+    t.l4 = (float*)p; p += n_l4 * 4;
+    t.h1 = (__half*)p; p += n_h1 * 2;
+    t.h2 = (__half*)p;
+    t.cap_tiles = tiles;
+    return 0;
+}
+
+constexpr int TC_SUB_TILES = 256;            // 32768 sites per pass: bounds the hoisted-projection scratch (5.5 GB)
+
+template <int CH, int KX>
+inline cudaError_t launch_lstm(const LstmArgs& a, int sm_count, cudaStream_t st) {
+    typedef LstmCfg<CH, KX> Cfg;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_lstm_tc<CH, KX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    int cpairs = a.n_tiles / 2;              // (forward, backward) cluster pairs, one per tile pair at most
+    if (cpairs > sm_count / 4) cpairs = sm_count / 4;
+    if (cpairs < 1) cpairs = 1;
+    k_lstm_tc<CH, KX><<<cpairs * 4, LSTM_THREADS, Cfg::SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+inline cudaError_t launch_gemm(const GemmArgs& g, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    int grid = g.m_tiles * g.n_tiles;
+    if (grid > sm_count) grid = sm_count;
+    k_gemm_tc<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
+    return cudaGetLastError();
+}
+
+// tensor int32 [n,33,C] (device) -> probs [n,24] (device).  Returns kernel launches, <0 on error.
+inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_t n, float* probs, cudaStream_t st,
+                      std::string* err) {
+    if (!t.ready) { *err = "weights not packed"; return -1; }
+    int launches = 0;
+    for (int64_t o = 0; o < n; o += (int64_t)TC_SUB_TILES * TC_TILE) {
+        const int64_t m = n - o < (int64_t)TC_SUB_TILES * TC_TILE ? n - o : (int64_t)TC_SUB_TILES * TC_TILE;
+        int tiles = (int)((m + TC_TILE - 1) / TC_TILE);
+        tiles += tiles & 1;                  // CTA pairs
+        if (tc_ensure(t, tiles, err)) return -1;
+        cudaError_t e;
+        LstmArgs a1;
+        a1.Wimg = t.img1; a1.tensor = tensor + o * NT * t.C; a1.C = t.C; a1.zx = nullptr; a1.hout = t.h1; a1.kb_out = 4;
+        a1.n_sites = m; a1.n_tiles = tiles; a1.err = t.err;
+        e = t.C == 18 ? launch_lstm<4, 48>(a1, t.sm_count, st) : launch_lstm<4, 64>(a1, t.sm_count, st);
+        if (e != cudaSuccess) { *err = std::string("lstm1: ") + cudaGetErrorString(e); return -1; }
+        ++launches;
+        GemmArgs g2;
+        g2.A = t.h1; g2.B = t.w2p; g2.bias = t.b2p; g2.out = t.zx2; g2.m_tiles = tiles * NT; g2.n_tiles = 10; g2.n_kb = 4;
+        g2.mode = 0; g2.err = t.err;
+        e = launch_gemm(g2, t.sm_count, st);
+        if (e != cudaSuccess) { *err = std::string("zx2 gemm: ") + cudaGetErrorString(e); return -1; }
+        ++launches;
+        LstmArgs a2;
+        a2.Wimg = t.img2; a2.tensor = nullptr; a2.C = t.C; a2.zx = t.zx2; a2.hout = t.h2; a2.kb_out = 5;
+        a2.n_sites = m; a2.n_tiles = tiles; a2.err = t.err;
+        e = launch_lstm<5, 0>(a2, t.sm_count, st);
+        if (e != cudaSuccess) { *err = std::string("lstm2: ") + cudaGetErrorString(e); return -1; }
+        ++launches;
+        GemmArgs g4;
+        g4.A = t.h2; g4.B = t.k4p; g4.bias = t.b4; g4.out = t.l4; g4.m_tiles = tiles; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
+        g4.mode = 1; g4.err = t.err;
+        e = launch_gemm(g4, t.sm_count, st);
+        if (e != cudaSuccess) { *err = std::string("l4 gemm: ") + cudaGetErrorString(e); return -1; }
+        ++launches;
+        k_heads<<<(unsigned)(m < 2048 ? m : 2048), 128, 0, st>>>(net, t.l4, probs + o * 24, m);
+        ++launches;
+    }
+    return launches;
+}
+
+// device-side protocol errors (bounded mbarrier waits) surface here
+inline int tc_check_error(TcNet& t, cudaStream_t st, int* code) {
+    int h[1] = {0};
+    if (!t.err) { *code = 0; return 0; }
+    cudaError_t e = cudaMemcpyAsync(h, t.err, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return -1;
+    *code = h[0];
+    if (h[0]) cudaMemsetAsync(t.err, 0, 4, st);
+    return 0;
+}
+
+}  // namespace c3r

@@ -170,6 +170,28 @@ class Engine:
         return out, float(ms.value)
 
 
+    def debug_fetch(self, which: int, n_sites: int):
+        """intermediate activations of the last tensor-core forward, unpacked to plain arrays:
+        0 -> h1 [n,33,256], 1 -> zx2 [n,33,2,640] (Keras gate columns), 2 -> h2 [n,33,320], 3 -> l4 [n,128]"""
+        tiles = (n_sites + 127) // 128
+        tiles += tiles & 1
+        sizes = {0: tiles * 33 * 4 * 8192 * 2, 1: tiles * 33 * 10 * 128 * 128 * 4, 2: tiles * 33 * 5 * 8192 * 2,
+                 3: tiles * 128 * 128 * 4}
+        buf = np.empty(sizes[which], np.uint8)
+        nb = C.c_int64(0)
+        self._check(self.lib.c3r_debug_fetch(self.ctx, which, buf.ctypes.data, buf.size, C.byref(nb)), "c3r_debug_fetch")
+        if which in (0, 2):
+            kb = 4 if which == 0 else 5
+            a = buf.view(np.float16).reshape(tiles, 33, kb, 8, 128, 8)        # [tile][t][kb][k8][row][8]
+            a = a.transpose(0, 4, 1, 2, 3, 5).reshape(tiles * 128, 33, kb * 64)
+            return a[:n_sites].astype(np.float32)
+        if which == 1:
+            a = buf.view(np.float32).reshape(tiles, 33, 2, 5, 4, 8, 128, 4)   # [tile][t][dir][chunk][gate][ug][row][4]
+            a = a.transpose(0, 6, 1, 2, 4, 3, 5, 7).reshape(tiles * 128, 33, 2, 4 * 160)   # gate, chunk*32 + ug*4 + i
+            return a[:n_sites]
+        return buf.view(np.float32).reshape(tiles * 128, 128)[:n_sites]
+
+
 # ---------------------------------------------------------------------- host formatting
 def alt_info_strings(res: ChunkResult, batch: ReadBatch, ref: np.ndarray, ref_start1: int) -> list:
     """alt_info text of each candidate exactly as the reference's producer prints it

@@ -42,7 +42,7 @@ class Result(C.Structure):
 
 
 EXPORTS = ["c3r_abi_version", "c3r_default_params", "c3r_create", "c3r_destroy", "c3r_last_error",
-           "c3r_set_weights", "c3r_submit_chunk", "c3r_wait", "c3r_release", "c3r_rerun_resident", "c3r_forward"]
+           "c3r_set_weights", "c3r_submit_chunk", "c3r_wait", "c3r_release", "c3r_rerun_resident", "c3r_forward", "c3r_debug_fetch"]
 
 _lib = None
 
@@ -71,5 +71,6 @@ def load():
     lib.c3r_release.argtypes = [C.c_void_p, C.c_int64]
     lib.c3r_rerun_resident.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.c3r_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float)]
+    lib.c3r_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     _lib = lib
     return lib

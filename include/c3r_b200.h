@@ -144,6 +144,11 @@ int c3r_rerun_resident(c3r_ctx* ctx, c3r_ticket ticket, float* total_ms, float* 
  * (clair3_rna/model.py:175-216 via predict_on_batch, call_variants.py:1505). */
 int c3r_forward(c3r_ctx* ctx, const int32_t* tensor, int64_t n, float* probs, float* device_ms);
 
+/* Diagnostics: copy an intermediate activation buffer of the last tensor-core forward to the
+ * host (which: 0 = LSTM1 output, packed fp16; 1 = LSTM2 input projection, fp32 ZX layout;
+ * 2 = LSTM2 output, packed fp16; 3 = L4 output, fp32 [sites,128]).  Layouts in csrc/nn_tc.cuh. */
+int c3r_debug_fetch(c3r_ctx* ctx, int which, void* dst, int64_t max_bytes, int64_t* n_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,19 +38,27 @@ def _lstm_dir(x, W, U, b, reverse):
     return torch.stack(out, dim=1)
 
 
-def forward(weights: dict, tensor: np.ndarray, dtype=torch.float32) -> np.ndarray:
-    """int32 [n,33,C] -> probabilities [n,24] (21 gt21 + 3 genotype)."""
+def forward(weights: dict, tensor: np.ndarray, dtype=torch.float32, intermediates: dict | None = None) -> np.ndarray:
+    """int32 [n,33,C] -> probabilities [n,24] (21 gt21 + 3 genotype).
+    `intermediates`, if given, receives h1 [n,33,256], zx2 [n,33,2,640], h2 [n,33,320], l4 [n,128]."""
     w = {k: torch.from_numpy(np.asarray(v)).to(dtype) for k, v in weights.items()}
     x = torch.from_numpy(np.asarray(tensor)).to(dtype)
     with torch.no_grad():
         for layer in ("LSTM1", "LSTM2"):
+            if intermediates is not None and layer == "LSTM2":
+                intermediates["zx2"] = torch.stack(
+                    [x @ w["LSTM2/%s/kernel" % d] + w["LSTM2/%s/bias" % d] for d in ("forward", "backward")], dim=2).numpy()
             f = _lstm_dir(x, w[layer + "/forward/kernel"], w[layer + "/forward/recurrent_kernel"],
                           w[layer + "/forward/bias"], False)
             b = _lstm_dir(x, w[layer + "/backward/kernel"], w[layer + "/backward/recurrent_kernel"],
                           w[layer + "/backward/bias"], True)
             x = torch.cat([f, b], dim=2)
+            if intermediates is not None:
+                intermediates["h1" if layer == "LSTM1" else "h2"] = x.numpy()
         v = x.reshape(x.shape[0], -1)
         l4 = selu(v @ w["L4/kernel"] + w["L4/bias"])
+        if intermediates is not None:
+            intermediates["l4"] = l4.numpy()
         a1 = selu(l4 @ w["L5_1/kernel"] + w["L5_1/bias"])
         a2 = selu(l4 @ w["L5_2/kernel"] + w["L5_2/bias"])
         y1 = torch.softmax(selu(a1 @ w["Y_gt21_logits/kernel"] + w["Y_gt21_logits/bias"]), dim=1)
