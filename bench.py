@@ -1,0 +1,299 @@
+#!/usr/bin/env python3
+"""Headline benchmark: candidate sites/sec (pileup tensor generation + network inference).
+
+Workload (BASELINE.json configs[1]): ont_r10_dorado_cdna on a synthetic chr20-sized
+transcriptome at 30x, one contig per GPU (weak scaling: rank r gets its own contig of
+the same size, no data-path collective).  A "step" is one pass of the hot path over the
+whole contig.
+
+  value        sites/s with the flat reads already resident in HBM (c3r_rerun_resident)
+  e2e          sites/s through the public API (Engine.call_chunk) from pinned host arrays,
+               H2D and D2H inside the timed region
+  roofline     the network kernels (tensor bound) and, separately, the count kernel (HBM bound)
+  cpu_baseline the oracle port of the reference CPU pipeline on a bounded sample
+
+`--impl reference` times the oracle port (the reference is Python + samtools + TensorFlow,
+none of which can run on the GPU box) with all host cores on bounded samples.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SITE = {18: 47.786e6, 30: 48.597e6}       # SURVEY.md §8(d), BASELINE.md §3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        z = json.load(open(p))
+        return dict(hbm=z["hbm_gbs"], tf_burst=z["bf16_tflops"], tf_sus=z["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+def dataset(cfg_idx, scale, contig_slot, cache_dir="/tmp/c3r_bench_cache"):
+    """reads + reference of one contig; `contig_slot` varies the seed per rank."""
+    import dataclasses
+    from clair3_rna_b200 import synth
+    from clair3_rna_b200.reads import ReadBatch
+    cfg = synth.config(cfg_idx, scale=scale)
+    cfg = dataclasses.replace(cfg, seed=cfg.seed + 1000 * contig_slot, contigs=cfg.contigs[:1])
+    os.makedirs(cache_dir, exist_ok=True)
+    key = "%s_s%g_r%d" % (cfg.name, scale, contig_slot)
+    path = os.path.join(cache_dir, key + ".npz")
+    ref = synth.Reference(cfg)
+    if os.path.exists(path):
+        batch = ReadBatch.load(path)
+    else:
+        batch = synth.make_contig_reads(cfg, 0, ref)
+        batch.save(path)
+    return cfg, batch, ref
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ CPU oracle legs
+def _cpu_worker(args):
+    """oracle port of the reference pipeline on one region: mpileup text -> tensors -> fp32 network"""
+    import torch
+    torch.set_num_threads(1)                 # call_variants.py:200-206
+    from oracle import pileup_oracle, model
+    batch, ref_seq, ref_start1, s1, e1, C, w, phased, padding = args
+    out = pileup_oracle.run_region(batch, ref_seq, ref_start1, s1, e1, phased=phased, padding=padding)
+    n = len(out["pos"])
+    for i in range(0, n, 200):               # predictBatchSize, param_p.py:51
+        model.forward(w, out["tensor"][i:i + 200])
+    return n
+
+
+def cpu_sample_regions(cfg, batch, ref, n_regions, span=60000):
+    """regions around the first read clusters of the contig (bounded sample)"""
+    from clair3_rna_b200 import synth
+    genes = synth.make_genes(cfg, 0, ref)
+    regs = []
+    contig = cfg.contigs[0][0]
+    for g in genes[:n_regions]:
+        s0, e0 = g.exons[0][0], g.exons[-1][1]
+        s1, e1 = max(1, s0 - 100), e0 + 100
+        sub = batch.fetch(s1, e1)
+        rs1 = max(1, s1 - 1000)
+        ref_seq = ref.fetch_str(contig, rs1 - 1, e1 + 1000)
+        regs.append((sub, ref_seq, rs1, s1, e1))
+    return regs
+
+
+def run_cpu(cfg, batch, ref, w, C, cores, n_regions):
+    import multiprocessing as mp
+    regs = cpu_sample_regions(cfg, batch, ref, n_regions)
+    jobs = [(b, r, rs, s, e, C, w, cfg.phased, cfg.padding) for (b, r, rs, s, e) in regs]
+    t0 = time.time()
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            ns = pool.map(_cpu_worker, jobs)
+    else:
+        ns = [_cpu_worker(j) for j in jobs]
+    dt = time.time() - t0
+    return sum(ns), dt
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--nn_impl", type=int, default=1)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from clair3_rna_b200 import weights, params as P
+    cfg, batch, ref = dataset(args.config, args.scale, rank)
+    contig, clen = cfg.contigs[0]
+    C = 30 if cfg.phased else 18
+    w = weights.synthetic(C, sharpen=8.0)
+    workload = "%s: %s, 1 contig %s of %d bp per GPU, %d reads, %.1fM aligned bases" % (
+        cfg.name, cfg.platform, contig, clen, batch.n_reads, batch.n_aligned_bases() / 1e6)
+    cores = len(os.sched_getaffinity(0))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # bounded sample per step so that W+K steps end within minutes
+        n_regions = max(cores, 8)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            n, dt = run_cpu(cfg, batch, ref, w, C, cores, n_regions)
+            if i >= args.warmup:
+                vals.append((n, dt))
+        n = sum(v[0] for v in vals)
+        dt = sum(v[1] for v in vals)
+        v = n / dt if dt > 0 else 0.0
+        sample = "%d gene regions of the workload per step (%d candidate sites/step), oracle port, %d worker processes" % (
+            n_regions, vals[0][0] if vals else 0, cores)
+        print(json.dumps({
+            "impl": "reference", "metric": "candidate sites/sec (tensor+inference)", "value": v, "unit": "sites/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / max(1, len(vals)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "sites/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    from clair3_rna_b200.engine import Engine
+    eng = Engine(local_rank, C, enable_padding=cfg.padding, nn_impl=args.nn_impl)
+    eng.set_weights(w)
+    # one chunk = the whole contig (all 5 Mb reference chunks batched into one submit)
+    region = (1, clen + P.NO_OF_POSITIONS)
+    ref_arr = ref.fetch(contig, 0, clen)
+    # pinned host staging for the e2e leg
+    pin = {}
+    for k in ("pos", "flag", "mapq", "hp", "cigar_off", "cigar", "seq_off", "seq"):
+        a = getattr(batch, k)
+        tsr = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).copy()).pin_memory()
+        pin[k] = tsr.numpy().view(a.dtype)
+    from clair3_rna_b200.reads import ReadBatch
+    pbatch = ReadBatch(batch.contig, **pin)
+    pref = torch.from_numpy(ref_arr.copy()).pin_memory().numpy()
+    h2d = sum(v.nbytes for v in pin.values()) + pref.nbytes
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg
+    ticket = eng.submit(pbatch, pref, 1, region[0], region[1])
+    res0 = eng.wait(ticket, release=False)
+    n_cand, n_rows = res0.n_cand, res0.n_rows
+    d2h = res0.pos.nbytes + res0.depth.nbytes + res0.probs.nbytes + res0.alt_off.nbytes + res0.alt_n.nbytes + res0.alt.nbytes
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        eng.rerun_resident(ticket)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    tot_ms, stage_acc, launches = 0.0, np.zeros(8), 0
+    t_wall0 = time.time()
+    for _ in range(args.steps):
+        flush.fill_(1)                       # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        ms, st, nl = eng.rerun_resident(ticket)
+        tot_ms += ms
+        stage_acc += np.array(st)
+        launches += nl
+    barrier()
+    sampler.stop_flag = True
+    eng.release(ticket)
+    t_dev = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+    n_all = torch.tensor([float(n_cand)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_all, op=dist.ReduceOp.SUM)
+    value = float(n_all.item()) * args.steps / (float(t_dev.item()) / 1e3)
+
+    # ---- end-to-end leg: public API, host arrays in, host results out
+    for _ in range(min(args.warmup, 2)):
+        eng.call_chunk(pbatch, pref, 1, region[0], region[1])
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        r = eng.call_chunk(pbatch, pref, 1, region[0], region[1])
+        assert r.n_cand == n_cand
+    barrier()
+    e2e_t = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e = float(n_all.item()) * args.steps / float(e2e_t.item())
+
+    if rank == 0:
+        pk = peaks()
+        st = stage_acc / args.steps                              # ms per step per stage
+        k5_ms, k2_ms = float(st[6]), float(st[3])
+        flops = FLOP_PER_SITE[C] * n_cand
+        ach_tf = flops / (k5_ms * 1e-3) / 1e12 if k5_ms > 0 else 0.0
+        # count kernel algorithmic bytes: 0.5 B/aligned base + 16 B/segment entry + 4*C+8 B/row
+        k2_bytes = 0.5 * batch.n_aligned_bases() + 16.0 * batch.n_ops + (4 * C + 8) * n_rows
+        ach_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+        line = {
+            "metric": "candidate sites/sec (tensor+inference)", "value": value, "unit": "sites/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(t_dev.item()) / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32 pileup + fp16/fp32-accumulate network" if args.nn_impl == 1 else "int32+f32",
+            "data": "synthetic",
+            "config": {"workload": workload, "candidates_per_gpu": n_cand, "rows_per_gpu": n_rows, "channels": C,
+                       "l2_flush": "256 MiB write between timed steps", "nn_impl": args.nn_impl},
+            "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "stage_ms": {"memset": float(st[0]), "k1_scan_rows": float(st[1]), "bin": float(st[2]), "k2_count": k2_ms,
+                         "k3_filter": float(st[4]), "k4_window_alt(+host sync)": float(st[5]), "k5_network": k5_ms},
+            "roofline": {"kernel": "k5 network (k_lstm_tc x2, k_gemm_tc x2, k_heads)", "bound": "tensor",
+                         "achieved": ach_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sus"],
+                         "traffic": None, "peak_source": pk["src"] + " bf16 sustained"},
+            "roofline_count": {"kernel": "k_count", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                               "frac": ach_gbs / pk["hbm"], "traffic": None, "algorithmic_bytes": k2_bytes,
+                               "peak_source": pk["src"]},
+        }
+        if not args.no_cpu_baseline:
+            n, dt = run_cpu(cfg, batch, ref, w, C, 1, 2)
+            line["cpu_baseline"] = {"value": n / dt if dt > 0 else 0.0, "unit": "sites/s", "cores": 1, "kind": "port",
+                                    "sample": "2 gene regions of the workload (%d candidate sites), oracle port, 1 process" % n}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
