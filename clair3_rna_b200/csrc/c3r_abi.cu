@@ -137,15 +137,7 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     CK(cudaMemsetAsync(s.covA.p, 0, (size_t)(d.NW + 4) * 4, st));
     CK(cudaMemsetAsync(s.covE.p, 0, (size_t)(d.NW + 4) * 4, st));
     CK(cudaMemsetAsync(s.wdiff.p, 0, (size_t)(d.NW + 4) * 8, st));
-    CK(cudaMemsetAsync(s.binc.p, 0, (size_t)(d.NT_ub + d.L_ub + 4) * 4, st));
-    CK(cudaMemsetAsync(s.bin_cur.p, 0, (size_t)(d.NT_ub + d.L_ub + 4) * 4, st));
     CK(cudaMemsetAsync(s.scalars.p, 0, 64, st));
-    if (d.padding) {
-        CK(cudaMemsetAsync(s.head_cnt.p, 0, (size_t)(d.L_ub + 2) * 4, st));
-        CK(cudaMemsetAsync(s.tail_cnt.p, 0, (size_t)(d.L_ub + 2) * 4, st));
-        CK(cudaMemsetAsync(s.skipdiff.p, 0, (size_t)(d.L_ub + 2) * 8, st));
-        CK(cudaMemsetAsync(s.deleted.p, 0, (size_t)(d.L_ub + 2), st));
-    }
     CK(cudaEventRecord(s.ev[1], st));
     if (d.n_reads > 0) {
         k_read_prepare<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, st>>>(d);
@@ -154,10 +146,12 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     { OpCigar op; op.d = d; if (d.n_ops > 0) L += device_scan(op, d.n_ops, (ScanElem*)s.scan_scratch.p, (ScanElem*)nullptr, st); }
     { OpWords op; op.d = d; L += device_scan(op, d.NW, (Int2*)s.scan_scratch.p, (Int2*)nullptr, st); }
     { OpRows op; op.d = d; L += device_scan(op, d.NW, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
+    k_clear_rows<<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[2], st));
     if (d.n_ops > 0) { k_bin<false><<<(unsigned)((d.n_ops + 255) / 256), 256, 0, st>>>(d); ++L; }
     if (d.padding) { OpSkip op; op.d = d; L += device_scan(op, d.L_ub, (Int2*)s.scan_scratch.p, (Int2*)nullptr, st); }
-    { OpBins op; op.d = d; L += device_scan(op, d.NT_ub + d.L_ub + 2, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
+    { OpTiles op; op.d = d; L += device_scan(op, d.NT_ub + 1, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
+    { OpEvents op; op.d = d; L += device_scan(op, d.L_ub + 1, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
     if (d.n_ops > 0) { k_bin<true><<<(unsigned)((d.n_ops + 255) / 256), 256, 0, st>>>(d); ++L; }
     CK(cudaEventRecord(s.ev[3], st));
     {
@@ -403,14 +397,17 @@ int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int6
     d.max_depth = pr.max_depth; d.skip_prop = pr.skip_proportion;
     d.ref_start0 = ref_start1 - 1; d.ref_len = ref_len;
     // host-side upper bounds from the CIGARs
-    int64_t md_len = 0, md_ops = 0, ent_ub = 0, ev_ub = 0;
+    // rows = positions under an M/=/X/D op, dilated by 16 on each side of every maximal block:
+    // a read contributes at most (its M/D length + 32 per N-separated block)
+    int64_t md_len = 0, n_skip = 0, ent_ub = 0, ev_ub = 0;
     for (int64_t k = 0; k < rd->n_ops; ++k) {
         const uint32_t c = rd->cigar[k], op = c & 15u;
         const int64_t len = c >> 4;
-        if (op == 0 || op == 2 || op == 7 || op == 8) { md_len += len; ++md_ops; ent_ub += len / 32 + 2; }
+        if (op == 0 || op == 2 || op == 7 || op == 8) { md_len += len; ent_ub += len / 32 + 2; }
+        if (op == 3) ++n_skip;
         if (op == 1 || op == 2) ++ev_ub;
     }
-    int64_t L_ub = md_len + 32 * md_ops + 64;
+    int64_t L_ub = md_len + 32 * (n_skip + rd->n_reads) + 64;
     if (L_ub > d.W) L_ub = d.W;
     if (L_ub < 64) L_ub = 64;
     d.L_ub = L_ub; d.NT_ub = (L_ub + 31) / 32 + 1;

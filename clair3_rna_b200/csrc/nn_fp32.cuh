@@ -160,38 +160,54 @@ __global__ void __launch_bounds__(256) k_lstm_step(const float* __restrict__ zx,
     }
 }
 
-// L5_1/L5_2 + the two SELU heads + softmax; one block of 128 threads per site
+// L5_1/L5_2 + the two SELU heads + softmax.  A block of 128 threads (one per hidden unit) takes
+// HS sites at a time so every weight is read once per HS sites.
+constexpr int HS = 16;
 __global__ void __launch_bounds__(128) k_heads(NetF32 w, const float* __restrict__ l4, float* __restrict__ probs, int64_t n) {
-    __shared__ float x[DENSE], a1[DENSE], a2[DENSE], y[24];
-    for (int64_t s = blockIdx.x; s < n; s += gridDim.x) {
-        const int j = threadIdx.x;
-        x[j] = l4[s * DENSE + j];
+    __shared__ float x[HS][DENSE], a1[HS][DENSE], a2[HS][DENSE], y[HS][24];
+    const int j = threadIdx.x;
+    for (int64_t s0 = (int64_t)blockIdx.x * HS; s0 < n; s0 += (int64_t)gridDim.x * HS) {
+        const int ns = (int)(n - s0 < HS ? n - s0 : HS);
+        for (int i = 0; i < HS; ++i) x[i][j] = i < ns ? l4[(s0 + i) * DENSE + j] : 0.0f;
         __syncthreads();
-        float s1 = w.b51[j], s2 = w.b52[j];
+        float s1[HS], s2[HS];
+#pragma unroll
+        for (int i = 0; i < HS; ++i) { s1[i] = w.b51[j]; s2[i] = w.b52[j]; }
         for (int k = 0; k < DENSE; ++k) {
-            s1 = fmaf(x[k], w.k51[k * DENSE + j], s1);
-            s2 = fmaf(x[k], w.k52[k * DENSE + j], s2);
+            const float w1 = w.k51[k * DENSE + j], w2 = w.k52[k * DENSE + j];
+#pragma unroll
+            for (int i = 0; i < HS; ++i) {
+                const float xv = x[i][k];
+                s1[i] = fmaf(xv, w1, s1[i]);
+                s2[i] = fmaf(xv, w2, s2[i]);
+            }
         }
-        a1[j] = seluf_(s1);
-        a2[j] = seluf_(s2);
+#pragma unroll
+        for (int i = 0; i < HS; ++i) { a1[i][j] = seluf_(s1[i]); a2[i][j] = seluf_(s2[i]); }
         __syncthreads();
-        if (j < 21) {
-            float v = w.by1[j];
-            for (int k = 0; k < DENSE; ++k) v = fmaf(a1[k], w.ky1[k * 21 + j], v);
-            y[j] = seluf_(v);
-        } else if (j < 24) {
-            float v = w.by2[j - 21];
-            for (int k = 0; k < DENSE; ++k) v = fmaf(a2[k], w.ky2[k * 3 + (j - 21)], v);
-            y[j] = seluf_(v);
+        // 24 outputs x HS sites = 384 dot products over 128 threads
+        for (int e = j; e < 24 * HS; e += 128) {
+            const int i = e / 24, o = e % 24;
+            float v;
+            if (o < 21) {
+                v = w.by1[o];
+                for (int k = 0; k < DENSE; ++k) v = fmaf(a1[i][k], w.ky1[k * 21 + o], v);
+            } else {
+                v = w.by2[o - 21];
+                for (int k = 0; k < DENSE; ++k) v = fmaf(a2[i][k], w.ky2[k * 3 + (o - 21)], v);
+            }
+            y[i][o] = seluf_(v);
         }
         __syncthreads();
-        if (j < 24) {
-            const int lo = j < 21 ? 0 : 21, hi = j < 21 ? 21 : 24;
-            float mx = y[lo];
-            for (int k = lo + 1; k < hi; ++k) mx = fmaxf(mx, y[k]);
+        for (int e = j; e < 24 * HS; e += 128) {
+            const int i = e / 24, o = e % 24;
+            if (i >= ns) continue;
+            const int lo = o < 21 ? 0 : 21, hi = o < 21 ? 21 : 24;
+            float mx = y[i][lo];
+            for (int k = lo + 1; k < hi; ++k) mx = fmaxf(mx, y[i][k]);
             float sum = 0.0f;
-            for (int k = lo; k < hi; ++k) sum += expf(y[k] - mx);
-            probs[s * 24 + j] = expf(y[j] - mx) / sum;
+            for (int k = lo; k < hi; ++k) sum += expf(y[i][k] - mx);
+            probs[(s0 + i) * 24 + o] = expf(y[i][o] - mx) / sum;
         }
         __syncthreads();
     }
@@ -240,7 +256,7 @@ inline int netf32_forward(const NetF32& w, const NetF32Scratch& s, const int32_t
     dim3 g4((DENSE + 63) / 64, (unsigned)((n + 63) / 64));
     k_sgemm<1><<<g4, 256, 0, st>>>(s.h2, w.k4, w.b4, s.l4, n, DENSE, L4_IN);
     ++launches;
-    k_heads<<<(unsigned)(n < 2048 ? n : 2048), 128, 0, st>>>(w, s.l4, probs, n);
+    k_heads<<<(unsigned)((n + HS - 1) / HS < 4096 ? (n + HS - 1) / HS : 4096), 128, 0, st>>>(w, s.l4, probs, n);
     ++launches;
     return launches;
 }

@@ -188,14 +188,19 @@ struct LstmArgs {
 
 constexpr int LSTM_THREADS = 320;            // warp 0: MMA issue, warp 1: x loader, warps 2-9: gates
 
-__device__ __forceinline__ float sigmoid_fast(float x) {
-    // 1 / (1 + 2^(-x*log2e)); ex2.approx + rcp.approx are ~1-2 ulp
-    return __frcp_rn(1.0f + exp2f(-1.4426950408889634f * x));
+// Gate math on the SFU: ex2.approx / rcp.approx (<= 2 ulp each), 8 SFU ops per (site, unit):
+//   sigmoid(x) = 1/(1+2^(-x log2e)),  tanh(x) = (1-b)/(1+b) with b = 2^(-2x log2e),
+//   sigmoid(i)*tanh(g) and sigmoid(o)*tanh(c) share one reciprocal each.
+// Exponents are clamped so (1+a)(1+b) stays finite (sigmoid(-30) and 1+tanh(-15) are below fp32 eps).
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float sig_times_tanh(float zs, float zt) {
+    const float a = ex2_approx(-LOG2E * fmaxf(zs, -30.0f));
+    const float b = ex2_approx(-2.0f * LOG2E * fmaxf(zt, -15.0f));
+    return (1.0f - b) * rcp_approx((1.0f + a) * (1.0f + b));
 }
-__device__ __forceinline__ float tanh_fast(float x) {
-    const float xc = fminf(fmaxf(x, -15.0f), 15.0f);
-    return 1.0f - 2.0f * __frcp_rn(1.0f + exp2f(2.8853900817779268f * xc));
-}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-LOG2E * x)); }
 
 template <int CH, int KX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_lstm_tc(LstmArgs a) {
@@ -393,11 +398,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
                         const float cp = step > 0 ? __uint_as_float(cprev[u]) : 0.0f;
-                        const float ig = sigmoid_fast(z[0][u]), fg = sigmoid_fast(z[1][u]);
-                        const float gg = tanh_fast(z[2][u]), og = sigmoid_fast(z[3][u]);
-                        const float cn = fg * cp + ig * gg;
+                        const float cn = fmaf(sigmoid_fast(z[1][u]), cp, sig_times_tanh(z[0][u], z[2][u]));
                         cnew[u] = __float_as_uint(cn);
-                        hh[u] = __float2half(og * tanh_fast(cn));
+                        hh[u] = __float2half(sig_times_tanh(z[3][u], cn));
                     }
                     ptx::tmem_st16(tmem + lane_addr + Cfg::C_COL + c * 32 + half * 16, cnew);
                     // h_t: next step's A operand (k index = unit) and the layer output
@@ -644,7 +647,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         e = launch_gemm(g4, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("l4 gemm: ") + cudaGetErrorString(e); return -1; }
         ++launches;
-        k_heads<<<(unsigned)(m < 2048 ? m : 2048), 128, 0, st>>>(net, t.l4, probs + o * 24, m);
+        k_heads<<<(unsigned)((m + HS - 1) / HS < 4096 ? (m + HS - 1) / HS : 4096), 128, 0, st>>>(net, t.l4, probs + o * 24, m);
         ++launches;
     }
     return launches;

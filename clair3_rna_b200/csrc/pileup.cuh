@@ -364,16 +364,42 @@ __global__ void k_bin(Dev d) {
     }
 }
 
-// exclusive scan of binc in place (tile offsets, then event offsets)
-struct OpBins {
+// exclusive scans of the bin counters in place; sizes come from the device-side row count
+struct OpTiles {
     typedef int32_t T;
     Dev d;
     __device__ T identity() const { return 0; }
     __device__ T combine(const T& x, const T& y) const { return x + y; }
-    __device__ int64_t size() const { return d.NT_ub + 1 + d.L_ub + 1; }
+    __device__ int64_t size() const { return (*d.n_rows + TILE_ROWS - 1) / TILE_ROWS + 1; }
     __device__ T load(int64_t i) const { return d.binc[i]; }
     __device__ void store(int64_t i, const T& incl, const T& own) const { d.binc[i] = incl - own; }
 };
+struct OpEvents {
+    typedef int32_t T;
+    Dev d;
+    __device__ T identity() const { return 0; }
+    __device__ T combine(const T& x, const T& y) const { return x + y; }
+    __device__ int64_t size() const { return *d.n_rows + 1; }
+    __device__ T load(int64_t i) const { return d.binc[d.NT_ub + 1 + i]; }
+    __device__ void store(int64_t i, const T& incl, const T& own) const { d.binc[d.NT_ub + 1 + i] = incl - own; }
+};
+// zero the live part of the row-space accumulators once the row count is known
+__global__ void k_clear_rows(Dev d) {
+    const int64_t L = *d.n_rows;
+    const int64_t nt = (L + TILE_ROWS - 1) / TILE_ROWS + 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= L + 1; i += stride) {
+        if (i < nt) { d.binc[i] = 0; d.bin_cur[i] = 0; }
+        d.binc[d.NT_ub + 1 + i] = 0;
+        d.bin_cur[d.NT_ub + 1 + i] = 0;
+        if (d.padding) {
+            d.head_cnt[i] = 0; d.tail_cnt[i] = 0;
+            Int2 z; z.a = 0; z.b = 0;
+            d.skipdiff[i] = z;
+            d.deleted[i] = 0;
+        }
+    }
+}
 
 struct OpSkip {
     typedef Int2 T;
