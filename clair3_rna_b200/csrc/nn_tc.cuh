@@ -35,9 +35,14 @@ constexpr int TC_KB = 64;                    // K per pipeline stage
 constexpr int TC_IMG = TC_TILE * TC_KB;      // halfs in one 128x64 operand image (16 KB)
 
 // ================================================================== GEMM
+// terms == 3 runs the split-precision product  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (A = A_hi + A_lo and
+// B = B_hi + B_lo as two fp16 terms each), which removes the fp16 rounding of both operands.
 struct GemmArgs {
     const __half* A;      // [m_tiles][n_kb][TC_IMG]
     const __half* B;      // [n_tiles][n_kb][TC_IMG]
+    const __half* A_lo;   // same layouts, low-order terms (terms == 3)
+    const __half* B_lo;
+    int terms;
     const float* bias;    // [n_tiles*128], GEMM column order
     float* out;
     int m_tiles, n_tiles, n_kb;
@@ -78,14 +83,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
                 const int m = tile / g.n_tiles, n = tile % g.n_tiles;
-                const __half* a = g.A + (size_t)m * g.n_kb * TC_IMG;
-                const __half* b = g.B + (size_t)n * g.n_kb * TC_IMG;
-                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
-                    const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
-                    ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 101);
-                    ptx::mbar_arrive_expect_tx(b_full + 8 * s, 2 * TC_IMG * 2);
-                    ptx::bulk_g2s(s_base + s * (2 * TC_IMG * 2), a + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
-                    ptx::bulk_g2s(s_base + s * (2 * TC_IMG * 2) + TC_IMG * 2, b + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
+                for (int term = 0; term < g.terms; ++term) {
+                    const __half* a = (term == 1 ? g.A_lo : g.A) + (size_t)m * g.n_kb * TC_IMG;
+                    const __half* b = (term == 2 ? g.B_lo : g.B) + (size_t)n * g.n_kb * TC_IMG;
+                    for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
+                        const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
+                        ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 101);
+                        ptx::mbar_arrive_expect_tx(b_full + 8 * s, 2 * TC_IMG * 2);
+                        ptx::bulk_g2s(s_base + s * (2 * TC_IMG * 2), a + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
+                        ptx::bulk_g2s(s_base + s * (2 * TC_IMG * 2) + TC_IMG * 2, b + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
+                    }
                 }
             }
         }
@@ -96,7 +103,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
                 ptx::mbar_wait(b_acce + 8 * slot, aph ^ 1, g.err, 102);
                 ptx::tc_fence_after();
-                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
+                const int n_kb_all = g.n_kb * g.terms;
+                for (int kb = 0; kb < n_kb_all; ++kb, ++it) {
                     const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
                     ptx::mbar_wait(b_full + 8 * s, ph, g.err, 103);
                     ptx::tc_fence_after();
@@ -179,7 +187,8 @@ struct LstmArgs {
     const int32_t* tensor;  // LSTM1: int32 windows [n][33][C]
     int C;
     const float* zx;        // LSTM2: hoisted projection, ZX layout [tile][33][2*CH][32][128][4]
-    __half* hout;           // packed output [tile][33][KB_OUT][TC_IMG]
+    __half* hout;           // packed output [tile][33][KB_OUT][TC_IMG], high-order fp16 term
+    __half* hout_lo;        // low-order term: h - fp16(h), same layout
     int kb_out;             // 64-column blocks per time step in hout (LSTM1: 4, LSTM2: 5)
     int64_t n_sites;        // valid sites (tensor rows); tiles beyond are zero
     int n_tiles;            // 128-site tiles (even)
@@ -352,6 +361,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                 const int t = dir == 0 ? step : NT - 1 - step;
                 uint8_t* ah = smem + Cfg::B_BYTES + nbuf * Cfg::AH_BYTES;
                 __half* hout_t = a.hout + ((size_t)tile * NT + t) * a.kb_out * TC_IMG;
+                __half* hout_lo_t = a.hout_lo + ((size_t)tile * NT + t) * a.kb_out * TC_IMG;
                 const bool has_acc = (KX > 0) || step > 0;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
@@ -395,12 +405,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     }
                     uint32_t cnew[16];
                     __align__(16) __half hh[16];
+                    __align__(16) __half hl[16];
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
                         const float cp = step > 0 ? __uint_as_float(cprev[u]) : 0.0f;
                         const float cn = fmaf(sigmoid_fast(z[1][u]), cp, sig_times_tanh(z[0][u], z[2][u]));
                         cnew[u] = __float_as_uint(cn);
-                        hh[u] = __float2half(sig_times_tanh(z[3][u], cn));
+                        const float hv = sig_times_tanh(z[3][u], cn);
+                        hh[u] = __float2half(hv);
+                        hl[u] = __float2half(hv - __half2float(hh[u]));
                     }
                     ptx::tmem_st16(tmem + lane_addr + Cfg::C_COL + c * 32 + half * 16, cnew);
                     // h_t: next step's A operand (k index = unit) and the layer output
@@ -411,8 +424,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         const int k8 = unit0 / 8 + g8;
                         *(uint4*)(ah + (size_t)k8 * (TC_TILE * 16) + row * 16) = pk;
                         const int col8 = (dir * U) / 8 + k8;                 // 8-column group in the concat [fwd | bwd]
-                        __half* o = hout_t + (size_t)(col8 / 8) * TC_IMG + (size_t)(col8 % 8) * (TC_TILE * 8) + row * 8;
-                        *(uint4*)o = pk;
+                        const size_t oo = (size_t)(col8 / 8) * TC_IMG + (size_t)(col8 % 8) * (TC_TILE * 8) + row * 8;
+                        *(uint4*)(hout_t + oo) = pk;
+                        *(uint4*)(hout_lo_t + oo) = *(const uint4*)(&hl[g8 * 8]);
                     }
                     ptx::tmem_wait_st();
                     ptx::tc_fence_before();
@@ -441,13 +455,13 @@ struct TcNet {
     int C = 18, KX = 48, sm_count = 148;
     void* wbuf = nullptr;          // all fp16 images + fp32 biases
     size_t wbytes = 0;
-    const __half *img1 = nullptr, *img2 = nullptr, *w2p = nullptr, *k4p = nullptr;
+    const __half *img1 = nullptr, *img2 = nullptr, *w2p = nullptr, *k4p = nullptr, *w2p_lo = nullptr, *k4p_lo = nullptr;
     const float *b2p = nullptr, *b4 = nullptr;
     // activation scratch (sized for cap_tiles 128-site tiles)
     void* abuf = nullptr;
     size_t abytes = 0;
     int cap_tiles = 0;
-    __half *h1 = nullptr, *h2 = nullptr;
+    __half *h1 = nullptr, *h2 = nullptr, *h1_lo = nullptr, *h2_lo = nullptr;
     float *zx2 = nullptr, *l4 = nullptr;
     int* err = nullptr;
     bool attr_set = false;
@@ -476,12 +490,14 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
     const size_t n_img2 = (size_t)2 * 2 * 5 * 64 * KT2;
     const size_t n_w2p = (size_t)10 * 4 * TC_IMG;                 // [n_tile][kb][128x64]
     const size_t n_k4p = (size_t)(L4_IN / TC_KB) * TC_IMG;
-    std::vector<__half> hb(n_img1 + n_img2 + n_w2p + n_k4p);
+    std::vector<__half> hb(n_img1 + n_img2 + 2 * n_w2p + 2 * n_k4p);
     std::vector<float> fb(2 * G2 + DENSE);
     __half* img1 = hb.data();
     __half* img2 = img1 + n_img1;
     __half* w2p = img2 + n_img2;
     __half* k4p = w2p + n_w2p;
+    __half* w2p_lo = k4p + n_k4p;
+    __half* k4p_lo = w2p_lo + n_w2p;
     auto split = [](float w, __half& hi, __half& lo) {
         hi = __float2half(w);
         lo = __float2half(w - __half2float(hi));
@@ -532,14 +548,18 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
                 const int gate = j / 32, ul = j % 32;
                 const int kc = gate * U2 + c * 32 + ul;
                 fb[(size_t)nt * 128 + j] = h[o_b2 + dir * G2 + kc];
-                for (int k = 0; k < H1W; ++k)
-                    w2p[((size_t)nt * 4 + k / TC_KB) * TC_IMG + img_index(128, j, k % TC_KB)] =
-                        __float2half(h[o_w2 + (size_t)k * 2 * G2 + dir * G2 + kc]);
+                for (int k = 0; k < H1W; ++k) {
+                    const size_t ix = ((size_t)nt * 4 + k / TC_KB) * TC_IMG + img_index(128, j, k % TC_KB);
+                    split(h[o_w2 + (size_t)k * 2 * G2 + dir * G2 + kc], w2p[ix], w2p_lo[ix]);
+                }
             }
         }
     for (int k = 0; k < L4_IN; ++k)
         for (int j = 0; j < DENSE; ++j)
-            k4p[(size_t)(k / TC_KB) * TC_IMG + img_index(128, j, k % TC_KB)] = __float2half(h[o_k4 + (size_t)k * DENSE + j]);
+        {
+            const size_t ix = (size_t)(k / TC_KB) * TC_IMG + img_index(128, j, k % TC_KB);
+            split(h[o_k4 + (size_t)k * DENSE + j], k4p[ix], k4p_lo[ix]);
+        }
     for (int j = 0; j < DENSE; ++j) fb[2 * G2 + j] = h[o_b4 + j];
 
     t.wbytes = hb.size() * 2 + fb.size() * 4 + 256;
@@ -554,6 +574,8 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
     t.img2 = t.img1 + n_img1;
     t.w2p = t.img2 + n_img2;
     t.k4p = t.w2p + n_w2p;
+    t.w2p_lo = t.k4p + n_k4p;
+    t.k4p_lo = t.w2p_lo + n_w2p;
     t.b2p = (const float*)(d + foff);
     t.b4 = t.b2p + 2 * G2;
     e = cudaMalloc((void**)&t.err, 64);
@@ -569,14 +591,16 @@ inline int tc_ensure(TcNet& t, int tiles, std::string* err) {
     t.abuf = nullptr;
     const size_t n_h1 = (size_t)tiles * NT * 4 * TC_IMG, n_h2 = (size_t)tiles * NT * 5 * TC_IMG;
     const size_t n_zx = (size_t)tiles * NT * 10 * 128 * 128, n_l4 = (size_t)tiles * 128 * DENSE;
-    t.abytes = (n_h1 + n_h2) * 2 + (n_zx + n_l4) * 4 + 1024;
+    t.abytes = (n_h1 + n_h2) * 2 * 2 + (n_zx + n_l4) * 4 + 1024;
     cudaError_t e = cudaMalloc(&t.abuf, t.abytes);
     if (e != cudaSuccess) { *err = std::string("activation scratch: ") + cudaGetErrorString(e); t.cap_tiles = 0; return -1; }
     uint8_t* p = (uint8_t*)t.abuf;
     t.zx2 = (float*)p; p += n_zx * 4;
     t.l4 = (float*)p; p += n_l4 * 4;
     t.h1 = (__half*)p; p += n_h1 * 2;
-    t.h2 = (__half*)p;
+    t.h1_lo = (__half*)p; p += n_h1 * 2;
+    t.h2 = (__half*)p; p += n_h2 * 2;
+    t.h2_lo = (__half*)p;
     t.cap_tiles = tiles;
     return 0;
 }
@@ -624,25 +648,25 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         if (tc_ensure(t, tiles, err)) return -1;
         cudaError_t e;
         LstmArgs a1;
-        a1.Wimg = t.img1; a1.tensor = tensor + o * NT * t.C; a1.C = t.C; a1.zx = nullptr; a1.hout = t.h1; a1.kb_out = 4;
+        a1.Wimg = t.img1; a1.tensor = tensor + o * NT * t.C; a1.C = t.C; a1.zx = nullptr; a1.hout = t.h1; a1.hout_lo = t.h1_lo; a1.kb_out = 4;
         a1.n_sites = m; a1.n_tiles = tiles; a1.err = t.err;
         e = t.C == 18 ? launch_lstm<4, 48>(a1, t.sm_count, st) : launch_lstm<4, 64>(a1, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("lstm1: ") + cudaGetErrorString(e); return -1; }
         ++launches;
         GemmArgs g2;
-        g2.A = t.h1; g2.B = t.w2p; g2.bias = t.b2p; g2.out = t.zx2; g2.m_tiles = tiles * NT; g2.n_tiles = 10; g2.n_kb = 4;
+        g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = 3; g2.bias = t.b2p; g2.out = t.zx2; g2.m_tiles = tiles * NT; g2.n_tiles = 10; g2.n_kb = 4;
         g2.mode = 0; g2.err = t.err;
         e = launch_gemm(g2, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("zx2 gemm: ") + cudaGetErrorString(e); return -1; }
         ++launches;
         LstmArgs a2;
-        a2.Wimg = t.img2; a2.tensor = nullptr; a2.C = t.C; a2.zx = t.zx2; a2.hout = t.h2; a2.kb_out = 5;
+        a2.Wimg = t.img2; a2.tensor = nullptr; a2.C = t.C; a2.zx = t.zx2; a2.hout = t.h2; a2.hout_lo = t.h2_lo; a2.kb_out = 5;
         a2.n_sites = m; a2.n_tiles = tiles; a2.err = t.err;
         e = launch_lstm<5, 0>(a2, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("lstm2: ") + cudaGetErrorString(e); return -1; }
         ++launches;
         GemmArgs g4;
-        g4.A = t.h2; g4.B = t.k4p; g4.bias = t.b4; g4.out = t.l4; g4.m_tiles = tiles; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
+        g4.A = t.h2; g4.B = t.k4p; g4.A_lo = t.h2_lo; g4.B_lo = t.k4p_lo; g4.terms = 3; g4.bias = t.b4; g4.out = t.l4; g4.m_tiles = tiles; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
         g4.mode = 1; g4.err = t.err;
         e = launch_gemm(g4, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("l4 gemm: ") + cudaGetErrorString(e); return -1; }
