@@ -163,6 +163,129 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
     if (warp == 1) ptx::tmem_dealloc<1>(tmem, 256);
 }
 
+// ------------------------------------------------------------------ B-stationary variant
+// LSTM2's hoisted input projection: K = 256 is short and N = 1280 wide, so a CTA keeps the weight
+// images of ONE 128-column tile (hi and lo terms, 128 KB) resident and streams only activations.
+// Per output tile it issues  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  and each A image is loaded once.
+// Grid = groups x n_tiles CTAs; group g walks m-tiles g, g+groups, ...; the n_tiles CTAs of a
+// group touch the same A tile at about the same time, so it is read from HBM once.
+constexpr int ZXG_KB = 4;                                   // K = 256
+constexpr int ZXG_STAGES = 5;
+constexpr int ZXG_SMEM = (2 * ZXG_KB + ZXG_STAGES) * TC_IMG * 2 + 1024;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t IMG_B = TC_IMG * 2;
+    uint64_t* bars = (uint64_t*)(smem + (2 * ZXG_KB + ZXG_STAGES) * IMG_B);
+    // bars: full[5] empty[5] acc_full[2] acc_empty[2] b_full
+    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 16);
+    const uint32_t s_base = ptx::smem_u32(smem);
+    const uint32_t s_bhi = s_base, s_blo = s_base + ZXG_KB * IMG_B, s_a = s_base + 2 * ZXG_KB * IMG_B;
+    const uint32_t b_full = ptx::smem_u32(bars), b_empty = b_full + 8 * ZXG_STAGES, b_accf = b_empty + 8 * ZXG_STAGES,
+                   b_acce = b_accf + 16, b_bres = b_acce + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < ZXG_STAGES; ++i) { ptx::mbar_init(b_full + 8 * i, 1); ptx::mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(b_accf + 8 * i, 1); ptx::mbar_init(b_acce + 8 * i, 4); }
+        ptx::mbar_init(b_bres, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_ptr_s), 256);
+        ptx::tmem_relinquish<1>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_s;
+    const int n = blockIdx.x % g.n_tiles, grp = blockIdx.x / g.n_tiles, n_grp = gridDim.x / g.n_tiles;
+    const uint32_t idesc = ptx::make_idesc_f16(128, 128);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(b_bres, 2 * ZXG_KB * IMG_B);
+            for (int kb = 0; kb < ZXG_KB; ++kb) {
+                ptx::bulk_g2s(s_bhi + kb * IMG_B, g.B + ((size_t)n * ZXG_KB + kb) * TC_IMG, IMG_B, b_bres);
+                ptx::bulk_g2s(s_blo + kb * IMG_B, g.B_lo + ((size_t)n * ZXG_KB + kb) * TC_IMG, IMG_B, b_bres);
+            }
+            uint32_t it = 0;
+            for (int m = grp; m < g.m_tiles; m += n_grp) {
+                for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {          // A_hi[0], A_lo[0], A_hi[1], ...
+                    const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
+                    ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 111);
+                    ptx::mbar_arrive_expect_tx(b_full + 8 * s, IMG_B);
+                    const __half* src = ((i & 1) ? g.A_lo : g.A) + ((size_t)m * ZXG_KB + (i >> 1)) * TC_IMG;
+                    ptx::bulk_g2s(s_a + s * IMG_B, src, IMG_B, b_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            ptx::mbar_wait(b_bres, 0, g.err, 112);
+            uint32_t it = 0, tc = 0;
+            for (int m = grp; m < g.m_tiles; m += n_grp, ++tc) {
+                const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
+                ptx::mbar_wait(b_acce + 8 * slot, aph ^ 1, g.err, 113);
+                ptx::tc_fence_after();
+                for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {
+                    const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
+                    const int kb = i >> 1;
+                    ptx::mbar_wait(b_full + 8 * s, ph, g.err, 114);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = s_a + s * IMG_B;
+                    const int nb = (i & 1) ? 1 : 2;                     // A_lo meets B_hi only
+#pragma unroll
+                    for (int bsel = 0; bsel < 2; ++bsel) {
+                        if (bsel >= nb) break;
+                        const uint32_t sb = (bsel ? s_blo : s_bhi) + kb * IMG_B;
+#pragma unroll
+                        for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
+                            const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                            const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                            ptx::mma_f16<1>(tmem + slot * 128, da, db, idesc, (i > 0 || bsel > 0 || k4 > 0) ? 1u : 0u);
+                        }
+                    }
+                    ptx::mma_commit_1(b_empty + 8 * s);
+                }
+                ptx::mma_commit_1(b_accf + 8 * slot);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        uint32_t tc = 0;
+        const float* bias = g.bias + (size_t)n * 128;
+        for (int m = grp; m < g.m_tiles; m += n_grp, ++tc) {
+            const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
+            ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 115);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 128;
+#pragma unroll 2
+            for (int j = 0; j < 8; ++j) {
+                uint32_t v[16];
+                ptx::tmem_ld16(taddr + j * 16, v);
+                ptx::tmem_wait_ld();
+                float4* o = (float4*)g.out + (((size_t)m * g.n_tiles + n) * 32 + j * 4) * 128 + row;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    float4 f;
+                    f.x = __uint_as_float(v[c4 * 4 + 0]) + bias[j * 16 + c4 * 4 + 0];
+                    f.y = __uint_as_float(v[c4 * 4 + 1]) + bias[j * 16 + c4 * 4 + 1];
+                    f.z = __uint_as_float(v[c4 * 4 + 2]) + bias[j * 16 + c4 * 4 + 2];
+                    f.w = __uint_as_float(v[c4 * 4 + 3]) + bias[j * 16 + c4 * 4 + 3];
+                    o[(size_t)c4 * 128] = f;
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc<1>(tmem, 256);
+}
+
 // ================================================================== LSTM layer
 // One CTA pair (cluster of 2, tcgen05 cta_group::2) = 256 sites x one direction.
 //   CH      gate-column chunks per step; a chunk = 32 units x 4 gates = 128 accumulator columns
@@ -623,6 +746,20 @@ inline cudaError_t launch_lstm(const LstmArgs& a, int sm_count, cudaStream_t st)
     return cudaGetLastError();
 }
 
+inline cudaError_t launch_gemm_zx(const GemmArgs& g, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_zx, cudaFuncAttributeMaxDynamicSharedMemorySize, ZXG_SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    int groups = sm_count / g.n_tiles;
+    if (groups > g.m_tiles) groups = g.m_tiles;
+    if (groups < 1) groups = 1;
+    k_gemm_zx<<<groups * g.n_tiles, GEMM_THREADS, ZXG_SMEM, st>>>(g);
+    return cudaGetLastError();
+}
+
 inline cudaError_t launch_gemm(const GemmArgs& g, int sm_count, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
@@ -656,7 +793,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         GemmArgs g2;
         g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = 3; g2.bias = t.b2p; g2.out = t.zx2; g2.m_tiles = tiles * NT; g2.n_tiles = 10; g2.n_kb = 4;
         g2.mode = 0; g2.err = t.err;
-        e = launch_gemm(g2, t.sm_count, st);
+        e = launch_gemm_zx(g2, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("zx2 gemm: ") + cudaGetErrorString(e); return -1; }
         ++launches;
         LstmArgs a2;
