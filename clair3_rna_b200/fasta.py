@@ -1,0 +1,30 @@
+"""Indexed FASTA access (replaces `samtools faidx`, /root/reference/shared/utils.py:168-194)."""
+import numpy as np
+
+
+def read_fai(path: str) -> dict:
+    fai = {}
+    with open(path + ".fai") as fp:
+        for row in fp:
+            c = row.rstrip("\n").split("\t")
+            fai[c[0]] = tuple(int(x) for x in c[1:5])       # length, offset, linebases, linewidth
+    return fai
+
+
+def fetch(path: str, fai: dict, contig: str, start1: int, end1: int) -> np.ndarray:
+    """upper-cased bases of the 1-based inclusive region, clipped to the contig."""
+    length, offset, linebases, linewidth = fai[contig]
+    start1, end1 = max(1, start1), min(length, end1)
+    if end1 < start1:
+        return np.zeros(0, np.uint8)
+    first_line, last_line = (start1 - 1) // linebases, (end1 - 1) // linebases
+    with open(path, "rb") as fp:
+        fp.seek(offset + first_line * linewidth)
+        raw = fp.read((last_line - first_line + 1) * linewidth)
+    a = np.frombuffer(raw, np.uint8)
+    a = a[(a != 10) & (a != 13)]
+    lo = (start1 - 1) - first_line * linebases
+    a = a[lo: lo + (end1 - start1 + 1)].copy()
+    lower = (a >= 97) & (a <= 122)
+    a[lower] -= 32
+    return a

@@ -1,0 +1,81 @@
+"""End to end through the drop-in `call_var_bam` entry point on the GPU: same argv as the
+reference's per-chunk driver, VCF compared with rows the reference's own decoder printed for
+the same candidates (tests/golden/decoder_*.npz, oracle probabilities)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden import cases as golden_cases
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _write_inputs(tmp, name):
+    from clair3_rna_b200 import weights
+    batch, ref_bytes, contig = golden_cases.build(name)
+    fa = os.path.join(tmp, "ref.fa")
+    with open(fa, "wb") as fp:
+        fp.write(b">" + contig.encode() + b"\n")
+        for i in range(0, len(ref_bytes), 60):
+            fp.write(ref_bytes[i:i + 60] + b"\n")
+    with open(fa + ".fai", "w") as fp:
+        fp.write("%s\t%d\t%d\t60\t61\n" % (contig, len(ref_bytes), len(contig) + 2))
+    batch.save(os.path.join(tmp, "reads.npz"))
+    C = 30 if golden_cases.CASES[name]["phased"] else 18
+    weights.save(os.path.join(tmp, "w.npz"), weights.synthetic(C, sharpen=8.0))
+    return fa, contig
+
+
+@pytest.mark.parametrize("name", ["cfg1_ont_drna", "pad_dense", "phased_noisy"])
+def test_call_var_bam_vcf(tmp_path, name):
+    from clair3_rna_b200 import call_var_bam
+    case = golden_cases.CASES[name]
+    tmp = str(tmp_path)
+    fa, contig = _write_inputs(tmp, name)
+    out = os.path.join(tmp, "pileup_%s_1.vcf" % contig)
+    argv = ["--chkpnt_fn", os.path.join(tmp, "w.npz"), "--bam_fn", os.path.join(tmp, "reads.npz"), "--ref_fn", fa,
+            "--call_fn", out, "--ctgName", contig, "--chunk_id", "1", "--chunk_num", "1", "--platform", case["platform"],
+            "--snp_min_af", str(case["snp_af"]), "--indel_min_af", str(case["indel_af"]), "--minMQ", str(case["min_mq"]),
+            "--minCoverage", str(case["min_cov"]), "--pileup", "--sampleName", "S"]
+    if case["phased"]:
+        argv += ["--enable_phasing_model", "True"]
+    if case["padding"]:
+        argv += ["--enable_padding_in_splice_junction_regions", "True"]
+    assert call_var_bam.main(argv) == 0
+    lines = open(out).read().splitlines()
+    assert lines[0] == "##fileformat=VCFv4.2" and lines[-1][0] != "#"
+    rows = [l for l in lines if not l.startswith("#")]
+    g = np.load(os.path.join(HERE, "golden", "decoder_" + name + ".npz"))
+    n = len(g["rows"]) // 2
+    want = [str(r) for r in g["rows"][:n] if str(r)]
+    assert len(rows) == len(want)
+    mismatch = 0
+    for a, b in zip(rows, want):
+        ca, cb = a.split("\t"), b.split("\t")
+        assert ca[1] == cb[1]                                   # same candidate positions
+        same = ca[:5] == cb[:5] and ca[9].split(":")[0] == cb[9].split(":")[0]
+        mismatch += 0 if same else 1
+    # calls are identical except where the two best outcomes are within the probability tolerance
+    assert mismatch <= max(1, len(rows) // 200), mismatch
+
+
+def test_no_record_means_no_file(tmp_path):
+    from clair3_rna_b200 import call_var_bam, weights
+    from clair3_rna_b200.reads import ReadBatch
+    tmp = str(tmp_path)
+    seq = b"ACGT" * 500
+    fa = os.path.join(tmp, "ref.fa")
+    with open(fa, "wb") as fp:
+        fp.write(b">chr1\n" + seq + b"\n")
+    with open(fa + ".fai", "w") as fp:
+        fp.write("chr1\t%d\t6\t%d\t%d\n" % (len(seq), len(seq), len(seq) + 1))
+    ReadBatch.from_records("chr1", []).save(os.path.join(tmp, "reads.npz"))
+    weights.save(os.path.join(tmp, "w.npz"), weights.synthetic(18))
+    out = os.path.join(tmp, "pileup_chr1_1.vcf")
+    open(out, "w").write("stale\n")
+    assert call_var_bam.main(["--chkpnt_fn", os.path.join(tmp, "w.npz"), "--bam_fn", os.path.join(tmp, "reads.npz"),
+                              "--ref_fn", fa, "--call_fn", out, "--ctgName", "chr1", "--chunk_id", "1",
+                              "--chunk_num", "1", "--pileup"]) == 0
+    assert not os.path.exists(out)
