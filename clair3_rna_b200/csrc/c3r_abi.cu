@@ -77,6 +77,8 @@ struct c3r_ctx {
     NetF32Scratch nscr;
     TcNet tc;                 // tensor-core path state (nn_tc.cuh)
     bool tc_dirty = false;    // a tensor-core forward ran since the last device error check
+    Buf ref_res;              // resident reference window (c3r_set_reference)
+    int64_t ref_res_start0 = 0, ref_res_len = 0;
     Buf fwd_in, fwd_out;      // c3r_forward staging
     cudaStream_t fwd_stream = nullptr;
 };
@@ -216,7 +218,7 @@ int run_stage_b(c3r_ctx* ctx, Slot& s) {
             k_rescale<<<grid, 128, 0, st>>>(d); ++L;
         }
         { OpAltOff op; op.d = d; L += device_scan(op, n, (long long*)s.scan_scratch.p, ((long long*)s.scalars.p) + 2, st); }
-        k_altinfo<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d); ++L;
+        k_altinfo<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d); ++L;
     }
     CK(cudaEventRecord(s.ev[6], st));
     CK(cudaEventRecord(s.ev_alt, st));
@@ -355,6 +357,7 @@ void c3r_destroy(c3r_ctx* ctx) {
     release(ctx->wbuf);
     release(ctx->nn_scratch);
     release(ctx->fwd_in);
+    release(ctx->ref_res);
     release(ctx->fwd_out);
     tc_release(ctx->tc);
     if (ctx->fwd_stream) cudaStreamDestroy(ctx->fwd_stream);
@@ -371,9 +374,25 @@ int c3r_set_weights(c3r_ctx* ctx, const c3r_weight_view* views, int n_views) {
     return build_net(ctx, w);
 }
 
+int c3r_set_reference(c3r_ctx* ctx, const uint8_t* ref, int64_t ref_start1, int64_t ref_len) {
+    if (!ctx || !ref || ref_len <= 0 || ref_start1 < 1) return C3R_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    if (ensure(ctx, ctx->ref_res, (size_t)ref_len + 16)) return C3R_ERR_CUDA;
+    CK(cudaMemcpy(ctx->ref_res.p, ref, (size_t)ref_len, cudaMemcpyHostToDevice));
+    ctx->ref_res_start0 = ref_start1 - 1;
+    ctx->ref_res_len = ref_len;
+    return C3R_OK;
+}
+
 int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
                      int64_t region_start1, int64_t region_end1, c3r_ticket* ticket) {
     if (!ctx || !rd || !ticket) return C3R_ERR_ARG;
+    if (!ref) {
+        if (!ctx->ref_res_len) return fail(ctx, C3R_ERR_STATE, "ref == NULL but c3r_set_reference was never called");
+        ref_start1 = ctx->ref_res_start0 + 1;
+        ref_len = ctx->ref_res_len;
+    }
     if (!ctx->have_weights) return fail(ctx, C3R_ERR_STATE, "c3r_set_weights must be called before c3r_submit_chunk");
     if (region_end1 < region_start1 || region_start1 < 1) return fail(ctx, C3R_ERR_ARG, "bad region");
     if (region_end1 > 0x7fff0000LL) return fail(ctx, C3R_ERR_CAPACITY, "positions must fit int32");
@@ -416,7 +435,7 @@ int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int6
     const int64_t R = rd->n_reads > 0 ? rd->n_reads : 1, O = rd->n_ops > 0 ? rd->n_ops : 1;
 #define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
     EN(pos, R * 4); EN(flag, R * 2); EN(mapq, R); EN(hp, R); EN(cigar_off, (R + 1) * 4); EN(cigar, O * 4);
-    EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 16); EN(ref, ref_len + 16);
+    EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 16); if (ref) { EN(ref, ref_len + 16); }
     EN(admit, R); EN(read_end, R * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_rid, O * 4);
     EN(covA, (d.NW + 4) * 4); EN(covE, (d.NW + 4) * 4); EN(rowR, (d.NW + 4) * 4); EN(wdiff, (d.NW + 4) * 8);
     EN(word_base, (d.NW + 4) * 4);
@@ -435,7 +454,7 @@ int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int6
 #undef EN
     d.pos = P<int32_t>(s.pos); d.flag = P<uint16_t>(s.flag); d.mapq = P<uint8_t>(s.mapq); d.hp = P<uint8_t>(s.hp);
     d.cigar_off = P<int32_t>(s.cigar_off); d.cigar = P<uint32_t>(s.cigar); d.seq_off = P<int64_t>(s.seq_off);
-    d.seq = P<uint8_t>(s.seq); d.ref = P<uint8_t>(s.ref);
+    d.seq = P<uint8_t>(s.seq); d.ref = ref ? P<uint8_t>(s.ref) : P<uint8_t>(ctx->ref_res);
     d.admit = P<uint8_t>(s.admit); d.read_end = P<int32_t>(s.read_end); d.op_head = P<int32_t>(s.op_head);
     d.op_x = P<int32_t>(s.op_x); d.op_y = P<uint32_t>(s.op_y); d.op_rid = P<int32_t>(s.op_rid);
     d.covA = P<uint32_t>(s.covA); d.covE = P<uint32_t>(s.covE); d.rowR = P<uint32_t>(s.rowR); d.wdiff = P<Int2>(s.wdiff);
@@ -462,7 +481,7 @@ int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int6
     }
     if (rd->n_ops > 0) CK(cudaMemcpyAsync(s.cigar.p, rd->cigar, rd->n_ops * 4, cudaMemcpyHostToDevice, st));
     if (rd->n_seq_bytes > 0) CK(cudaMemcpyAsync(s.seq.p, rd->seq, rd->n_seq_bytes, cudaMemcpyHostToDevice, st));
-    if (ref_len > 0) CK(cudaMemcpyAsync(s.ref.p, ref, ref_len, cudaMemcpyHostToDevice, st));
+    if (ref && ref_len > 0) CK(cudaMemcpyAsync(s.ref.p, ref, ref_len, cudaMemcpyHostToDevice, st));
     s.in_use = true;
     int rc = run_stage_a(ctx, s);
     if (!rc) rc = read_scalars(ctx, s);

@@ -318,7 +318,8 @@ struct LstmArgs {
     int* err;
 };
 
-constexpr int LSTM_THREADS = 320;            // warp 0: MMA issue, warp 1: x loader, warps 2-9: gates
+constexpr int LSTM_GATE_WARPS = 16;          // 4 per TMEM lane quarter, 8 units of a chunk each
+constexpr int LSTM_THREADS = 64 + 32 * LSTM_GATE_WARPS;   // warp 0: MMA issue, warp 1: x loader, then the gate warps
 
 // Gate math on the SFU: ex2.approx / rcp.approx (<= 2 ulp each), 8 SFU ops per (site, unit):
 //   sigmoid(x) = 1/(1+2^(-x log2e)),  tanh(x) = (1-b)/(1+b) with b = 2^(-2x log2e),
@@ -358,7 +359,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
     if (threadIdx.x == 0) {
         ptx::mbar_init(b_w, 1);
         ptx::mbar_init(b_accf, 1); ptx::mbar_init(b_accf + 8, 1);
-        ptx::mbar_init(b_acce, 16); ptx::mbar_init(b_acce + 8, 16);      // 8 gate warps x 2 CTAs
+        ptx::mbar_init(b_acce, 2 * LSTM_GATE_WARPS); ptx::mbar_init(b_acce + 8, 2 * LSTM_GATE_WARPS);   // gate warps x 2 CTAs
         ptx::mbar_init(b_xr, 2); ptx::mbar_init(b_xr + 8, 2);            // loader warp x 2 CTAs
         ptx::mbar_init(b_step, 1); ptx::mbar_init(b_step + 8, 1);
         ptx::fence_barrier_init();
@@ -473,9 +474,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
             }
         } else {
             // ------------------------------------------------ gates: TMEM -> c, h
-            const int gw = warp - 2;                         // 0..7
+            const int gw = warp - 2;                         // 0..15
             const int q = warp & 3;                          // TMEM lane quarter this warp may access
-            const int half = gw >> 2;                        // which 16 units of the chunk
+            const int sub = gw >> 2;                         // which 8 units of the chunk's 32
             const int row = q * 32 + lane;
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
             for (int step = 0; step < NT; ++step) {
@@ -490,7 +491,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                 for (int c = 0; c < CH; ++c) {
                     const uint32_t use = base_use + step * CH + c;
                     const uint32_t slot = use & 1;
-                    float z[4][16];
+                    float z[4][8];
                     if (KX == 0) {
                         // hoisted projection: [tile][t][dir*CH + c][gate*8 + ug][row][4]
                         const float4* zp = (const float4*)a.zx +
@@ -498,8 +499,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
 #pragma unroll
                         for (int gte = 0; gte < 4; ++gte)
 #pragma unroll
-                            for (int ug = 0; ug < 4; ++ug) {
-                                const float4 f = zp[(size_t)(gte * 8 + half * 4 + ug) * 128];
+                            for (int ug = 0; ug < 2; ++ug) {
+                                const float4 f = zp[(size_t)(gte * 8 + sub * 2 + ug) * 128];
                                 z[gte][ug * 4 + 0] = f.x; z[gte][ug * 4 + 1] = f.y;
                                 z[gte][ug * 4 + 2] = f.z; z[gte][ug * 4 + 3] = f.w;
                             }
@@ -507,30 +508,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
 #pragma unroll
                         for (int gte = 0; gte < 4; ++gte)
 #pragma unroll
-                            for (int u = 0; u < 16; ++u) z[gte][u] = 0.0f;
+                            for (int u = 0; u < 8; ++u) z[gte][u] = 0.0f;
                     }
                     ptx::mbar_wait(b_accf + 8 * slot, (use >> 1) & 1, a.err, 208);
                     ptx::tc_fence_after();
-                    uint32_t cprev[16];
+                    uint32_t cprev[8];
+                    uint32_t v[4][8];
                     if (has_acc) {
 #pragma unroll
-                        for (int gte = 0; gte < 4; ++gte) {
-                            uint32_t v[16];
-                            ptx::tmem_ld16(tmem + lane_addr + slot * 128 + gte * 32 + half * 16, v);
-                            ptx::tmem_wait_ld();
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) z[gte][u] += __uint_as_float(v[u]);
-                        }
+                        for (int gte = 0; gte < 4; ++gte)
+                            ptx::tmem_ld8(tmem + lane_addr + slot * 128 + gte * 32 + sub * 8, v[gte]);
                     }
-                    if (step > 0) {
-                        ptx::tmem_ld16(tmem + lane_addr + Cfg::C_COL + c * 32 + half * 16, cprev);
-                        ptx::tmem_wait_ld();
-                    }
-                    uint32_t cnew[16];
-                    __align__(16) __half hh[16];
-                    __align__(16) __half hl[16];
+                    if (step > 0) ptx::tmem_ld8(tmem + lane_addr + Cfg::C_COL + c * 32 + sub * 8, cprev);
+                    ptx::tmem_wait_ld();
+                    if (has_acc) {
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
+                        for (int gte = 0; gte < 4; ++gte)
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) z[gte][u] += __uint_as_float(v[gte][u]);
+                    }
+                    uint32_t cnew[8];
+                    __align__(16) __half hh[8];
+                    __align__(16) __half hl[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
                         const float cp = step > 0 ? __uint_as_float(cprev[u]) : 0.0f;
                         const float cn = fmaf(sigmoid_fast(z[1][u]), cp, sig_times_tanh(z[0][u], z[2][u]));
                         cnew[u] = __float_as_uint(cn);
@@ -538,22 +539,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         hh[u] = __float2half(hv);
                         hl[u] = __float2half(hv - __half2float(hh[u]));
                     }
-                    ptx::tmem_st16(tmem + lane_addr + Cfg::C_COL + c * 32 + half * 16, cnew);
-                    // h_t: next step's A operand (k index = unit) and the layer output
-                    const int unit0 = c * 32 + half * 16;
-#pragma unroll
-                    for (int g8 = 0; g8 < 2; ++g8) {
-                        const uint4 pk = *(const uint4*)(&hh[g8 * 8]);
-                        const int k8 = unit0 / 8 + g8;
+                    ptx::tmem_st8(tmem + lane_addr + Cfg::C_COL + c * 32 + sub * 8, cnew);
+                    // h_t: next step's A operand (k index = unit) and the layer output (hi + lo terms)
+                    {
+                        const uint4 pk = *(const uint4*)hh;
+                        const int k8 = c * 4 + sub;
                         *(uint4*)(ah + (size_t)k8 * (TC_TILE * 16) + row * 16) = pk;
                         const int col8 = (dir * U) / 8 + k8;                 // 8-column group in the concat [fwd | bwd]
                         const size_t oo = (size_t)(col8 / 8) * TC_IMG + (size_t)(col8 % 8) * (TC_TILE * 8) + row * 8;
                         *(uint4*)(hout_t + oo) = pk;
-                        *(uint4*)(hout_lo_t + oo) = *(const uint4*)(&hl[g8 * 8]);
+                        *(uint4*)(hout_lo_t + oo) = *(const uint4*)hl;
                     }
                     ptx::tmem_wait_st();
                     ptx::tc_fence_before();
-                    ptx::fence_proxy_async();
+                    // the MMA of step+1 starts only after this warp's LAST arrival of the step, so one
+                    // generic->async proxy fence before that arrival covers all of its h writes
+                    if (c == CH - 1) ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_cluster(b_acce + 8 * slot, 0);
                 }

@@ -496,8 +496,38 @@ __global__ void __launch_bounds__(256) k_count(Dev d) {
         for (int32_t s = s0; s < s1; s += 32) {
             const int n = min(32, s1 - s);
             if (lane < n) ebuf[warp][lane] = d.entries[s + lane];
+            else { SegEntry z; z.x = 0; z.len = 0; z.y = 0; z.info = 0; ebuf[warp][lane] = z; }
             __syncwarp();
-            for (int j = 0; j < n; ++j) acc_entry(d, ebuf[warp][j], p, a);
+            // batches of 8 entries: issue the 8 sequence-byte loads, then consume them, so each
+            // lane keeps 8 independent global loads in flight instead of one
+            for (int j0 = 0; j0 < n; j0 += 8) {
+                uint32_t by[8], qq[8];
+                int32_t kind[8];                         // 0 none, 1 base, 2 deletion
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const SegEntry e = ebuf[warp][j0 + u];
+                    const uint32_t off = (uint32_t)(p - e.x);
+                    const bool in = off < (uint32_t)(e.len & 0x7fffffff);
+                    kind[u] = in ? (e.len < 0 ? 2 : 1) : 0;
+                    qq[u] = e.y + off;
+                    by[u] = kind[u] == 1 ? (uint32_t)d.seq[qq[u] >> 1] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t info = ebuf[warp][j0 + u].info;
+                    const uint32_t rev = info & 1u;
+                    if (kind[u] == 2) { if (rev) ++a.star_r; else ++a.star_f; }
+                    else if (kind[u] == 1) {
+                        const uint32_t nib = (qq[u] & 1u) ? (by[u] & 15u) : (by[u] >> 4);
+                        if (__popc(nib) == 1) {
+                            const unsigned long long inc = 1ull << (16 * (__ffs(nib) - 1));
+                            if (rev) a.r += inc; else a.f += inc;
+                            const uint32_t hp = (info >> 1) & 3u;
+                            if (hp == 1) a.p += inc; else if (hp == 2) a.m += inc;
+                        }
+                    }
+                }
+            }
             __syncwarp();
         }
         // the row vector lives in this lane's slice of the staging tile (dynamic channel
@@ -750,23 +780,46 @@ struct OpAltOff {
 
 // alleles in alt_dict insertion order (create_tensor_pileup.py:223,235,251,259-261): keys are
 // case-folded, so the two strands of one allele merge and keep the earlier first occurrence.
-__global__ void k_altinfo(Dev d) {
+// One warp per candidate: the lanes split the tile's segment list to find the first read
+// showing each base; lane 0 then builds the (short) allele list.
+__global__ void __launch_bounds__(256) k_altinfo(Dev d) {
     const int64_t n = *d.n_cand < d.cand_cap ? *d.n_cand : d.cand_cap;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n) return;
     const int32_t row = d.cand_row[i];
     const int32_t p = d.row_pos[row];
     const int64_t off = d.alt_off[i];
     const int32_t* ev_off = d.binc + d.NT_ub + 1;
     const int32_t e0 = ev_off[row] - ev_off[0], e1 = ev_off[row + 1] - ev_off[0];
+    // first-occurrence key of each base among the reads covering p
+    uint32_t key[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    {
+        const int32_t t = row >> 5;
+        for (int32_t s = d.binc[t] + lane; s < d.binc[t + 1]; s += 32) {
+            const SegEntry e = d.entries[s];
+            if (e.len < 0) continue;
+            const uint32_t o = (uint32_t)(p - e.x);
+            if (o >= (uint32_t)e.len) continue;
+            const uint32_t nib = nib_at(d.seq, e.y + o);
+            if (__popc(nib) != 1) continue;
+            const int c = __ffs(nib) - 1;
+            const uint32_t kk = (e.info >> 4) * 2u;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) if (b == c && kk < key[b]) key[b] = kk;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) key[b] = min(key[b], __shfl_xor_sync(0xffffffffu, key[b], sft));
+    }
+    if (lane != 0) return;
     if (off + 4 + (e1 - e0) > d.alt_cap) { atomicExch(d.err, 4); d.alt_n[i] = 0; return; }
     AltEntry* out = d.alt + off;
     int m = 0;
     bool acgt;
     const int ri = ref_index(d, p, &acgt);
     const char L4[4] = {'A', 'C', 'G', 'T'};
-    uint32_t key[6];
-    first_keys(d, row, p, key);
     const int32_t* v = d.counts + (int64_t)row * d.C;
     int32_t alt_cnt = 0;
     for (int b = 0; b < 4; ++b) {

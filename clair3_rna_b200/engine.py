@@ -110,8 +110,13 @@ class Engine:
             views[i].n_elem = v.size
         self._check(self.lib.c3r_set_weights(self.ctx, views, len(arrs)), "c3r_set_weights")
 
+    def set_reference(self, ref: np.ndarray, ref_start1: int = 1):
+        """keep a reference window resident on the GPU; later submits may pass ref=None"""
+        ref = np.ascontiguousarray(ref, np.uint8)
+        self._check(self.lib.c3r_set_reference(self.ctx, ref.ctypes.data, ref_start1, int(ref.size)), "c3r_set_reference")
+
     # ------------------------------------------------------------------
-    def submit(self, batch: ReadBatch, ref: np.ndarray, ref_start1: int, region_start1: int, region_end1: int) -> int:
+    def submit(self, batch: ReadBatch, ref, ref_start1: int, region_start1: int, region_end1: int) -> int:
         rd = L.Reads()
         rd.n_reads, rd.n_ops, rd.n_seq_bytes = batch.n_reads, batch.n_ops, int(batch.seq.size)
         arrs = dict(pos=np.ascontiguousarray(batch.pos, np.int32), flag=np.ascontiguousarray(batch.flag, np.uint16),
@@ -121,9 +126,13 @@ class Engine:
                     seq_off=np.ascontiguousarray(batch.seq_off, np.int64), seq=np.ascontiguousarray(batch.seq, np.uint8))
         for k, v in arrs.items():
             setattr(rd, k, v.ctypes.data)
-        ref = np.ascontiguousarray(ref, np.uint8)
         t = C.c_int64(-1)
-        self._check(self.lib.c3r_submit_chunk(self.ctx, C.byref(rd), ref.ctypes.data, ref_start1, int(ref.size),
+        if ref is None:
+            rp, rn = None, 0
+        else:
+            ref = np.ascontiguousarray(ref, np.uint8)
+            rp, rn = ref.ctypes.data, int(ref.size)
+        self._check(self.lib.c3r_submit_chunk(self.ctx, C.byref(rd), rp, ref_start1, rn,
                                               region_start1, region_end1, C.byref(t)), "c3r_submit_chunk")
         return int(t.value)
 

@@ -42,7 +42,7 @@ class Result(C.Structure):
 
 
 EXPORTS = ["c3r_abi_version", "c3r_default_params", "c3r_create", "c3r_destroy", "c3r_last_error",
-           "c3r_set_weights", "c3r_submit_chunk", "c3r_wait", "c3r_release", "c3r_rerun_resident", "c3r_forward", "c3r_debug_fetch"]
+           "c3r_set_weights", "c3r_set_reference", "c3r_submit_chunk", "c3r_wait", "c3r_release", "c3r_rerun_resident", "c3r_forward", "c3r_debug_fetch"]
 
 _lib = None
 
@@ -65,6 +65,7 @@ def load():
     lib.c3r_last_error.argtypes = [C.c_void_p]
     lib.c3r_last_error.restype = C.c_char_p
     lib.c3r_set_weights.argtypes = [C.c_void_p, C.POINTER(WeightView), C.c_int]
+    lib.c3r_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
     lib.c3r_submit_chunk.argtypes = [C.c_void_p, C.POINTER(Reads), C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_int64, C.POINTER(C.c_int64)]
     lib.c3r_wait.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Result)]

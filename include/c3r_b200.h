@@ -125,10 +125,16 @@ const char* c3r_last_error(c3r_ctx* ctx);
 
 int c3r_set_weights(c3r_ctx* ctx, const c3r_weight_view* views, int n_views);
 
+/* Keep the reference bases of a contig (or any window of it) resident on the device, like the
+ * weights: later c3r_submit_chunk calls may then pass ref = NULL.  Replaces the per-chunk
+ * `samtools faidx` of shared/utils.py:168-194 (the reference re-reads it for every chunk). */
+int c3r_set_reference(c3r_ctx* ctx, const uint8_t* ref, int64_t ref_start1, int64_t ref_len);
+
 /* One (contig, chunk): replaces one `call_var_bam` producer|consumer pipeline up
  * to the 24 probabilities (clair3_rna/call_var_bam.py:278-295).
  *   ref / ref_start1 / ref_len: upper-case reference bytes of [ref_start1, ref_start1+ref_len)
  *                               (create_tensor_pileup.py:416-428, expandReferenceRegion)
+ *                               ref == NULL: use the window given to c3r_set_reference
  *   region_start1..region_end1: the 1-based inclusive mpileup region (:412-415)          */
 int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* reads, const uint8_t* ref, int64_t ref_start1,
                      int64_t ref_len, int64_t region_start1, int64_t region_end1, c3r_ticket* ticket);
