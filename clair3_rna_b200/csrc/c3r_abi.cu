@@ -76,6 +76,7 @@ struct c3r_ctx {
     Buf nn_scratch;
     NetF32Scratch nscr;
     TcNet tc;                 // tensor-core path state (nn_tc.cuh)
+    bool exact_bounds = false; // capacity bounds from an exact host pass over the CIGARs (retry path)
     bool tc_dirty = false;    // a tensor-core forward ran since the last device error check
     Buf ref_res;              // resident reference window (c3r_set_reference)
     int64_t ref_res_start0 = 0, ref_res_len = 0;
@@ -385,9 +386,24 @@ int c3r_set_reference(c3r_ctx* ctx, const uint8_t* ref, int64_t ref_start1, int6
     return C3R_OK;
 }
 
+static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
+                       int64_t region_start1, int64_t region_end1, c3r_ticket* ticket);
+
 int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
                      int64_t region_start1, int64_t region_end1, c3r_ticket* ticket) {
     if (!ctx || !rd || !ticket) return C3R_ERR_ARG;
+    ctx->exact_bounds = false;
+    int rc = submit_once(ctx, rd, ref, ref_start1, ref_len, region_start1, region_end1, ticket);
+    if (rc == C3R_ERR_CAPACITY && ctx->err.find("device capacity") != std::string::npos) {
+        ctx->exact_bounds = true;                   // unusual CIGARs: redo with exact bounds
+        rc = submit_once(ctx, rd, ref, ref_start1, ref_len, region_start1, region_end1, ticket);
+        ctx->exact_bounds = false;
+    }
+    return rc;
+}
+
+static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
+                       int64_t region_start1, int64_t region_end1, c3r_ticket* ticket) {
     if (!ref) {
         if (!ctx->ref_res_len) return fail(ctx, C3R_ERR_STATE, "ref == NULL but c3r_set_reference was never called");
         ref_start1 = ctx->ref_res_start0 + 1;
@@ -416,15 +432,25 @@ int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int6
     d.max_depth = pr.max_depth; d.skip_prop = pr.skip_proportion;
     d.ref_start0 = ref_start1 - 1; d.ref_len = ref_len;
     // host-side upper bounds from the CIGARs
-    // rows = positions under an M/=/X/D op, dilated by 16 on each side of every maximal block:
-    // a read contributes at most (its M/D length + 32 per N-separated block)
+    // Capacity bounds.  Rows = positions under an M/=/X/D op, dilated by 16 on each side of every
+    // N-separated block: a read contributes at most (its M/D length + 32 per block).  The cheap
+    // bounds below avoid a host pass over the CIGARs (M bases <= SEQ bases; deletions are assumed
+    // not to outnumber the sequenced bases); if a chunk breaks that assumption the device-side
+    // capacity checks fire and the caller-visible retry in this function uses the exact pass.
     int64_t md_len = 0, n_skip = 0, ent_ub = 0, ev_ub = 0;
-    for (int64_t k = 0; k < rd->n_ops; ++k) {
-        const uint32_t c = rd->cigar[k], op = c & 15u;
-        const int64_t len = c >> 4;
-        if (op == 0 || op == 2 || op == 7 || op == 8) { md_len += len; ent_ub += len / 32 + 2; }
-        if (op == 3) ++n_skip;
-        if (op == 1 || op == 2) ++ev_ub;
+    if (ctx->exact_bounds) {
+        for (int64_t k = 0; k < rd->n_ops; ++k) {
+            const uint32_t c = rd->cigar[k], op = c & 15u;
+            const int64_t len = c >> 4;
+            if (op == 0 || op == 2 || op == 7 || op == 8) { md_len += len; ent_ub += len / 32 + 2; }
+            if (op == 3) ++n_skip;
+            if (op == 1 || op == 2) ++ev_ub;
+        }
+    } else {
+        md_len = 4 * rd->n_seq_bytes;
+        n_skip = rd->n_ops;
+        ent_ub = md_len / 32 + 2 * rd->n_ops;
+        ev_ub = rd->n_ops;
     }
     int64_t L_ub = md_len + 32 * (n_skip + rd->n_reads) + 64;
     if (L_ub > d.W) L_ub = d.W;
