@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
     uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * 2 * TC_IMG * 2);
     // bars: full[4] empty[4] acc_full[2] acc_empty[2], then tmem ptr
     uint32_t* tmem_ptr_s = (uint32_t*)(bars + 12);
+    float* bias_s = (float*)(bars + 32);                    // staged per tile by the epilogue warps
     const uint32_t s_base = ptx::smem_u32(smem);
     const uint32_t b_full = ptx::smem_u32(bars), b_empty = b_full + 32, b_accf = b_full + 64, b_acce = b_full + 80;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,7 +131,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
             ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 104);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 128;
-            const float* bias = g.bias + (size_t)n * 128;
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's readers are done
+            bias_s[threadIdx.x - 64] = g.bias[(size_t)n * 128 + (threadIdx.x - 64)];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float* bias = bias_s;
 #pragma unroll 1
             for (int j = 0; j < 8; ++j) {
                 uint32_t v[16];
@@ -179,6 +183,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
     uint64_t* bars = (uint64_t*)(smem + (2 * ZXG_KB + ZXG_STAGES) * IMG_B);
     // bars: full[5] empty[5] acc_full[2] acc_empty[2] b_full
     uint32_t* tmem_ptr_s = (uint32_t*)(bars + 16);
+    float* bias_s = (float*)(bars + 32);                    // this CTA's 128 bias values (n is fixed per CTA)
+    if (threadIdx.x < 128) bias_s[threadIdx.x] = g.bias[(size_t)(blockIdx.x % g.n_tiles) * 128 + threadIdx.x];
     const uint32_t s_base = ptx::smem_u32(smem);
     const uint32_t s_bhi = s_base, s_blo = s_base + ZXG_KB * IMG_B, s_a = s_base + 2 * ZXG_KB * IMG_B;
     const uint32_t b_full = ptx::smem_u32(bars), b_empty = b_full + 8 * ZXG_STAGES, b_accf = b_empty + 8 * ZXG_STAGES,
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t tc = 0;
-        const float* bias = g.bias + (size_t)n * 128;
+        const float* bias = bias_s;
         for (int m = grp; m < g.m_tiles; m += n_grp, ++tc) {
             const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
             ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 115);
@@ -540,16 +546,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         hl[u] = __float2half(hv - __half2float(hh[u]));
                     }
                     ptx::tmem_st8(tmem + lane_addr + Cfg::C_COL + c * 32 + sub * 8, cnew);
-                    // h_t: next step's A operand (k index = unit) and the layer output (hi + lo terms)
-                    {
-                        const uint4 pk = *(const uint4*)hh;
-                        const int k8 = c * 4 + sub;
-                        *(uint4*)(ah + (size_t)k8 * (TC_TILE * 16) + row * 16) = pk;
-                        const int col8 = (dir * U) / 8 + k8;                 // 8-column group in the concat [fwd | bwd]
-                        const size_t oo = (size_t)(col8 / 8) * TC_IMG + (size_t)(col8 % 8) * (TC_TILE * 8) + row * 8;
-                        *(uint4*)(hout_t + oo) = pk;
-                        *(uint4*)(hout_lo_t + oo) = *(const uint4*)hl;
-                    }
+                    // h_t: next step's A operand (k index = unit)
+                    const uint4 pk = *(const uint4*)hh;
+                    const int k8 = c * 4 + sub;
+                    *(uint4*)(ah + (size_t)k8 * (TC_TILE * 16) + row * 16) = pk;
                     ptx::tmem_wait_st();
                     ptx::tc_fence_before();
                     // the MMA of step+1 starts only after this warp's LAST arrival of the step, so one
@@ -557,6 +557,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     if (c == CH - 1) ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_cluster(b_acce + 8 * slot, 0);
+                    // layer output (hi + lo fp16 terms) goes out AFTER the arrival: the release fence of
+                    // the arrival would otherwise wait for these HBM stores on the recurrence's critical path
+                    {
+                        const int col8 = (dir * U) / 8 + k8;                 // 8-column group in the concat [fwd | bwd]
+                        const size_t oo = (size_t)(col8 / 8) * TC_IMG + (size_t)(col8 % 8) * (TC_TILE * 8) + row * 8;
+                        *(uint4*)(hout_t + oo) = pk;
+                        *(uint4*)(hout_lo_t + oo) = *(const uint4*)hl;
+                    }
                 }
             }
             // the step_done commits multicast to this CTA have landed before it may exit
