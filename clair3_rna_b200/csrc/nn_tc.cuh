@@ -349,12 +349,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
     const uint32_t s_base = ptx::smem_u32(smem);
     const uint32_t s_B = s_base, s_AH = s_base + Cfg::B_BYTES, s_AX = s_AH + 2 * Cfg::AH_BYTES;
     uint64_t* bars = (uint64_t*)(smem + Cfg::BAR_OFF);
-    // barriers: 0 w_full | 1,2 acc_full[2] | 3,4 acc_empty[2] | 5,6 x_ready[2] | 7,8 step_done[2] ; then tmem ptr
+    // barriers: 0 w_full | 1,2 acc_full[2] | 3,4 acc_empty[2] (local gate warps) | 5,6 x_ready[2] |
+    //           7,8 step_done[2] | 9,10 acc_empty_peer[2] (leader only: one relayed arrival per use from the peer) ; tmem ptr
     // Every wait below targets the current or the immediately preceding phase of its barrier
     // (mbarrier parity waits cannot tell phases further apart).
     const uint32_t b0 = ptx::smem_u32(bars);
     const uint32_t b_w = b0, b_accf = b0 + 8, b_acce = b0 + 24, b_xr = b0 + 40, b_step = b0 + 56;
-    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 10);
+    const uint32_t b_accr = b0 + 72;
+    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 12);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     // clusters come in (forward, backward) pairs so a cluster keeps one direction's weights resident
@@ -365,7 +367,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
     if (threadIdx.x == 0) {
         ptx::mbar_init(b_w, 1);
         ptx::mbar_init(b_accf, 1); ptx::mbar_init(b_accf + 8, 1);
-        ptx::mbar_init(b_acce, 2 * LSTM_GATE_WARPS); ptx::mbar_init(b_acce + 8, 2 * LSTM_GATE_WARPS);   // gate warps x 2 CTAs
+        ptx::mbar_init(b_acce, LSTM_GATE_WARPS); ptx::mbar_init(b_acce + 8, LSTM_GATE_WARPS);   // this CTA's gate warps
+        ptx::mbar_init(b_accr, 1); ptx::mbar_init(b_accr + 8, 1);                                 // peer's relay
         ptx::mbar_init(b_xr, 2); ptx::mbar_init(b_xr + 8, 2);            // loader warp x 2 CTAs
         ptx::mbar_init(b_step, 1); ptx::mbar_init(b_step + 8, 1);
         ptx::fence_barrier_init();
@@ -407,12 +410,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         const uint32_t use = base_use + step * CH + c;
                         const uint32_t slot = use & 1;
                         // slot free (its previous use drained by both CTAs) ...
-                        ptx::mbar_wait_cluster(b_acce + 8 * slot, ((use >> 1) & 1) ^ 1, a.err, 203);
+                        ptx::mbar_wait(b_acce + 8 * slot, ((use >> 1) & 1) ^ 1, a.err, 203);
+                        ptx::mbar_wait_cluster(b_accr + 8 * slot, ((use >> 1) & 1) ^ 1, a.err, 213);
                         // ... and, at the start of a step, every chunk of the previous step finished
                         // (h complete): the other slot's latest use is use-1.
                         if (c == 0 && use > 0) {
                             const uint32_t prev = use - 1;
-                            ptx::mbar_wait_cluster(b_acce + 8 * (prev & 1), (prev >> 1) & 1, a.err, 204);
+                            ptx::mbar_wait(b_acce + 8 * (prev & 1), (prev >> 1) & 1, a.err, 204);
+                            ptx::mbar_wait_cluster(b_accr + 8 * (prev & 1), (prev >> 1) & 1, a.err, 214);
                         }
                         ptx::tc_fence_after();
                         const uint32_t sb = s_B + c * (64 * KT * 2);
@@ -441,6 +446,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         ptx::mma_commit_2_mcast(b_accf + 8 * slot, 3);
                     }
                     ptx::mma_commit_2_mcast(b_step + 8 * buf, 3);
+                }
+            }
+            if (rank == 1 && lane == 0) {
+                // relay: one cluster-scope arrival per accumulator use on behalf of this CTA's 16 gate
+                // warps, so the expensive cluster release fence is off their critical path
+                for (int u = 0; u < NT * CH; ++u) {
+                    const uint32_t use = base_use + u;
+                    const uint32_t slot = use & 1;
+                    ptx::mbar_wait(b_acce + 8 * slot, (use >> 1) & 1, a.err, 215);
+                    ptx::mbar_arrive_cluster(b_accr + 8 * slot, 0);
                 }
             }
         } else if (warp == 1) {
@@ -556,7 +571,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     // generic->async proxy fence before that arrival covers all of its h writes
                     if (c == CH - 1) ptx::fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_cluster(b_acce + 8 * slot, 0);
+                    if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
                     // layer output (hi + lo fp16 terms) goes out AFTER the arrival: the release fence of
                     // the arrival would otherwise wait for these HBM stores on the recurrence's critical path
                     {
