@@ -21,6 +21,7 @@
 // Math restated from /root/reference/clair3_rna/model.py:126-216.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -216,6 +217,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
             }
             uint32_t it = 0;
             for (int m = grp; m < g.m_tiles; m += n_grp) {
+                // the group's CTAs stream the same A tile: one of them pulls the tile two iterations
+                // ahead into L2 so the demand copies below are L2 hits instead of HBM round trips
+                if (n == 0) {
+                    const int mp = m + 2 * n_grp;
+                    if (mp < g.m_tiles) {
+                        ptx::bulk_prefetch_l2(g.A + (size_t)mp * ZXG_KB * TC_IMG, ZXG_KB * IMG_B);
+                        ptx::bulk_prefetch_l2(g.A_lo + (size_t)mp * ZXG_KB * TC_IMG, ZXG_KB * IMG_B);
+                    }
+                }
                 for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {          // A_hi[0], A_lo[0], A_hi[1], ...
                     const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
                     ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 111);
@@ -313,7 +323,7 @@ struct LstmCfg {
 
 struct LstmArgs {
     const __half* Wimg;     // [2 dirs][2 ranks][B_BYTES/2] operand images
-    const int32_t* tensor;  // LSTM1: int32 windows [n][33][C]
+    const __half* xop;      // LSTM1: x operand images [tile][33][KX/8][128][8] (k_xop)
     int C;
     const float* zx;        // LSTM2: hoisted projection, ZX layout [tile][33][2*CH][32][128][4]
     __half* hout;           // packed output [tile][33][KB_OUT][TC_IMG], high-order fp16 term
@@ -322,7 +332,12 @@ struct LstmArgs {
     int64_t n_sites;        // valid sites (tensor rows); tiles beyond are zero
     int n_tiles;            // 128-site tiles (even)
     int* err;
+    long long* trace;       // optional [2 ranks][33 steps][8 chunks][8 events] SM-clock stamps of cluster 0, work item 0
 };
+
+__device__ __forceinline__ void lstm_trace(const LstmArgs& a, bool on, uint32_t rank, int step, int c, int ev) {
+    if (on) a.trace[(((size_t)rank * NT + step) * 8 + c) * 8 + ev] = clock64();
+}
 
 constexpr int LSTM_GATE_WARPS = 16;          // 4 per TMEM lane quarter, 8 units of a chunk each
 constexpr int LSTM_THREADS = 64 + 32 * LSTM_GATE_WARPS;   // warp 0: MMA issue, warp 1: x loader, then the gate warps
@@ -356,7 +371,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
     const uint32_t b0 = ptx::smem_u32(bars);
     const uint32_t b_w = b0, b_accf = b0 + 8, b_acce = b0 + 24, b_xr = b0 + 40, b_step = b0 + 56;
     const uint32_t b_accr = b0 + 72;
-    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 12);
+    const uint32_t b_xl = b0 + 88;                           // 11,12: this CTA's x tile landed (bulk copy tx)
+    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 14);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     // clusters come in (forward, backward) pairs so a cluster keeps one direction's weights resident
@@ -369,7 +385,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
         ptx::mbar_init(b_accf, 1); ptx::mbar_init(b_accf + 8, 1);
         ptx::mbar_init(b_acce, LSTM_GATE_WARPS); ptx::mbar_init(b_acce + 8, LSTM_GATE_WARPS);   // this CTA's gate warps
         ptx::mbar_init(b_accr, 1); ptx::mbar_init(b_accr + 8, 1);                                 // peer's relay
-        ptx::mbar_init(b_xr, 2); ptx::mbar_init(b_xr + 8, 2);            // loader warp x 2 CTAs
+        ptx::mbar_init(b_xr, 1); ptx::mbar_init(b_xr + 8, 1);            // peer's x tile landed (relayed)
+        ptx::mbar_init(b_xl, 1); ptx::mbar_init(b_xl + 8, 1);
         ptx::mbar_init(b_step, 1); ptx::mbar_init(b_step + 8, 1);
         ptx::fence_barrier_init();
         // this CTA's half of the direction's weights: resident for the whole kernel
@@ -398,6 +415,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
         const int tile = tile_pair * 2 + (int)rank;          // this CTA's 128 sites
         const uint32_t base_use = work_it * (uint32_t)(NT * CH);     // accumulator uses before this work item
         const uint32_t base_step = work_it * (uint32_t)NT;
+        const bool tr = a.trace != nullptr && cluster_id == 0 && work_it == 0 && lane == 0;
 
         if (warp == 0) {
             // ------------------------------------------------ MMA issue (leader CTA, one thread)
@@ -405,7 +423,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                 for (int step = 0; step < NT; ++step) {
                     const uint32_t gstep = base_step + step;
                     const uint32_t buf = gstep & 1;
-                    if (KX > 0) ptx::mbar_wait_cluster(b_xr + 8 * buf, (gstep >> 1) & 1, a.err, 202);
+                    if (KX > 0) {
+                        ptx::mbar_wait(b_xl + 8 * buf, (gstep >> 1) & 1, a.err, 202);
+                        ptx::mbar_wait_cluster(b_xr + 8 * buf, (gstep >> 1) & 1, a.err, 212);
+                    }
                     for (int c = 0; c < CH; ++c) {
                         const uint32_t use = base_use + step * CH + c;
                         const uint32_t slot = use & 1;
@@ -420,6 +441,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                             ptx::mbar_wait_cluster(b_accr + 8 * (prev & 1), (prev >> 1) & 1, a.err, 214);
                         }
                         ptx::tc_fence_after();
+                        lstm_trace(a, tr, 0, step, c, 0);
                         const uint32_t sb = s_B + c * (64 * KT * 2);
                         bool first = true;
                         if (KX > 0) {
@@ -444,6 +466,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         }
                         // (LSTM2, step 0: no MMA at all; the commit below still fires the barrier)
                         ptx::mma_commit_2_mcast(b_accf + 8 * slot, 3);
+                        lstm_trace(a, tr, 0, step, c, 1);
                     }
                     ptx::mma_commit_2_mcast(b_step + 8 * buf, 3);
                 }
@@ -456,41 +479,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     const uint32_t slot = use & 1;
                     ptx::mbar_wait(b_acce + 8 * slot, (use >> 1) & 1, a.err, 215);
                     ptx::mbar_arrive_cluster(b_accr + 8 * slot, 0);
+                    lstm_trace(a, tr, 1, u / CH, u % CH, 5);
                 }
             }
         } else if (warp == 1) {
-            // ------------------------------------------------ LSTM1: x_t -> fp16 operand tile
-            if (KX > 0) {
-                const int C = a.C;
+            // ------------------------------------------------ LSTM1: x_t operand tile, one bulk copy per step
+            if (KX > 0 && lane == 0) {
                 for (int step = 0; step < NT; ++step) {
                     const uint32_t gstep = base_step + step;
                     const uint32_t buf = gstep & 1;
                     // buffer `buf` was last read by the MMAs of global step gstep-2
                     if (gstep >= 2) ptx::mbar_wait(b_step + 8 * buf, ((gstep >> 1) - 1) & 1, a.err, 205);
+                    lstm_trace(a, tr, rank, step, 0, 6);
                     const int t = dir == 0 ? step : NT - 1 - step;
-                    uint8_t* ax = smem + (Cfg::B_BYTES + 2 * Cfg::AH_BYTES) + buf * Cfg::AX_BYTES;
-                    for (int r = lane; r < TC_TILE; r += 32) {
-                        const int64_t site = (int64_t)tile * TC_TILE + r;
-                        __align__(16) __half hv[KX > 0 ? KX : 8];
-#pragma unroll
-                        for (int k = 0; k < KX; ++k) hv[k] = __float2half(0.0f);
-                        if (site < a.n_sites) {
-                            const int32_t* src = a.tensor + (site * NT + t) * C;
-                            for (int cch = 0; cch < C; ++cch) {
-                                const __half h = __float2half((float)src[cch]);
-                                hv[cch] = h;
-                                hv[C + cch] = h;
-                            }
-                        }
-                        hv[2 * C] = __float2half(1.0f);
-                        hv[2 * C + 1] = __float2half(1.0f);
-#pragma unroll
-                        for (int k8 = 0; k8 < KX / 8; ++k8)
-                            *(uint4*)(ax + (size_t)k8 * (TC_TILE * 16) + r * 16) = *(const uint4*)(&hv[k8 * 8]);
+                    ptx::mbar_arrive_expect_tx(b_xl + 8 * buf, Cfg::AX_BYTES);
+                    ptx::bulk_g2s(s_AX + buf * Cfg::AX_BYTES,
+                                  a.xop + ((size_t)tile * NT + t) * (size_t)(KX * TC_TILE), Cfg::AX_BYTES, b_xl + 8 * buf);
+                    if (rank == 1) {                         // tell the leader this CTA's tile has landed
+                        ptx::mbar_wait(b_xl + 8 * buf, (gstep >> 1) & 1, a.err, 206);
+                        ptx::mbar_arrive_cluster(b_xr + 8 * buf, 0);
                     }
-                    ptx::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_cluster(b_xr + 8 * buf, 0);
+                    lstm_trace(a, tr, rank, step, 0, 7);
                 }
             }
         } else {
@@ -508,6 +517,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                 __half* hout_t = a.hout + ((size_t)tile * NT + t) * a.kb_out * TC_IMG;
                 __half* hout_lo_t = a.hout_lo + ((size_t)tile * NT + t) * a.kb_out * TC_IMG;
                 const bool has_acc = (KX > 0) || step > 0;
+                if (KX == 0 && step + 1 < NT && (lane & 7) == 0) {
+                    // next step's hoisted projection: one L2 prefetch per 128-byte line this warp will read
+                    const int tn = dir == 0 ? step + 1 : NT - 2 - step;
+                    const float4* zn = (const float4*)a.zx + ((((size_t)tile * NT + tn) * (2 * CH) + dir * CH) * 32) * 128 + row;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+#pragma unroll
+                        for (int gte = 0; gte < 4; ++gte)
+#pragma unroll
+                            for (int ug = 0; ug < 2; ++ug)
+                                ptx::prefetch_l2(zn + (size_t)(c * 32 + gte * 8 + sub * 2 + ug) * 128);
+                }
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const uint32_t use = base_use + step * CH + c;
@@ -533,6 +554,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     }
                     ptx::mbar_wait(b_accf + 8 * slot, (use >> 1) & 1, a.err, 208);
                     ptx::tc_fence_after();
+                    lstm_trace(a, tr && gw == 0, rank, step, c, 2);
                     uint32_t cprev[8];
                     uint32_t v[4][8];
                     if (has_acc) {
@@ -542,6 +564,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     }
                     if (step > 0) ptx::tmem_ld8(tmem + lane_addr + Cfg::C_COL + c * 32 + sub * 8, cprev);
                     ptx::tmem_wait_ld();
+                    lstm_trace(a, tr && gw == 0, rank, step, c, 3);
                     if (has_acc) {
 #pragma unroll
                         for (int gte = 0; gte < 4; ++gte)
@@ -572,6 +595,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     if (c == CH - 1) ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
+                    lstm_trace(a, tr && gw == 0, rank, step, c, 4);
                     // layer output (hi + lo fp16 terms) goes out AFTER the arrival: the release fence of
                     // the arrival would otherwise wait for these HBM stores on the recurrence's critical path
                     {
@@ -596,6 +620,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
     if (warp == 0) ptx::tmem_dealloc<2>(tmem, Cfg::TMEM_COLS);
 }
 
+// int32 windows [n][33][C] -> LSTM1 x operand images [tile][33][KX/8][128 rows][8 halfs]:
+//   k < C: x, C <= k < 2C: x again (meets W_lo), k = 2C, 2C+1: 1 (meets b_hi, b_lo), rest 0.
+// Block = one (tile, t), thread = one site; each k-group is one coalesced 2 KB store.
+template <int C, int KX>
+__global__ void __launch_bounds__(TC_TILE) k_xop(const int32_t* __restrict__ tensor, __half* __restrict__ xop, int64_t n_sites) {
+    const int tile = blockIdx.x / NT, t = blockIdx.x % NT, r = threadIdx.x;
+    const int64_t site = (int64_t)tile * TC_TILE + r;
+    __align__(16) __half hv[KX];
+#pragma unroll
+    for (int k = 0; k < KX; ++k) hv[k] = __float2half(0.0f);
+    if (site < n_sites) {
+        const int2* src = (const int2*)(tensor + (site * NT + t) * C);       // rows are 8-byte aligned (C even)
+#pragma unroll
+        for (int j = 0; j < C / 2; ++j) {
+            const int2 v = src[j];
+            hv[2 * j] = hv[C + 2 * j] = __float2half((float)v.x);
+            hv[2 * j + 1] = hv[C + 2 * j + 1] = __float2half((float)v.y);
+        }
+    }
+    hv[2 * C] = __float2half(1.0f);
+    hv[2 * C + 1] = __float2half(1.0f);
+    __half* dst = xop + ((size_t)tile * NT + t) * (size_t)(KX * TC_TILE) + r * 8;
+#pragma unroll
+    for (int k8 = 0; k8 < KX / 8; ++k8) *(uint4*)(dst + (size_t)k8 * (TC_TILE * 8)) = *(const uint4*)(&hv[k8 * 8]);
+}
+
 // ================================================================== host side
 struct TcNet {
     int ready = 0;
@@ -608,9 +658,10 @@ struct TcNet {
     void* abuf = nullptr;
     size_t abytes = 0;
     int cap_tiles = 0;
-    __half *h1 = nullptr, *h2 = nullptr, *h1_lo = nullptr, *h2_lo = nullptr;
+    __half *h1 = nullptr, *h2 = nullptr, *h1_lo = nullptr, *h2_lo = nullptr, *xop = nullptr;
     float *zx2 = nullptr, *l4 = nullptr;
     int* err = nullptr;
+    long long* trace = nullptr;    // [2 layers][2][33][8][8], filled when C3R_TRACE is set
     bool attr_set = false;
 };
 
@@ -618,6 +669,7 @@ inline void tc_release(TcNet& t) {
     if (t.wbuf) cudaFree(t.wbuf);
     if (t.abuf) cudaFree(t.abuf);
     if (t.err) cudaFree(t.err);
+    if (t.trace) cudaFree(t.trace);
     t = TcNet();
 }
 
@@ -728,6 +780,10 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
     e = cudaMalloc((void**)&t.err, 64);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     cudaMemset(t.err, 0, 64);
+    if (getenv("C3R_TRACE")) {
+        cudaMalloc((void**)&t.trace, 2 * 2 * NT * 8 * 8 * sizeof(long long));
+        cudaMemset(t.trace, 0, 2 * 2 * NT * 8 * 8 * sizeof(long long));
+    }
     t.ready = 1;
     return 0;
 }
@@ -738,7 +794,8 @@ inline int tc_ensure(TcNet& t, int tiles, std::string* err) {
     t.abuf = nullptr;
     const size_t n_h1 = (size_t)tiles * NT * 4 * TC_IMG, n_h2 = (size_t)tiles * NT * 5 * TC_IMG;
     const size_t n_zx = (size_t)tiles * NT * 10 * 128 * 128, n_l4 = (size_t)tiles * 128 * DENSE;
-    t.abytes = (n_h1 + n_h2) * 2 * 2 + (n_zx + n_l4) * 4 + 1024;
+    const size_t n_xop = (size_t)tiles * NT * 64 * TC_TILE;
+    t.abytes = (n_h1 + n_h2) * 2 * 2 + n_xop * 2 + (n_zx + n_l4) * 4 + 1024;
     cudaError_t e = cudaMalloc(&t.abuf, t.abytes);
     if (e != cudaSuccess) { *err = std::string("activation scratch: ") + cudaGetErrorString(e); t.cap_tiles = 0; return -1; }
     uint8_t* p = (uint8_t*)t.abuf;
@@ -747,7 +804,8 @@ inline int tc_ensure(TcNet& t, int tiles, std::string* err) {
     t.h1 = (__half*)p; p += n_h1 * 2;
     t.h1_lo = (__half*)p; p += n_h1 * 2;
     t.h2 = (__half*)p; p += n_h2 * 2;
-    t.h2_lo = (__half*)p;
+    t.h2_lo = (__half*)p; p += n_h2 * 2;
+    t.xop = (__half*)p;
     t.cap_tiles = tiles;
     return 0;
 }
@@ -808,9 +866,12 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         tiles += tiles & 1;                  // CTA pairs
         if (tc_ensure(t, tiles, err)) return -1;
         cudaError_t e;
+        if (t.C == 18) k_xop<18, 48><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
+        else k_xop<30, 64><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
+        ++launches;
         LstmArgs a1;
-        a1.Wimg = t.img1; a1.tensor = tensor + o * NT * t.C; a1.C = t.C; a1.zx = nullptr; a1.hout = t.h1; a1.hout_lo = t.h1_lo; a1.kb_out = 4;
-        a1.n_sites = m; a1.n_tiles = tiles; a1.err = t.err;
+        a1.Wimg = t.img1; a1.xop = t.xop; a1.C = t.C; a1.zx = nullptr; a1.hout = t.h1; a1.hout_lo = t.h1_lo; a1.kb_out = 4;
+        a1.n_sites = m; a1.n_tiles = tiles; a1.err = t.err; a1.trace = t.trace;
         e = t.C == 18 ? launch_lstm<4, 48>(a1, t.sm_count, st) : launch_lstm<4, 64>(a1, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("lstm1: ") + cudaGetErrorString(e); return -1; }
         ++launches;
@@ -821,8 +882,8 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         if (e != cudaSuccess) { *err = std::string("zx2 gemm: ") + cudaGetErrorString(e); return -1; }
         ++launches;
         LstmArgs a2;
-        a2.Wimg = t.img2; a2.tensor = nullptr; a2.C = t.C; a2.zx = t.zx2; a2.hout = t.h2; a2.hout_lo = t.h2_lo; a2.kb_out = 5;
-        a2.n_sites = m; a2.n_tiles = tiles; a2.err = t.err;
+        a2.Wimg = t.img2; a2.xop = nullptr; a2.C = t.C; a2.zx = t.zx2; a2.hout = t.h2; a2.hout_lo = t.h2_lo; a2.kb_out = 5;
+        a2.n_sites = m; a2.n_tiles = tiles; a2.err = t.err; a2.trace = t.trace ? t.trace + 2 * NT * 8 * 8 : nullptr;
         e = launch_lstm<5, 0>(a2, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("lstm2: ") + cudaGetErrorString(e); return -1; }
         ++launches;
