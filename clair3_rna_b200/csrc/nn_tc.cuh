@@ -48,6 +48,7 @@ struct GemmArgs {
     float* out;
     int m_tiles, n_tiles, n_kb;
     int mode;             // 0: ZX layout [m][n][32 col-groups][128 rows][4]   1: row-major [m*128+r][n_tiles*128] + SELU
+    int dbg;              // experiments: 1 = skip the output stores, 2 = hi*hi term only
     int* err;
 };
 
@@ -168,33 +169,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
     if (warp == 1) ptx::tmem_dealloc<1>(tmem, 256);
 }
 
-// ------------------------------------------------------------------ B-stationary variant
-// LSTM2's hoisted input projection: K = 256 is short and N = 1280 wide, so a CTA keeps the weight
-// images of ONE 128-column tile (hi and lo terms, 128 KB) resident and streams only activations.
-// Per output tile it issues  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  and each A image is loaded once.
-// Grid = groups x n_tiles CTAs; group g walks m-tiles g, g+groups, ...; the n_tiles CTAs of a
-// group touch the same A tile at about the same time, so it is read from HBM once.
+// ------------------------------------------------------------------ A-stationary variant
+// LSTM2's hoisted input projection (K = 256, N = 1280).  A CTA keeps the activation images of ONE
+// 128-site m-tile resident (hi and lo fp16 terms, 128 KB) and streams the weight images of the ten
+// 128-column n-tiles through a 5-stage ring: the weights total 1.3 MB and stay L2-hot, so the ring
+// sees L2 latency only, while each activation tile is read from HBM exactly once.
+// Per output tile:  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
 constexpr int ZXG_KB = 4;                                   // K = 256
 constexpr int ZXG_STAGES = 5;
-constexpr int ZXG_SMEM = (2 * ZXG_KB + ZXG_STAGES) * TC_IMG * 2 + 1024;
+constexpr int ZXG_SMEM = (2 * ZXG_KB + ZXG_STAGES) * TC_IMG * 2 + 8192;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t IMG_B = TC_IMG * 2;
     uint64_t* bars = (uint64_t*)(smem + (2 * ZXG_KB + ZXG_STAGES) * IMG_B);
-    // bars: full[5] empty[5] acc_full[2] acc_empty[2] b_full
-    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 16);
-    float* bias_s = (float*)(bars + 32);                    // this CTA's 128 bias values (n is fixed per CTA)
-    if (threadIdx.x < 128) bias_s[threadIdx.x] = g.bias[(size_t)(blockIdx.x % g.n_tiles) * 128 + threadIdx.x];
+    // bars: full[5] empty[5] acc_full[2] acc_empty[2] a_full a_empty ; tmem ptr ; bias[n_tiles*128]
+    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 18);
+    float* bias_s = (float*)(bars + 32);
+    for (int i = threadIdx.x; i < g.n_tiles * 128; i += GEMM_THREADS) bias_s[i] = g.bias[i];
     const uint32_t s_base = ptx::smem_u32(smem);
-    const uint32_t s_bhi = s_base, s_blo = s_base + ZXG_KB * IMG_B, s_a = s_base + 2 * ZXG_KB * IMG_B;
+    const uint32_t s_ahi = s_base, s_alo = s_base + ZXG_KB * IMG_B, s_b = s_base + 2 * ZXG_KB * IMG_B;
     const uint32_t b_full = ptx::smem_u32(bars), b_empty = b_full + 8 * ZXG_STAGES, b_accf = b_empty + 8 * ZXG_STAGES,
-                   b_acce = b_accf + 16, b_bres = b_acce + 16;
+                   b_acce = b_accf + 16, b_afull = b_acce + 16, b_aempty = b_afull + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < ZXG_STAGES; ++i) { ptx::mbar_init(b_full + 8 * i, 1); ptx::mbar_init(b_empty + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(b_accf + 8 * i, 1); ptx::mbar_init(b_acce + 8 * i, 4); }
-        ptx::mbar_init(b_bres, 1);
+        ptx::mbar_init(b_afull, 1);
+        ptx::mbar_init(b_aempty, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -205,96 +207,96 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_ptr_s;
-    const int n = blockIdx.x % g.n_tiles, grp = blockIdx.x / g.n_tiles, n_grp = gridDim.x / g.n_tiles;
     const uint32_t idesc = ptx::make_idesc_f16(128, 128);
 
     if (warp == 0) {
         if (lane == 0) {
-            ptx::mbar_arrive_expect_tx(b_bres, 2 * ZXG_KB * IMG_B);
-            for (int kb = 0; kb < ZXG_KB; ++kb) {
-                ptx::bulk_g2s(s_bhi + kb * IMG_B, g.B + ((size_t)n * ZXG_KB + kb) * TC_IMG, IMG_B, b_bres);
-                ptx::bulk_g2s(s_blo + kb * IMG_B, g.B_lo + ((size_t)n * ZXG_KB + kb) * TC_IMG, IMG_B, b_bres);
-            }
-            uint32_t it = 0;
-            for (int m = grp; m < g.m_tiles; m += n_grp) {
-                // the group's CTAs stream the same A tile: one of them pulls the tile two iterations
-                // ahead into L2 so the demand copies below are L2 hits instead of HBM round trips
-                if (n == 0) {
-                    const int mp = m + 2 * n_grp;
-                    if (mp < g.m_tiles) {
-                        ptx::bulk_prefetch_l2(g.A + (size_t)mp * ZXG_KB * TC_IMG, ZXG_KB * IMG_B);
-                        ptx::bulk_prefetch_l2(g.A_lo + (size_t)mp * ZXG_KB * TC_IMG, ZXG_KB * IMG_B);
+            uint32_t it = 0, mi = 0;
+            for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x, ++mi) {
+                const int mn = m + gridDim.x;                 // next m-tile of this CTA: pull it towards L2 now
+                if (mn < g.m_tiles) {
+                    ptx::bulk_prefetch_l2(g.A + (size_t)mn * ZXG_KB * TC_IMG, ZXG_KB * IMG_B);
+                    ptx::bulk_prefetch_l2(g.A_lo + (size_t)mn * ZXG_KB * TC_IMG, ZXG_KB * IMG_B);
+                }
+                ptx::mbar_wait(b_aempty, (mi & 1) ^ 1, g.err, 111);     // previous m-tile's MMAs are done with A
+                ptx::mbar_arrive_expect_tx(b_afull, 2 * ZXG_KB * IMG_B);
+                ptx::bulk_g2s(s_ahi, g.A + (size_t)m * ZXG_KB * TC_IMG, ZXG_KB * IMG_B, b_afull);
+                ptx::bulk_g2s(s_alo, g.A_lo + (size_t)m * ZXG_KB * TC_IMG, ZXG_KB * IMG_B, b_afull);
+                for (int n = 0; n < g.n_tiles; ++n)
+                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {      // B_hi[0], B_lo[0], B_hi[1], ...
+                        const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
+                        ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 112);
+                        ptx::mbar_arrive_expect_tx(b_full + 8 * s, IMG_B);
+                        const __half* src = ((i & 1) ? g.B_lo : g.B) + ((size_t)n * ZXG_KB + (i >> 1)) * TC_IMG;
+                        ptx::bulk_g2s(s_b + s * IMG_B, src, IMG_B, b_full + 8 * s);
                     }
-                }
-                for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {          // A_hi[0], A_lo[0], A_hi[1], ...
-                    const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
-                    ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 111);
-                    ptx::mbar_arrive_expect_tx(b_full + 8 * s, IMG_B);
-                    const __half* src = ((i & 1) ? g.A_lo : g.A) + ((size_t)m * ZXG_KB + (i >> 1)) * TC_IMG;
-                    ptx::bulk_g2s(s_a + s * IMG_B, src, IMG_B, b_full + 8 * s);
-                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            ptx::mbar_wait(b_bres, 0, g.err, 112);
-            uint32_t it = 0, tc = 0;
-            for (int m = grp; m < g.m_tiles; m += n_grp, ++tc) {
-                const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
-                ptx::mbar_wait(b_acce + 8 * slot, aph ^ 1, g.err, 113);
-                ptx::tc_fence_after();
-                for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {
-                    const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
-                    const int kb = i >> 1;
-                    ptx::mbar_wait(b_full + 8 * s, ph, g.err, 114);
+            uint32_t it = 0, tc = 0, mi = 0;
+            for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x, ++mi) {
+                ptx::mbar_wait(b_afull, mi & 1, g.err, 113);
+                for (int n = 0; n < g.n_tiles; ++n, ++tc) {
+                    const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
+                    ptx::mbar_wait(b_acce + 8 * slot, aph ^ 1, g.err, 114);
                     ptx::tc_fence_after();
-                    const uint32_t sa = s_a + s * IMG_B;
-                    const int nb = (i & 1) ? 1 : 2;                     // A_lo meets B_hi only
+                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {
+                        const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
+                        const int kb = i >> 1;
+                        ptx::mbar_wait(b_full + 8 * s, ph, g.err, 115);
+                        ptx::tc_fence_after();
+                        const uint32_t sb = s_b + s * IMG_B;
+                        const int na = (i & 1) ? 1 : 2;                 // B_lo meets A_hi only
 #pragma unroll
-                    for (int bsel = 0; bsel < 2; ++bsel) {
-                        if (bsel >= nb) break;
-                        const uint32_t sb = (bsel ? s_blo : s_bhi) + kb * IMG_B;
+                        for (int asel = 0; asel < 2; ++asel) {
+                            if (asel >= na) break;
+                            const uint32_t sa = (asel ? s_alo : s_ahi) + kb * IMG_B;
 #pragma unroll
-                        for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
-                            const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                            const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                            ptx::mma_f16<1>(tmem + slot * 128, da, db, idesc, (i > 0 || bsel > 0 || k4 > 0) ? 1u : 0u);
+                            for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
+                                const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                ptx::mma_f16<1>(tmem + slot * 128, da, db, idesc, (i > 0 || asel > 0 || k4 > 0) ? 1u : 0u);
+                            }
                         }
+                        ptx::mma_commit_1(b_empty + 8 * s);
                     }
-                    ptx::mma_commit_1(b_empty + 8 * s);
+                    ptx::mma_commit_1(b_accf + 8 * slot);
                 }
-                ptx::mma_commit_1(b_accf + 8 * slot);
+                ptx::mma_commit_1(b_aempty);
             }
         }
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t tc = 0;
-        const float* bias = bias_s;
-        for (int m = grp; m < g.m_tiles; m += n_grp, ++tc) {
-            const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
-            ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 115);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 128;
+        for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x) {
+            for (int n = 0; n < g.n_tiles; ++n, ++tc) {
+                const float* bias = bias_s + n * 128;
+                const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
+                ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 116);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 128;
 #pragma unroll 2
-            for (int j = 0; j < 8; ++j) {
-                uint32_t v[16];
-                ptx::tmem_ld16(taddr + j * 16, v);
-                ptx::tmem_wait_ld();
-                float4* o = (float4*)g.out + (((size_t)m * g.n_tiles + n) * 32 + j * 4) * 128 + row;
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t v[16];
+                    ptx::tmem_ld16(taddr + j * 16, v);
+                    ptx::tmem_wait_ld();
+                    float4* o = (float4*)g.out + (((size_t)m * g.n_tiles + n) * 32 + j * 4) * 128 + row;
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    float4 f;
-                    f.x = __uint_as_float(v[c4 * 4 + 0]) + bias[j * 16 + c4 * 4 + 0];
-                    f.y = __uint_as_float(v[c4 * 4 + 1]) + bias[j * 16 + c4 * 4 + 1];
-                    f.z = __uint_as_float(v[c4 * 4 + 2]) + bias[j * 16 + c4 * 4 + 2];
-                    f.w = __uint_as_float(v[c4 * 4 + 3]) + bias[j * 16 + c4 * 4 + 3];
-                    o[(size_t)c4 * 128] = f;
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        float4 f;
+                        f.x = __uint_as_float(v[c4 * 4 + 0]) + bias[j * 16 + c4 * 4 + 0];
+                        f.y = __uint_as_float(v[c4 * 4 + 1]) + bias[j * 16 + c4 * 4 + 1];
+                        f.z = __uint_as_float(v[c4 * 4 + 2]) + bias[j * 16 + c4 * 4 + 2];
+                        f.w = __uint_as_float(v[c4 * 4 + 3]) + bias[j * 16 + c4 * 4 + 3];
+                        o[(size_t)c4 * 128] = f;
+                    }
                 }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
         }
     }
     ptx::tc_fence_before();
@@ -483,6 +485,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                 }
             }
         } else if (warp == 1) {
+            // ------------------------------------------------ LSTM2: keep the hoisted projection two chunks ahead in L2
+            if (KX == 0 && lane == 0) {
+                // one (tile, t, dir, chunk) block of zx2 is 64 KB contiguous
+                for (int u = 0; u < NT * CH; ++u) {
+                    const int step = u / CH, c = u % CH;
+                    const int t = dir == 0 ? step : NT - 1 - step;
+                    ptx::bulk_prefetch_l2((const float*)a.zx + ((((size_t)tile * NT + t) * (2 * CH) + dir * CH + c) * 32) * 128 * 4, 65536);
+                    if (u >= 2) {                            // pace on the MMA commits: use u-2 is complete
+                        const uint32_t use = base_use + u - 2;
+                        ptx::mbar_wait(b_accf + 8 * (use & 1), (use >> 1) & 1, a.err, 216);
+                    }
+                }
+            }
             // ------------------------------------------------ LSTM1: x_t operand tile, one bulk copy per step
             if (KX > 0 && lane == 0) {
                 for (int step = 0; step < NT; ++step) {
@@ -517,18 +532,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                 __half* hout_t = a.hout + ((size_t)tile * NT + t) * a.kb_out * TC_IMG;
                 __half* hout_lo_t = a.hout_lo + ((size_t)tile * NT + t) * a.kb_out * TC_IMG;
                 const bool has_acc = (KX > 0) || step > 0;
-                if (KX == 0 && step + 1 < NT && (lane & 7) == 0) {
-                    // next step's hoisted projection: one L2 prefetch per 128-byte line this warp will read
-                    const int tn = dir == 0 ? step + 1 : NT - 2 - step;
-                    const float4* zn = (const float4*)a.zx + ((((size_t)tile * NT + tn) * (2 * CH) + dir * CH) * 32) * 128 + row;
-#pragma unroll
-                    for (int c = 0; c < CH; ++c)
-#pragma unroll
-                        for (int gte = 0; gte < 4; ++gte)
-#pragma unroll
-                            for (int ug = 0; ug < 2; ++ug)
-                                ptx::prefetch_l2(zn + (size_t)(c * 32 + gte * 8 + sub * 2 + ug) * 128);
-                }
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const uint32_t use = base_use + step * CH + c;
@@ -835,10 +838,8 @@ inline cudaError_t launch_gemm_zx(const GemmArgs& g, int sm_count, cudaStream_t 
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    int groups = sm_count / g.n_tiles;
-    if (groups > g.m_tiles) groups = g.m_tiles;
-    if (groups < 1) groups = 1;
-    k_gemm_zx<<<groups * g.n_tiles, GEMM_THREADS, ZXG_SMEM, st>>>(g);
+    int grid = g.m_tiles < sm_count ? g.m_tiles : sm_count;
+    k_gemm_zx<<<grid, GEMM_THREADS, ZXG_SMEM, st>>>(g);
     return cudaGetLastError();
 }
 
@@ -877,7 +878,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         ++launches;
         GemmArgs g2;
         g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = 3; g2.bias = t.b2p; g2.out = t.zx2; g2.m_tiles = tiles * NT; g2.n_tiles = 10; g2.n_kb = 4;
-        g2.mode = 0; g2.err = t.err;
+        g2.mode = 0; g2.err = t.err; g2.dbg = getenv("C3R_ZX_DBG") ? atoi(getenv("C3R_ZX_DBG")) : 0;
         e = launch_gemm_zx(g2, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("zx2 gemm: ") + cudaGetErrorString(e); return -1; }
         ++launches;
@@ -889,7 +890,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         ++launches;
         GemmArgs g4;
         g4.A = t.h2; g4.B = t.k4p; g4.A_lo = t.h2_lo; g4.B_lo = t.k4p_lo; g4.terms = 3; g4.bias = t.b4; g4.out = t.l4; g4.m_tiles = tiles; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
-        g4.mode = 1; g4.err = t.err;
+        g4.mode = 1; g4.err = t.err; g4.dbg = 0;
         e = launch_gemm(g4, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("l4 gemm: ") + cudaGetErrorString(e); return -1; }
         ++launches;
