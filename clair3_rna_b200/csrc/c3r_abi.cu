@@ -643,7 +643,7 @@ int c3r_debug_fetch(c3r_ctx* ctx, int which, void* dst, int64_t max_bytes, int64
         case 1: src = t.zx2; bytes = tiles * NT * 10 * 128 * 128 * 4; break;
         case 2: src = t.h2; bytes = tiles * NT * 5 * TC_IMG * 2; break;
         case 3: src = t.l4; bytes = tiles * 128 * DENSE * 4; break;
-        case 4: src = t.trace; bytes = t.trace ? 2 * 2 * NT * 8 * 8 * sizeof(long long) : 0; break;
+        case 4: src = t.trace; bytes = t.trace ? (2 * 2 * NT * 8 * 8 + 64 * 32) * sizeof(long long) : 0; break;
         default: return fail(ctx, C3R_ERR_ARG, "unknown buffer");
     }
     if ((int64_t)bytes > max_bytes) bytes = (size_t)max_bytes;

@@ -49,6 +49,7 @@ struct GemmArgs {
     int m_tiles, n_tiles, n_kb;
     int mode;             // 0: ZX layout [m][n][32 col-groups][128 rows][4]   1: row-major [m*128+r][n_tiles*128] + SELU
     int dbg;              // experiments: 1 = skip the output stores, 2 = hi*hi term only
+    long long* trace;     // optional [64 tiles][32 events] SM-clock stamps of CTA 0
     int* err;
 };
 
@@ -171,22 +172,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
 
 // ------------------------------------------------------------------ A-stationary variant
 // LSTM2's hoisted input projection (K = 256, N = 1280).  A CTA keeps the activation images of ONE
-// 128-site m-tile resident (hi and lo fp16 terms, 128 KB) and streams the weight images of the ten
-// 128-column n-tiles through a 5-stage ring: the weights total 1.3 MB and stay L2-hot, so the ring
-// sees L2 latency only, while each activation tile is read from HBM exactly once.
+// 128-site m-tile resident (hi and lo fp16 terms, 128 KB) and streams the weight images of the five
+// 256-column n-tiles through a 5-stage ring (16 KB stages = 256 columns x 32 k): the weights total
+// 1.3 MB and stay L2-hot, while each activation tile is read from HBM exactly once.
+// N = 256 per tcgen05.mma keeps the shared-memory operand traffic (4 KB of A + 8 KB of B per
+// 128 cycles) under the 128 B/cycle port limit, which a 128x128 SS-mode MMA sits exactly on.
 // Per output tile:  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
-constexpr int ZXG_KB = 4;                                   // K = 256
+constexpr int ZXG_KB = 4;                                   // K = 256 = 4 resident 128x64 A images per term
+constexpr int ZXG_NB = 8;                                   // 32-k weight images per (n-tile, term)
 constexpr int ZXG_STAGES = 5;
 constexpr int ZXG_SMEM = (2 * ZXG_KB + ZXG_STAGES) * TC_IMG * 2 + 8192;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr uint32_t IMG_B = TC_IMG * 2;
+    constexpr uint32_t IMG_B = TC_IMG * 2;                  // 16 KB: a 128x64 A image or a 256x32 B image
     uint64_t* bars = (uint64_t*)(smem + (2 * ZXG_KB + ZXG_STAGES) * IMG_B);
-    // bars: full[5] empty[5] acc_full[2] acc_empty[2] a_full a_empty ; tmem ptr ; bias[n_tiles*128]
+    // bars: full[5] empty[5] acc_full[2] acc_empty[2] a_full a_empty ; tmem ptr ; bias[n_tiles*256]
     uint32_t* tmem_ptr_s = (uint32_t*)(bars + 18);
     float* bias_s = (float*)(bars + 32);
-    for (int i = threadIdx.x; i < g.n_tiles * 128; i += GEMM_THREADS) bias_s[i] = g.bias[i];
+    const int n_tiles = g.n_tiles;                          // 256-column tiles
+    for (int i = threadIdx.x; i < n_tiles * 256; i += GEMM_THREADS) bias_s[i] = g.bias[i];
     const uint32_t s_base = ptx::smem_u32(smem);
     const uint32_t s_ahi = s_base, s_alo = s_base + ZXG_KB * IMG_B, s_b = s_base + 2 * ZXG_KB * IMG_B;
     const uint32_t b_full = ptx::smem_u32(bars), b_empty = b_full + 8 * ZXG_STAGES, b_accf = b_empty + 8 * ZXG_STAGES,
@@ -200,14 +205,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_ptr_s), 256);
+        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_ptr_s), 512);
         ptx::tmem_relinquish<1>();
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_ptr_s;
-    const uint32_t idesc = ptx::make_idesc_f16(128, 128);
+    const uint32_t idesc = ptx::make_idesc_f16(128, 256);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -220,14 +225,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
                 }
                 ptx::mbar_wait(b_aempty, (mi & 1) ^ 1, g.err, 111);     // previous m-tile's MMAs are done with A
                 ptx::mbar_arrive_expect_tx(b_afull, 2 * ZXG_KB * IMG_B);
-                ptx::bulk_g2s(s_ahi, g.A + (size_t)m * ZXG_KB * TC_IMG, ZXG_KB * IMG_B, b_afull);
-                ptx::bulk_g2s(s_alo, g.A_lo + (size_t)m * ZXG_KB * TC_IMG, ZXG_KB * IMG_B, b_afull);
-                for (int n = 0; n < g.n_tiles; ++n)
-                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {      // B_hi[0], B_lo[0], B_hi[1], ...
+                for (int kb = 0; kb < ZXG_KB; ++kb) {
+                    ptx::bulk_g2s(s_ahi + kb * IMG_B, g.A + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull);
+                    ptx::bulk_g2s(s_alo + kb * IMG_B, g.A_lo + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull);
+                }
+                for (int n = 0; n < n_tiles; ++n)
+                    for (int i = 0; i < 2 * ZXG_NB; ++i, ++it) {      // B_hi[0], B_lo[0], B_hi[1], ...
                         const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
                         ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 112);
+                        if (g.trace && blockIdx.x == 0 && it / 16 < 64 && i < 8) g.trace[(it / 16) * 32 + i] = clock64();
                         ptx::mbar_arrive_expect_tx(b_full + 8 * s, IMG_B);
-                        const __half* src = ((i & 1) ? g.B_lo : g.B) + ((size_t)n * ZXG_KB + (i >> 1)) * TC_IMG;
+                        const __half* src = ((i & 1) ? g.B_lo : g.B) + ((size_t)n * ZXG_NB + (i >> 1)) * TC_IMG;
                         ptx::bulk_g2s(s_b + s * IMG_B, src, IMG_B, b_full + 8 * s);
                     }
             }
@@ -237,31 +245,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
             uint32_t it = 0, tc = 0, mi = 0;
             for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x, ++mi) {
                 ptx::mbar_wait(b_afull, mi & 1, g.err, 113);
-                for (int n = 0; n < g.n_tiles; ++n, ++tc) {
+                for (int n = 0; n < n_tiles; ++n, ++tc) {
                     const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
                     ptx::mbar_wait(b_acce + 8 * slot, aph ^ 1, g.err, 114);
                     ptx::tc_fence_after();
-                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {
+                    const bool trm = g.trace && blockIdx.x == 0 && tc < 64;
+                    if (trm) g.trace[tc * 32 + 16] = clock64();
+                    for (int i = 0; i < 2 * ZXG_NB; ++i, ++it) {
                         const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
-                        const int kb = i >> 1;
+                        const int kb32 = i >> 1;                        // k = 32*kb32 .. +32
                         ptx::mbar_wait(b_full + 8 * s, ph, g.err, 115);
                         ptx::tc_fence_after();
+                        if (trm && i < 8) g.trace[tc * 32 + 8 + i] = clock64();
                         const uint32_t sb = s_b + s * IMG_B;
                         const int na = (i & 1) ? 1 : 2;                 // B_lo meets A_hi only
 #pragma unroll
                         for (int asel = 0; asel < 2; ++asel) {
                             if (asel >= na) break;
-                            const uint32_t sa = (asel ? s_alo : s_ahi) + kb * IMG_B;
+                            // A image kb32/2 holds k = 64*(kb32/2) ..; this stage covers its half (kb32 & 1)
+                            const uint32_t sa = (asel ? s_alo : s_ahi) + (kb32 >> 1) * IMG_B + (kb32 & 1) * 4 * (TC_TILE * 16);
 #pragma unroll
-                            for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
-                                const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                                const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                                ptx::mma_f16<1>(tmem + slot * 128, da, db, idesc, (i > 0 || asel > 0 || k4 > 0) ? 1u : 0u);
+                            for (int k2 = 0; k2 < 2; ++k2) {
+                                const uint64_t da = ptx::make_smem_desc(sa + k2 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                const uint64_t db = ptx::make_smem_desc(sb + k2 * 2 * (256 * 16), 256 * 16, 128);
+                                ptx::mma_f16<1>(tmem + slot * 256, da, db, idesc, (i > 0 || asel > 0 || k2 > 0) ? 1u : 0u);
                             }
                         }
                         ptx::mma_commit_1(b_empty + 8 * s);
                     }
                     ptx::mma_commit_1(b_accf + 8 * slot);
+                    if (trm) g.trace[tc * 32 + 17] = clock64();
                 }
                 ptx::mma_commit_1(b_aempty);
             }
@@ -271,18 +284,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
         const int row = q * 32 + lane;
         uint32_t tc = 0;
         for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x) {
-            for (int n = 0; n < g.n_tiles; ++n, ++tc) {
-                const float* bias = bias_s + n * 128;
+            for (int n = 0; n < n_tiles; ++n, ++tc) {
+                const float* bias = bias_s + n * 256;
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
                 ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 116);
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 128;
+                const bool tre = g.trace && blockIdx.x == 0 && tc < 64 && warp == 2 && lane == 0;
+                if (tre) g.trace[tc * 32 + 18] = clock64();
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 256;
 #pragma unroll 2
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     uint32_t v[16];
                     ptx::tmem_ld16(taddr + j * 16, v);
                     ptx::tmem_wait_ld();
-                    float4* o = (float4*)g.out + (((size_t)m * g.n_tiles + n) * 32 + j * 4) * 128 + row;
+                    // ZX layout is per 128-column chunk: [m][n128][32 col-groups][128 rows][4]
+                    float4* o = (float4*)g.out + (((size_t)m * (2 * n_tiles) + 2 * n + (j >> 3)) * 32 + (j & 7) * 4) * 128 + row;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         float4 f;
@@ -296,12 +312,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
+                if (tre) g.trace[tc * 32 + 19] = clock64();
             }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc<1>(tmem, 256);
+    if (warp == 1) ptx::tmem_dealloc<1>(tmem, 512);
 }
 
 // ================================================================== LSTM layer
@@ -742,16 +759,18 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
                 }
             }
         }
-    // hoisted LSTM2 input projection: B[n_tile = dir*5 + chunk][kb][128 x 64], bias in the same column order
+    // hoisted LSTM2 input projection.  GEMM column = (dir*5 + chunk)*128 + gate*32 + unit_local; the weight
+    // images are [n256 = column/256][kb32 = k/32][256 rows x 32 k], bias in the same column order
     for (int dir = 0; dir < 2; ++dir)
         for (int c = 0; c < 5; ++c) {
             const int nt = dir * 5 + c;
             for (int j = 0; j < 128; ++j) {
                 const int gate = j / 32, ul = j % 32;
                 const int kc = gate * U2 + c * 32 + ul;
-                fb[(size_t)nt * 128 + j] = h[o_b2 + dir * G2 + kc];
+                const int col = nt * 128 + j;
+                fb[col] = h[o_b2 + dir * G2 + kc];
                 for (int k = 0; k < H1W; ++k) {
-                    const size_t ix = ((size_t)nt * 4 + k / TC_KB) * TC_IMG + img_index(128, j, k % TC_KB);
+                    const size_t ix = ((size_t)(col / 256) * 8 + k / 32) * TC_IMG + img_index(256, col % 256, k % 32);
                     split(h[o_w2 + (size_t)k * 2 * G2 + dir * G2 + kc], w2p[ix], w2p_lo[ix]);
                 }
             }
@@ -784,8 +803,8 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     cudaMemset(t.err, 0, 64);
     if (getenv("C3R_TRACE")) {
-        cudaMalloc((void**)&t.trace, 2 * 2 * NT * 8 * 8 * sizeof(long long));
-        cudaMemset(t.trace, 0, 2 * 2 * NT * 8 * 8 * sizeof(long long));
+        cudaMalloc((void**)&t.trace, (2 * 2 * NT * 8 * 8 + 64 * 32) * sizeof(long long));
+        cudaMemset(t.trace, 0, (2 * 2 * NT * 8 * 8 + 64 * 32) * sizeof(long long));
     }
     t.ready = 1;
     return 0;
@@ -877,8 +896,8 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         if (e != cudaSuccess) { *err = std::string("lstm1: ") + cudaGetErrorString(e); return -1; }
         ++launches;
         GemmArgs g2;
-        g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = 3; g2.bias = t.b2p; g2.out = t.zx2; g2.m_tiles = tiles * NT; g2.n_tiles = 10; g2.n_kb = 4;
-        g2.mode = 0; g2.err = t.err; g2.dbg = getenv("C3R_ZX_DBG") ? atoi(getenv("C3R_ZX_DBG")) : 0;
+        g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = 3; g2.bias = t.b2p; g2.out = t.zx2; g2.m_tiles = tiles * NT; g2.n_tiles = 5; g2.n_kb = 4;
+        g2.mode = 0; g2.err = t.err; g2.dbg = getenv("C3R_ZX_DBG") ? atoi(getenv("C3R_ZX_DBG")) : 0; g2.trace = t.trace ? t.trace + 2 * 2 * NT * 8 * 8 : nullptr;
         e = launch_gemm_zx(g2, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("zx2 gemm: ") + cudaGetErrorString(e); return -1; }
         ++launches;
@@ -890,7 +909,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         ++launches;
         GemmArgs g4;
         g4.A = t.h2; g4.B = t.k4p; g4.A_lo = t.h2_lo; g4.B_lo = t.k4p_lo; g4.terms = 3; g4.bias = t.b4; g4.out = t.l4; g4.m_tiles = tiles; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
-        g4.mode = 1; g4.err = t.err; g4.dbg = 0;
+        g4.mode = 1; g4.err = t.err; g4.dbg = 0; g4.trace = nullptr;
         e = launch_gemm(g4, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("l4 gemm: ") + cudaGetErrorString(e); return -1; }
         ++launches;
