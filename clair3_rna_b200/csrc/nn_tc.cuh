@@ -215,14 +215,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
     const uint32_t idesc = ptx::make_idesc_f16(128, 256);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (lane != 0) {
+            // lanes 1..31: pull the NEXT m-tile's activation images (2 x 64 KB, read once from HBM)
+            // towards L2 one 128-byte line at a time while lane 0 feeds the ring for the current one
+            for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x) {
+                const int mn = m + gridDim.x;
+                if (mn >= g.m_tiles) break;
+                const uint8_t* ph = (const uint8_t*)(g.A + (size_t)mn * ZXG_KB * TC_IMG);
+                const uint8_t* pl = (const uint8_t*)(g.A_lo + (size_t)mn * ZXG_KB * TC_IMG);
+                for (uint32_t o = (lane - 1) * 128; o < ZXG_KB * IMG_B; o += 31 * 128) {
+                    ptx::prefetch_l2(ph + o);
+                    ptx::prefetch_l2(pl + o);
+                }
+                // pace: one prefetch round per m-tile (the A-full barrier completes once per m-tile)
+                ptx::mbar_wait(b_afull, ((m - blockIdx.x) / gridDim.x) & 1, g.err, 117);
+            }
+        } else {
             uint32_t it = 0, mi = 0;
             for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x, ++mi) {
-                const int mn = m + gridDim.x;                 // next m-tile of this CTA: pull it towards L2 now
-                if (mn < g.m_tiles) {
-                    ptx::bulk_prefetch_l2(g.A + (size_t)mn * ZXG_KB * TC_IMG, ZXG_KB * IMG_B);
-                    ptx::bulk_prefetch_l2(g.A_lo + (size_t)mn * ZXG_KB * TC_IMG, ZXG_KB * IMG_B);
-                }
                 ptx::mbar_wait(b_aempty, (mi & 1) ^ 1, g.err, 111);     // previous m-tile's MMAs are done with A
                 ptx::mbar_arrive_expect_tx(b_afull, 2 * ZXG_KB * IMG_B);
                 for (int kb = 0; kb < ZXG_KB; ++kb) {
