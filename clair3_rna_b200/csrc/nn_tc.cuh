@@ -215,22 +215,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
     const uint32_t idesc = ptx::make_idesc_f16(128, 256);
 
     if (warp == 0) {
-        if (lane != 0) {
-            // lanes 1..31: pull the NEXT m-tile's activation images (2 x 64 KB, read once from HBM)
-            // towards L2 one 128-byte line at a time while lane 0 feeds the ring for the current one
-            for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x) {
-                const int mn = m + gridDim.x;
-                if (mn >= g.m_tiles) break;
-                const uint8_t* ph = (const uint8_t*)(g.A + (size_t)mn * ZXG_KB * TC_IMG);
-                const uint8_t* pl = (const uint8_t*)(g.A_lo + (size_t)mn * ZXG_KB * TC_IMG);
-                for (uint32_t o = (lane - 1) * 128; o < ZXG_KB * IMG_B; o += 31 * 128) {
-                    ptx::prefetch_l2(ph + o);
-                    ptx::prefetch_l2(pl + o);
-                }
-                // pace: one prefetch round per m-tile (the A-full barrier completes once per m-tile)
-                ptx::mbar_wait(b_afull, ((m - blockIdx.x) / gridDim.x) & 1, g.err, 117);
-            }
-        } else {
+        if (lane == 0) {
             uint32_t it = 0, mi = 0;
             for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x, ++mi) {
                 ptx::mbar_wait(b_aempty, (mi & 1) ^ 1, g.err, 111);     // previous m-tile's MMAs are done with A
@@ -294,6 +279,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
         const int row = q * 32 + lane;
         uint32_t tc = 0;
         for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x) {
+            {
+                // pull the NEXT m-tile's activation images (2 x 64 KB, read once from HBM) towards L2,
+                // one 128-byte line per prefetch, spread over the 128 epilogue threads
+                const int mn = m + gridDim.x;
+                if (mn < g.m_tiles) {
+                    const uint8_t* ph = (const uint8_t*)(g.A + (size_t)mn * ZXG_KB * TC_IMG);
+                    const uint8_t* pl = (const uint8_t*)(g.A_lo + (size_t)mn * ZXG_KB * TC_IMG);
+                    for (uint32_t o = (threadIdx.x - 64) * 128; o < ZXG_KB * IMG_B; o += 128 * 128) {
+                        ptx::prefetch_l2(ph + o);
+                        ptx::prefetch_l2(pl + o);
+                    }
+                }
+            }
             for (int n = 0; n < n_tiles; ++n, ++tc) {
                 const float* bias = bias_s + n * 256;
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
