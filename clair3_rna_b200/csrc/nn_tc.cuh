@@ -170,135 +170,143 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
     if (warp == 1) ptx::tmem_dealloc<1>(tmem, 256);
 }
 
-// ------------------------------------------------------------------ A-stationary variant
-// LSTM2's hoisted input projection (K = 256, N = 1280).  A CTA keeps the activation images of ONE
-// 128-site m-tile resident (hi and lo fp16 terms, 128 KB) and streams the weight images of the five
-// 256-column n-tiles through a 5-stage ring (16 KB stages = 256 columns x 32 k): the weights total
-// 1.3 MB and stay L2-hot, while each activation tile is read from HBM exactly once.
-// N = 256 per tcgen05.mma keeps the shared-memory operand traffic (4 KB of A + 8 KB of B per
-// 128 cycles) under the 128 B/cycle port limit, which a 128x128 SS-mode MMA sits exactly on.
-// Per output tile:  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
+// ------------------------------------------------------------------ A-stationary 2-CTA variant
+// LSTM2's hoisted input projection (K = 256, N = 1280) as tcgen05 cta_group::2 MMAs (M = 256, N = 256).
+// A CTA pair owns two 128-site m-tiles: each CTA keeps ITS tile's activation images resident (hi and
+// lo fp16 terms, 128 KB) and streams ITS half (128 of 256 columns) of the weight images through a
+// 5-stage ring of 16 KB stages (128 columns x 64 k).  Compared with one CTA per tile this halves both
+// the L2->SMEM weight traffic per output (the limiter of the 1-CTA version: 5.3 TB/s) and the
+// shared-memory operand bytes per MMA.  Per output tile:  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
+// Only the leader CTA issues MMAs; the peer relays "my stage / my A tile has landed" with one
+// cluster-scope arrival each, commits are multicast to both CTAs.
 constexpr int ZXG_KB = 4;                                   // K = 256 = 4 resident 128x64 A images per term
-constexpr int ZXG_NB = 8;                                   // 32-k weight images per (n-tile, term)
 constexpr int ZXG_STAGES = 5;
 constexpr int ZXG_SMEM = (2 * ZXG_KB + ZXG_STAGES) * TC_IMG * 2 + 8192;
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr uint32_t IMG_B = TC_IMG * 2;                  // 16 KB: a 128x64 A image or a 256x32 B image
+    constexpr uint32_t IMG_B = TC_IMG * 2;                  // 16 KB: a 128x64 image
     uint64_t* bars = (uint64_t*)(smem + (2 * ZXG_KB + ZXG_STAGES) * IMG_B);
-    // bars: full[5] empty[5] acc_full[2] acc_empty[2] a_full a_empty ; tmem ptr ; bias[n_tiles*256]
-    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 18);
+    // bars: 0-4 full | 5-9 empty | 10,11 acc_full | 12,13 acc_empty | 14 a_full | 15 a_empty |
+    //       16-20 peer_full (leader) | 21 peer_a_full (leader) ; tmem ptr ; bias
+    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 24);
     float* bias_s = (float*)(bars + 32);
     const int n_tiles = g.n_tiles;                          // 256-column tiles
     for (int i = threadIdx.x; i < n_tiles * 256; i += GEMM_THREADS) bias_s[i] = g.bias[i];
     const uint32_t s_base = ptx::smem_u32(smem);
     const uint32_t s_ahi = s_base, s_alo = s_base + ZXG_KB * IMG_B, s_b = s_base + 2 * ZXG_KB * IMG_B;
-    const uint32_t b_full = ptx::smem_u32(bars), b_empty = b_full + 8 * ZXG_STAGES, b_accf = b_empty + 8 * ZXG_STAGES,
-                   b_acce = b_accf + 16, b_afull = b_acce + 16, b_aempty = b_afull + 8;
+    const uint32_t b0 = ptx::smem_u32(bars);
+    const uint32_t b_full = b0, b_empty = b0 + 40, b_accf = b0 + 80, b_acce = b0 + 96, b_afull = b0 + 112,
+                   b_aempty = b0 + 120, b_pfull = b0 + 128, b_pafull = b0 + 168;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int m_pairs = g.m_tiles / 2;                      // m_tiles is even (tiles come in pairs)
     if (threadIdx.x == 0) {
-        for (int i = 0; i < ZXG_STAGES; ++i) { ptx::mbar_init(b_full + 8 * i, 1); ptx::mbar_init(b_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(b_accf + 8 * i, 1); ptx::mbar_init(b_acce + 8 * i, 4); }
-        ptx::mbar_init(b_afull, 1);
-        ptx::mbar_init(b_aempty, 1);
+        for (int i = 0; i < ZXG_STAGES; ++i) {
+            ptx::mbar_init(b_full + 8 * i, 1); ptx::mbar_init(b_empty + 8 * i, 1); ptx::mbar_init(b_pfull + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(b_accf + 8 * i, 1); ptx::mbar_init(b_acce + 8 * i, 8); }
+        ptx::mbar_init(b_afull, 1); ptx::mbar_init(b_aempty, 1); ptx::mbar_init(b_pafull, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc<1>(ptx::smem_u32(tmem_ptr_s), 512);
-        ptx::tmem_relinquish<1>();
+        ptx::tmem_alloc<2>(ptx::smem_u32(tmem_ptr_s), 512);
+        ptx::tmem_relinquish<2>();
     }
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_ptr_s;
-    const uint32_t idesc = ptx::make_idesc_f16(128, 256);
+    const uint32_t idesc = ptx::make_idesc_f16(256, 256);
 
     if (warp == 0) {
         if (lane == 0) {
+            // ---------------------------------------------------- producer (both CTAs, own data)
             uint32_t it = 0, mi = 0;
-            for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x, ++mi) {
-                ptx::mbar_wait(b_aempty, (mi & 1) ^ 1, g.err, 111);     // previous m-tile's MMAs are done with A
+            for (int mp = pair; mp < m_pairs; mp += n_pairs, ++mi) {
+                const int m = 2 * mp + (int)rank;
+                ptx::mbar_wait(b_aempty, (mi & 1) ^ 1, g.err, 111);     // previous pair-tile's MMAs are done with A
                 ptx::mbar_arrive_expect_tx(b_afull, 2 * ZXG_KB * IMG_B);
                 for (int kb = 0; kb < ZXG_KB; ++kb) {
                     ptx::bulk_g2s(s_ahi + kb * IMG_B, g.A + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull);
                     ptx::bulk_g2s(s_alo + kb * IMG_B, g.A_lo + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull);
                 }
                 for (int n = 0; n < n_tiles; ++n)
-                    for (int i = 0; i < 2 * ZXG_NB; ++i, ++it) {      // B_hi[0], B_lo[0], B_hi[1], ...
+                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {      // B_hi[0], B_lo[0], B_hi[1], ... (k blocks of 64)
                         const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
                         ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 112);
-                        if (g.trace && blockIdx.x == 0 && it / 16 < 64 && i < 8) g.trace[(it / 16) * 32 + i] = clock64();
                         ptx::mbar_arrive_expect_tx(b_full + 8 * s, IMG_B);
-                        const __half* src = ((i & 1) ? g.B_lo : g.B) + ((size_t)n * ZXG_NB + (i >> 1)) * TC_IMG;
+                        // weight images are [n256][rank half][kb64][128 x 64]
+                        const __half* src = ((i & 1) ? g.B_lo : g.B) + ((((size_t)n * 2 + rank) * ZXG_KB) + (i >> 1)) * TC_IMG;
                         ptx::bulk_g2s(s_b + s * IMG_B, src, IMG_B, b_full + 8 * s);
                     }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && rank == 1) {
+            // ---------------------------------------------------- peer relay: landed -> leader
+            uint32_t it = 0, mi = 0;
+            for (int mp = pair; mp < m_pairs; mp += n_pairs, ++mi) {
+                ptx::mbar_wait(b_afull, mi & 1, g.err, 121);
+                ptx::mbar_arrive_cluster(b_pafull, 0);
+                for (int n = 0; n < n_tiles; ++n)
+                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {
+                        const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
+                        ptx::mbar_wait(b_full + 8 * s, ph, g.err, 122);
+                        ptx::mbar_arrive_cluster(b_pfull + 8 * s, 0);
+                    }
+            }
+        }
+        if (lane == 0 && rank == 0) {
+            // ---------------------------------------------------- MMA issue (leader)
             uint32_t it = 0, tc = 0, mi = 0;
-            for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x, ++mi) {
+            for (int mp = pair; mp < m_pairs; mp += n_pairs, ++mi) {
                 ptx::mbar_wait(b_afull, mi & 1, g.err, 113);
+                ptx::mbar_wait_cluster(b_pafull, mi & 1, g.err, 123);
                 for (int n = 0; n < n_tiles; ++n, ++tc) {
                     const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
-                    ptx::mbar_wait(b_acce + 8 * slot, aph ^ 1, g.err, 114);
+                    ptx::mbar_wait_cluster(b_acce + 8 * slot, aph ^ 1, g.err, 114);
                     ptx::tc_fence_after();
-                    const bool trm = g.trace && blockIdx.x == 0 && tc < 64;
-                    if (trm) g.trace[tc * 32 + 16] = clock64();
-                    for (int i = 0; i < 2 * ZXG_NB; ++i, ++it) {
+                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {
                         const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
-                        const int kb32 = i >> 1;                        // k = 32*kb32 .. +32
+                        const int kb = i >> 1;
                         ptx::mbar_wait(b_full + 8 * s, ph, g.err, 115);
+                        ptx::mbar_wait_cluster(b_pfull + 8 * s, ph, g.err, 125);
                         ptx::tc_fence_after();
-                        if (trm && i < 8) g.trace[tc * 32 + 8 + i] = clock64();
                         const uint32_t sb = s_b + s * IMG_B;
                         const int na = (i & 1) ? 1 : 2;                 // B_lo meets A_hi only
 #pragma unroll
                         for (int asel = 0; asel < 2; ++asel) {
                             if (asel >= na) break;
-                            // A image kb32/2 holds k = 64*(kb32/2) ..; this stage covers its half (kb32 & 1)
-                            const uint32_t sa = (asel ? s_alo : s_ahi) + (kb32 >> 1) * IMG_B + (kb32 & 1) * 4 * (TC_TILE * 16);
+                            const uint32_t sa = (asel ? s_alo : s_ahi) + kb * IMG_B;
 #pragma unroll
-                            for (int k2 = 0; k2 < 2; ++k2) {
-                                const uint64_t da = ptx::make_smem_desc(sa + k2 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                                const uint64_t db = ptx::make_smem_desc(sb + k2 * 2 * (256 * 16), 256 * 16, 128);
-                                ptx::mma_f16<1>(tmem + slot * 256, da, db, idesc, (i > 0 || asel > 0 || k2 > 0) ? 1u : 0u);
+                            for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
+                                const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                ptx::mma_f16<2>(tmem + slot * 256, da, db, idesc, (i > 0 || asel > 0 || k4 > 0) ? 1u : 0u);
                             }
                         }
-                        ptx::mma_commit_1(b_empty + 8 * s);
+                        ptx::mma_commit_2_mcast(b_empty + 8 * s, 3);
                     }
-                    ptx::mma_commit_1(b_accf + 8 * slot);
-                    if (trm) g.trace[tc * 32 + 17] = clock64();
+                    ptx::mma_commit_2_mcast(b_accf + 8 * slot, 3);
                 }
-                ptx::mma_commit_1(b_aempty);
+                ptx::mma_commit_2_mcast(b_aempty, 3);
             }
         }
     } else {
+        // -------------------------------------------------------- epilogue (both CTAs, own rows)
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t tc = 0;
-        for (int m = blockIdx.x; m < g.m_tiles; m += gridDim.x) {
-            {
-                // pull the NEXT m-tile's activation images (2 x 64 KB, read once from HBM) towards L2,
-                // one 128-byte line per prefetch, spread over the 128 epilogue threads
-                const int mn = m + gridDim.x;
-                if (mn < g.m_tiles) {
-                    const uint8_t* ph = (const uint8_t*)(g.A + (size_t)mn * ZXG_KB * TC_IMG);
-                    const uint8_t* pl = (const uint8_t*)(g.A_lo + (size_t)mn * ZXG_KB * TC_IMG);
-                    for (uint32_t o = (threadIdx.x - 64) * 128; o < ZXG_KB * IMG_B; o += 128 * 128) {
-                        ptx::prefetch_l2(ph + o);
-                        ptx::prefetch_l2(pl + o);
-                    }
-                }
-            }
+        for (int mp = pair; mp < m_pairs; mp += n_pairs) {
+            const int m = 2 * mp + (int)rank;
             for (int n = 0; n < n_tiles; ++n, ++tc) {
                 const float* bias = bias_s + n * 256;
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
                 ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 116);
                 ptx::tc_fence_after();
-                const bool tre = g.trace && blockIdx.x == 0 && tc < 64 && warp == 2 && lane == 0;
-                if (tre) g.trace[tc * 32 + 18] = clock64();
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 256;
 #pragma unroll 2
                 for (int j = 0; j < 16; ++j) {
@@ -319,14 +327,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
-                if (tre) g.trace[tc * 32 + 19] = clock64();
+                if (lane == 0) ptx::mbar_arrive_cluster(b_acce + 8 * slot, 0);
             }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc<1>(tmem, 512);
+    ptx::cluster_sync();
+    if (warp == 1) ptx::tmem_dealloc<2>(tmem, 512);
 }
 
 // ================================================================== LSTM layer
@@ -768,7 +776,7 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
             }
         }
     // hoisted LSTM2 input projection.  GEMM column = (dir*5 + chunk)*128 + gate*32 + unit_local; the weight
-    // images are [n256 = column/256][kb32 = k/32][256 rows x 32 k], bias in the same column order
+    // images are [n256 = column/256][half = CTA rank][kb64][128 rows x 64 k], bias in the same column order
     for (int dir = 0; dir < 2; ++dir)
         for (int c = 0; c < 5; ++c) {
             const int nt = dir * 5 + c;
@@ -778,7 +786,8 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
                 const int col = nt * 128 + j;
                 fb[col] = h[o_b2 + dir * G2 + kc];
                 for (int k = 0; k < H1W; ++k) {
-                    const size_t ix = ((size_t)(col / 256) * 8 + k / 32) * TC_IMG + img_index(256, col % 256, k % 32);
+                    const int n256 = col / 256, half = (col % 256) / 128, r = col % 128;
+                    const size_t ix = (((size_t)n256 * 2 + half) * 4 + k / TC_KB) * TC_IMG + img_index(128, r, k % TC_KB);
                     split(h[o_w2 + (size_t)k * 2 * G2 + dir * G2 + kc], w2p[ix], w2p_lo[ix]);
                 }
             }
@@ -865,8 +874,9 @@ inline cudaError_t launch_gemm_zx(const GemmArgs& g, int sm_count, cudaStream_t 
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    int grid = g.m_tiles < sm_count ? g.m_tiles : sm_count;
-    k_gemm_zx<<<grid, GEMM_THREADS, ZXG_SMEM, st>>>(g);
+    int pairs = g.m_tiles / 2 < sm_count / 2 ? g.m_tiles / 2 : sm_count / 2;
+    if (pairs < 1) pairs = 1;
+    k_gemm_zx<<<pairs * 2, GEMM_THREADS, ZXG_SMEM, st>>>(g);
     return cudaGetLastError();
 }
 
