@@ -173,31 +173,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
 // ------------------------------------------------------------------ A-stationary 2-CTA variant
 // LSTM2's hoisted input projection (K = 256, N = 1280) as tcgen05 cta_group::2 MMAs (M = 256, N = 256).
 // A CTA pair owns two 128-site m-tiles: each CTA keeps ITS tile's activation images resident (hi and
-// lo fp16 terms, 128 KB) and streams ITS half (128 of 256 columns) of the weight images through a
-// 5-stage ring of 16 KB stages (128 columns x 64 k).  Compared with one CTA per tile this halves both
-// the L2->SMEM weight traffic per output (the limiter of the 1-CTA version: 5.3 TB/s) and the
-// shared-memory operand bytes per MMA.  Per output tile:  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
-// Only the leader CTA issues MMAs; the peer relays "my stage / my A tile has landed" with one
+// lo fp16 terms, 4 x 32 KB, one per 64-wide k block) and streams ITS half (128 of 256 columns) of the
+// weight images through a 3-stage ring of 32 KB stages (hi and lo image of one k block).
+// Per stage 12 MMAs:  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  for the four k16 steps of the block.
+// The activation images are re-loaded per k block as soon as the last n-tile has consumed that block
+// (a_free[kb] -> a_full[kb]), so switching m-tiles overlaps with the tail of the previous one.
+// Only the leader CTA issues MMAs; the peer relays "my stage / my A block has landed" with one
 // cluster-scope arrival each, commits are multicast to both CTAs.
-constexpr int ZXG_KB = 4;                                   // K = 256 = 4 resident 128x64 A images per term
-constexpr int ZXG_STAGES = 5;
-constexpr int ZXG_SMEM = (2 * ZXG_KB + ZXG_STAGES) * TC_IMG * 2 + 8192;
+constexpr int ZXG_KB = 4;                                   // K = 256 = 4 k blocks of 64
+constexpr int ZXG_STAGES = 3;
+constexpr int ZXG_THREADS = 224;                            // + warp 6: activation (A) loader
+constexpr int ZXG_SMEM = (2 * ZXG_KB + 2 * ZXG_STAGES) * TC_IMG * 2 + 1024 + 512;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_gemm_zx(GemmArgs g) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_gemm_zx(GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr uint32_t IMG_B = TC_IMG * 2;                  // 16 KB: a 128x64 image
-    uint64_t* bars = (uint64_t*)(smem + (2 * ZXG_KB + ZXG_STAGES) * IMG_B);
-    // bars: 0-4 full | 5-9 empty | 10,11 acc_full | 12,13 acc_empty | 14 a_full | 15 a_empty |
-    //       16-20 peer_full (leader) | 21 peer_a_full (leader) ; tmem ptr ; bias
-    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 24);
-    float* bias_s = (float*)(bars + 32);
+    uint8_t* tail = smem + (2 * ZXG_KB + 2 * ZXG_STAGES) * IMG_B;
+    float* bias_s = (float*)tail;                           // this n-tile's 256 bias values
+    uint64_t* bars = (uint64_t*)(tail + 1024);
+    // bars: 0-2 full | 3-5 empty | 6,7 acc_full | 8,9 acc_empty | 10-13 a_full | 14-17 a_free |
+    //       18-20 peer_full (leader) | 21-24 peer_a_full (leader) ; tmem ptr
+    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 26);
     const int n_tiles = g.n_tiles;                          // 256-column tiles
-    for (int i = threadIdx.x; i < n_tiles * 256; i += GEMM_THREADS) bias_s[i] = g.bias[i];
     const uint32_t s_base = ptx::smem_u32(smem);
-    const uint32_t s_ahi = s_base, s_alo = s_base + ZXG_KB * IMG_B, s_b = s_base + 2 * ZXG_KB * IMG_B;
+    const uint32_t s_a = s_base, s_b = s_base + 2 * ZXG_KB * IMG_B;     // A: [kb][hi | lo], B ring: [stage][hi | lo]
     const uint32_t b0 = ptx::smem_u32(bars);
-    const uint32_t b_full = b0, b_empty = b0 + 40, b_accf = b0 + 80, b_acce = b0 + 96, b_afull = b0 + 112,
-                   b_aempty = b0 + 120, b_pfull = b0 + 128, b_pafull = b0 + 168;
+    const uint32_t b_full = b0, b_empty = b0 + 24, b_accf = b0 + 48, b_acce = b0 + 64, b_afull = b0 + 80,
+                   b_afree = b0 + 112, b_pfull = b0 + 144, b_pafull = b0 + 168;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -207,7 +209,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
             ptx::mbar_init(b_full + 8 * i, 1); ptx::mbar_init(b_empty + 8 * i, 1); ptx::mbar_init(b_pfull + 8 * i, 1);
         }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(b_accf + 8 * i, 1); ptx::mbar_init(b_acce + 8 * i, 8); }
-        ptx::mbar_init(b_afull, 1); ptx::mbar_init(b_aempty, 1); ptx::mbar_init(b_pafull, 1);
+        for (int i = 0; i < ZXG_KB; ++i) {
+            ptx::mbar_init(b_afull + 8 * i, 1); ptx::mbar_init(b_afree + 8 * i, 1); ptx::mbar_init(b_pafull + 8 * i, 1);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -223,76 +227,88 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---------------------------------------------------- producer (both CTAs, own data)
-            uint32_t it = 0, mi = 0;
-            for (int mp = pair; mp < m_pairs; mp += n_pairs, ++mi) {
-                const int m = 2 * mp + (int)rank;
-                ptx::mbar_wait(b_aempty, (mi & 1) ^ 1, g.err, 111);     // previous pair-tile's MMAs are done with A
-                ptx::mbar_arrive_expect_tx(b_afull, 2 * ZXG_KB * IMG_B);
-                for (int kb = 0; kb < ZXG_KB; ++kb) {
-                    ptx::bulk_g2s(s_ahi + kb * IMG_B, g.A + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull);
-                    ptx::bulk_g2s(s_alo + kb * IMG_B, g.A_lo + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull);
-                }
+            // ---------------------------------------------------- weight ring producer (both CTAs, own half)
+            uint32_t it = 0;
+            for (int mp = pair; mp < m_pairs; mp += n_pairs)
                 for (int n = 0; n < n_tiles; ++n)
-                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {      // B_hi[0], B_lo[0], B_hi[1], ... (k blocks of 64)
+                    for (int kb = 0; kb < ZXG_KB; ++kb, ++it) {
                         const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
                         ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 112);
-                        ptx::mbar_arrive_expect_tx(b_full + 8 * s, IMG_B);
+                        ptx::mbar_arrive_expect_tx(b_full + 8 * s, 2 * IMG_B);
                         // weight images are [n256][rank half][kb64][128 x 64]
-                        const __half* src = ((i & 1) ? g.B_lo : g.B) + ((((size_t)n * 2 + rank) * ZXG_KB) + (i >> 1)) * TC_IMG;
-                        ptx::bulk_g2s(s_b + s * IMG_B, src, IMG_B, b_full + 8 * s);
+                        const size_t off = ((((size_t)n * 2 + rank) * ZXG_KB) + kb) * TC_IMG;
+                        ptx::bulk_g2s(s_b + s * 2 * IMG_B, g.B + off, IMG_B, b_full + 8 * s);
+                        ptx::bulk_g2s(s_b + s * 2 * IMG_B + IMG_B, g.B_lo + off, IMG_B, b_full + 8 * s);
+                    }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            // ---------------------------------------------------- activation loader (both CTAs, own tile)
+            uint32_t mi = 0;
+            for (int mp = pair; mp < m_pairs; mp += n_pairs, ++mi) {
+                const int m = 2 * mp + (int)rank;
+                for (int kb = 0; kb < ZXG_KB; ++kb) {
+                    ptx::mbar_wait(b_afree + 8 * kb, (mi & 1) ^ 1, g.err, 111);    // last n-tile of the previous pair used it
+                    ptx::mbar_arrive_expect_tx(b_afull + 8 * kb, 2 * IMG_B);
+                    ptx::bulk_g2s(s_a + kb * 2 * IMG_B, g.A + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull + 8 * kb);
+                    ptx::bulk_g2s(s_a + kb * 2 * IMG_B + IMG_B, g.A_lo + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull + 8 * kb);
+                }
+                if (rank == 1)
+                    for (int kb = 0; kb < ZXG_KB; ++kb) {
+                        ptx::mbar_wait(b_afull + 8 * kb, mi & 1, g.err, 121);
+                        ptx::mbar_arrive_cluster(b_pafull + 8 * kb, 0);
                     }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 1) {
-            // ---------------------------------------------------- peer relay: landed -> leader
-            uint32_t it = 0, mi = 0;
-            for (int mp = pair; mp < m_pairs; mp += n_pairs, ++mi) {
-                ptx::mbar_wait(b_afull, mi & 1, g.err, 121);
-                ptx::mbar_arrive_cluster(b_pafull, 0);
+            // ---------------------------------------------------- peer relay: stage landed -> leader
+            uint32_t it = 0;
+            for (int mp = pair; mp < m_pairs; mp += n_pairs)
                 for (int n = 0; n < n_tiles; ++n)
-                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {
+                    for (int kb = 0; kb < ZXG_KB; ++kb, ++it) {
                         const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
                         ptx::mbar_wait(b_full + 8 * s, ph, g.err, 122);
                         ptx::mbar_arrive_cluster(b_pfull + 8 * s, 0);
                     }
-            }
         }
         if (lane == 0 && rank == 0) {
             // ---------------------------------------------------- MMA issue (leader)
             uint32_t it = 0, tc = 0, mi = 0;
             for (int mp = pair; mp < m_pairs; mp += n_pairs, ++mi) {
-                ptx::mbar_wait(b_afull, mi & 1, g.err, 113);
-                ptx::mbar_wait_cluster(b_pafull, mi & 1, g.err, 123);
                 for (int n = 0; n < n_tiles; ++n, ++tc) {
                     const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
                     ptx::mbar_wait_cluster(b_acce + 8 * slot, aph ^ 1, g.err, 114);
                     ptx::tc_fence_after();
-                    for (int i = 0; i < 2 * ZXG_KB; ++i, ++it) {
+                    const bool trm = g.trace && blockIdx.x == 0 && tc < 64;
+                    if (trm) g.trace[tc * 32 + 16] = clock64();
+                    for (int kb = 0; kb < ZXG_KB; ++kb, ++it) {
                         const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
-                        const int kb = i >> 1;
+                        if (n == 0) {                                   // this pair-tile's activation block
+                            ptx::mbar_wait(b_afull + 8 * kb, mi & 1, g.err, 113);
+                            ptx::mbar_wait_cluster(b_pafull + 8 * kb, mi & 1, g.err, 123);
+                        }
                         ptx::mbar_wait(b_full + 8 * s, ph, g.err, 115);
                         ptx::mbar_wait_cluster(b_pfull + 8 * s, ph, g.err, 125);
                         ptx::tc_fence_after();
-                        const uint32_t sb = s_b + s * IMG_B;
-                        const int na = (i & 1) ? 1 : 2;                 // B_lo meets A_hi only
+                        if (trm) g.trace[tc * 32 + 8 + kb] = clock64();
+                        const uint32_t sa = s_a + kb * 2 * IMG_B, sb = s_b + s * 2 * IMG_B;
 #pragma unroll
-                        for (int asel = 0; asel < 2; ++asel) {
-                            if (asel >= na) break;
-                            const uint32_t sa = (asel ? s_alo : s_ahi) + kb * IMG_B;
+                        for (int term = 0; term < 3; ++term) {          // A_hi*B_hi, A_lo*B_hi, A_hi*B_lo
+                            const uint32_t ta = sa + (term == 1 ? IMG_B : 0), tb = sb + (term == 2 ? IMG_B : 0);
 #pragma unroll
                             for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
-                                const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                                const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                                ptx::mma_f16<2>(tmem + slot * 256, da, db, idesc, (i > 0 || asel > 0 || k4 > 0) ? 1u : 0u);
+                                const uint64_t da = ptx::make_smem_desc(ta + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                const uint64_t db = ptx::make_smem_desc(tb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                ptx::mma_f16<2>(tmem + slot * 256, da, db, idesc, (kb > 0 || term > 0 || k4 > 0) ? 1u : 0u);
                             }
                         }
                         ptx::mma_commit_2_mcast(b_empty + 8 * s, 3);
+                        if (n == n_tiles - 1) ptx::mma_commit_2_mcast(b_afree + 8 * kb, 3);   // block kb may be re-loaded
                     }
                     ptx::mma_commit_2_mcast(b_accf + 8 * slot, 3);
+                    if (trm) g.trace[tc * 32 + 17] = clock64();
                 }
-                ptx::mma_commit_2_mcast(b_aempty, 3);
             }
         }
     } else {
@@ -303,10 +319,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
         for (int mp = pair; mp < m_pairs; mp += n_pairs) {
             const int m = 2 * mp + (int)rank;
             for (int n = 0; n < n_tiles; ++n, ++tc) {
-                const float* bias = bias_s + n * 256;
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's bias readers are done
+                bias_s[threadIdx.x - 64] = g.bias[(size_t)n * 256 + (threadIdx.x - 64)];
+                bias_s[threadIdx.x + 64] = g.bias[(size_t)n * 256 + (threadIdx.x + 64)];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const float* bias = bias_s;
                 ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 116);
                 ptx::tc_fence_after();
+                const bool tre = g.trace && blockIdx.x == 0 && tc < 64 && warp == 2 && lane == 0;
+                if (tre) g.trace[tc * 32 + 18] = clock64();
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 256;
 #pragma unroll 2
                 for (int j = 0; j < 16; ++j) {
@@ -328,6 +350,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1) k_g
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive_cluster(b_acce + 8 * slot, 0);
+                if (tre) g.trace[tc * 32 + 19] = clock64();
             }
         }
     }
@@ -876,7 +899,7 @@ inline cudaError_t launch_gemm_zx(const GemmArgs& g, int sm_count, cudaStream_t 
     }
     int pairs = g.m_tiles / 2 < sm_count / 2 ? g.m_tiles / 2 : sm_count / 2;
     if (pairs < 1) pairs = 1;
-    k_gemm_zx<<<pairs * 2, GEMM_THREADS, ZXG_SMEM, st>>>(g);
+    k_gemm_zx<<<pairs * 2, ZXG_THREADS, ZXG_SMEM, st>>>(g);
     return cudaGetLastError();
 }
 

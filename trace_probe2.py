@@ -15,5 +15,5 @@ T = buf[2 * 2 * 33 * 8 * 8:].reshape(64, 32)
 t0 = T[5, 16]
 for tc in range(5, 13):
     r = T[tc]
-    print("tile %2d | acce_ok %6d | loads issued %s | full seen %s | commit %6d | epi start %6d done %6d" % (
-        tc, r[16] - t0, [int(v - t0) for v in r[0:8]], [int(v - t0) for v in r[8:16]], r[17] - t0, r[18] - t0, r[19] - t0))
+    print("tile %2d | acce_ok %6d | stage ready %s | commit %6d | epi %6d..%6d" % (
+        tc, r[16] - t0, [int(v - t0) for v in r[8:12]], r[17] - t0, r[18] - t0, r[19] - t0))
