@@ -318,6 +318,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
         uint32_t tc = 0;
         for (int mp = pair; mp < m_pairs; mp += n_pairs) {
             const int m = 2 * mp + (int)rank;
+            {
+                // pull the NEXT pair-tile's activation images (2 x 64 KB, read once from HBM) towards L2 now,
+                // one 128-byte line per prefetch over the 128 epilogue threads: the bulk copies that re-load
+                // them later are then L2 hits and do not stall the (in-order) copy queue of the weight ring
+                const int mn = m + 2 * n_pairs;
+                if (mn < g.m_tiles) {
+                    const uint8_t* ph = (const uint8_t*)(g.A + (size_t)mn * ZXG_KB * TC_IMG);
+                    const uint8_t* pl = (const uint8_t*)(g.A_lo + (size_t)mn * ZXG_KB * TC_IMG);
+                    for (uint32_t o = (threadIdx.x - 64) * 128; o < ZXG_KB * IMG_B; o += 128 * 128) {
+                        ptx::prefetch_l2(ph + o);
+                        ptx::prefetch_l2(pl + o);
+                    }
+                }
+            }
             for (int n = 0; n < n_tiles; ++n, ++tc) {
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's bias readers are done
