@@ -78,6 +78,8 @@ struct c3r_ctx {
     TcNet tc;                 // tensor-core path state (nn_tc.cuh)
     bool exact_bounds = false; // capacity bounds from an exact host pass over the CIGARs (retry path)
     bool tc_dirty = false;    // a tensor-core forward ran since the last device error check
+    Buf thr;                  // allele-frequency threshold tables (k_thr_table)
+    int count_grid = 0;       // resident blocks of k_count
     Buf ref_res;              // resident reference window (c3r_set_reference)
     int64_t ref_res_start0 = 0, ref_res_len = 0;
     Buf fwd_in, fwd_out;      // c3r_forward staging
@@ -158,8 +160,8 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     if (d.n_ops > 0) { k_bin<true><<<(unsigned)((d.n_ops + 255) / 256), 256, 0, st>>>(d); ++L; }
     CK(cudaEventRecord(s.ev[3], st));
     {
-        const unsigned grid = (unsigned)(ctx->sm_count * 4);
-        if (d.C == 18) k_count<18><<<grid, 256, 0, st>>>(d); else k_count<30><<<grid, 256, 0, st>>>(d);
+        const unsigned grid = (unsigned)ctx->count_grid;
+        if (d.C == 18) k_count<18><<<grid, COUNT_WARPS * 32, 0, st>>>(d); else k_count<30><<<grid, COUNT_WARPS * 32, 0, st>>>(d);
         ++L;
     }
     CK(cudaEventRecord(s.ev[4], st));
@@ -332,6 +334,16 @@ int c3r_create(c3r_ctx** out, int device_ordinal, const c3r_params* params) {
         if (ensure_pin(ctx, s.h_scalars, 256)) return C3R_ERR_CUDA;
     }
     CK(cudaStreamCreateWithFlags(&ctx->fwd_stream, cudaStreamNonBlocking));
+    if (ensure(ctx, ctx->thr, 2 * THR_N * sizeof(uint16_t))) return C3R_ERR_CUDA;
+    k_thr_table<<<(THR_N + 255) / 256, 256>>>((uint16_t*)ctx->thr.p, (uint16_t*)ctx->thr.p + THR_N, params->snp_min_af, params->indel_min_af);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    {
+        int per_sm = 0;
+        if (params->channels == 18) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count<18>, COUNT_WARPS * 32, 0));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count<30>, COUNT_WARPS * 32, 0));
+        ctx->count_grid = ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+    }
     return C3R_OK;
 }
 
@@ -359,6 +371,7 @@ void c3r_destroy(c3r_ctx* ctx) {
     release(ctx->nn_scratch);
     release(ctx->fwd_in);
     release(ctx->ref_res);
+    release(ctx->thr);
     release(ctx->fwd_out);
     tc_release(ctx->tc);
     if (ctx->fwd_stream) cudaStreamDestroy(ctx->fwd_stream);
@@ -425,12 +438,14 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     memset(&d, 0, sizeof d);
     const c3r_params& pr = ctx->prm;
     d.n_reads = rd->n_reads; d.n_ops = rd->n_ops;
+    d.n_seq_words = (rd->n_seq_bytes + 32) / 4;
     d.R0 = (int32_t)(region_start1 - 1); d.R1 = (int32_t)region_end1;
     d.W = (int64_t)d.R1 - d.R0; d.NW = (d.W + 31) / 32;
     d.C = pr.channels; d.min_cov = pr.min_coverage; d.min_mq = pr.min_mq; d.excl = pr.excl_flags;
     d.snp_af = pr.snp_min_af; d.indel_af = pr.indel_min_af; d.padding = pr.enable_padding;
     d.max_depth = pr.max_depth; d.skip_prop = pr.skip_proportion;
     d.ref_start0 = ref_start1 - 1; d.ref_len = ref_len;
+    d.thr_snp = (const uint16_t*)ctx->thr.p; d.thr_indel = (const uint16_t*)ctx->thr.p + THR_N;
     // host-side upper bounds from the CIGARs
     // Capacity bounds.  Rows = positions under an M/=/X/D op, dilated by 16 on each side of every
     // N-separated block: a read contributes at most (its M/D length + 32 per block).  The cheap
@@ -461,7 +476,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     const int64_t R = rd->n_reads > 0 ? rd->n_reads : 1, O = rd->n_ops > 0 ? rd->n_ops : 1;
 #define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
     EN(pos, R * 4); EN(flag, R * 2); EN(mapq, R); EN(hp, R); EN(cigar_off, (R + 1) * 4); EN(cigar, O * 4);
-    EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 16); if (ref) { EN(ref, ref_len + 16); }
+    EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 64); if (ref) { EN(ref, ref_len + 16); }
     EN(admit, R); EN(read_end, R * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_rid, O * 4);
     EN(covA, (d.NW + 4) * 4); EN(covE, (d.NW + 4) * 4); EN(rowR, (d.NW + 4) * 4); EN(wdiff, (d.NW + 4) * 8);
     EN(word_base, (d.NW + 4) * 4);

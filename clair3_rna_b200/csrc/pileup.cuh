@@ -31,9 +31,9 @@ constexpr int TILE_ROWS = 32;
 
 struct SegEntry {              // an M/=/X or D op clipped to nothing: lanes test coverage themselves
     int32_t x;                 // reference start (0-based)
-    int32_t len;               // reference length; bit 31 set = deletion (`*`/`#`)
-    uint32_t y;                // query start (base index into the nibble pool) for M
-    uint32_t info;             // rid << 4 | hp(2 bits) << 1 | reverse
+    int32_t len;               // reference length of an M/=/X op; 0 for a deletion
+    uint32_t yx;               // M/=/X: query start - x (mod 2^32), base index of position p is yx + p; D: its length
+    uint32_t info;             // rid << 4 | deletion (`*`/`#`) << 3 | hp(2 bits) << 1 | reverse
 };
 
 struct IndelEvent {
@@ -65,11 +65,13 @@ struct Dev {
     int64_t n_reads, n_ops;
     const int32_t* pos; const uint16_t* flag; const uint8_t* mapq; const uint8_t* hp;
     const int32_t* cigar_off; const uint32_t* cigar; const int64_t* seq_off; const uint8_t* seq;
+    int64_t n_seq_words;          // readable 32-bit words of the sequence buffer (incl. the slack after the last read)
     const uint8_t* ref; int64_t ref_start0; int64_t ref_len;
     int32_t R0, R1; int64_t W; int64_t NW;            // region (0-based half open), words
     // ---- params
     int32_t C; int32_t min_cov; int32_t min_mq; uint32_t excl; double snp_af, indel_af;
     int32_t padding; int32_t max_depth; double skip_prop;
+    const uint16_t* thr_snp; const uint16_t* thr_indel;     // THR_N entries each (k_thr_table)
     // ---- per read / per op
     uint8_t* admit; int32_t* read_end; int32_t* op_head;
     int32_t* op_x; uint32_t* op_y; int32_t* op_rid;
@@ -301,9 +303,9 @@ __global__ void k_bin(Dev d) {
                 const int32_t slot = tile_cnt[t] + atomicAdd(&d.bin_cur[t], 1);
                 SegEntry e;
                 e.x = x;
-                e.len = len | (op == 2 ? (int32_t)0x80000000 : 0);
-                e.y = d.op_y[k];
-                e.info = ((uint32_t)r << 4) | (hp << 1) | rev;
+                e.len = op == 2 ? 0 : len;
+                e.yx = op == 2 ? (uint32_t)len : d.op_y[k] - (uint32_t)x;
+                e.info = ((uint32_t)r << 4) | (op == 2 ? 8u : 0u) | (hp << 1) | rev;
                 if (slot < d.entries_ub) d.entries[slot] = e; else atomicExch(d.err, 2);
             }
         }
@@ -423,28 +425,6 @@ struct OpSkip {
 // accumulates its own column in registers (four 16-bit fields per 64-bit word), so the
 // histogram needs no atomics at all; rows leave through shared memory as coalesced
 // 16-byte stores.
-struct RowAcc {
-    unsigned long long f, r, p, m;      // A,C,G,T counts: forward, reverse, HP=1, HP=2
-    int32_t star_f, star_r;
-};
-
-__device__ __forceinline__ void acc_entry(const Dev& d, const SegEntry& e, int32_t p, RowAcc& a) {
-    const int32_t len = e.len & 0x7fffffff;
-    const uint32_t off = (uint32_t)(p - e.x);
-    if (off >= (uint32_t)len) return;
-    const uint32_t rev = e.info & 1u;
-    if (e.len < 0) {
-        if (rev) ++a.star_r; else ++a.star_f;
-        return;
-    }
-    const uint32_t nib = nib_at(d.seq, e.y + off);
-    if (__popc(nib) != 1) return;                    // N and ambiguity codes: not counted
-    const unsigned long long inc = 1ull << (16 * (__ffs(nib) - 1));
-    if (rev) a.r += inc; else a.f += inc;
-    const uint32_t hp = (e.info >> 1) & 3u;
-    if (hp == 1) a.p += inc; else if (hp == 2) a.m += inc;
-}
-
 __device__ __forceinline__ bool ins_equal(const Dev& d, const IndelEvent& a, const IndelEvent& b, bool fold_strand) {
     if (a.len != b.len) return false;
     if (!fold_strand && ((a.info ^ b.info) & 1u)) return false;
@@ -460,10 +440,10 @@ __device__ void first_keys(const Dev& d, int32_t row, int32_t p, uint32_t key[6]
     const int32_t t = row >> 5;
     for (int32_t s = d.binc[t]; s < d.binc[t + 1]; ++s) {
         const SegEntry e = d.entries[s];
-        if (e.len < 0) continue;
+        if (e.info & 8u) continue;
         const uint32_t off = (uint32_t)(p - e.x);
         if (off >= (uint32_t)e.len) continue;
-        const uint32_t nib = nib_at(d.seq, e.y + off);
+        const uint32_t nib = nib_at(d.seq, e.yx + (uint32_t)p);
         if (__popc(nib) != 1) continue;
         const int c = __ffs(nib) - 1;
         const uint32_t kk = (e.info >> 4) * 2u;
@@ -479,79 +459,230 @@ __device__ void first_keys(const Dev& d, int32_t row, int32_t p, uint32_t key[6]
     }
 }
 
+// allele-frequency thresholds as integer tables: thr[depth] = smallest count c >= 1 with
+// (double)c / (double)max(depth, 1) >= af, the reference's float64 test (create_tensor_pileup.py:270-277)
+// evaluated once per depth instead of once per row and class.  Depths >= THR_N use the division.
+constexpr int THR_N = 4096;
+__global__ void k_thr_table(uint16_t* thr_snp, uint16_t* thr_indel, double snp_af, double indel_af) {
+    const int dpt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dpt >= THR_N) return;
+    const double den = dpt > 0 ? (double)dpt : 1.0;
+    for (int which = 0; which < 2; ++which) {
+        const double af = which ? indel_af : snp_af;
+        int c = 1;
+        const int lim = dpt > 1 ? dpt : 1;
+        while (c <= lim && !((double)c / den >= af)) ++c;
+        (which ? thr_indel : thr_snp)[dpt] = (uint16_t)(c <= lim ? c : 0xffff);
+    }
+}
+
+// four 8-bit fields -> four 16-bit fields
+__device__ __forceinline__ unsigned long long widen8(uint32_t v) {
+    const uint32_t lo = __byte_perm(v, 0, 0x4140), hi = __byte_perm(v, 0, 0x4342);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// ------------------------------------------------------------- K2: counting (design)
+// One warp per 32-row tile, lane = row, no atomics.  Per round of <= 32 segment entries:
+//   staging  (lane = entry)  each lane cuts ITS read's 32-base window over the tile's positions out of the
+//            4-bit sequence (5 word loads, nibble swap, funnel shift), clears bases outside the segment and
+//            ambiguity codes, and drops the 16 bytes into a shared-memory slot; slots are grouped by
+//            (strand, phase class) with each group padded to a multiple of 4 zero slots;
+//   consume  (lane = row)    per slot: one shared load, shift, mask, multiply-spread of the one-hot nibble
+//            into four 8-bit fields, add - 6 instructions per (row, read) instead of an address
+//            computation and a dependent global load per (row, read).
+// Tiles whose rows are not consecutive positions (a run ends inside the tile) are processed run by run.
+constexpr int COUNT_WARPS = 8;
+constexpr int SLOT_WORDS = 8;                // 4 data words, word 4 = 0 (lanes outside the run read it), 3 spare
+
+__device__ __forceinline__ uint32_t nibmask(int n) {         // low n nibbles set, n clamped to 0..8
+    n = n < 0 ? 0 : n;
+    return n >= 8 ? 0xffffffffu : ((1u << (4 * n)) - 1u);
+}
+// keep only one-hot nibbles (A=1, C=2, G=4, T=8); N, other ambiguity codes and '=' count nothing
+__device__ __forceinline__ uint32_t keep_onehot(uint32_t x) {
+    const uint32_t c = x - ((x >> 1) & 0x77777777u) - ((x >> 2) & 0x33333333u) - ((x >> 3) & 0x11111111u);
+    const uint32_t t = c ^ 0x11111111u;                      // nibble == 0  <=>  popcount == 1
+    const uint32_t nz = (t | (t >> 1) | (t >> 2) | (t >> 3)) & 0x11111111u;
+    return x & ((nz ^ 0x11111111u) * 15u);
+}
+
 template <int C>
-__global__ void __launch_bounds__(256) k_count(Dev d) {
-    __shared__ __align__(16) int32_t stage[8][TILE_ROWS * C];
-    __shared__ __align__(16) SegEntry ebuf[8][32];
+__global__ void __launch_bounds__(COUNT_WARPS * 32) k_count(Dev d) {
+    constexpr int NG = C == 30 ? 6 : 2;                      // slot groups: strand x {unphased, HP1, HP2}
+    constexpr int NSLOT = 32 + 4 * NG;
+    __shared__ __align__(16) int32_t stage[COUNT_WARPS][TILE_ROWS * C];
+    __shared__ __align__(16) uint32_t slots[COUNT_WARPS][NSLOT][SLOT_WORDS];
+    __shared__ uint2 dels[COUNT_WARPS][32];                  // deletion entries of the round: coverage mask, strand
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const int64_t L = *d.n_rows;
     const int64_t n_tiles = (L + TILE_ROWS - 1) / TILE_ROWS;
     const int32_t* ev_off = d.binc + d.NT_ub + 1;
-    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < n_tiles; t += (int64_t)gridDim.x * 8) {
+    const uint32_t* __restrict__ seqw = (const uint32_t*)d.seq;
+    const int64_t n_seq_words = d.n_seq_words;
+    for (int j = lane; j < NSLOT; j += 32) {                 // words 4..7 of every slot stay zero
+        *(uint4*)&slots[warp][j][0] = make_uint4(0, 0, 0, 0);
+        *(uint4*)&slots[warp][j][4] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    const int64_t t_stride = (int64_t)gridDim.x * COUNT_WARPS;
+    int64_t t = (int64_t)blockIdx.x * COUNT_WARPS + warp;
+    // software pipeline across tiles: the entry range of tile t+2 and the first round's entries of tile t+1
+    // are requested while tile t is processed
+    int32_t s0 = 0, s1 = 0, s0n = 0, s1n = 0;
+    if (t < n_tiles) { s0 = d.binc[t]; s1 = d.binc[t + 1]; }
+    if (t + t_stride < n_tiles) { s0n = d.binc[t + t_stride]; s1n = d.binc[t + t_stride + 1]; }
+    SegEntry pre;
+    pre.x = 0; pre.len = 0; pre.yx = 0; pre.info = 0;
+    if (s0 + lane < s1) pre = d.entries[s0 + lane];
+    for (; t < n_tiles; t += t_stride) {
         const int64_t row = t * TILE_ROWS + lane;
         const bool live = row < L;
         const int32_t p = live ? d.row_pos[row] : -0x40000000;
-        RowAcc a; a.f = a.r = a.p = a.m = 0; a.star_f = a.star_r = 0;
-        const int32_t s0 = d.binc[t], s1 = d.binc[t + 1];
-        for (int32_t s = s0; s < s1; s += 32) {
-            const int n = min(32, s1 - s);
-            if (lane < n) ebuf[warp][lane] = d.entries[s + lane];
-            else { SegEntry z; z.x = 0; z.len = 0; z.y = 0; z.info = 0; ebuf[warp][lane] = z; }
-            __syncwarp();
-            // batches of 8 entries: issue the 8 sequence-byte loads, then consume them, so each
-            // lane keeps 8 independent global loads in flight instead of one
-            for (int j0 = 0; j0 < n; j0 += 8) {
-                uint32_t by[8], qq[8];
-                int32_t kind[8];                         // 0 none, 1 base, 2 deletion
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const SegEntry e = ebuf[warp][j0 + u];
-                    const uint32_t off = (uint32_t)(p - e.x);
-                    const bool in = off < (uint32_t)(e.len & 0x7fffffff);
-                    kind[u] = in ? (e.len < 0 ? 2 : 1) : 0;
-                    qq[u] = e.y + off;
-                    by[u] = kind[u] == 1 ? (uint32_t)d.seq[qq[u] >> 1] : 0u;
+        const SegEntry first = pre;
+        pre.x = 0; pre.len = 0; pre.yx = 0; pre.info = 0;
+        if (s0n + lane < s1n) pre = d.entries[s0n + lane];
+        const int64_t tnn = t + 2 * t_stride;
+        int32_t s0nn = 0, s1nn = 0;
+        if (tnn < n_tiles) { s0nn = d.binc[tnn]; s1nn = d.binc[tnn + 1]; }
+        // runs of consecutive positions inside the tile
+        const int32_t p_prev = __shfl_up_sync(0xffffffffu, p, 1);
+        const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+        const uint32_t start_mask = __ballot_sync(0xffffffffu, live && (lane == 0 || p != p_prev + 1));
+        const int n_live = __popc(live_mask);
+        // wide accumulators: A,C,G,T as four 16-bit fields (forward, reverse, HP=1, HP=2); `*` / `#` counts
+        unsigned long long wf = 0, wr = 0, wp = 0, wm = 0;
+        uint32_t wst = 0;                                    // star_f | star_r << 16
+        // narrow accumulators (four 8-bit fields), folded into the wide ones every 7 rounds (<= 224 per field)
+        uint32_t nf = 0, nr = 0, np = 0, nm = 0, nst = 0;    // nst: star_f | star_r << 8
+        int rounds = 0;
+        for (uint32_t sm = start_mask; sm; sm &= sm - 1) {
+            const int ra = __ffs(sm) - 1;
+            const uint32_t rest = sm & (sm - 1);
+            const int rb = rest ? __ffs(rest) - 1 : n_live;
+            const int32_t P0 = __shfl_sync(0xffffffffu, p, ra);
+            const int nrun = rb - ra;
+            const bool in_run = lane >= ra && lane < rb;
+            const int k = lane - ra;                         // this row's base index inside the window
+            const uint32_t* lane_slot = &slots[warp][0][in_run ? (k >> 3) : 4];
+            const uint32_t lane_sh = (uint32_t)(k & 7) * 4u;
+            const uint32_t lane_bit = in_run ? (1u << k) : 0u;
+            for (int32_t s = s0; s < s1; s += 32) {
+                SegEntry e;
+                if (s == s0 && sm == start_mask) e = first;
+                else {
+                    e.x = 0; e.len = 0; e.yx = 0; e.info = 0;
+                    if (s + lane < s1) e = d.entries[s + lane];
                 }
+                // ---------------------------------------------------------------- staging (lane = entry)
+                const bool is_del = (e.info & 8u) != 0u;
+                const int32_t span = is_del ? (int32_t)e.yx : e.len;
+                int k0 = e.x - P0, k1 = e.x + span - P0;     // window bases covered by the op: [k0, k1)
+                k0 = k0 < 0 ? 0 : k0;
+                k1 = k1 > nrun ? nrun : k1;
+                const bool hit = k1 > k0;
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if (hit && !is_del) {
+                    const long long q0 = (long long)(uint32_t)(e.yx + (uint32_t)e.x) + ((long long)P0 - e.x);
+                    const long long wb = q0 >> 3;            // floor: q0 is negative when the op starts inside the window
+                    const uint32_t sh = ((uint32_t)q0 & 7u) * 4u;
+                    uint32_t v[5];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t info = ebuf[warp][j0 + u].info;
-                    const uint32_t rev = info & 1u;
-                    if (kind[u] == 2) { if (rev) ++a.star_r; else ++a.star_f; }
-                    else if (kind[u] == 1) {
-                        const uint32_t nib = (qq[u] & 1u) ? (by[u] & 15u) : (by[u] >> 4);
-                        if (__popc(nib) == 1) {
-                            const unsigned long long inc = 1ull << (16 * (__ffs(nib) - 1));
-                            if (rev) a.r += inc; else a.f += inc;
-                            const uint32_t hp = (info >> 1) & 3u;
-                            if (hp == 1) a.p += inc; else if (hp == 2) a.m += inc;
+                    for (int i = 0; i < 5; ++i) {
+                        const long long wi = wb + i;
+                        uint32_t x = (wi >= 0 && wi < n_seq_words) ? seqw[wi] : 0u;
+                        v[i] = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);     // base j of the word at bits 4j..4j+3
+                    }
+                    w.x = keep_onehot(__funnelshift_r(v[0], v[1], sh) & nibmask(k1) & ~nibmask(k0));
+                    w.y = keep_onehot(__funnelshift_r(v[1], v[2], sh) & nibmask(k1 - 8) & ~nibmask(k0 - 8));
+                    w.z = keep_onehot(__funnelshift_r(v[2], v[3], sh) & nibmask(k1 - 16) & ~nibmask(k0 - 16));
+                    w.w = keep_onehot(__funnelshift_r(v[3], v[4], sh) & nibmask(k1 - 24) & ~nibmask(k0 - 24));
+                }
+                const uint32_t rev = e.info & 1u;
+                int grp = (int)rev;
+                if (C == 30) {
+                    const uint32_t hp = (e.info >> 1) & 3u;
+                    grp = (int)rev * 3 + (hp == 1 ? 1 : hp == 2 ? 2 : 0);
+                }
+                int end_all = 0;
+                int cnt4g[NG];
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, hit && !is_del && grp == g);
+                    const int cnt = __popc(bal), cnt4 = (cnt + 3) & ~3;
+                    if (hit && !is_del && grp == g) *(uint4*)&slots[warp][end_all + __popc(bal & lt_mask)][0] = w;
+                    if (lane < cnt4 - cnt) *(uint4*)&slots[warp][end_all + cnt + lane][0] = make_uint4(0, 0, 0, 0);
+                    end_all += cnt4;
+                    cnt4g[g] = cnt4;
+                }
+                const uint32_t dbal = __ballot_sync(0xffffffffu, hit && is_del);
+                if (hit && is_del) {
+                    const uint32_t cov = (k1 >= 32 ? 0xffffffffu : ((1u << k1) - 1u)) & ~((1u << k0) - 1u);
+                    dels[warp][__popc(dbal & lt_mask)] = make_uint2(cov, rev);
+                }
+                __syncwarp();
+                // ---------------------------------------------------------------- consume (lane = row)
+                {
+                    int j = 0;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        uint32_t acc = 0;
+                        for (const int je = j + cnt4g[g]; j < je; j += 4) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const uint32_t nib = (lane_slot[(j + u) * SLOT_WORDS] >> lane_sh) & 15u;
+                                acc += (nib * 0x204081u) & 0x01010101u;
+                            }
+                        }
+                        if (C == 30) {
+                            if (g < 3) nf += acc; else nr += acc;
+                            if (g % 3 == 1) np += acc; else if (g % 3 == 2) nm += acc;
+                        } else {
+                            if (g == 0) nf += acc; else nr += acc;
                         }
                     }
+                    const int nd = __popc(dbal);
+                    for (int i = 0; i < nd; ++i) {
+                        const uint2 dl = dels[warp][i];
+                        if (dl.x & lane_bit) nst += 1u << (dl.y * 8u);
+                    }
+                }
+                __syncwarp();
+                if (++rounds == 7) {
+                    wf += widen8(nf); wr += widen8(nr);
+                    if (C == 30) { wp += widen8(np); wm += widen8(nm); }
+                    wst += (nst & 0xffu) | ((nst & 0xff00u) << 8);
+                    nf = nr = np = nm = nst = 0;
+                    rounds = 0;
                 }
             }
-            __syncwarp();
         }
+        wf += widen8(nf); wr += widen8(nr);
+        if (C == 30) { wp += widen8(np); wm += widen8(nm); }
+        wst += (nst & 0xffu) | ((nst & 0xff00u) << 8);
+        s0 = s0n; s1 = s1n; s0n = s0nn; s1n = s1nn;
         // the row vector lives in this lane's slice of the staging tile (dynamic channel
         // indices would otherwise force a register array into local memory)
         int32_t* v = &stage[warp][lane * C];
 #pragma unroll
         for (int i = 0; i < C; ++i) v[i] = 0;
-        int32_t depth = 0;
-        uint8_t flag = 0;
         if (live) {
+            const int32_t star_f = (int32_t)(wst & 0xffffu), star_r = (int32_t)(wst >> 16);
             int32_t bf[4], br[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                bf[i] = (int32_t)((a.f >> (16 * i)) & 0xffff);
-                br[i] = (int32_t)((a.r >> (16 * i)) & 0xffff);
+                bf[i] = (int32_t)((wf >> (16 * i)) & 0xffff);
+                br[i] = (int32_t)((wr >> (16 * i)) & 0xffff);
                 v[i] = bf[i];
                 v[9 + i] = br[i];
             }
-            v[8] = a.star_f; v[17] = a.star_r;
+            v[8] = star_f; v[17] = star_r;
             if (C == 30) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    v[18 + i] = (int32_t)((a.p >> (16 * i)) & 0xffff);
-                    v[24 + i] = (int32_t)((a.m >> (16 * i)) & 0xffff);
+                    v[18 + i] = (int32_t)((wp >> (16 * i)) & 0xffff);
+                    v[24 + i] = (int32_t)((wm >> (16 * i)) & 0xffff);
                 }
             }
             // indel events of this row: per strand totals and the largest distinct allele
@@ -580,7 +711,7 @@ __global__ void __launch_bounds__(256) k_count(Dev d) {
                 if (same > v[ch]) v[ch] = same;
             }
             const int32_t fsum = bf[0] + bf[1] + bf[2] + bf[3], rsum = br[0] + br[1] + br[2] + br[3];
-            depth = fsum + rsum + a.star_f + a.star_r;
+            const int32_t depth = fsum + rsum + star_f + star_r;
             bool acgt;
             const int ri = ref_index(d, p, &acgt);
             // candidate predicate (create_tensor_pileup.py:268-299, 536, 555)
@@ -588,20 +719,28 @@ __global__ void __launch_bounds__(256) k_count(Dev d) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) cls[i] = bf[i] + br[i];
             cls[4] = ins_cnt; cls[5] = del_cnt;
-            const double den = depth > 0 ? (double)depth : 1.0;
+            const int32_t cls_ref = ri == 0 ? cls[0] : ri == 1 ? cls[1] : ri == 2 ? cls[2] : cls[3];
             bool pass_snp = false, pass_indel = false;
+            if (depth < THR_N) {
+                const int32_t ts = d.thr_snp[depth], ti = d.thr_indel[depth];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (i != ri && cls[i] > 0 && (double)cls[i] / den >= d.snp_af) pass_snp = true;
-            if (cls[4] > 0 && (double)cls[4] / den >= d.indel_af) pass_indel = true;
-            if (cls[5] > 0 && (double)cls[5] / den >= d.indel_af) pass_indel = true;
+                for (int i = 0; i < 4; ++i) if (i != ri && cls[i] >= ts) pass_snp = true;
+                pass_indel = cls[4] >= ti || cls[5] >= ti;
+            } else {
+                const double den = (double)depth;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i != ri && cls[i] > 0 && (double)cls[i] / den >= d.snp_af) pass_snp = true;
+                if (cls[4] > 0 && (double)cls[4] / den >= d.indel_af) pass_indel = true;
+                if (cls[5] > 0 && (double)cls[5] / den >= d.indel_af) pass_indel = true;
+            }
             bool pass = pass_snp || pass_indel;
             if (!pass) {
                 int32_t top = 0;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) top = cls[i] > top ? cls[i] : top;
                 if (top > 0) {
-                    if (cls[ri] < top) pass = true;
+                    if (cls_ref < top) pass = true;
                     else {
                         bool tie = false;
 #pragma unroll
@@ -615,14 +754,14 @@ __global__ void __launch_bounds__(256) k_count(Dev d) {
                 }
             }
             if (depth > 0 && (d.snp_af == 0.0 || d.indel_af == 0.0)) pass = true;
-            flag = (acgt && pass && depth >= d.min_cov) ? 1 : 0;
+            const uint8_t flag = (acgt && pass && depth >= d.min_cov) ? 1 : 0;
             v[ri] = -fsum;
             v[9 + ri] = -rsum;
             d.row_depth[row] = depth;
             d.row_flag[row] = flag;
             d.row_inscnt[row] = ins_cnt;
-            d.row_delcnt[row] = del_cnt + a.star_f + a.star_r;
-            if (d.padding) { Int2 cr; cr.a = v[ri]; cr.b = v[9 + ri]; d.cur_ref[row] = cr; }
+            d.row_delcnt[row] = del_cnt + star_f + star_r;
+            if (d.padding) { Int2 cr; cr.a = -fsum; cr.b = -rsum; d.cur_ref[row] = cr; }
         }
         // rows of a tile are contiguous in HBM: write 16 B per lane per step from the staging tile
         __syncwarp();
@@ -798,10 +937,10 @@ __global__ void __launch_bounds__(256) k_altinfo(Dev d) {
         const int32_t t = row >> 5;
         for (int32_t s = d.binc[t] + lane; s < d.binc[t + 1]; s += 32) {
             const SegEntry e = d.entries[s];
-            if (e.len < 0) continue;
+            if (e.info & 8u) continue;
             const uint32_t o = (uint32_t)(p - e.x);
             if (o >= (uint32_t)e.len) continue;
-            const uint32_t nib = nib_at(d.seq, e.y + o);
+            const uint32_t nib = nib_at(d.seq, e.yx + (uint32_t)p);
             if (__popc(nib) != 1) continue;
             const int c = __ffs(nib) - 1;
             const uint32_t kk = (e.info >> 4) * 2u;
