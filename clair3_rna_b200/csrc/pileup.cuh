@@ -496,8 +496,9 @@ constexpr int COUNT_WARPS = 8;
 constexpr int SLOT_WORDS = 8;                // 4 data words, word 4 = 0 (lanes outside the run read it), 3 spare
 
 __device__ __forceinline__ uint32_t nibmask(int n) {         // low n nibbles set, n clamped to 0..8
-    n = n < 0 ? 0 : n;
-    return n >= 8 ? 0xffffffffu : ((1u << (4 * n)) - 1u);
+    uint32_t m;                                              // shl.b32 clamps the shift amount: 1 << 32 == 0
+    asm("shl.b32 %0, 1, %1;" : "=r"(m) : "r"((uint32_t)(n < 0 ? 0 : 4 * n)));
+    return m - 1u;
 }
 // keep only one-hot nibbles (A=1, C=2, G=4, T=8); N, other ambiguity codes and '=' count nothing
 __device__ __forceinline__ uint32_t keep_onehot(uint32_t x) {
@@ -540,6 +541,15 @@ __global__ void __launch_bounds__(COUNT_WARPS * 32) k_count(Dev d) {
         const int64_t row = t * TILE_ROWS + lane;
         const bool live = row < L;
         const int32_t p = live ? d.row_pos[row] : -0x40000000;
+        // epilogue operands requested now, consumed after the rounds
+        int32_t ev0 = 0, ev1 = 0;
+        uint8_t ref_c = (uint8_t)'N';
+        if (live) {
+            ev0 = ev_off[row]; ev1 = ev_off[row + 1];
+            const int64_t ro = (int64_t)p - d.ref_start0;
+            if (ro >= 0 && ro < d.ref_len) ref_c = d.ref[ro];
+        }
+        const int32_t ev_base = ev_off[0];
         const SegEntry first = pre;
         pre.x = 0; pre.len = 0; pre.yx = 0; pre.info = 0;
         if (s0n + lane < s1n) pre = d.entries[s0n + lane];
@@ -686,7 +696,7 @@ __global__ void __launch_bounds__(COUNT_WARPS * 32) k_count(Dev d) {
                 }
             }
             // indel events of this row: per strand totals and the largest distinct allele
-            const int32_t e0 = ev_off[row] - ev_off[0], e1 = ev_off[row + 1] - ev_off[0];
+            const int32_t e0 = ev0 - ev_base, e1 = ev1 - ev_base;
             int32_t ins_cnt = 0, del_cnt = 0;
             for (int32_t s = e0; s < e1; ++s) {
                 const IndelEvent e = d.events[s];
@@ -712,8 +722,11 @@ __global__ void __launch_bounds__(COUNT_WARPS * 32) k_count(Dev d) {
             }
             const int32_t fsum = bf[0] + bf[1] + bf[2] + bf[3], rsum = br[0] + br[1] + br[2] + br[3];
             const int32_t depth = fsum + rsum + star_f + star_r;
-            bool acgt;
-            const int ri = ref_index(d, p, &acgt);
+            uint8_t rc = ref_c;
+            if (rc >= 'a') rc -= 32;
+            const int ri_raw = rc == 'A' ? 0 : rc == 'C' ? 1 : rc == 'G' ? 2 : rc == 'T' ? 3 : -1;
+            const bool acgt = ri_raw >= 0;
+            const int ri = acgt ? ri_raw : 0;
             // candidate predicate (create_tensor_pileup.py:268-299, 536, 555)
             int32_t cls[6];
 #pragma unroll
