@@ -293,8 +293,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                         ptx::tc_fence_after();
                         if (trm) g.trace[tc * 32 + 8 + kb] = clock64();
                         const uint32_t sa = s_a + kb * 2 * IMG_B, sb = s_b + s * 2 * IMG_B;
-#pragma unroll
-                        for (int term = 0; term < 3; ++term) {          // A_hi*B_hi, A_lo*B_hi, A_hi*B_lo
+                        for (int term = 0; term < g.terms; ++term) {    // A_hi*B_hi, A_lo*B_hi, A_hi*B_lo
                             const uint32_t ta = sa + (term == 1 ? IMG_B : 0), tb = sb + (term == 2 ? IMG_B : 0);
 #pragma unroll
                             for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
@@ -414,10 +413,18 @@ __device__ __forceinline__ void lstm_trace(const LstmArgs& a, bool on, uint32_t 
 constexpr int LSTM_GATE_WARPS = 16;          // 4 per TMEM lane quarter, 8 units of a chunk each
 constexpr int LSTM_THREADS = 64 + 32 * LSTM_GATE_WARPS;   // warp 0: MMA issue, warp 1: x loader, then the gate warps
 
-// Gate math on the SFU: ex2.approx / rcp.approx (<= 2 ulp each), 8 SFU ops per (site, unit):
+// Gate math on the SFU.  Default: tanh.approx.f32 (MUFU.TANH, max relative error 2^-11), sigmoid as
+// 0.5*tanh(0.5x)+0.5 - 5 SFU ops per (site, unit).  Its error is of the size of the fp16 rounding h
+// already goes through as the next step's MMA operand; measured effect on the output probabilities
+// versus the ex2/rcp form: none (max |dp| 2.53e-4 vs 2.55e-4 on the stress weights, tools/prec_probe.py).
+// LSTM_EXACT_GATES = true selects ex2.approx / rcp.approx (<= 2 ulp each), 8 SFU ops per (site, unit):
 //   sigmoid(x) = 1/(1+2^(-x log2e)),  tanh(x) = (1-b)/(1+b) with b = 2^(-2x log2e),
-//   sigmoid(i)*tanh(g) and sigmoid(o)*tanh(c) share one reciprocal each.
-// Exponents are clamped so (1+a)(1+b) stays finite (sigmoid(-30) and 1+tanh(-15) are below fp32 eps).
+//   sigmoid(i)*tanh(g) and sigmoid(o)*tanh(c) share one reciprocal each, exponents clamped so
+//   (1+a)(1+b) stays finite (sigmoid(-30) and 1+tanh(-15) are below fp32 eps).
+#ifndef C3R_EXACT_GATES
+#define C3R_EXACT_GATES 0
+#endif
+constexpr bool LSTM_EXACT_GATES = C3R_EXACT_GATES != 0;
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 constexpr float LOG2E = 1.4426950408889634f;
@@ -427,6 +434,8 @@ __device__ __forceinline__ float sig_times_tanh(float zs, float zt) {
     return (1.0f - b) * rcp_approx((1.0f + a) * (1.0f + b));
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-LOG2E * x)); }
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_tanh(float x) { return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f); }
 
 template <int CH, int KX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_lstm_tc(LstmArgs a) {
@@ -650,9 +659,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const float cp = step > 0 ? __uint_as_float(cprev[u]) : 0.0f;
-                        const float cn = fmaf(sigmoid_fast(z[1][u]), cp, sig_times_tanh(z[0][u], z[2][u]));
+                        float cn, hv;
+                        if (LSTM_EXACT_GATES) {
+                            cn = fmaf(sigmoid_fast(z[1][u]), cp, sig_times_tanh(z[0][u], z[2][u]));
+                            hv = sig_times_tanh(z[3][u], cn);
+                        } else {
+                            cn = fmaf(sigmoid_tanh(z[1][u]), cp, sigmoid_tanh(z[0][u]) * tanh_approx(z[2][u]));
+                            hv = sigmoid_tanh(z[3][u]) * tanh_approx(cn);
+                        }
                         cnew[u] = __float_as_uint(cn);
-                        const float hv = sig_times_tanh(z[3][u], cn);
                         hh[u] = __float2half(hv);
                         hl[u] = __float2half(hv - __half2float(hh[u]));
                     }
@@ -951,7 +966,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         if (e != cudaSuccess) { *err = std::string("lstm1: ") + cudaGetErrorString(e); return -1; }
         ++launches;
         GemmArgs g2;
-        g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = 3; g2.bias = t.b2p; g2.out = t.zx2; g2.m_tiles = tiles * NT; g2.n_tiles = 5; g2.n_kb = 4;
+        g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = getenv("C3R_ZX_TERMS") ? atoi(getenv("C3R_ZX_TERMS")) : 3; g2.bias = t.b2p; g2.out = t.zx2; g2.m_tiles = tiles * NT; g2.n_tiles = 5; g2.n_kb = 4;
         g2.mode = 0; g2.err = t.err; g2.dbg = getenv("C3R_ZX_DBG") ? atoi(getenv("C3R_ZX_DBG")) : 0; g2.trace = t.trace ? t.trace + 2 * 2 * NT * 8 * 8 : nullptr;
         e = launch_gemm_zx(g2, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("zx2 gemm: ") + cudaGetErrorString(e); return -1; }
@@ -963,7 +978,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         if (e != cudaSuccess) { *err = std::string("lstm2: ") + cudaGetErrorString(e); return -1; }
         ++launches;
         GemmArgs g4;
-        g4.A = t.h2; g4.B = t.k4p; g4.A_lo = t.h2_lo; g4.B_lo = t.k4p_lo; g4.terms = 3; g4.bias = t.b4; g4.out = t.l4; g4.m_tiles = tiles; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
+        g4.A = t.h2; g4.B = t.k4p; g4.A_lo = t.h2_lo; g4.B_lo = t.k4p_lo; g4.terms = getenv("C3R_L4_TERMS") ? atoi(getenv("C3R_L4_TERMS")) : 3; g4.bias = t.b4; g4.out = t.l4; g4.m_tiles = tiles; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
         g4.mode = 1; g4.err = t.err; g4.dbg = 0; g4.trace = nullptr;
         e = launch_gemm(g4, t.sm_count, st);
         if (e != cudaSuccess) { *err = std::string("l4 gemm: ") + cudaGetErrorString(e); return -1; }
