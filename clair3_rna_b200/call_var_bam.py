@@ -6,8 +6,9 @@ shared/utils.py:get_header plus one row per candidate, the file being absent whe
 no record (call_variants.py:1594-1599).  Instead of piping create_tensor_pileup text into
 call_variants it hands the chunk's flat alignment records to libc3r_b200.so.
 
-Inputs this round: --bam_fn is a flat-read .npz (clair3_rna_b200.reads.ReadBatch.save);
-a BGZF/BAM reader is the next §8(f) row.  --chkpnt_fn is an .npz of Keras-layout weights
+Inputs: --bam_fn is an indexed BAM (read by csrc/bam_io.cpp: BGZF inflate + BAI region fetch,
+the part of `samtools mpileup -r` that touches the file) or a flat-read .npz
+(clair3_rna_b200.reads.ReadBatch.save).  --chkpnt_fn is an .npz of Keras-layout weights
 (clair3_rna_b200.weights); TF checkpoints need TensorFlow to read and are converted offline.
 """
 from __future__ import annotations
@@ -98,8 +99,6 @@ def call_chunk_to_rows(eng, batch, ref, ref_start1, start1, end1, contig, qual):
 def run(args) -> int:
     if args.gvcf or args.enable_variant_calling_at_sequence_head_and_tail or args.bed_fn or args.vcf_fn:
         sys.exit("[ERROR] --gvcf / --bed_fn / --vcf_fn / head-and-tail calling are outside this path (SURVEY.md §8f)")
-    if not args.bam_fn.endswith(".npz"):
-        sys.exit("[ERROR] --bam_fn must be a flat-read .npz this round (BAM/BGZF reader: SURVEY.md §8f rank 1)")
     from .engine import Engine
     fai = fasta.read_fai(args.ref_fn)
     if args.ctgName not in fai:
@@ -107,7 +106,14 @@ def run(args) -> int:
     contig_len = fai[args.ctgName][0]
     s1, e1, rs1, re1 = chunk_region(args, contig_len)
     ref = fasta.fetch(args.ref_fn, fai, args.ctgName, rs1, re1)
-    batch = ReadBatch.load(args.bam_fn).fetch(s1, e1)
+    if args.bam_fn.endswith(".npz"):
+        batch = ReadBatch.load(args.bam_fn).fetch(s1, e1)
+    else:
+        from .bam import BamFile
+        with BamFile(args.bam_fn) as bf:
+            if args.ctgName not in bf.references:
+                sys.exit("[ERROR] contig %s not in the header of %s" % (args.ctgName, args.bam_fn))
+            batch = bf.fetch(args.ctgName, s1, e1)
     C = P.CHANNEL_SIZE + (P.PHASED_CHANNEL_SIZE if args.enable_phasing_model else 0)
     eng = Engine(args.device, C, snp_min_af=args.snp_min_af, indel_min_af=args.indel_min_af,
                  min_coverage=args.minCoverage, min_mq=args.minMQ,

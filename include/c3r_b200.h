@@ -155,6 +155,36 @@ int c3r_forward(c3r_ctx* ctx, const int32_t* tensor, int64_t n, float* probs, fl
  * 2 = LSTM2 output, packed fp16; 3 = L4 output, fp32 [sites,128]).  Layouts in csrc/nn_tc.cuh. */
 int c3r_debug_fetch(c3r_ctx* ctx, int which, void* dst, int64_t max_bytes, int64_t* n_bytes);
 
+/* ------------------------------------------------------------------------------------------
+ * BAM / BGZF / BAI input (host side, zlib; csrc/bam_io.cpp).  The reference reads the BAM only
+ * through external samtools: `samtools mpileup BAM -r ctg:s-e ...` (src/create_tensor_pileup.py:
+ * 436-451) and `samtools idxstats BAM` (run_clair3_rna:187).  c3r_bam_fetch is the index fetch
+ * of that mpileup call: the records overlapping the 1-based inclusive region, in file order,
+ * as the flat arrays c3r_submit_chunk takes (flag / MAPQ filtering stays on the device).
+ * Buffers behind the returned c3r_reads belong to the handle and are valid until the next
+ * c3r_bam_fetch on it or c3r_bam_close.  A handle is not thread safe.                        */
+typedef struct c3r_bam c3r_bam;
+
+/* index_path NULL: <path>.bai, then <path minus .bam>.bai.  n_threads <= 0: all host cores
+ * (BGZF blocks are inflated in parallel).  *out is set even on failure (for c3r_bam_error). */
+int c3r_bam_open(const char* path, const char* index_path, int n_threads, c3r_bam** out);
+void c3r_bam_close(c3r_bam* bam);
+const char* c3r_bam_error(c3r_bam* bam);
+int c3r_bam_n_ref(c3r_bam* bam);
+const char* c3r_bam_ref_name(c3r_bam* bam, int tid);
+int64_t c3r_bam_ref_len(c3r_bam* bam, int tid);
+const char* c3r_bam_header_text(c3r_bam* bam);
+/* mapped / unmapped record counts of a reference from the index (samtools idxstats columns 3, 4) */
+int c3r_bam_idxstats(c3r_bam* bam, int tid, int64_t* n_mapped, int64_t* n_unmapped);
+int c3r_bam_fetch(c3r_bam* bam, int tid, int64_t start1, int64_t end1, c3r_reads* out);
+
+/* Writes a coordinate-sorted BAM and <path>.bai from flat records, batches[r] = records of
+ * reference r (NULL = none): fixtures for the reader and for the drop-in entry point (there is
+ * no samtools in the build image).  level: zlib level, -1 = default.  header_text NULL: minimal
+ * @HD/@SQ header.                                                                           */
+int c3r_bam_write(const char* path, int n_ref, const char* const* names, const int64_t* lens,
+                  const c3r_reads* const* batches, int level, const char* header_text);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,19 +23,22 @@ def _write_inputs(tmp, name):
     with open(fa + ".fai", "w") as fp:
         fp.write("%s\t%d\t%d\t60\t61\n" % (contig, len(ref_bytes), len(contig) + 2))
     batch.save(os.path.join(tmp, "reads.npz"))
+    from clair3_rna_b200 import bam
+    bam.write_bam(os.path.join(tmp, "reads.bam"), [(contig, len(ref_bytes))], {contig: batch})
     C = 30 if golden_cases.CASES[name]["phased"] else 18
     weights.save(os.path.join(tmp, "w.npz"), weights.synthetic(C, sharpen=8.0))
     return fa, contig
 
 
+@pytest.mark.parametrize("reads", ["reads.bam", "reads.npz"])
 @pytest.mark.parametrize("name", ["cfg1_ont_drna", "pad_dense", "phased_noisy"])
-def test_call_var_bam_vcf(tmp_path, name):
+def test_call_var_bam_vcf(tmp_path, name, reads):
     from clair3_rna_b200 import call_var_bam
     case = golden_cases.CASES[name]
     tmp = str(tmp_path)
     fa, contig = _write_inputs(tmp, name)
     out = os.path.join(tmp, "pileup_%s_1.vcf" % contig)
-    argv = ["--chkpnt_fn", os.path.join(tmp, "w.npz"), "--bam_fn", os.path.join(tmp, "reads.npz"), "--ref_fn", fa,
+    argv = ["--chkpnt_fn", os.path.join(tmp, "w.npz"), "--bam_fn", os.path.join(tmp, reads), "--ref_fn", fa,
             "--call_fn", out, "--ctgName", contig, "--chunk_id", "1", "--chunk_num", "1", "--platform", case["platform"],
             "--snp_min_af", str(case["snp_af"]), "--indel_min_af", str(case["indel_af"]), "--minMQ", str(case["min_mq"]),
             "--minCoverage", str(case["min_cov"]), "--pileup", "--sampleName", "S"]
