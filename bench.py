@@ -39,6 +39,19 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
 
 
+def measured_traffic(workload_name):
+    """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/), when it is of this workload"""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    z = json.load(open(p))
+    if z.get("workload") != workload_name:
+        return None, None
+    d = z["dram_bytes_per_launch"]
+    k5 = sum(v for k, v in d.items() if k.startswith("k_lstm_tc") or k in ("k_gemm_zx", "k_heads", "k_gemm_tc"))
+    return k5, d.get("k_count<18>")
+
+
 def dataset(cfg_idx, scale, contig_slot, cache_dir="/tmp/c3r_bench_cache"):
     """reads + reference of one contig; `contig_slot` varies the seed per rank."""
     import dataclasses
@@ -269,6 +282,7 @@ def main():
         pk = peaks()
         st = stage_acc / args.steps                              # ms per step per stage
         k5_ms, k2_ms = float(st[6]), float(st[3])
+        tr_k5, tr_k2 = measured_traffic(cfg.name) if args.scale == 1.0 else (None, None)
         flops = FLOP_PER_SITE[C] * n_cand
         ach_tf = flops / (k5_ms * 1e-3) / 1e12 if k5_ms > 0 else 0.0
         # count kernel algorithmic bytes: 0.5 B/aligned base + 16 B/segment entry + 4*C+8 B/row
@@ -289,9 +303,10 @@ def main():
                          "k3_filter": float(st[4]), "k4_window_alt(+host sync)": float(st[5]), "k5_network": k5_ms},
             "roofline": {"kernel": "k5 network (k_lstm_tc x2, k_gemm_tc x2, k_heads)", "bound": "tensor",
                          "achieved": ach_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sus"],
-                         "traffic": None, "peak_source": pk["src"] + " bf16 sustained"},
+                         "traffic": tr_k5, "traffic_source": "profiles/r1_traffic.json (ncu dram bytes, sum over the K5 kernels captured)" if tr_k5 else None,
+                         "peak_source": pk["src"] + " bf16 sustained"},
             "roofline_count": {"kernel": "k_count", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                               "frac": ach_gbs / pk["hbm"], "traffic": None, "algorithmic_bytes": k2_bytes,
+                               "frac": ach_gbs / pk["hbm"], "traffic": tr_k2, "algorithmic_bytes": k2_bytes,
                                "peak_source": pk["src"]},
         }
         if not args.no_cpu_baseline:
