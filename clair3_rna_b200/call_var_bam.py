@@ -81,9 +81,13 @@ def chunk_region(args, contig_len):
     return 1, contig_len + P.NO_OF_POSITIONS, 1, contig_len
 
 
-def call_chunk_to_rows(eng, batch, ref, ref_start1, start1, end1, contig, qual):
-    from .engine import alt_info_strings, flank_strings
+def call_chunk_to_rows(eng, batch, ref, ref_start1, start1, end1, contig, qual, native=True):
+    """GPU pass + decode.  native=True decodes through c3r_decode_vcf (C++, all host cores); native=False is
+    the per-candidate Python decoder the native one is checked against (tests/test_decode_native_cpu.py)."""
+    from .engine import alt_info_strings, flank_strings, decode_vcf_rows
     res = eng.call_chunk(batch, ref, ref_start1, start1, end1)
+    if native:
+        return decode_vcf_rows(res, batch, ref, ref_start1, contig, qual=qual), res
     alts = alt_info_strings(res, batch, ref, ref_start1)
     flanks = flank_strings(res, ref, ref_start1)
     rows = []

@@ -201,6 +201,38 @@ class Engine:
         return buf.view(np.float32).reshape(tiles * 128, 128)[:n_sites]
 
 
+# ---------------------------------------------------------------------- native decode
+def decode_vcf_rows(res: ChunkResult, batch: ReadBatch, ref: np.ndarray, ref_start1: int, contig: str,
+                    qual=P.QUAL_CUT_OFF, show_ref: bool = True, threads: int = 0) -> list:
+    """VCF data lines of every candidate through c3r_decode_vcf (csrc/decode.cpp): the native, multi-threaded
+    form of decoder.vcf_row over alt_info_strings / flank_strings."""
+    from .bam import reads_struct
+    lib = L.load()
+    keep = []
+    r = L.Result()
+    arrs = dict(pos=np.ascontiguousarray(res.pos, np.int32), depth=np.ascontiguousarray(res.depth, np.int32),
+                probs=np.ascontiguousarray(res.probs, np.float32), alt_off=np.ascontiguousarray(res.alt_off, np.int64),
+                alt_n=np.ascontiguousarray(res.alt_n, np.int32), alt=np.ascontiguousarray(res.alt))
+    r.n_rows, r.n_cand = res.n_rows, res.n_cand
+    for k, a in arrs.items():
+        setattr(r, k, a.ctypes.data if a.size else None)
+    rd = reads_struct(batch, keep)
+    ref = np.ascontiguousarray(ref, np.uint8)
+    text, nb, nr = C.c_void_p(), C.c_int64(0), C.c_int64(0)
+    rc = lib.c3r_decode_vcf(C.byref(r), C.byref(rd), ref.ctypes.data, int(ref_start1), int(ref.size), contig.encode(),
+                            -1.0 if qual is None else float(qual), int(show_ref), threads,
+                            C.byref(text), C.byref(nb), C.byref(nr))
+    if rc != 0:
+        raise C3RError("c3r_decode_vcf failed (rc=%d)" % rc)
+    try:
+        s = C.string_at(text, nb.value).decode("ascii") if nb.value else ""
+    finally:
+        lib.c3r_free_text(text)
+    rows = s.split("\n")[:-1] if s else []
+    assert len(rows) == nr.value
+    return rows
+
+
 # ---------------------------------------------------------------------- host formatting
 def alt_info_strings(res: ChunkResult, batch: ReadBatch, ref: np.ndarray, ref_start1: int) -> list:
     """alt_info text of each candidate exactly as the reference's producer prints it

@@ -44,7 +44,8 @@ class Result(C.Structure):
 EXPORTS = ["c3r_abi_version", "c3r_default_params", "c3r_create", "c3r_destroy", "c3r_last_error",
            "c3r_set_weights", "c3r_set_reference", "c3r_submit_chunk", "c3r_wait", "c3r_release", "c3r_rerun_resident", "c3r_forward", "c3r_debug_fetch",
            "c3r_bam_open", "c3r_bam_close", "c3r_bam_error", "c3r_bam_n_ref", "c3r_bam_ref_name", "c3r_bam_ref_len",
-           "c3r_bam_header_text", "c3r_bam_idxstats", "c3r_bam_fetch", "c3r_bam_write"]
+           "c3r_bam_header_text", "c3r_bam_idxstats", "c3r_bam_fetch", "c3r_bam_write",
+           "c3r_decode_vcf", "c3r_free_text"]
 
 _lib = None
 
@@ -91,5 +92,10 @@ def load():
     lib.c3r_bam_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.POINTER(Reads)]
     lib.c3r_bam_write.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64),
                                   C.POINTER(C.POINTER(Reads)), C.c_int, C.c_char_p]
+    lib.c3r_decode_vcf.argtypes = [C.POINTER(Result), C.POINTER(Reads), C.c_void_p, C.c_int64, C.c_int64, C.c_char_p,
+                                   C.c_double, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int64)]
+    lib.c3r_free_text.argtypes = [C.c_void_p]
+    lib.c3r_free_text.restype = None
     _lib = lib
     return lib

@@ -156,6 +156,21 @@ int c3r_forward(c3r_ctx* ctx, const int32_t* tensor, int64_t n, float* probs, fl
 int c3r_debug_fetch(c3r_ctx* ctx, int which, void* dst, int64_t max_bytes, int64_t* n_bytes);
 
 /* ------------------------------------------------------------------------------------------
+ * Probabilities + allele table -> VCF data lines (host, multi-threaded; csrc/decode.cpp).  Replaces the
+ * per-candidate Python of output_with / output_from (clair3_rna/call_variants.py:684-1392, options as
+ * forwarded by call_var_bam.py:247-272: --pileup --showRef, add_indel_length False).  One line per
+ * candidate of `res` in order ("CHROM POS . REF ALT QUAL FILTER . GT:GQ:DP:AD:AF ..."), candidates whose
+ * centre reference base is outside the IUPAC table are skipped (clair3_rna/utils.py:113).
+ *   reads: the records `res` was computed from (inserted bases are read from reads->seq)
+ *   ref / ref_start1 / ref_len: the reference window given to c3r_submit_chunk
+ *   qual_cut: --qual (2); < 0 disables the LowQual filter.  n_threads <= 0: all host cores.
+ * *text is malloc'ed, NUL terminated, *n_bytes long; release it with c3r_free_text.               */
+int c3r_decode_vcf(const c3r_result* res, const c3r_reads* reads, const uint8_t* ref, int64_t ref_start1,
+                   int64_t ref_len, const char* contig, double qual_cut, int show_ref, int n_threads,
+                   char** text, int64_t* n_bytes, int64_t* n_rows);
+void c3r_free_text(char* text);
+
+/* ------------------------------------------------------------------------------------------
  * BAM / BGZF / BAI input (host side, zlib; csrc/bam_io.cpp).  The reference reads the BAM only
  * through external samtools: `samtools mpileup BAM -r ctg:s-e ...` (src/create_tensor_pileup.py:
  * 436-451) and `samtools idxstats BAM` (run_clair3_rna:187).  c3r_bam_fetch is the index fetch
