@@ -49,9 +49,9 @@ struct Slot {
     Buf covA, covE, rowR, wdiff, word_base;
     // row space
     Buf row_pos, counts, row_depth, row_flag, head_cnt, tail_cnt, skipdiff, max_skip, row_ins, row_del;
-    Buf binc, bin_cur, entries, events;
+    Buf binc, bin_cur, events, raw, cov, cov_tile, refnib;
     Buf cand_row, cand_pos, cand_depth, tensor, alt_off, alt_n, alt, cur_ref, deleted, probs;
-    Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32)
+    Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32) [4] max read span (i64) [5] raw row events (i64)
     Buf scan_scratch;
     // pinned results
     Pin h_scalars, h_pos, h_depth, h_probs, h_alt_off, h_alt_n, h_alt, h_tensor, h_row_pos, h_counts, h_row_depth;
@@ -79,8 +79,8 @@ struct c3r_ctx {
     bool exact_bounds = false; // capacity bounds from an exact host pass over the CIGARs (retry path)
     bool tc_dirty = false;    // a tensor-core forward ran since the last device error check
     Buf thr;                  // allele-frequency threshold tables (k_thr_table)
-    int count_grid = 0;       // resident blocks of k_count
     Buf ref_res;              // resident reference window (c3r_set_reference)
+    Buf refnib_res;           // its one-hot nibble form (k_refnib)
     int64_t ref_res_start0 = 0, ref_res_len = 0;
     Buf fwd_in, fwd_out;      // c3r_forward staging
     cudaStream_t fwd_stream = nullptr;
@@ -153,16 +153,17 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     { OpRows op; op.d = d; L += device_scan(op, d.NW, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
     k_clear_rows<<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[2], st));
-    if (d.n_ops > 0) { k_bin<false><<<(unsigned)((d.n_ops + 255) / 256), 256, 0, st>>>(d); ++L; }
+    if (d.n_ops > 0) { k_cmp<<<(unsigned)((d.n_ops + CMP_THREADS - 1) / CMP_THREADS), CMP_THREADS, 0, st>>>(d); ++L; }
     if (d.padding) { OpSkip op; op.d = d; L += device_scan(op, d.L_ub, (Int2*)s.scan_scratch.p, (Int2*)nullptr, st); }
-    { OpTiles op; op.d = d; L += device_scan(op, d.NT_ub + 1, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
     { OpEvents op; op.d = d; L += device_scan(op, d.L_ub + 1, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
-    if (d.n_ops > 0) { k_bin<true><<<(unsigned)((d.n_ops + 255) / 256), 256, 0, st>>>(d); ++L; }
+    k_scatter<<<(unsigned)(ctx->sm_count * 32), 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[3], st));
     {
-        const unsigned grid = (unsigned)ctx->count_grid;
-        if (d.C == 18) k_count<18><<<grid, COUNT_WARPS * 32, 0, st>>>(d); else k_count<30><<<grid, COUNT_WARPS * 32, 0, st>>>(d);
-        ++L;
+        int64_t nb = (d.L_ub + COV_TILE - 1) / COV_TILE;
+        const unsigned grid = (unsigned)(nb < ctx->sm_count * 16 ? nb : ctx->sm_count * 16);
+        if (d.C == 18) { k_cov_aggr<4><<<1, 1024, 0, st>>>(d); k_rows<18><<<grid, ROWS_WARPS * 32, 0, st>>>(d); }
+        else { k_cov_aggr<6><<<1, 1024, 0, st>>>(d); k_rows<30><<<grid, ROWS_WARPS * 32, 0, st>>>(d); }
+        L += 2;
     }
     CK(cudaEventRecord(s.ev[4], st));
     { OpCand op; op.d = d; L += device_scan(op, d.L_ub, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
@@ -338,12 +339,6 @@ int c3r_create(c3r_ctx** out, int device_ordinal, const c3r_params* params) {
     k_thr_table<<<(THR_N + 255) / 256, 256>>>((uint16_t*)ctx->thr.p, (uint16_t*)ctx->thr.p + THR_N, params->snp_min_af, params->indel_min_af);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    {
-        int per_sm = 0;
-        if (params->channels == 18) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count<18>, COUNT_WARPS * 32, 0));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count<30>, COUNT_WARPS * 32, 0));
-        ctx->count_grid = ctx->sm_count * (per_sm > 0 ? per_sm : 1);
-    }
     return C3R_OK;
 }
 
@@ -356,7 +351,7 @@ void c3r_destroy(c3r_ctx* ctx) {
         Buf* bs[] = {&s.pos, &s.flag, &s.mapq, &s.hp, &s.cigar_off, &s.cigar, &s.seq_off, &s.seq, &s.ref, &s.admit,
                      &s.read_end, &s.op_head, &s.op_x, &s.op_y, &s.op_rid, &s.covA, &s.covE, &s.rowR, &s.wdiff,
                      &s.word_base, &s.row_pos, &s.counts, &s.row_depth, &s.row_flag, &s.head_cnt, &s.tail_cnt,
-                     &s.skipdiff, &s.max_skip, &s.row_ins, &s.row_del, &s.binc, &s.bin_cur, &s.entries, &s.events,
+                     &s.skipdiff, &s.max_skip, &s.row_ins, &s.row_del, &s.binc, &s.bin_cur, &s.events, &s.raw, &s.cov, &s.cov_tile, &s.refnib,
                      &s.cand_row, &s.cand_pos, &s.cand_depth, &s.tensor, &s.alt_off, &s.alt_n, &s.alt, &s.cur_ref,
                      &s.deleted, &s.probs, &s.scalars, &s.scan_scratch};
         for (Buf* b : bs) release(*b);
@@ -371,6 +366,7 @@ void c3r_destroy(c3r_ctx* ctx) {
     release(ctx->nn_scratch);
     release(ctx->fwd_in);
     release(ctx->ref_res);
+    release(ctx->refnib_res);
     release(ctx->thr);
     release(ctx->fwd_out);
     tc_release(ctx->tc);
@@ -396,6 +392,11 @@ int c3r_set_reference(c3r_ctx* ctx, const uint8_t* ref, int64_t ref_start1, int6
     CK(cudaMemcpy(ctx->ref_res.p, ref, (size_t)ref_len, cudaMemcpyHostToDevice));
     ctx->ref_res_start0 = ref_start1 - 1;
     ctx->ref_res_len = ref_len;
+    const int64_t nw = (ref_len + 7) / 8;
+    if (ensure(ctx, ctx->refnib_res, (size_t)nw * 4)) return C3R_ERR_CUDA;
+    k_refnib<<<(unsigned)((nw + 255) / 256), 256>>>((const uint8_t*)ctx->ref_res.p, ref_len, (uint32_t*)ctx->refnib_res.p, nw);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
     return C3R_OK;
 }
 
@@ -438,7 +439,6 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     memset(&d, 0, sizeof d);
     const c3r_params& pr = ctx->prm;
     d.n_reads = rd->n_reads; d.n_ops = rd->n_ops;
-    d.n_seq_words = (rd->n_seq_bytes + 32) / 4;
     d.R0 = (int32_t)(region_start1 - 1); d.R1 = (int32_t)region_end1;
     d.W = (int64_t)d.R1 - d.R0; d.NW = (d.W + 31) / 32;
     d.C = pr.channels; d.min_cov = pr.min_coverage; d.min_mq = pr.min_mq; d.excl = pr.excl_flags;
@@ -452,26 +452,27 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     // bounds below avoid a host pass over the CIGARs (M bases <= SEQ bases; deletions are assumed
     // not to outnumber the sequenced bases); if a chunk breaks that assumption the device-side
     // capacity checks fire and the caller-visible retry in this function uses the exact pass.
-    int64_t md_len = 0, n_skip = 0, ent_ub = 0, ev_ub = 0;
+    // Row events = indel tokens (<= ops) + read bases that differ from the reference: sized for one base in
+    // four on the first attempt, for every base on the retry.
+    int64_t md_len = 0, n_skip = 0, ev_ub = 0;
     if (ctx->exact_bounds) {
         for (int64_t k = 0; k < rd->n_ops; ++k) {
             const uint32_t c = rd->cigar[k], op = c & 15u;
             const int64_t len = c >> 4;
-            if (op == 0 || op == 2 || op == 7 || op == 8) { md_len += len; ent_ub += len / 32 + 2; }
+            if (op == 0 || op == 2 || op == 7 || op == 8) md_len += len;
             if (op == 3) ++n_skip;
-            if (op == 1 || op == 2) ++ev_ub;
         }
+        ev_ub = rd->n_ops + 2 * rd->n_seq_bytes;
     } else {
         md_len = 4 * rd->n_seq_bytes;
         n_skip = rd->n_ops;
-        ent_ub = md_len / 32 + 2 * rd->n_ops;
-        ev_ub = rd->n_ops;
+        ev_ub = rd->n_ops + rd->n_seq_bytes / 2;
     }
     int64_t L_ub = md_len + 32 * (n_skip + rd->n_reads) + 64;
     if (L_ub > d.W) L_ub = d.W;
     if (L_ub < 64) L_ub = 64;
-    d.L_ub = L_ub; d.NT_ub = (L_ub + 31) / 32 + 1;
-    d.entries_ub = ent_ub + 8; d.events_ub = ev_ub + 8;
+    d.L_ub = L_ub;
+    d.events_ub = ev_ub + 8;
     d.cand_cap = L_ub;
     const int64_t R = rd->n_reads > 0 ? rd->n_reads : 1, O = rd->n_ops > 0 ? rd->n_ops : 1;
 #define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
@@ -483,13 +484,15 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     EN(row_pos, (L_ub + 2) * 4); EN(counts, ((L_ub + 32) * d.C) * 4); EN(row_depth, (L_ub + 2) * 4); EN(row_flag, L_ub + 2);
     EN(head_cnt, (L_ub + 2) * 4); EN(tail_cnt, (L_ub + 2) * 4); EN(skipdiff, (L_ub + 2) * 8); EN(max_skip, (L_ub + 2) * 4);
     EN(row_ins, (L_ub + 2) * 4); EN(row_del, (L_ub + 2) * 4);
-    EN(binc, (d.NT_ub + L_ub + 4) * 4); EN(bin_cur, (d.NT_ub + L_ub + 4) * 4);
-    EN(entries, d.entries_ub * sizeof(SegEntry)); EN(events, d.events_ub * sizeof(IndelEvent));
+    EN(binc, (L_ub + 4) * 4); EN(bin_cur, (L_ub + 4) * 4);
+    EN(events, d.events_ub * sizeof(RowEvent)); EN(raw, d.events_ub * sizeof(RowEvent));
+    EN(cov, (L_ub + 4) * NCOV_MAX * 4); EN(cov_tile, (L_ub / COV_TILE + 4) * NCOV_MAX * 4);
+    if (ref) { EN(refnib, ((ref_len + 7) / 8 + 1) * 4); }
     EN(cand_row, (L_ub + 2) * 4); EN(cand_pos, (L_ub + 2) * 4); EN(cand_depth, (L_ub + 2) * 4);
     EN(cur_ref, (L_ub + 2) * 8); EN(deleted, L_ub + 2);
     {
         int64_t mx = d.n_ops > d.NW ? d.n_ops : d.NW;
-        if (d.NT_ub + L_ub + 4 > mx) mx = d.NT_ub + L_ub + 4;
+        if (L_ub + 4 > mx) mx = L_ub + 4;
         EN(scan_scratch, (mx / SCAN_TILE + 2) * sizeof(ScanElem));
     }
 #undef EN
@@ -505,8 +508,12 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.row_flag = P<uint8_t>(s.row_flag); d.head_cnt = P<int32_t>(s.head_cnt); d.tail_cnt = P<int32_t>(s.tail_cnt);
     d.skipdiff = P<Int2>(s.skipdiff); d.max_skip = P<int32_t>(s.max_skip);
     d.row_inscnt = P<int32_t>(s.row_ins); d.row_delcnt = P<int32_t>(s.row_del);
-    d.binc = P<int32_t>(s.binc); d.bin_cur = P<int32_t>(s.bin_cur); d.entries = P<SegEntry>(s.entries);
-    d.events = P<IndelEvent>(s.events);
+    d.binc = P<int32_t>(s.binc); d.bin_cur = P<int32_t>(s.bin_cur);
+    d.events = P<RowEvent>(s.events); d.raw = P<RowEvent>(s.raw); d.cov = P<int32_t>(s.cov); d.cov_tile = P<int32_t>(s.cov_tile);
+    d.n_raw = P<int64_t>(s.scalars) + 5;
+    d.refnib = ref ? P<uint32_t>(s.refnib) : P<uint32_t>(ctx->refnib_res);
+    d.n_ref_words = (ref_len + 7) / 8;
+    d.max_span = P<int64_t>(s.scalars) + 4;
     d.cand_row = P<int32_t>(s.cand_row); d.cand_pos = P<int32_t>(s.cand_pos); d.cand_depth = P<int32_t>(s.cand_depth);
     d.cur_ref = P<Int2>(s.cur_ref); d.deleted = P<uint8_t>(s.deleted);
 
@@ -522,7 +529,12 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     }
     if (rd->n_ops > 0) CK(cudaMemcpyAsync(s.cigar.p, rd->cigar, rd->n_ops * 4, cudaMemcpyHostToDevice, st));
     if (rd->n_seq_bytes > 0) CK(cudaMemcpyAsync(s.seq.p, rd->seq, rd->n_seq_bytes, cudaMemcpyHostToDevice, st));
-    if (ref && ref_len > 0) CK(cudaMemcpyAsync(s.ref.p, ref, ref_len, cudaMemcpyHostToDevice, st));
+    if (ref && ref_len > 0) {
+        CK(cudaMemcpyAsync(s.ref.p, ref, ref_len, cudaMemcpyHostToDevice, st));
+        const int64_t nw = (ref_len + 7) / 8;
+        k_refnib<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>((const uint8_t*)s.ref.p, ref_len, (uint32_t*)s.refnib.p, nw);
+        ++s.launches;
+    }
     s.in_use = true;
     int rc = run_stage_a(ctx, s);
     if (!rc) rc = read_scalars(ctx, s);

@@ -16,8 +16,8 @@
 //       word_base[w] = rank of the first row of word w  (row(p) = word_base + popc(bits below p))
 //   row space  L rows (device-side count), rows of consecutive positions are consecutive
 //       counts[L][C] int32, row_pos[L], row_depth[L], row_flag[L], max_skip[L]
-//   bins   32-row tiles; tile_entries = M/D segments overlapping the tile (16 B each);
-//          ev = indel events in CSR by row (16 B each)
+//       cov[L][4|6] coverage difference rows (per strand M and D coverage, M coverage per haplotype)
+//   row events (CSR by row, 16 B each): read bases that differ from the reference, and indel tokens
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -29,18 +29,12 @@ constexpr int WIN = 33;
 constexpr int FLANK = 16;
 constexpr int TILE_ROWS = 32;
 
-struct SegEntry {              // an M/=/X or D op clipped to nothing: lanes test coverage themselves
-    int32_t x;                 // reference start (0-based)
-    int32_t len;               // reference length of an M/=/X op; 0 for a deletion
-    uint32_t yx;               // M/=/X: query start - x (mod 2^32), base index of position p is yx + p; D: its length
-    uint32_t info;             // rid << 4 | deletion (`*`/`#`) << 3 | hp(2 bits) << 1 | reverse
-};
-
-struct IndelEvent {
+struct RowEvent {              // something other than "a base equal to the reference" at a row
     uint32_t info;             // rid << 4 | hp << 2 | is_del << 1 | reverse
-    int32_t len;
-    uint32_t y;                // insertion: base index of inserted bases
-    uint32_t pad;
+    int32_t len;               // > 0: indel token of that length;  0: a read base that differs from the reference
+    uint32_t yb;               // indel: base index of the inserted bases;  mismatch: 0..3 = A,C,G,T, 4 = N / ambiguity
+                               // code (counts nothing, but is not the reference base)
+    int32_t row;
 };
 
 struct AltEntry {              // mirrors c3r_alt_entry
@@ -65,7 +59,6 @@ struct Dev {
     int64_t n_reads, n_ops;
     const int32_t* pos; const uint16_t* flag; const uint8_t* mapq; const uint8_t* hp;
     const int32_t* cigar_off; const uint32_t* cigar; const int64_t* seq_off; const uint8_t* seq;
-    int64_t n_seq_words;          // readable 32-bit words of the sequence buffer (incl. the slack after the last read)
     const uint8_t* ref; int64_t ref_start0; int64_t ref_len;
     int32_t R0, R1; int64_t W; int64_t NW;            // region (0-based half open), words
     // ---- params
@@ -78,14 +71,19 @@ struct Dev {
     // ---- position space
     uint32_t* covA; uint32_t* covE; uint32_t* rowR; Int2* wdiff; int32_t* word_base;
     // ---- row space
-    int64_t L_ub; int64_t NT_ub;
+    int64_t L_ub;
     int64_t* n_rows;            // device scalar L
     int32_t* row_pos; int32_t* counts; int32_t* row_depth; uint8_t* row_flag;
     int32_t* head_cnt; int32_t* tail_cnt; Int2* skipdiff; int32_t* max_skip;
     int32_t* row_inscnt; int32_t* row_delcnt;
-    // ---- bins: binc = [tile counts (NT_ub+1)] [event counts (L_ub+1)]
-    int32_t* binc; int32_t* bin_cur; SegEntry* entries; IndelEvent* events;
-    int64_t entries_ub, events_ub;
+    // ---- row events (CSR by row): binc = event counts, then offsets (L_ub+2); cov = coverage difference rows
+    int32_t* binc; int32_t* bin_cur; RowEvent* events;
+    RowEvent* raw; int64_t* n_raw; // events in discovery order (k_cmp) before the counting sort (k_scatter)
+    int64_t events_ub;
+    int32_t* cov;                  // [L_ub+2][4 or 6]: Mf Mr Df Dr [M_hp1 M_hp2]
+    int32_t* cov_tile;             // [L_ub/256+2][4 or 6]: sums of cov over tiles of 256 rows, then their exclusive prefix
+    const uint32_t* refnib; int64_t n_ref_words;     // one-hot reference nibbles of the loaded window (k_refnib)
+    int64_t* max_span;             // device scalar: longest reference span of an admitted read
     // ---- candidates
     int64_t* n_cand; int32_t* cand_row; int64_t cand_cap;
     int32_t* cand_pos; int32_t* cand_depth;
@@ -198,6 +196,8 @@ struct OpCigar {
         if (k + 1 == d.cigar_off[r + 1]) {          // last op: the read's whole span
             const int32_t end = d.pos[r] + (int32_t)(incl.v >> 32);
             d.read_end[r] = end;
+            if ((long long)(incl.v >> 32) > *(volatile long long*)d.max_span)      // few reads raise the maximum
+                atomicMax((unsigned long long*)d.max_span, (unsigned long long)(incl.v >> 32));
             int64_t a = (int64_t)d.pos[r] - d.R0, b = (int64_t)end - d.R0;
             if (a < 0) a = 0;
             if (b > d.W) b = d.W;
@@ -263,137 +263,267 @@ struct OpRows {
     }
 };
 
-// --------------------------------------------------- bins: count / fill pass
-// One thread per CIGAR op.  FILL=false counts tile entries and events, FILL=true writes them.
-template <bool FILL>
-__global__ void k_bin(Dev d) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= d.n_ops) return;
-    const int32_t r = d.op_rid[k];
-    if (r < 0 || !d.admit[r]) return;
-    const uint32_t c = d.cigar[k];
-    const uint32_t op = c & 15u;
-    const int32_t len = (int32_t)(c >> 4);
-    if (!op_consumes_ref(op) || len == 0) return;
-    const int32_t x = d.op_x[k];
-    const uint32_t rev = (d.flag[r] >> 4) & 1u;
-    uint32_t hp = d.hp[r];
-    hp = hp == 1 ? 1u : hp == 2 ? 2u : 0u;
-    int32_t a = x < d.R0 ? d.R0 : x;
-    int32_t b = x + len > d.R1 ? d.R1 : x + len;
-    int32_t* tile_cnt = d.binc;
-    int32_t* ev_cnt = d.binc + d.NT_ub + 1;
+__device__ __forceinline__ uint32_t nibmask(int n) {         // low n nibbles set, n clamped to 0..8
+    uint32_t m;                                              // shl.b32 clamps the shift amount: 1 << 32 == 0
+    asm("shl.b32 %0, 1, %1;" : "=r"(m) : "r"((uint32_t)(n < 0 ? 0 : 4 * n)));
+    return m - 1u;
+}
 
-    if (op == 3) {                                   // N: `>` / `<` over [a, b)
-        if (d.padding && b > a) {
-            const int32_t ra = row_lower_bound(d, a), rb = row_lower_bound(d, b);
-            if (!FILL && rb > ra) {
-                int32_t* f = rev ? &d.skipdiff[0].b : &d.skipdiff[0].a;
-                atomicAdd(&f[2 * (int64_t)ra], 1);
-                atomicAdd(&f[2 * (int64_t)rb], -1);
+// ------------------------------------------------ reference as one-hot nibbles
+// refnib: one 4-bit code per reference position of the loaded window (A=1, C=2, G=4, T=8 like BAM's
+// nt16, anything else 0), position i of the window at bits 4*(i&7) of word i>>3.  Built once per
+// reference window; read bases are compared against it eight at a time.
+__global__ void k_refnib(const uint8_t* __restrict__ ref, int64_t ref_len, uint32_t* __restrict__ out, int64_t n_words) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int64_t o = w * 8 + j;
+        uint8_t c = o < ref_len ? ref[o] : (uint8_t)'N';
+        if (c >= 'a') c -= 32;
+        const uint32_t nib = c == 'A' ? 1u : c == 'C' ? 2u : c == 'G' ? 4u : c == 'T' ? 8u : 0u;
+        v |= nib << (4 * j);
+    }
+    out[w] = v;
+}
+
+// --------------------------------------------------- row events: compare pass
+// K2 counts relative to the reference: a read base that equals the reference base leaves no trace of
+// its own; it is accounted for by the per-strand coverage of its op (a +1/-1 pair in the row-space
+// difference array `cov`, prefix-summed in k_rows).  Only bases that differ from the reference (1-3 % of
+// them), N / ambiguity codes, and the indel tokens become *row events*.
+//   ref-base count of a row = coverage - mismatch events;  other bases = their mismatch events.
+// k_cmp: one thread per CIGAR op for the bookkeeping; the sequence words of a warp's 32 ops are then dealt
+// out to its lanes one word each.  Read bases are compared 8 at a time (one 32-bit word of nt16 nibbles against the one-hot reference
+// nibbles, funnel-shifted into register).  Events are staged in shared memory and appended to the raw
+// list with one global atomic per block; k_scatter then counting-sorts them by row (CSR).
+constexpr int NCOV_MAX = 6;                  // Mf Mr Df Dr [M_hp1 M_hp2]
+constexpr int CMP_THREADS = 256;
+constexpr int CMP_STAGE = 1536;              // events staged per block (24 KB)
+constexpr int COV_TILE = 256;                // rows per k_rows block / coverage aggregate
+
+struct CmpOp {                               // an M/=/X op clipped to the region
+    int32_t w0, w1;                          // sequence words [w0, w1] holding its bases
+    int32_t lo, hi;                          // first base inside w0, one past the last base inside w1 (0..8)
+    int64_t kw;                              // reference-nibble word of sequence word w: w + kw
+    uint32_t sh;                             // funnel shift (bits) between the two
+    int32_t rbase;                           // row of base 8*w + j: rbase + 8*w + j
+    uint32_t info;                           // rid << 4 | hp << 2 | rev   (is_del bit clear)
+};
+
+struct EventStage {
+    RowEvent buf[CMP_STAGE];
+    int n;
+    int base;
+};
+
+__device__ __forceinline__ void emit_event(const Dev& d, EventStage& st, int32_t row, uint32_t info, int32_t len, uint32_t yb) {
+    RowEvent e;
+    e.info = info; e.len = len; e.yb = yb; e.row = row;
+    const int i = atomicAdd(&st.n, 1);
+    if (i < CMP_STAGE) { st.buf[i] = e; return; }
+    const long long slot = (long long)atomicAdd((unsigned long long*)d.n_raw, 1ull);     // stage full: straight to the list
+    if (slot < d.events_ub) { d.raw[slot] = e; atomicAdd(&d.binc[row], 1); } else atomicExch(d.err, 3);
+}
+
+__device__ __forceinline__ void cmp_emit(const Dev& d, EventStage& st, const CmpOp& c, int32_t w, uint32_t rw, uint32_t x) {
+    while (x) {
+        const int j = (__ffs(x) - 1) >> 2;
+        x &= ~(0xfu << (4 * j));
+        const uint32_t nib = (rw >> (4 * j)) & 15u;
+        const uint32_t code = nib == 1 ? 0u : nib == 2 ? 1u : nib == 4 ? 2u : nib == 8 ? 3u : 4u;
+        emit_event(d, st, c.rbase + 8 * w + j, c.info, 0, code);
+    }
+}
+
+// sequence word w (8 bases) of one op against the reference
+__device__ __forceinline__ void cmp_one(const Dev& d, EventStage& st, const CmpOp& c, int32_t w) {
+    uint32_t rw = ((const uint32_t*)d.seq)[w];
+    rw = ((rw & 0x0f0f0f0fu) << 4) | ((rw >> 4) & 0x0f0f0f0fu);              // base j of the word at bits 4j..4j+3
+    const int64_t wi = w + c.kw;
+    const uint32_t f0 = (wi >= 0 && wi < d.n_ref_words) ? d.refnib[wi] : 0u;
+    const uint32_t f1 = (wi + 1 >= 0 && wi + 1 < d.n_ref_words) ? d.refnib[wi + 1] : 0u;
+    uint32_t x = rw ^ __funnelshift_r(f0, f1, c.sh);
+    if (w == c.w0) x &= ~nibmask(c.lo);
+    if (w == c.w1) x &= nibmask(c.hi);
+    if (x) cmp_emit(d, st, c, w, rw, x);
+}
+
+__global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
+    __shared__ EventStage st;
+    __shared__ CmpOp wops[CMP_THREADS / 32][32];         // the warp's ops, so that any lane can take any word
+    __shared__ int32_t wpre[CMP_THREADS / 32][32];       // exclusive prefix of their word counts
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int NC = d.C == 30 ? 6 : 4;
+    if (threadIdx.x == 0) st.n = 0;
+    __syncthreads();
+    CmpOp cmp;
+    cmp.w0 = 0; cmp.w1 = -1; cmp.lo = 0; cmp.hi = 8; cmp.kw = 0; cmp.sh = 0; cmp.rbase = 0; cmp.info = 0;
+    do {
+        if (k >= d.n_ops) break;
+        const int32_t r = d.op_rid[k];
+        if (r < 0 || !d.admit[r]) break;
+        const uint32_t c = d.cigar[k];
+        const uint32_t op = c & 15u;
+        const int32_t len = (int32_t)(c >> 4);
+        if (!op_consumes_ref(op) || len == 0) break;
+        const int32_t x = d.op_x[k];
+        const uint32_t rev = (d.flag[r] >> 4) & 1u;
+        uint32_t hp = d.hp[r];
+        hp = hp == 1 ? 1u : hp == 2 ? 2u : 0u;
+        const int32_t a = x < d.R0 ? d.R0 : x;
+        const int32_t b = x + len > d.R1 ? d.R1 : x + len;
+
+        if (op == 3) {                                   // N: `>` / `<` over [a, b)
+            if (d.padding && b > a) {
+                const int32_t ra = row_lower_bound(d, a), rb = row_lower_bound(d, b);
+                if (rb > ra) {
+                    int32_t* f = rev ? &d.skipdiff[0].b : &d.skipdiff[0].a;
+                    atomicAdd(&f[2 * (int64_t)ra], 1);
+                    atomicAdd(&f[2 * (int64_t)rb], -1);
+                }
+            }
+            break;
+        }
+        if (b > a) {                                     // M/=/X or D segment: rows ra .. ra + (b - a) - 1 are consecutive
+            const int32_t ra = row_lower_bound(d, a), rb = ra + (b - a);
+            const int ch = (op == 2 ? 2 : 0) + (int)rev;
+            atomicAdd(d.cov + (int64_t)ra * NC + ch, 1);
+            atomicAdd(d.cov + (int64_t)rb * NC + ch, -1);
+            const bool hpc = NC == 6 && op != 2 && hp;
+            if (hpc) { atomicAdd(d.cov + (int64_t)ra * NC + 3 + hp, 1); atomicAdd(d.cov + (int64_t)rb * NC + 3 + hp, -1); }
+            if (ra / COV_TILE != rb / COV_TILE) {        // the pair straddles coverage tiles: keep the tile sums right
+                atomicAdd(d.cov_tile + (int64_t)(ra / COV_TILE) * NC + ch, 1);
+                atomicAdd(d.cov_tile + (int64_t)(rb / COV_TILE) * NC + ch, -1);
+                if (hpc) {
+                    atomicAdd(d.cov_tile + (int64_t)(ra / COV_TILE) * NC + 3 + hp, 1);
+                    atomicAdd(d.cov_tile + (int64_t)(rb / COV_TILE) * NC + 3 + hp, -1);
+                }
+            }
+            if (op != 2) {
+                const int64_t qa = (int64_t)d.op_y[k] + (a - x);             // base index of position a
+                const int64_t qb = qa + (b - a);
+                cmp.w0 = (int32_t)(qa >> 3); cmp.w1 = (int32_t)((qb - 1) >> 3);
+                cmp.lo = (int)(qa & 7); cmp.hi = (int)(qb - 8 * (int64_t)cmp.w1);
+                const int64_t K = ((int64_t)a - d.ref_start0) - qa;          // reference offset of base q: q + K
+                cmp.kw = K >> 3;
+                cmp.sh = ((uint32_t)K & 7u) * 4u;
+                cmp.rbase = (int32_t)((int64_t)ra - qa);
+                cmp.info = ((uint32_t)r << 4) | (hp << 2) | rev;
             }
         }
-    } else if (b > a) {                              // M/=/X or D segment
-        const int32_t ra = row_lower_bound(d, a);
-        const int32_t rb = ra + (b - a) - 1;
-        for (int32_t t = ra >> 5; t <= (rb >> 5); ++t) {
-            if (!FILL) {
-                atomicAdd(&tile_cnt[t], 1);
-            } else {
-                const int32_t slot = tile_cnt[t] + atomicAdd(&d.bin_cur[t], 1);
-                SegEntry e;
-                e.x = x;
-                e.len = op == 2 ? 0 : len;
-                e.yx = op == 2 ? (uint32_t)len : d.op_y[k] - (uint32_t)x;
-                e.info = ((uint32_t)r << 4) | (op == 2 ? 8u : 0u) | (hp << 1) | rev;
-                if (slot < d.entries_ub) d.entries[slot] = e; else atomicExch(d.err, 2);
+        // head / tail marks (only consumed by the padding rule)
+        if (d.padding) {
+            if (x == d.pos[r] && x >= d.R0 && x < d.R1) {
+                bool first = true;                       // first reference-consuming op of the read
+                for (int32_t j = d.cigar_off[r]; j < k; ++j)
+                    if (op_consumes_ref(d.cigar[j] & 15u) && (d.cigar[j] >> 4)) first = false;
+                if (first) atomicAdd(&d.head_cnt[row_lower_bound(d, x)], 1);
+            }
+            const int32_t end = d.read_end[r];
+            if (x + len == end && end - 1 >= d.R0 && end - 1 < d.R1)
+                atomicAdd(&d.tail_cnt[row_lower_bound(d, end - 1)], 1);
+        }
+        // indel tokens attach to the last column of an M/=/X/D op (htslib resolve_cigar2)
+        const int32_t last = x + len - 1;
+        if (last < d.R0 || last >= d.R1) break;
+        const int32_t kend = d.cigar_off[r + 1];
+        int64_t j = k + 1;
+        if (j >= kend) break;
+        int32_t ins_len = 0, del_len = 0;
+        const uint32_t op2 = d.cigar[j] & 15u;
+        if (op2 == 1) {
+            for (; j < kend; ++j) {
+                const uint32_t o = d.cigar[j] & 15u;
+                if (o == 1) ins_len += (int32_t)(d.cigar[j] >> 4);
+                else if (o != 6) break;
             }
         }
-    }
-    // head / tail marks (only consumed by the padding rule)
-    if (d.padding && !FILL) {
-        if (x == d.pos[r] && x >= d.R0 && x < d.R1 && op != 3) {
-            // first reference-consuming op of the read
-            bool first = true;
-            for (int32_t j = d.cigar_off[r]; j < k; ++j)
-                if (op_consumes_ref(d.cigar[j] & 15u) && (d.cigar[j] >> 4)) first = false;
-            if (first) atomicAdd(&d.head_cnt[row_lower_bound(d, x)], 1);
+        if (j < kend && (d.cigar[j] & 15u) == 2 && op != 2) {
+            for (; j < kend; ++j) {
+                if ((d.cigar[j] & 15u) == 2) del_len += (int32_t)(d.cigar[j] >> 4);
+                else break;
+            }
         }
-        const int32_t end = d.read_end[r];
-        if (x + len == end && end - 1 >= d.R0 && end - 1 < d.R1 && op != 3)
-            atomicAdd(&d.tail_cnt[row_lower_bound(d, end - 1)], 1);
-    }
-    // indel tokens attach to the last column of an M/=/X/D op (htslib resolve_cigar2)
-    if (op == 3) return;
-    const int32_t last = x + len - 1;
-    if (last < d.R0 || last >= d.R1) return;
-    const int32_t kend = d.cigar_off[r + 1];
-    int64_t j = k + 1;
-    if (j >= kend) return;
-    int32_t ins_len = 0, del_len = 0;
-    uint32_t op2 = d.cigar[j] & 15u;
-    if (op2 == 1) {
-        for (; j < kend; ++j) {
-            const uint32_t o = d.cigar[j] & 15u;
-            if (o == 1) ins_len += (int32_t)(d.cigar[j] >> 4);
-            else if (o != 6) break;
-        }
-    }
-    if (j < kend && (d.cigar[j] & 15u) == 2 && op != 2) {
-        for (; j < kend; ++j) {
-            if ((d.cigar[j] & 15u) == 2) del_len += (int32_t)(d.cigar[j] >> 4);
-            else break;
-        }
-    }
-    if (!ins_len && !del_len) return;
-    const int32_t row = row_lower_bound(d, last);
-    for (int which = 0; which < 2; ++which) {
-        const int32_t l = which ? del_len : ins_len;
-        if (!l) continue;
-        if (!FILL) {
-            atomicAdd(&ev_cnt[row], 1);
-        } else {
-            const int64_t base = (int64_t)ev_cnt[row] - ev_cnt[0];
-            const int32_t slot = (int32_t)base + atomicAdd(&d.bin_cur[d.NT_ub + 1 + row], 1);
-            IndelEvent e;
-            e.info = ((uint32_t)r << 4) | (hp << 2) | ((uint32_t)which << 1) | rev;
-            e.len = l;
+        if (!ins_len && !del_len) break;
+        const int32_t row = row_lower_bound(d, last);
+        for (int which = 0; which < 2; ++which) {
+            const int32_t l = which ? del_len : ins_len;
+            if (!l) continue;
             // inserted bases start right after this op's query bases (M) or at its query position (D)
-            e.y = d.op_y[k] + (op_is_match(op) ? (uint32_t)len : 0u);
-            e.pad = 0;
-            if (slot < d.events_ub) d.events[slot] = e; else atomicExch(d.err, 3);
+            emit_event(d, st, row, ((uint32_t)r << 4) | (hp << 2) | ((uint32_t)which << 1) | rev, l,
+                       d.op_y[k] + (op_is_match(op) ? (uint32_t)len : 0u));
+        }
+    } while (0);
+
+    // ---- read bases against the reference: the words of the warp's 32 ops are dealt out lane by lane, so lanes
+    // stay busy whatever the op lengths (M ops of 3 bases next to HiFi matches of kilobases)
+    {
+        const int warp = threadIdx.x >> 5;
+        const int32_t cnt = cmp.w1 - cmp.w0 + 1;         // 0 for everything that is not an M/=/X op
+        int32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const int32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        wops[warp][lane] = cmp;
+        wpre[warp][lane] = incl - cnt;
+        __syncwarp();
+        for (int32_t g = lane; g < total; g += 32) {
+            int i = 0;                                   // last op whose prefix is <= g (ops without words share a prefix
+#pragma unroll                                           // with their successor, so the last one is the owner)
+            for (int stp = 16; stp > 0; stp >>= 1) if (wpre[warp][i + stp] <= g) i += stp;
+            const CmpOp c = wops[warp][i];
+            cmp_one(d, st, c, c.w0 + (g - wpre[warp][i]));
+        }
+    }
+    // ---- staged events -> raw list (one global atomic per block), per-row counters
+    __syncthreads();
+    const int n = st.n < CMP_STAGE ? st.n : CMP_STAGE;
+    if (threadIdx.x == 0 && n > 0) st.base = (int)atomicAdd((unsigned long long*)d.n_raw, (unsigned long long)n);
+    __syncthreads();
+    if (n > 0) {
+        const long long base = st.base;
+        if (base + n > d.events_ub) { if (threadIdx.x == 0) atomicExch(d.err, 3); return; }
+        for (int i = threadIdx.x; i < n; i += CMP_THREADS) {
+            const RowEvent e = st.buf[i];
+            d.raw[base + i] = e;
+            atomicAdd(&d.binc[e.row], 1);
         }
     }
 }
 
-// exclusive scans of the bin counters in place; sizes come from the device-side row count
-struct OpTiles {
-    typedef int32_t T;
-    Dev d;
-    __device__ T identity() const { return 0; }
-    __device__ T combine(const T& x, const T& y) const { return x + y; }
-    __device__ int64_t size() const { return (*d.n_rows + TILE_ROWS - 1) / TILE_ROWS + 1; }
-    __device__ T load(int64_t i) const { return d.binc[i]; }
-    __device__ void store(int64_t i, const T& incl, const T& own) const { d.binc[i] = incl - own; }
-};
+// exclusive scan of the per-row event counters in place
 struct OpEvents {
     typedef int32_t T;
     Dev d;
     __device__ T identity() const { return 0; }
     __device__ T combine(const T& x, const T& y) const { return x + y; }
     __device__ int64_t size() const { return *d.n_rows + 1; }
-    __device__ T load(int64_t i) const { return d.binc[d.NT_ub + 1 + i]; }
-    __device__ void store(int64_t i, const T& incl, const T& own) const { d.binc[d.NT_ub + 1 + i] = incl - own; }
+    __device__ T load(int64_t i) const { return d.binc[i]; }
+    __device__ void store(int64_t i, const T& incl, const T& own) const { d.binc[i] = incl - own; }
 };
+// raw events -> CSR by row
+__global__ void k_scatter(Dev d) {
+    const int64_t n = *d.n_raw < d.events_ub ? *d.n_raw : d.events_ub;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const RowEvent e = d.raw[i];
+        const int64_t slot = (int64_t)d.binc[e.row] - d.binc[0] + atomicAdd(&d.bin_cur[e.row], 1);
+        d.events[slot] = e;
+    }
+}
 // zero the live part of the row-space accumulators once the row count is known
 __global__ void k_clear_rows(Dev d) {
     const int64_t L = *d.n_rows;
-    const int64_t nt = (L + TILE_ROWS - 1) / TILE_ROWS + 1;
+    const int NC = d.C == 30 ? 6 : 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= L + 1; i += stride) {
-        if (i < nt) { d.binc[i] = 0; d.bin_cur[i] = 0; }
-        d.binc[d.NT_ub + 1 + i] = 0;
-        d.bin_cur[d.NT_ub + 1 + i] = 0;
+        d.binc[i] = 0;
+        d.bin_cur[i] = 0;
+        for (int c = 0; c < NC; ++c) d.cov[i * NC + c] = 0;
+        if (i <= L / COV_TILE + 1) for (int c = 0; c < NC; ++c) d.cov_tile[i * NC + c] = 0;
         if (d.padding) {
             d.head_cnt[i] = 0; d.tail_cnt[i] = 0;
             Int2 z; z.a = 0; z.b = 0;
@@ -420,43 +550,59 @@ struct OpSkip {
     }
 };
 
-// ------------------------------------------------------------- K2: counting
-// One warp per 32-row tile, lane = row.  Each lane walks the tile's segment list and
-// accumulates its own column in registers (four 16-bit fields per 64-bit word), so the
-// histogram needs no atomics at all; rows leave through shared memory as coalesced
-// 16-byte stores.
-__device__ __forceinline__ bool ins_equal(const Dev& d, const IndelEvent& a, const IndelEvent& b, bool fold_strand) {
+// ------------------------------------------------------------- K2: rows
+__device__ __forceinline__ bool ins_equal(const Dev& d, const RowEvent& a, const RowEvent& b, bool fold_strand) {
     if (a.len != b.len) return false;
     if (!fold_strand && ((a.info ^ b.info) & 1u)) return false;
     for (int32_t i = 0; i < a.len; ++i)
-        if (nib_at(d.seq, a.y + i) != nib_at(d.seq, b.y + i)) return false;
+        if (nib_at(d.seq, a.yb + i) != nib_at(d.seq, b.yb + i)) return false;
     return true;
+}
+
+// first read (BAM order) that shows the reference base at position p, as key rid * 2.  Reference-relative
+// counting keeps no per-read record of matching bases, so this walks the reads that can reach p: those
+// starting within the longest read span before it.  Only count ties ask for it.
+__device__ uint32_t first_ref_read(const Dev& d, int32_t p, uint32_t ref_nib) {
+    const int64_t span = *d.max_span;
+    int64_t lo = 0, hi = d.n_reads;                      // first read with pos > p - span
+    while (lo < hi) {
+        const int64_t m = (lo + hi) >> 1;
+        if ((int64_t)d.pos[m] > (int64_t)p - span) hi = m; else lo = m + 1;
+    }
+    for (int64_t r = lo; r < d.n_reads && d.pos[r] <= p; ++r) {
+        if (!d.admit[r] || d.read_end[r] <= p) continue;
+        int32_t x = d.pos[r];
+        uint32_t y = (uint32_t)d.seq_off[r];
+        for (int32_t k = d.cigar_off[r]; k < d.cigar_off[r + 1]; ++k) {
+            const uint32_t c = d.cigar[k], op = c & 15u;
+            const int32_t len = (int32_t)(c >> 4);
+            if (op_consumes_ref(op)) {
+                if (p < x + len) {
+                    if (op_is_match(op) && nib_at(d.seq, y + (uint32_t)(p - x)) == ref_nib) return (uint32_t)r * 2u;
+                    break;
+                }
+                x += len;
+            }
+            if (op_consumes_qry(op)) y += (uint32_t)len;
+        }
+    }
+    return 0xffffffffu;
 }
 
 // first-occurrence key (read ordinal * 2 + is_indel_token) of each allele class at a row;
 // only needed to break count ties the way Counter/dict insertion order does.
-__device__ void first_keys(const Dev& d, int32_t row, int32_t p, uint32_t key[6]) {
+__device__ void first_keys(const Dev& d, int32_t row, int32_t p, int ri, bool acgt, uint32_t key[6]) {
     for (int i = 0; i < 6; ++i) key[i] = 0xffffffffu;
-    const int32_t t = row >> 5;
-    for (int32_t s = d.binc[t]; s < d.binc[t + 1]; ++s) {
-        const SegEntry e = d.entries[s];
-        if (e.info & 8u) continue;
-        const uint32_t off = (uint32_t)(p - e.x);
-        if (off >= (uint32_t)e.len) continue;
-        const uint32_t nib = nib_at(d.seq, e.yx + (uint32_t)p);
-        if (__popc(nib) != 1) continue;
-        const int c = __ffs(nib) - 1;
-        const uint32_t kk = (e.info >> 4) * 2u;
-        if (kk < key[c]) key[c] = kk;
-    }
-    const int32_t* ev_off = d.binc + d.NT_ub + 1;
-    const int32_t e0 = ev_off[row] - ev_off[0], e1 = ev_off[row + 1] - ev_off[0];
+    const int32_t e0 = d.binc[row] - d.binc[0], e1 = d.binc[row + 1] - d.binc[0];
     for (int32_t s = e0; s < e1; ++s) {
-        const IndelEvent e = d.events[s];
-        const int c = (e.info & 2u) ? 5 : 4;
-        const uint32_t kk = (e.info >> 4) * 2u + 1u;
+        const RowEvent e = d.events[s];
+        int c;
+        uint32_t kk = (e.info >> 4) * 2u;
+        if (e.len == 0) { if (e.yb > 3u) continue; c = (int)e.yb; }
+        else { c = (e.info & 2u) ? 5 : 4; kk += 1u; }
         if (kk < key[c]) key[c] = kk;
     }
+    if (acgt) key[ri] = first_ref_read(d, p, 1u << ri);
 }
 
 // allele-frequency thresholds as integer tables: thr[depth] = smallest count c >= 1 with
@@ -476,257 +622,176 @@ __global__ void k_thr_table(uint16_t* thr_snp, uint16_t* thr_indel, double snp_a
     }
 }
 
-// four 8-bit fields -> four 16-bit fields
-__device__ __forceinline__ unsigned long long widen8(uint32_t v) {
-    const uint32_t lo = __byte_perm(v, 0, 0x4140), hi = __byte_perm(v, 0, 0x4342);
-    return ((unsigned long long)hi << 32) | lo;
-}
-
-// ------------------------------------------------------------- K2: counting (design)
-// One warp per 32-row tile, lane = row, no atomics.  Per round of <= 32 segment entries:
-//   staging  (lane = entry)  each lane cuts ITS read's 32-base window over the tile's positions out of the
-//            4-bit sequence (5 word loads, nibble swap, funnel shift), clears bases outside the segment and
-//            ambiguity codes, and drops the 16 bytes into a shared-memory slot; slots are grouped by
-//            (strand, phase class) with each group padded to a multiple of 4 zero slots;
-//   consume  (lane = row)    per slot: one shared load, shift, mask, multiply-spread of the one-hot nibble
-//            into four 8-bit fields, add - 6 instructions per (row, read) instead of an address
-//            computation and a dependent global load per (row, read).
-// Tiles whose rows are not consecutive positions (a run ends inside the tile) are processed run by run.
-constexpr int COUNT_WARPS = 8;
-constexpr int SLOT_WORDS = 8;                // 4 data words, word 4 = 0 (lanes outside the run read it), 3 spare
-
-__device__ __forceinline__ uint32_t nibmask(int n) {         // low n nibbles set, n clamped to 0..8
-    uint32_t m;                                              // shl.b32 clamps the shift amount: 1 << 32 == 0
-    asm("shl.b32 %0, 1, %1;" : "=r"(m) : "r"((uint32_t)(n < 0 ? 0 : 4 * n)));
-    return m - 1u;
-}
-// keep only one-hot nibbles (A=1, C=2, G=4, T=8); N, other ambiguity codes and '=' count nothing
-__device__ __forceinline__ uint32_t keep_onehot(uint32_t x) {
-    const uint32_t c = x - ((x >> 1) & 0x77777777u) - ((x >> 2) & 0x33333333u) - ((x >> 3) & 0x11111111u);
-    const uint32_t t = c ^ 0x11111111u;                      // nibble == 0  <=>  popcount == 1
-    const uint32_t nz = (t | (t >> 1) | (t >> 2) | (t >> 3)) & 0x11111111u;
-    return x & ((nz ^ 0x11111111u) * 15u);
-}
-
-template <int C>
-__global__ void __launch_bounds__(COUNT_WARPS * 32) k_count(Dev d) {
-    constexpr int NG = C == 30 ? 6 : 2;                      // slot groups: strand x {unphased, HP1, HP2}
-    constexpr int NSLOT = 32 + 4 * NG;
-    __shared__ __align__(16) int32_t stage[COUNT_WARPS][TILE_ROWS * C];
-    __shared__ __align__(16) uint32_t slots[COUNT_WARPS][NSLOT][SLOT_WORDS];
-    __shared__ uint2 dels[COUNT_WARPS][32];                  // deletion entries of the round: coverage mask, strand
+// exclusive prefix of the coverage tile sums, in place (single block; there is one tile per 256 rows)
+template <int NC>
+struct CovVec { int32_t v[NC]; };
+template <int NC>
+__global__ void __launch_bounds__(1024) k_cov_aggr(Dev d) {
+    __shared__ int32_t wtot[32][NC];
+    __shared__ int32_t carry[NC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const int64_t L = *d.n_rows;
-    const int64_t n_tiles = (L + TILE_ROWS - 1) / TILE_ROWS;
-    const int32_t* ev_off = d.binc + d.NT_ub + 1;
-    const uint32_t* __restrict__ seqw = (const uint32_t*)d.seq;
-    const int64_t n_seq_words = d.n_seq_words;
-    for (int j = lane; j < NSLOT; j += 32) {                 // words 4..7 of every slot stay zero
-        *(uint4*)&slots[warp][j][0] = make_uint4(0, 0, 0, 0);
-        *(uint4*)&slots[warp][j][4] = make_uint4(0, 0, 0, 0);
-    }
-    __syncwarp();
-    const int64_t t_stride = (int64_t)gridDim.x * COUNT_WARPS;
-    int64_t t = (int64_t)blockIdx.x * COUNT_WARPS + warp;
-    // software pipeline across tiles: the entry range of tile t+2 and the first round's entries of tile t+1
-    // are requested while tile t is processed
-    int32_t s0 = 0, s1 = 0, s0n = 0, s1n = 0;
-    if (t < n_tiles) { s0 = d.binc[t]; s1 = d.binc[t + 1]; }
-    if (t + t_stride < n_tiles) { s0n = d.binc[t + t_stride]; s1n = d.binc[t + t_stride + 1]; }
-    SegEntry pre;
-    pre.x = 0; pre.len = 0; pre.yx = 0; pre.info = 0;
-    if (s0 + lane < s1) pre = d.entries[s0 + lane];
-    for (; t < n_tiles; t += t_stride) {
-        const int64_t row = t * TILE_ROWS + lane;
-        const bool live = row < L;
-        const int32_t p = live ? d.row_pos[row] : -0x40000000;
-        // epilogue operands requested now, consumed after the rounds
-        int32_t ev0 = 0, ev1 = 0;
-        uint8_t ref_c = (uint8_t)'N';
-        if (live) {
-            ev0 = ev_off[row]; ev1 = ev_off[row + 1];
-            const int64_t ro = (int64_t)p - d.ref_start0;
-            if (ro >= 0 && ro < d.ref_len) ref_c = d.ref[ro];
+    const int64_t nt = *d.n_rows / COV_TILE + 1;
+    if (threadIdx.x < NC) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < nt; b0 += 1024) {
+        const int64_t i = b0 + threadIdx.x;
+        int32_t own[NC], x[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            own[c] = i < nt ? d.cov_tile[i * NC + c] : 0;
+            x[c] = own[c];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x[c], o); if (lane >= o) x[c] += y; }
         }
-        const int32_t ev_base = ev_off[0];
-        const SegEntry first = pre;
-        pre.x = 0; pre.len = 0; pre.yx = 0; pre.info = 0;
-        if (s0n + lane < s1n) pre = d.entries[s0n + lane];
-        const int64_t tnn = t + 2 * t_stride;
-        int32_t s0nn = 0, s1nn = 0;
-        if (tnn < n_tiles) { s0nn = d.binc[tnn]; s1nn = d.binc[tnn + 1]; }
-        // runs of consecutive positions inside the tile
-        const int32_t p_prev = __shfl_up_sync(0xffffffffu, p, 1);
-        const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
-        const uint32_t start_mask = __ballot_sync(0xffffffffu, live && (lane == 0 || p != p_prev + 1));
-        const int n_live = __popc(live_mask);
-        // wide accumulators: A,C,G,T as four 16-bit fields (forward, reverse, HP=1, HP=2); `*` / `#` counts
-        unsigned long long wf = 0, wr = 0, wp = 0, wm = 0;
-        uint32_t wst = 0;                                    // star_f | star_r << 16
-        // narrow accumulators (four 8-bit fields), folded into the wide ones every 7 rounds (<= 224 per field)
-        uint32_t nf = 0, nr = 0, np = 0, nm = 0, nst = 0;    // nst: star_f | star_r << 8
-        int rounds = 0;
-        for (uint32_t sm = start_mask; sm; sm &= sm - 1) {
-            const int ra = __ffs(sm) - 1;
-            const uint32_t rest = sm & (sm - 1);
-            const int rb = rest ? __ffs(rest) - 1 : n_live;
-            const int32_t P0 = __shfl_sync(0xffffffffu, p, ra);
-            const int nrun = rb - ra;
-            const bool in_run = lane >= ra && lane < rb;
-            const int k = lane - ra;                         // this row's base index inside the window
-            const uint32_t* lane_slot = &slots[warp][0][in_run ? (k >> 3) : 4];
-            const uint32_t lane_sh = (uint32_t)(k & 7) * 4u;
-            const uint32_t lane_bit = in_run ? (1u << k) : 0u;
-            for (int32_t s = s0; s < s1; s += 32) {
-                SegEntry e;
-                if (s == s0 && sm == start_mask) e = first;
-                else {
-                    e.x = 0; e.len = 0; e.yx = 0; e.info = 0;
-                    if (s + lane < s1) e = d.entries[s + lane];
-                }
-                // ---------------------------------------------------------------- staging (lane = entry)
-                const bool is_del = (e.info & 8u) != 0u;
-                const int32_t span = is_del ? (int32_t)e.yx : e.len;
-                int k0 = e.x - P0, k1 = e.x + span - P0;     // window bases covered by the op: [k0, k1)
-                k0 = k0 < 0 ? 0 : k0;
-                k1 = k1 > nrun ? nrun : k1;
-                const bool hit = k1 > k0;
-                uint4 w = make_uint4(0, 0, 0, 0);
-                if (hit && !is_del) {
-                    const long long q0 = (long long)(uint32_t)(e.yx + (uint32_t)e.x) + ((long long)P0 - e.x);
-                    const long long wb = q0 >> 3;            // floor: q0 is negative when the op starts inside the window
-                    const uint32_t sh = ((uint32_t)q0 & 7u) * 4u;
-                    uint32_t v[5];
+        if (lane == 31)
 #pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        const long long wi = wb + i;
-                        uint32_t x = (wi >= 0 && wi < n_seq_words) ? seqw[wi] : 0u;
-                        v[i] = ((x & 0x0f0f0f0fu) << 4) | ((x >> 4) & 0x0f0f0f0fu);     // base j of the word at bits 4j..4j+3
-                    }
-                    w.x = keep_onehot(__funnelshift_r(v[0], v[1], sh) & nibmask(k1) & ~nibmask(k0));
-                    w.y = keep_onehot(__funnelshift_r(v[1], v[2], sh) & nibmask(k1 - 8) & ~nibmask(k0 - 8));
-                    w.z = keep_onehot(__funnelshift_r(v[2], v[3], sh) & nibmask(k1 - 16) & ~nibmask(k0 - 16));
-                    w.w = keep_onehot(__funnelshift_r(v[3], v[4], sh) & nibmask(k1 - 24) & ~nibmask(k0 - 24));
-                }
-                const uint32_t rev = e.info & 1u;
-                int grp = (int)rev;
-                if (C == 30) {
-                    const uint32_t hp = (e.info >> 1) & 3u;
-                    grp = (int)rev * 3 + (hp == 1 ? 1 : hp == 2 ? 2 : 0);
-                }
-                int end_all = 0;
-                int cnt4g[NG];
+            for (int c = 0; c < NC; ++c) wtot[warp][c] = x[c];
+        __syncthreads();
+        if (warp == 0) {                                 // scan of the 32 warp totals
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const uint32_t bal = __ballot_sync(0xffffffffu, hit && !is_del && grp == g);
-                    const int cnt = __popc(bal), cnt4 = (cnt + 3) & ~3;
-                    if (hit && !is_del && grp == g) *(uint4*)&slots[warp][end_all + __popc(bal & lt_mask)][0] = w;
-                    if (lane < cnt4 - cnt) *(uint4*)&slots[warp][end_all + cnt + lane][0] = make_uint4(0, 0, 0, 0);
-                    end_all += cnt4;
-                    cnt4g[g] = cnt4;
-                }
-                const uint32_t dbal = __ballot_sync(0xffffffffu, hit && is_del);
-                if (hit && is_del) {
-                    const uint32_t cov = (k1 >= 32 ? 0xffffffffu : ((1u << k1) - 1u)) & ~((1u << k0) - 1u);
-                    dels[warp][__popc(dbal & lt_mask)] = make_uint2(cov, rev);
-                }
-                __syncwarp();
-                // ---------------------------------------------------------------- consume (lane = row)
-                {
-                    int j = 0;
+            for (int c = 0; c < NC; ++c) {
+                int32_t t = wtot[lane][c];
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        uint32_t acc = 0;
-                        for (const int je = j + cnt4g[g]; j < je; j += 4) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const uint32_t nib = (lane_slot[(j + u) * SLOT_WORDS] >> lane_sh) & 15u;
-                                acc += (nib * 0x204081u) & 0x01010101u;
-                            }
-                        }
-                        if (C == 30) {
-                            if (g < 3) nf += acc; else nr += acc;
-                            if (g % 3 == 1) np += acc; else if (g % 3 == 2) nm += acc;
-                        } else {
-                            if (g == 0) nf += acc; else nr += acc;
-                        }
-                    }
-                    const int nd = __popc(dbal);
-                    for (int i = 0; i < nd; ++i) {
-                        const uint2 dl = dels[warp][i];
-                        if (dl.x & lane_bit) nst += 1u << (dl.y * 8u);
-                    }
-                }
-                __syncwarp();
-                if (++rounds == 7) {
-                    wf += widen8(nf); wr += widen8(nr);
-                    if (C == 30) { wp += widen8(np); wm += widen8(nm); }
-                    wst += (nst & 0xffu) | ((nst & 0xff00u) << 8);
-                    nf = nr = np = nm = nst = 0;
-                    rounds = 0;
-                }
+                for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+                wtot[lane][c] = t;                       // inclusive
             }
         }
-        wf += widen8(nf); wr += widen8(nr);
-        if (C == 30) { wp += widen8(np); wm += widen8(nm); }
-        wst += (nst & 0xffu) | ((nst & 0xff00u) << 8);
-        s0 = s0n; s1 = s1n; s0n = s0nn; s1n = s1nn;
-        // the row vector lives in this lane's slice of the staging tile (dynamic channel
-        // indices would otherwise force a register array into local memory)
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int32_t before = carry[c] + (warp ? wtot[warp - 1][c] : 0);
+            if (i < nt) d.cov_tile[i * NC + c] = before + x[c] - own[c];
+        }
+        __syncthreads();
+        if (threadIdx.x < NC) carry[threadIdx.x] += wtot[31][threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// K2 proper.  Block = one coverage tile of 256 rows (grid-stride); thread = row, warp = 32 consecutive
+// rows.  Coverage = tile prefix + in-block prefix of the difference rows; the row's events give everything else:
+// mismatching bases, I/I1/D/D1, phased channels; then the candidate predicate (integer AF threshold
+// tables, first-occurrence tie-break) and the row leaves through shared memory as 16-byte coalesced stores.
+constexpr int ROWS_WARPS = 8;
+template <int C>
+__global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(Dev d) {
+    constexpr int NC = C == 30 ? 6 : 4;
+    static_assert(ROWS_WARPS * 32 == COV_TILE, "one block per coverage tile");
+    __shared__ __align__(16) int32_t stage[ROWS_WARPS][TILE_ROWS * C];
+    __shared__ int32_t wtot[ROWS_WARPS][NC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t L = *d.n_rows;
+    const int32_t ev_base = d.binc[0];
+    for (int64_t tile = blockIdx.x; tile * COV_TILE < L; tile += gridDim.x) {
+        const int64_t base = tile * COV_TILE;
+        const int64_t row = base + threadIdx.x;
+        const bool live = row < L;
+        int32_t carry[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) carry[c] = d.cov_tile[tile * NC + c];
+        // ---- operands of the row, requested together
+        int32_t cv[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) cv[c] = 0;
+        int32_t p = 0, e0 = 0, e1 = 0;
+        uint8_t rc = (uint8_t)'N';
+        if (live) {
+            if (NC == 4) { const int4 t = *(const int4*)(d.cov + row * 4); cv[0] = t.x; cv[1] = t.y; cv[2] = t.z; cv[3] = t.w; }
+            else {
+                const int2* q = (const int2*)(d.cov + row * 6);
+                const int2 t0 = q[0], t1 = q[1], t2 = q[2];
+                cv[0] = t0.x; cv[1] = t0.y; cv[2] = t1.x; cv[3] = t1.y; cv[NC - 2] = t2.x; cv[NC - 1] = t2.y;
+            }
+            p = d.row_pos[row];
+            e0 = d.binc[row] - ev_base; e1 = d.binc[row + 1] - ev_base;
+            const int64_t ro = (int64_t)p - d.ref_start0;
+            if (ro >= 0 && ro < d.ref_len) rc = d.ref[ro];
+        }
+        // ---- block-wide inclusive prefix of the coverage differences
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            int32_t x = cv[c];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            cv[c] = x;
+        }
+        __syncthreads();                                 // previous sub-tile's readers of wtot are done
+        if (lane == 31)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) wtot[warp][c] = cv[c];
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            int32_t before = carry[c];
+#pragma unroll
+            for (int w = 0; w < ROWS_WARPS; ++w) if (w < warp) before += wtot[w][c];
+            cv[c] += before;
+        }
+        // ---- events of the row
         int32_t* v = &stage[warp][lane * C];
 #pragma unroll
         for (int i = 0; i < C; ++i) v[i] = 0;
         if (live) {
-            const int32_t star_f = (int32_t)(wst & 0xffffu), star_r = (int32_t)(wst >> 16);
-            int32_t bf[4], br[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                bf[i] = (int32_t)((wf >> (16 * i)) & 0xffff);
-                br[i] = (int32_t)((wr >> (16 * i)) & 0xffff);
-                v[i] = bf[i];
-                v[9 + i] = br[i];
-            }
-            v[8] = star_f; v[17] = star_r;
-            if (C == 30) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    v[18 + i] = (int32_t)((wp >> (16 * i)) & 0xffff);
-                    v[24 + i] = (int32_t)((wm >> (16 * i)) & 0xffff);
-                }
-            }
-            // indel events of this row: per strand totals and the largest distinct allele
-            const int32_t e0 = ev0 - ev_base, e1 = ev1 - ev_base;
+            unsigned long long wf = 0, wr = 0, wp = 0, wm = 0;       // mismatching A,C,G,T as four 16-bit fields
+            int32_t mm_f = 0, mm_r = 0, mm_p = 0, mm_m = 0;          // all mismatch events incl. N / ambiguity codes
             int32_t ins_cnt = 0, del_cnt = 0;
             for (int32_t s = e0; s < e1; ++s) {
-                const IndelEvent e = d.events[s];
-                const bool is_del = e.info & 2u, rev = e.info & 1u;
+                const RowEvent e = d.events[s];
+                const uint32_t rev = e.info & 1u;
                 const uint32_t hp = (e.info >> 2) & 3u;
+                if (e.len == 0) {
+                    const unsigned long long inc = e.yb < 4u ? 1ull << (16 * e.yb) : 0ull;
+                    if (rev) { wr += inc; ++mm_r; } else { wf += inc; ++mm_f; }
+                    if (C == 30) {
+                        if (hp == 1) { wp += inc; ++mm_p; } else if (hp == 2) { wm += inc; ++mm_m; }
+                    }
+                    continue;
+                }
+                const bool is_del = e.info & 2u;
                 if (is_del) { ++del_cnt; ++v[rev ? 15 : 6]; } else { ++ins_cnt; ++v[rev ? 13 : 4]; }
                 if (C == 30) {
                     if (hp == 1) ++v[is_del ? 23 : 22]; else if (hp == 2) ++v[is_del ? 29 : 28];
                 }
                 bool seen = false;
                 for (int32_t q = e0; q < s && !seen; ++q) {
-                    const IndelEvent o = d.events[q];
-                    if (((o.info ^ e.info) & 3u) == 0 && (is_del ? o.len == e.len : ins_equal(d, o, e, false))) seen = true;
+                    const RowEvent o = d.events[q];
+                    if (o.len != 0 && ((o.info ^ e.info) & 3u) == 0 && (is_del ? o.len == e.len : ins_equal(d, o, e, false))) seen = true;
                 }
                 if (seen) continue;
                 int32_t same = 1;
                 for (int32_t q = s + 1; q < e1; ++q) {
-                    const IndelEvent o = d.events[q];
-                    if (((o.info ^ e.info) & 3u) == 0 && (is_del ? o.len == e.len : ins_equal(d, o, e, false))) ++same;
+                    const RowEvent o = d.events[q];
+                    if (o.len != 0 && ((o.info ^ e.info) & 3u) == 0 && (is_del ? o.len == e.len : ins_equal(d, o, e, false))) ++same;
                 }
                 const int ch = is_del ? (rev ? 16 : 7) : (rev ? 14 : 5);
                 if (same > v[ch]) v[ch] = same;
             }
-            const int32_t fsum = bf[0] + bf[1] + bf[2] + bf[3], rsum = br[0] + br[1] + br[2] + br[3];
-            const int32_t depth = fsum + rsum + star_f + star_r;
-            uint8_t rc = ref_c;
             if (rc >= 'a') rc -= 32;
             const int ri_raw = rc == 'A' ? 0 : rc == 'C' ? 1 : rc == 'G' ? 2 : rc == 'T' ? 3 : -1;
             const bool acgt = ri_raw >= 0;
             const int ri = acgt ? ri_raw : 0;
+            int32_t bf[4], br[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bf[i] = (int32_t)((wf >> (16 * i)) & 0xffff);
+                br[i] = (int32_t)((wr >> (16 * i)) & 0xffff);
+                if (acgt && i == ri) { bf[i] += cv[0] - mm_f; br[i] += cv[1] - mm_r; }   // matching bases = coverage - mismatches
+                v[i] = bf[i];
+                v[9 + i] = br[i];
+            }
+            const int32_t star_f = cv[2], star_r = cv[3];
+            v[8] = star_f; v[17] = star_r;
+            if (C == 30) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int32_t a1 = (int32_t)((wp >> (16 * i)) & 0xffff), a2 = (int32_t)((wm >> (16 * i)) & 0xffff);
+                    if (acgt && i == ri) { a1 += cv[NC - 2] - mm_p; a2 += cv[NC - 1] - mm_m; }
+                    v[18 + i] = a1;
+                    v[24 + i] = a2;
+                }
+            }
+            const int32_t fsum = bf[0] + bf[1] + bf[2] + bf[3], rsum = br[0] + br[1] + br[2] + br[3];
+            const int32_t depth = fsum + rsum + star_f + star_r;
             // candidate predicate (create_tensor_pileup.py:268-299, 536, 555)
             int32_t cls[6];
 #pragma unroll
@@ -760,7 +825,7 @@ __global__ void __launch_bounds__(COUNT_WARPS * 32) k_count(Dev d) {
                         for (int i = 0; i < 6; ++i) if (i != ri && cls[i] == top) tie = true;
                         if (tie) {
                             uint32_t key[6];
-                            first_keys(d, (int32_t)row, p, key);
+                            first_keys(d, (int32_t)row, p, ri, acgt, key);
                             for (int i = 0; i < 6; ++i) if (i != ri && cls[i] == top && key[i] < key[ri]) pass = true;
                         }
                     }
@@ -776,14 +841,17 @@ __global__ void __launch_bounds__(COUNT_WARPS * 32) k_count(Dev d) {
             d.row_delcnt[row] = del_cnt + star_f + star_r;
             if (d.padding) { Int2 cr; cr.a = -fsum; cr.b = -rsum; d.cur_ref[row] = cr; }
         }
-        // rows of a tile are contiguous in HBM: write 16 B per lane per step from the staging tile
+        // rows of a warp are contiguous in HBM: write 16 B per lane per step from the staging tile
         __syncwarp();
-        const int64_t rows_here = min((int64_t)TILE_ROWS, L - t * TILE_ROWS);
-        const int n_int = (int)rows_here * C;
-        int32_t* out = d.counts + t * TILE_ROWS * C;          // 32*C*4 bytes per tile: 16 B aligned
-        for (int i = lane * 4; i < n_int; i += 128) {
-            if (i + 4 <= n_int) *(int4*)(out + i) = *(const int4*)(&stage[warp][i]);
-            else for (int q = i; q < n_int; ++q) out[q] = stage[warp][q];
+        const int64_t wrow0 = base + warp * 32;
+        if (wrow0 < L) {
+            const int64_t rows_here = min((int64_t)TILE_ROWS, L - wrow0);
+            const int n_int = (int)rows_here * C;
+            int32_t* out = d.counts + wrow0 * C;                 // 32*C*4 bytes per warp tile: 16 B aligned
+            for (int i = lane * 4; i < n_int; i += 128) {
+                if (i + 4 <= n_int) *(int4*)(out + i) = *(const int4*)(&stage[warp][i]);
+                else for (int q = i; q < n_int; ++q) out[q] = stage[warp][q];
+            }
         }
         __syncwarp();
     }
@@ -924,16 +992,15 @@ struct OpAltOff {
     __device__ int64_t size() const { return *d.n_cand < d.cand_cap ? *d.n_cand : d.cand_cap; }
     __device__ T load(int64_t i) const {
         const int32_t row = d.cand_row[i];
-        const int32_t* ev_off = d.binc + d.NT_ub + 1;
-        return 4 + (ev_off[row + 1] - ev_off[row]);
+        return 4 + (d.binc[row + 1] - d.binc[row]);
     }
     __device__ void store(int64_t i, const T& incl, const T& own) const { d.alt_off[i] = incl - own; }
 };
 
 // alleles in alt_dict insertion order (create_tensor_pileup.py:223,235,251,259-261): keys are
 // case-folded, so the two strands of one allele merge and keep the earlier first occurrence.
-// One warp per candidate: the lanes split the tile's segment list to find the first read
-// showing each base; lane 0 then builds the (short) allele list.
+// One warp per candidate: the lanes split the row's events to find the first read showing each
+// non-reference base; lane 0 then builds the (short) allele list.
 __global__ void __launch_bounds__(256) k_altinfo(Dev d) {
     const int64_t n = *d.n_cand < d.cand_cap ? *d.n_cand : d.cand_cap;
     const int lane = threadIdx.x & 31;
@@ -942,23 +1009,16 @@ __global__ void __launch_bounds__(256) k_altinfo(Dev d) {
     const int32_t row = d.cand_row[i];
     const int32_t p = d.row_pos[row];
     const int64_t off = d.alt_off[i];
-    const int32_t* ev_off = d.binc + d.NT_ub + 1;
-    const int32_t e0 = ev_off[row] - ev_off[0], e1 = ev_off[row + 1] - ev_off[0];
-    // first-occurrence key of each base among the reads covering p
+    const int32_t e0 = d.binc[row] - d.binc[0], e1 = d.binc[row + 1] - d.binc[0];
+    // first-occurrence key of each non-reference base: the earliest read among the row's mismatch events
     uint32_t key[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
     {
-        const int32_t t = row >> 5;
-        for (int32_t s = d.binc[t] + lane; s < d.binc[t + 1]; s += 32) {
-            const SegEntry e = d.entries[s];
-            if (e.info & 8u) continue;
-            const uint32_t o = (uint32_t)(p - e.x);
-            if (o >= (uint32_t)e.len) continue;
-            const uint32_t nib = nib_at(d.seq, e.yx + (uint32_t)p);
-            if (__popc(nib) != 1) continue;
-            const int c = __ffs(nib) - 1;
+        for (int32_t s = e0 + lane; s < e1; s += 32) {
+            const RowEvent e = d.events[s];
+            if (e.len != 0 || e.yb > 3u) continue;
             const uint32_t kk = (e.info >> 4) * 2u;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) if (b == c && kk < key[b]) key[b] = kk;
+            for (int b = 0; b < 4; ++b) if (b == (int)e.yb && kk < key[b]) key[b] = kk;
         }
 #pragma unroll
         for (int b = 0; b < 4; ++b)
@@ -983,22 +1043,23 @@ __global__ void __launch_bounds__(256) k_altinfo(Dev d) {
         out[m++] = e;
     }
     for (int32_t s = e0; s < e1; ++s) {
-        const IndelEvent ev = d.events[s];
+        const RowEvent ev = d.events[s];
+        if (ev.len == 0) continue;
         const bool is_del = ev.info & 2u;
         bool seen = false;
         for (int32_t q = e0; q < s && !seen; ++q) {
-            const IndelEvent o = d.events[q];
-            if (((o.info ^ ev.info) & 2u) == 0 && (is_del ? o.len == ev.len : ins_equal(d, o, ev, true))) seen = true;
+            const RowEvent o = d.events[q];
+            if (o.len != 0 && ((o.info ^ ev.info) & 2u) == 0 && (is_del ? o.len == ev.len : ins_equal(d, o, ev, true))) seen = true;
         }
         if (seen) continue;
         int32_t cnt = 0;
-        uint32_t first = 0xffffffffu, first_y = ev.y;
+        uint32_t first = 0xffffffffu, first_y = ev.yb;
         for (int32_t q = s; q < e1; ++q) {
-            const IndelEvent o = d.events[q];
-            if (((o.info ^ ev.info) & 2u) == 0 && (is_del ? o.len == ev.len : ins_equal(d, o, ev, true))) {
+            const RowEvent o = d.events[q];
+            if (o.len != 0 && ((o.info ^ ev.info) & 2u) == 0 && (is_del ? o.len == ev.len : ins_equal(d, o, ev, true))) {
                 ++cnt;
                 const uint32_t kk = (o.info >> 4) * 2u + 1u;
-                if (kk < first) { first = kk; first_y = o.y; }
+                if (kk < first) { first = kk; first_y = o.yb; }
             }
         }
         AltEntry e;

@@ -14,9 +14,11 @@
 //       __device__ int64_t size() const;                 // element count (may read device memory)
 //   };
 //
-// Grids are sized from a host-side upper bound; tiles beyond size() exit.  A three
-// pass scan reads the input twice; it is used because every scan here is far smaller
-// than the count/tensor traffic and a look-back scan can spin forever if a
+// The host only knows an upper bound of most sizes (row and candidate counts live on the
+// device), so the tile passes run as grid-stride loops over ceil(size()/SCAN_TILE) tiles on a
+// grid of at most SCAN_MAX_GRID blocks: no block is launched just to find out it has nothing
+// to do.  A three pass scan reads the input twice; it is used because every scan here is far
+// smaller than the count/tensor traffic and a look-back scan can spin forever if a
 // predecessor tile is not resident.
 #pragma once
 #include <cstdint>
@@ -27,6 +29,7 @@ namespace c3r {
 constexpr int SCAN_BT = 256;      // threads per block
 constexpr int SCAN_IPT = 8;       // items per thread
 constexpr int SCAN_TILE = SCAN_BT * SCAN_IPT;
+constexpr int SCAN_MAX_GRID = 148 * 8;
 
 template <class Op>
 __device__ __forceinline__ typename Op::T block_scan_exclusive(const Op& op, typename Op::T v,
@@ -54,17 +57,17 @@ __global__ void __launch_bounds__(SCAN_BT) scan_reduce_kernel(Op op, typename Op
     typedef typename Op::T T;
     __shared__ T smem[SCAN_BT];
     const int64_t n = op.size();
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-    if (base >= n) return;
-    const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_IPT;
-    T acc = op.identity();
+    for (int64_t tile = blockIdx.x; tile * SCAN_TILE < n; tile += gridDim.x) {
+        const int64_t i0 = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_IPT;
+        T acc = op.identity();
 #pragma unroll
-    for (int k = 0; k < SCAN_IPT; ++k)
-        if (i0 + k < n) acc = op.combine(acc, op.load(i0 + k));
-    __shared__ T tot;
-    block_scan_exclusive(op, acc, smem, threadIdx.x == 0 ? &tot : (T*)nullptr);
-    // thread SCAN_BT-1's inclusive value is the tile aggregate
-    if (threadIdx.x == SCAN_BT - 1) tile_aggr[blockIdx.x] = smem[SCAN_BT - 1];
+        for (int k = 0; k < SCAN_IPT; ++k)
+            if (i0 + k < n) acc = op.combine(acc, op.load(i0 + k));
+        block_scan_exclusive(op, acc, smem, (T*)nullptr);
+        // thread SCAN_BT-1's inclusive value is the tile aggregate
+        if (threadIdx.x == SCAN_BT - 1) tile_aggr[tile] = smem[SCAN_BT - 1];
+        __syncthreads();
+    }
 }
 
 // single block: tile_aggr[0..nb) -> exclusive prefix in place; total to *total_out
@@ -96,26 +99,27 @@ __global__ void __launch_bounds__(SCAN_BT) scan_apply_kernel(Op op, const typena
     typedef typename Op::T T;
     __shared__ T smem[SCAN_BT];
     const int64_t n = op.size();
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-    if (base >= n) return;
-    const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_IPT;
-    T own[SCAN_IPT];
-    T acc = op.identity();
+    for (int64_t tile = blockIdx.x; tile * SCAN_TILE < n; tile += gridDim.x) {
+        const int64_t i0 = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_IPT;
+        T own[SCAN_IPT];
+        T acc = op.identity();
 #pragma unroll
-    for (int k = 0; k < SCAN_IPT; ++k) {
-        if (i0 + k < n) {
-            own[k] = op.load(i0 + k);
-            acc = op.combine(acc, own[k]);
+        for (int k = 0; k < SCAN_IPT; ++k) {
+            if (i0 + k < n) {
+                own[k] = op.load(i0 + k);
+                acc = op.combine(acc, own[k]);
+            }
         }
-    }
-    T excl = block_scan_exclusive(op, acc, smem, (T*)nullptr);
-    T run = op.combine(tile_excl[blockIdx.x], excl);
+        T excl = block_scan_exclusive(op, acc, smem, (T*)nullptr);
+        T run = op.combine(tile_excl[tile], excl);
 #pragma unroll
-    for (int k = 0; k < SCAN_IPT; ++k) {
-        if (i0 + k < n) {
-            run = op.combine(run, own[k]);
-            op.store(i0 + k, run, own[k]);
+        for (int k = 0; k < SCAN_IPT; ++k) {
+            if (i0 + k < n) {
+                run = op.combine(run, own[k]);
+                op.store(i0 + k, run, own[k]);
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -125,7 +129,8 @@ template <class Op>
 inline int device_scan(const Op& op, int64_t n_upper, typename Op::T* scratch, typename Op::T* total_out,
                        cudaStream_t stream) {
     if (n_upper <= 0) n_upper = 1;
-    const unsigned nb = (unsigned)((n_upper + SCAN_TILE - 1) / SCAN_TILE);
+    int64_t nb64 = (n_upper + SCAN_TILE - 1) / SCAN_TILE;
+    const unsigned nb = (unsigned)(nb64 < SCAN_MAX_GRID ? nb64 : SCAN_MAX_GRID);
     scan_reduce_kernel<Op><<<nb, SCAN_BT, 0, stream>>>(op, scratch);
     scan_aggr_kernel<Op><<<1, SCAN_BT, 0, stream>>>(op, scratch, total_out);
     scan_apply_kernel<Op><<<nb, SCAN_BT, 0, stream>>>(op, scratch);
