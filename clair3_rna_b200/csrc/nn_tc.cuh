@@ -36,7 +36,7 @@ constexpr int TC_KB = 64;                    // K per pipeline stage
 constexpr int TC_IMG = TC_TILE * TC_KB;      // halfs in one 128x64 operand image (16 KB)
 
 // ================================================================== GEMM
-// terms == 3 runs the split-precision product  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (A = A_hi + A_lo and
+// Both GEMMs run the split-precision product  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (A = A_hi + A_lo and
 // B = B_hi + B_lo as two fp16 terms each), which removes the fp16 rounding of both operands.
 struct GemmArgs {
     const __half* A;      // [m_tiles][n_kb][TC_IMG]
@@ -53,14 +53,17 @@ struct GemmArgs {
     int* err;
 };
 
-constexpr int GEMM_STAGES = 4;
+// One pipeline stage = one 64-wide k block of all four operand images (A_hi, A_lo, B_hi, B_lo; 64 KB), consumed by the
+// three split-precision products, so every operand byte crosses L2 -> shared memory once.
+constexpr int GEMM_STAGES = 3;
 constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM = GEMM_STAGES * 2 * TC_IMG * 2 + 1024;
+constexpr int GEMM_STAGE_BYTES = 4 * TC_IMG * 2;
+constexpr int GEMM_SMEM = GEMM_STAGES * GEMM_STAGE_BYTES + 1024;
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * 2 * TC_IMG * 2);
-    // bars: full[4] empty[4] acc_full[2] acc_empty[2], then tmem ptr
+    uint64_t* bars = (uint64_t*)(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+    // bars: full[4] empty[4] acc_full[2] acc_empty[2] (slots for 4 stages, GEMM_STAGES used), then tmem ptr
     uint32_t* tmem_ptr_s = (uint32_t*)(bars + 12);
     float* bias_s = (float*)(bars + 32);                    // staged per tile by the epilogue warps
     const uint32_t s_base = ptx::smem_u32(smem);
@@ -87,16 +90,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
                 const int m = tile / g.n_tiles, n = tile % g.n_tiles;
-                for (int term = 0; term < g.terms; ++term) {
-                    const __half* a = (term == 1 ? g.A_lo : g.A) + (size_t)m * g.n_kb * TC_IMG;
-                    const __half* b = (term == 2 ? g.B_lo : g.B) + (size_t)n * g.n_kb * TC_IMG;
-                    for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
-                        const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
-                        ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 101);
-                        ptx::mbar_arrive_expect_tx(b_full + 8 * s, 2 * TC_IMG * 2);
-                        ptx::bulk_g2s(s_base + s * (2 * TC_IMG * 2), a + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
-                        ptx::bulk_g2s(s_base + s * (2 * TC_IMG * 2) + TC_IMG * 2, b + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
-                    }
+                const size_t ao = (size_t)m * g.n_kb * TC_IMG, bo = (size_t)n * g.n_kb * TC_IMG;
+                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
+                    const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
+                    const uint32_t dst = s_base + s * GEMM_STAGE_BYTES;
+                    ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 101);
+                    ptx::mbar_arrive_expect_tx(b_full + 8 * s, GEMM_STAGE_BYTES);
+                    ptx::bulk_g2s(dst, g.A + ao + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
+                    ptx::bulk_g2s(dst + TC_IMG * 2, g.A_lo + ao + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
+                    ptx::bulk_g2s(dst + 2 * TC_IMG * 2, g.B + bo + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
+                    ptx::bulk_g2s(dst + 3 * TC_IMG * 2, g.B_lo + bo + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
                 }
             }
         }
@@ -107,17 +110,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
                 ptx::mbar_wait(b_acce + 8 * slot, aph ^ 1, g.err, 102);
                 ptx::tc_fence_after();
-                const int n_kb_all = g.n_kb * g.terms;
-                for (int kb = 0; kb < n_kb_all; ++kb, ++it) {
+                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
                     const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
                     ptx::mbar_wait(b_full + 8 * s, ph, g.err, 103);
                     ptx::tc_fence_after();
-                    const uint32_t sa = s_base + s * (2 * TC_IMG * 2), sb = sa + TC_IMG * 2;
+                    const uint32_t st0 = s_base + s * GEMM_STAGE_BYTES;
 #pragma unroll
-                    for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
-                        const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                        const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                        ptx::mma_f16<1>(tmem + slot * 128, da, db, idesc, (kb > 0 || k4 > 0) ? 1u : 0u);
+                    for (int term = 0; term < 3; ++term) {              // A_hi*B_hi, A_lo*B_hi, A_hi*B_lo
+                        const uint32_t sa = st0 + (term == 1 ? TC_IMG * 2 : 0), sb = st0 + (term == 2 ? 3 : 2) * TC_IMG * 2;
+#pragma unroll
+                        for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
+                            const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                            const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                            ptx::mma_f16<1>(tmem + slot * 128, da, db, idesc, (kb > 0 || term > 0 || k4 > 0) ? 1u : 0u);
+                        }
                     }
                     ptx::mma_commit_1(b_empty + 8 * s);
                 }
