@@ -127,3 +127,30 @@ def test_empty_and_ragged_inputs():
     r = eng.call_chunk(filt, ref, 1, 1, 800)
     assert r.n_rows == 0 and r.n_cand == 0
     eng.close()
+
+
+@pytest.mark.parametrize("name,snp_af,indel_af,min_cov", [("ties_lowdepth", 0.7, 0.7, 2), ("cfg1_ont_drna", 0.55, 0.9, 2),
+                                                            ("phased_noisy", 0.95, 0.95, 1)])
+def test_high_thresholds_exercise_the_tie_break(name, snp_af, indel_af, min_cov):
+    """With allele-frequency thresholds this high the AF tests rarely pass, so candidates come from the
+    `top class != reference` rule and its first-occurrence tie-break (create_tensor_pileup.py:279): the device
+    resolves the reference base's first read by walking the reads that can reach the position (first_ref_read)."""
+    from clair3_rna_b200 import weights
+    from clair3_rna_b200.engine import Engine, alt_info_strings
+    from oracle import pileup_oracle
+    case = golden_cases.CASES[name]
+    batch, ref_bytes, contig = golden_cases.build(name)
+    ref = np.frombuffer(ref_bytes, np.uint8)
+    C = 30 if case["phased"] else 18
+    eng = Engine(0, C, snp_min_af=snp_af, indel_min_af=indel_af, min_coverage=min_cov, min_mq=case["min_mq"],
+                 enable_padding=case["padding"], nn_impl=0, keep_tensor=True)
+    eng.set_weights(weights.synthetic(C))
+    res = eng.call_chunk(batch, ref, 1, 1, len(ref_bytes) + 33)
+    eng.close()
+    ora = pileup_oracle.run_region(batch, ref_bytes.decode("ascii"), 1, 1, len(ref_bytes) + 33, snp_min_af=snp_af,
+                                   indel_min_af=indel_af, min_coverage=min_cov, min_mq=case["min_mq"],
+                                   padding=case["padding"], phased=case["phased"])
+    assert len(ora["pos"]) > 0
+    assert res.pos.tolist() == ora["pos"].tolist()
+    assert np.array_equal(res.tensor, ora["tensor"])
+    assert alt_info_strings(res, batch, ref, 1) == ora["alt_info"]
