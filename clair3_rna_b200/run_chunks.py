@@ -1,0 +1,147 @@
+"""Pileup calling of a whole BAM on one or more GPUs: the CHUNK_LIST loop of the reference's workflow
+(`parallel -j THREADS ... call_var_bam :::: CHUNK_LIST` then `sort_vcf`, /root/reference/run_clair3_rna:
+378-381, 441-449, 681-706, 868-889) as one process per GPU.
+
+    python -m clair3_rna_b200.run_chunks --bam_fn x.bam --ref_fn ref.fa --chkpnt_fn w.npz --output out.vcf
+    python -m torch.distributed.run --nproc-per-node 8 -m clair3_rna_b200.run_chunks ...        # 8 GPUs
+
+Shards = (contig, chunk) with the reference's geometry (chunk_num = ceil(len / 5 Mb)); they are independent, so
+ranks share nothing on the data path: each rank owns one GPU, takes its shards by greedy LPT on the per-contig
+mapped-read counts of the BAM index (what `samtools idxstats` gives run_clair3_rna:187), and only VCF rows are
+gathered on rank 0 (gloo/nccl `gather_object`), merged with sort_vcf semantics (sharder.merge_rows).
+
+Inside a rank the stages of consecutive shards overlap: while the GPU runs shard i (c3r_submit_chunk returns
+once the work is queued), the host fetches + inflates the BAM blocks of shard i+1 and decodes the rows of
+shard i-1 (c3r_decode_vcf, all host cores).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+from . import params as P
+from . import decoder, fasta, sharder, weights as W
+from .synth import chunk_geometry
+
+
+def build_shards(contigs, mapped, chunk_size=P.CHUNK_SIZE):
+    """contigs [(name, len)], mapped {name: reads} -> ([(name, len, chunk_id1, chunk_num)], [cost])"""
+    shards, costs = [], []
+    for name, length in contigs:
+        n = mapped.get(name, 0)
+        if n <= 0:
+            continue
+        num = max(1, -(-length // chunk_size))
+        for i in range(num):
+            shards.append((name, length, i + 1, num))
+            costs.append(n / num)
+    return shards, costs
+
+
+def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, world=1, phased=False, padding=False,
+        snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF, min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ,
+        qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None):
+    from .bam import BamFile
+    from .engine import Engine, decode_vcf_rows
+    fai = fasta.read_fai(ref_fn)
+    bf = BamFile(bam_fn)
+    idx = {n: m for n, _, m, _ in bf.idxstats()}
+    ctgs = [(n, l) for n, l in zip(bf.references, bf.lengths) if n in fai and (contigs is None or n in contigs)]
+    shards, costs = build_shards(ctgs, idx)
+    owner = sharder.assign(costs, world)
+    mine = [i for i in range(len(shards)) if owner[i] == rank]
+    C = P.CHANNEL_SIZE + (P.PHASED_CHANNEL_SIZE if phased else 0)
+    eng = Engine(device, C, snp_min_af=snp_min_af, indel_min_af=indel_min_af, min_coverage=min_coverage,
+                 min_mq=min_mq, enable_padding=padding)
+    eng.set_weights(W.load(chkpnt_fn))
+    t0 = time.time()
+    rows_of = {}
+    n_cand = 0
+
+    def load(i):
+        name, length, cid, num = shards[i]
+        _, _, s1, e1, rs1, re1 = chunk_geometry(length, cid, num)
+        batch = bf.fetch(name, s1, e1)
+        ref = fasta.fetch(ref_fn, fai, name, rs1, re1)
+        return name, batch, ref, rs1, s1, e1
+
+    pending = None                                   # (shard index, ticket, name, batch, ref, rs1)
+    for i in mine + [None]:
+        nxt = None
+        if i is not None:
+            name, batch, ref, rs1, s1, e1 = load(i)
+            nxt = (i, eng.submit(batch, ref, rs1, s1, e1), name, batch, ref, rs1)
+        if pending is not None:
+            j, ticket, pname, pbatch, pref, prs1 = pending
+            res = eng.wait(ticket)
+            n_cand += res.n_cand
+            rows_of[j] = decode_vcf_rows(res, pbatch, pref, prs1, pname, qual=qual)
+        pending = nxt
+    eng.close()
+    bf.close()
+    if stats is not None:
+        stats.update(shards=len(mine), candidates=n_cand, seconds=time.time() - t0)
+    if world > 1:
+        if gather is None:
+            import torch.distributed as dist
+
+            def gather(obj):
+                out = [None] * world if rank == 0 else None
+                dist.gather_object(obj, out, dst=0)
+                return out
+        parts = gather(rows_of)
+        if rank != 0:
+            return None
+        rows_of = {}
+        for p in parts:
+            rows_of.update(p)
+    merged = sharder.merge_rows([rows_of[i] for i in range(len(shards))], [n for n, _ in ctgs])
+    if os.path.exists(output):
+        os.remove(output)
+    if merged:                                       # like the reference: no file when there is no record
+        header = decoder.vcf_header([(n, fai[n][0]) for n in fai], sample_name, ref_fn)
+        with open(output, "w") as fp:
+            fp.write(header + "\n")
+            fp.write("\n".join(merged) + "\n")
+    return merged
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="pileup calling of a whole BAM on the GPU(s) of one node")
+    ap.add_argument("--bam_fn", required=True)
+    ap.add_argument("--ref_fn", required=True)
+    ap.add_argument("--chkpnt_fn", required=True)
+    ap.add_argument("--output", required=True)
+    ap.add_argument("--ctgName", default=None, help="comma separated contigs (default: all with mapped reads)")
+    ap.add_argument("--sampleName", default="SAMPLE")
+    ap.add_argument("--snp_min_af", type=float, default=P.SNP_MIN_AF)
+    ap.add_argument("--indel_min_af", type=float, default=P.INDEL_MIN_AF)
+    ap.add_argument("--minCoverage", type=int, default=P.MIN_COVERAGE)
+    ap.add_argument("--minMQ", type=int, default=P.MIN_MQ)
+    ap.add_argument("--qual", type=int, default=P.QUAL_CUT_OFF)
+    ap.add_argument("--enable_phasing_model", action="store_true")
+    ap.add_argument("--enable_padding_in_splice_junction_regions", action="store_true")
+    a = ap.parse_args(argv)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")              # only VCF rows travel: no device collective on the data path
+    stats = {}
+    run(a.bam_fn, a.ref_fn, a.chkpnt_fn, a.output, contigs=a.ctgName.split(",") if a.ctgName else None, device=local,
+        rank=rank, world=world, phased=a.enable_phasing_model, padding=a.enable_padding_in_splice_junction_regions,
+        snp_min_af=a.snp_min_af, indel_min_af=a.indel_min_af, min_coverage=a.minCoverage, min_mq=a.minMQ, qual=a.qual,
+        sample_name=a.sampleName, stats=stats)
+    print("[rank %d] %d shards, %d candidates in %.2f s" % (rank, stats["shards"], stats["candidates"], stats["seconds"]),
+          file=sys.stderr)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
