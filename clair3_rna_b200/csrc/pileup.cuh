@@ -222,6 +222,8 @@ struct OpWords {
 
 // -------------------------------------------- S3: rows = dilate16(E) & A, rank
 __device__ __forceinline__ uint32_t row_word(const Dev& d, int64_t w) {
+    uint32_t a = d.covA[w];
+    if (a == 0u) return 0u;                          // most of a contig: no read, no row (and no covE loads)
     const uint32_t e0 = w > 0 ? d.covE[w - 1] : 0u, e1 = d.covE[w], e2 = (w + 1 < d.NW) ? d.covE[w + 1] : 0u;
     // 96-bit smear by 16 to the left and to the right; only the middle word is needed
     // left smear (towards higher positions): bit i set if any of bits i-16..i set
@@ -232,7 +234,6 @@ __device__ __forceinline__ uint32_t row_word(const Dev& d, int64_t w) {
     unsigned long long dn = hi;                                       // smear towards lower bits
     dn |= dn >> 1; dn |= dn >> 2; dn |= dn >> 4; dn |= dn >> 8; dn |= dn >> 1;
     const uint32_t dil = (uint32_t)(up >> 32) | (uint32_t)dn;
-    uint32_t a = d.covA[w];
     // clear bits beyond the region end
     const int64_t last = d.W - (w << 5);
     if (last < 32) a &= last <= 0 ? 0u : (0xffffffffu >> (32 - last));
@@ -246,7 +247,7 @@ struct OpRows {
     __device__ int64_t size() const { return d.NW; }
     __device__ T load(int64_t w) const { return __popc(row_word(d, w)); }
     __device__ void store(int64_t w, const T& incl, const T& own) const {
-        uint32_t bits = row_word(d, w);
+        uint32_t bits = own ? row_word(d, w) : 0u;
         int32_t base = incl - own;
         d.rowR[w] = bits;
         d.word_base[w] = base;
@@ -303,13 +304,13 @@ constexpr int CMP_THREADS = 256;
 constexpr int CMP_STAGE = 1536;              // events staged per block (24 KB)
 constexpr int COV_TILE = 256;                // rows per k_rows block / coverage aggregate
 
-struct CmpOp {                               // an M/=/X op clipped to the region
+struct __align__(16) CmpOp {                 // an M/=/X op clipped to the region (32 bytes: two 16-byte shared loads)
     int32_t w0, w1;                          // sequence words [w0, w1] holding its bases
-    int32_t lo, hi;                          // first base inside w0, one past the last base inside w1 (0..8)
-    int64_t kw;                              // reference-nibble word of sequence word w: w + kw
+    int32_t kw;                              // reference-nibble word of sequence word w: w + kw
     uint32_t sh;                             // funnel shift (bits) between the two
     int32_t rbase;                           // row of base 8*w + j: rbase + 8*w + j
     uint32_t info;                           // rid << 4 | hp << 2 | rev   (is_del bit clear)
+    uint32_t m0, m1;                         // nibbles of word w0 / of word w1 that belong to the op
 };
 
 struct EventStage {
@@ -341,12 +342,15 @@ __device__ __forceinline__ void cmp_emit(const Dev& d, EventStage& st, const Cmp
 __device__ __forceinline__ void cmp_one(const Dev& d, EventStage& st, const CmpOp& c, int32_t w) {
     uint32_t rw = ((const uint32_t*)d.seq)[w];
     rw = ((rw & 0x0f0f0f0fu) << 4) | ((rw >> 4) & 0x0f0f0f0fu);              // base j of the word at bits 4j..4j+3
-    const int64_t wi = w + c.kw;
-    const uint32_t f0 = (wi >= 0 && wi < d.n_ref_words) ? d.refnib[wi] : 0u;
-    const uint32_t f1 = (wi + 1 >= 0 && wi + 1 < d.n_ref_words) ? d.refnib[wi + 1] : 0u;
+    const int32_t wi = w + c.kw;
+    uint32_t f0, f1;
+    if ((uint32_t)wi < (uint32_t)(d.n_ref_words - 1)) { f0 = d.refnib[wi]; f1 = d.refnib[wi + 1]; }
+    else {                                                                   // op reaches over an end of the loaded reference
+        f0 = (wi >= 0 && wi < d.n_ref_words) ? d.refnib[wi] : 0u;
+        f1 = (wi + 1 >= 0 && wi + 1 < d.n_ref_words) ? d.refnib[wi + 1] : 0u;
+    }
     uint32_t x = rw ^ __funnelshift_r(f0, f1, c.sh);
-    if (w == c.w0) x &= ~nibmask(c.lo);
-    if (w == c.w1) x &= nibmask(c.hi);
+    x &= (w == c.w0 ? c.m0 : 0xffffffffu) & (w == c.w1 ? c.m1 : 0xffffffffu);
     if (x) cmp_emit(d, st, c, w, rw, x);
 }
 
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
     if (threadIdx.x == 0) st.n = 0;
     __syncthreads();
     CmpOp cmp;
-    cmp.w0 = 0; cmp.w1 = -1; cmp.lo = 0; cmp.hi = 8; cmp.kw = 0; cmp.sh = 0; cmp.rbase = 0; cmp.info = 0;
+    cmp.w0 = 0; cmp.w1 = -1; cmp.kw = 0; cmp.sh = 0; cmp.rbase = 0; cmp.info = 0; cmp.m0 = 0; cmp.m1 = 0;
     do {
         if (k >= d.n_ops) break;
         const int32_t r = d.op_rid[k];
@@ -406,9 +410,9 @@ __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
                 const int64_t qa = (int64_t)d.op_y[k] + (a - x);             // base index of position a
                 const int64_t qb = qa + (b - a);
                 cmp.w0 = (int32_t)(qa >> 3); cmp.w1 = (int32_t)((qb - 1) >> 3);
-                cmp.lo = (int)(qa & 7); cmp.hi = (int)(qb - 8 * (int64_t)cmp.w1);
+                cmp.m0 = ~nibmask((int)(qa & 7)); cmp.m1 = nibmask((int)(qb - 8 * (int64_t)cmp.w1));
                 const int64_t K = ((int64_t)a - d.ref_start0) - qa;          // reference offset of base q: q + K
-                cmp.kw = K >> 3;
+                cmp.kw = (int32_t)(K >> 3);
                 cmp.sh = ((uint32_t)K & 7u) * 4u;
                 cmp.rbase = (int32_t)((int64_t)ra - qa);
                 cmp.info = ((uint32_t)r << 4) | (hp << 2) | rev;
