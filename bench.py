@@ -281,11 +281,11 @@ def main():
     if rank == 0:
         pk = peaks()
         st = stage_acc / args.steps                              # ms per step per stage
-        k5_ms, k2_ms = float(st[6]), float(st[3])
+        k5_ms, k2_ms = float(st[6]), float(st[2]) + float(st[3])    # K2 = compare/event pass + row pass
         tr_k5, tr_k2 = measured_traffic(cfg.name) if args.scale == 1.0 else (None, None)
         flops = FLOP_PER_SITE[C] * n_cand
         ach_tf = flops / (k5_ms * 1e-3) / 1e12 if k5_ms > 0 else 0.0
-        # count kernel algorithmic bytes: 0.5 B/aligned base + 16 B/segment entry + 4*C+8 B/row
+        # count path algorithmic bytes: 0.5 B/aligned base + 16 B/op + 4*C+8 B/row
         k2_bytes = 0.5 * batch.n_aligned_bases() + 16.0 * batch.n_ops + (4 * C + 8) * n_rows
         ach_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
         line = {
@@ -299,13 +299,13 @@ def main():
             "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "stage_ms": {"memset": float(st[0]), "k1_scan_rows": float(st[1]), "bin": float(st[2]), "k2_count": k2_ms,
+            "stage_ms": {"memset": float(st[0]), "k1_scan_rows": float(st[1]), "k2_compare_events": float(st[2]), "k2_rows": float(st[3]),
                          "k3_filter": float(st[4]), "k4_window_alt(+host sync)": float(st[5]), "k5_network": k5_ms},
             "roofline": {"kernel": "k5 network (k_lstm_tc x2, k_gemm_tc x2, k_heads)", "bound": "tensor",
                          "achieved": ach_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sus"],
                          "traffic": tr_k5, "traffic_source": "profiles/r1_traffic.json (ncu dram bytes, sum over the K5 kernels captured)" if tr_k5 else None,
                          "peak_source": pk["src"] + " bf16 sustained"},
-            "roofline_count": {"kernel": "k_count", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
+            "roofline_count": {"kernel": "K2 count path (k_cmp, event scan, k_scatter, k_cov_aggr, k_rows)", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                "frac": ach_gbs / pk["hbm"], "traffic": tr_k2, "algorithmic_bytes": k2_bytes,
                                "peak_source": pk["src"]},
         }

@@ -109,7 +109,7 @@ typedef struct {
     const int32_t* row_pos;    /* [n_rows] 1-based, or NULL (keep_rows)                */
     const int32_t* row_counts; /* [n_rows*channels] or NULL (keep_rows)                */
     const int32_t* row_depth;  /* [n_rows] or NULL (keep_rows)                         */
-    float stage_ms[8];         /* device time of: 0 H2D, 1 K1 scan+rows, 2 bin, 3 K2 count, 4 K3 filter,
+    float stage_ms[8];         /* device time of: 0 H2D, 1 K1 scan+rows, 2 K2 compare + row events, 3 K2 rows, 4 K3 filter,
                                   5 K4 window+alt, 6 K5 network, 7 D2H                  */
     int32_t kernel_launches;   /* kernels launched for this ticket                     */
 } c3r_result;
