@@ -31,6 +31,26 @@
 
 namespace c3r {
 
+// The hoisted LSTM2 input projection zx2 is the largest array of the network (41 KB per site and direction) and
+// both its producer (k_gemm_zx) and its consumer (k_lstm_tc<5,0>) are bound by moving it through HBM, so it is
+// stored as 24-bit floats (fp32 rounded to 15 mantissa bits, relative error 2^-17, far below the fp16 operand
+// rounding of the recurrent MMA): 4 values in 3 words, planar so that every store and load stays coalesced:
+//   [tile][t][dir*CH + chunk][32 col-groups][3 planes][128 rows] uint32
+constexpr int ZX_CHUNK_WORDS = 32 * 3 * 128;
+__device__ __forceinline__ uint32_t f24_bits(float v) { return (__float_as_uint(v) + 0x80u) >> 8; }
+__device__ __forceinline__ void pack24(float a, float b, float c, float d, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+    const uint32_t ud = f24_bits(d);
+    w0 = f24_bits(a) | (ud << 24);
+    w1 = f24_bits(b) | ((ud >> 8) << 24);
+    w2 = f24_bits(c) | ((ud >> 16) << 24);
+}
+__device__ __forceinline__ void unpack24(uint32_t w0, uint32_t w1, uint32_t w2, float& a, float& b, float& c, float& d) {
+    a = __uint_as_float(w0 << 8);
+    b = __uint_as_float(w1 << 8);
+    c = __uint_as_float(w2 << 8);
+    d = __uint_as_float(((w0 >> 24) | ((w1 >> 24) << 8) | ((w2 >> 24) << 16)) << 8);
+}
+
 constexpr int TC_TILE = 128;                 // sites per CTA tile
 constexpr int TC_KB = 64;                    // K per pipeline stage
 constexpr int TC_IMG = TC_TILE * TC_KB;      // halfs in one 128x64 operand image (16 KB)
@@ -47,7 +67,7 @@ struct GemmArgs {
     const float* bias;    // [n_tiles*128], GEMM column order
     float* out;
     int m_tiles, n_tiles, n_kb;
-    int mode;             // 0: ZX layout [m][n][32 col-groups][128 rows][4]   1: row-major [m*128+r][n_tiles*128] + SELU
+    int mode;             // 0: 24-bit ZX layout [m][n][32 col-groups][3][128 rows]   1: row-major [m*128+r][n_tiles*128] + SELU
     int dbg;              // experiments: 1 = skip the output stores, 2 = hi*hi term only
     long long* trace;     // optional [64 tiles][32 events] SM-clock stamps of CTA 0
     int* err;
@@ -354,16 +374,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                     uint32_t v[16];
                     ptx::tmem_ld16(taddr + j * 16, v);
                     ptx::tmem_wait_ld();
-                    // ZX layout is per 128-column chunk: [m][n128][32 col-groups][128 rows][4]
-                    float4* o = (float4*)g.out + (((size_t)m * (2 * n_tiles) + 2 * n + (j >> 3)) * 32 + (j & 7) * 4) * 128 + row;
+                    // ZX layout is per 128-column chunk: [m][n128][32 col-groups][3 planes][128 rows], 24-bit floats
+                    uint32_t* o = (uint32_t*)g.out + ((((size_t)m * (2 * n_tiles) + 2 * n + (j >> 3)) * 32 + (j & 7) * 4) * 3) * 128 + row;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
-                        float4 f;
-                        f.x = __uint_as_float(v[c4 * 4 + 0]) + bias[j * 16 + c4 * 4 + 0];
-                        f.y = __uint_as_float(v[c4 * 4 + 1]) + bias[j * 16 + c4 * 4 + 1];
-                        f.z = __uint_as_float(v[c4 * 4 + 2]) + bias[j * 16 + c4 * 4 + 2];
-                        f.w = __uint_as_float(v[c4 * 4 + 3]) + bias[j * 16 + c4 * 4 + 3];
-                        o[(size_t)c4 * 128] = f;
+                        uint32_t w0, w1, w2;
+                        pack24(__uint_as_float(v[c4 * 4 + 0]) + bias[j * 16 + c4 * 4 + 0],
+                               __uint_as_float(v[c4 * 4 + 1]) + bias[j * 16 + c4 * 4 + 1],
+                               __uint_as_float(v[c4 * 4 + 2]) + bias[j * 16 + c4 * 4 + 2],
+                               __uint_as_float(v[c4 * 4 + 3]) + bias[j * 16 + c4 * 4 + 3], w0, w1, w2);
+                        o[(size_t)(c4 * 3 + 0) * 128] = w0;
+                        o[(size_t)(c4 * 3 + 1) * 128] = w1;
+                        o[(size_t)(c4 * 3 + 2) * 128] = w2;
                     }
                 }
                 ptx::tc_fence_before();
@@ -402,7 +424,7 @@ struct LstmArgs {
     const __half* Wimg;     // [2 dirs][2 ranks][B_BYTES/2] operand images
     const __half* xop;      // LSTM1: x operand images [tile][33][KX/8][128][8] (k_xop)
     int C;
-    const float* zx;        // LSTM2: hoisted projection, ZX layout [tile][33][2*CH][32][128][4]
+    const float* zx;        // LSTM2: hoisted projection, 24-bit ZX layout [tile][33][2*CH][32][3][128] (words)
     __half* hout;           // packed output [tile][33][KB_OUT][TC_IMG], high-order fp16 term
     __half* hout_lo;        // low-order term: h - fp16(h), same layout
     int kb_out;             // 64-column blocks per time step in hout (LSTM1: 4, LSTM2: 5)
@@ -572,11 +594,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
         } else if (warp == 1) {
             // ------------------------------------------------ LSTM2: keep the hoisted projection two chunks ahead in L2
             if (KX == 0 && lane == 0) {
-                // one (tile, t, dir, chunk) block of zx2 is 64 KB contiguous
+                // one (tile, t, dir, chunk) block of zx2 is 48 KB contiguous
                 for (int u = 0; u < NT * CH; ++u) {
                     const int step = u / CH, c = u % CH;
                     const int t = dir == 0 ? step : NT - 1 - step;
-                    ptx::bulk_prefetch_l2((const float*)a.zx + ((((size_t)tile * NT + t) * (2 * CH) + dir * CH + c) * 32) * 128 * 4, 65536);
+                    ptx::bulk_prefetch_l2((const uint32_t*)a.zx + (((size_t)tile * NT + t) * (2 * CH) + dir * CH + c) * ZX_CHUNK_WORDS, ZX_CHUNK_WORDS * 4);
                     if (u >= 2) {                            // pace on the MMA commits: use u-2 is complete
                         const uint32_t use = base_use + u - 2;
                         ptx::mbar_wait(b_accf + 8 * (use & 1), (use >> 1) & 1, a.err, 216);
@@ -621,24 +643,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                 for (int c = 0; c < CH; ++c) {
                     const uint32_t use = base_use + step * CH + c;
                     const uint32_t slot = use & 1;
-                    float z[4][8];
+                    uint32_t zw[4][2][3];                        // LSTM2: this thread's 32 hoisted values, 24-bit packed
                     if (KX == 0) {
-                        // hoisted projection: [tile][t][dir*CH + c][gate*8 + ug][row][4]
-                        const float4* zp = (const float4*)a.zx +
-                            ((((size_t)tile * NT + t) * (2 * CH) + dir * CH + c) * 32) * 128 + row;
+                        // hoisted projection: [tile][t][dir*CH + c][gate*8 + ug][plane][row]; requested before the wait
+                        const uint32_t* zp = (const uint32_t*)a.zx +
+                            (((size_t)tile * NT + t) * (2 * CH) + dir * CH + c) * ZX_CHUNK_WORDS + row;
 #pragma unroll
                         for (int gte = 0; gte < 4; ++gte)
 #pragma unroll
-                            for (int ug = 0; ug < 2; ++ug) {
-                                const float4 f = zp[(size_t)(gte * 8 + sub * 2 + ug) * 128];
-                                z[gte][ug * 4 + 0] = f.x; z[gte][ug * 4 + 1] = f.y;
-                                z[gte][ug * 4 + 2] = f.z; z[gte][ug * 4 + 3] = f.w;
-                            }
-                    } else {
+                            for (int ug = 0; ug < 2; ++ug)
 #pragma unroll
-                        for (int gte = 0; gte < 4; ++gte)
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) z[gte][u] = 0.0f;
+                                for (int pl = 0; pl < 3; ++pl)
+                                    zw[gte][ug][pl] = zp[(size_t)((gte * 8 + sub * 2 + ug) * 3 + pl) * 128];
                     }
                     ptx::mbar_wait(b_accf + 8 * slot, (use >> 1) & 1, a.err, 208);
                     ptx::tc_fence_after();
@@ -653,11 +669,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     if (step > 0) ptx::tmem_ld8(tmem + lane_addr + Cfg::C_COL + c * 32 + sub * 8, cprev);
                     ptx::tmem_wait_ld();
                     lstm_trace(a, tr && gw == 0, rank, step, c, 3);
-                    if (has_acc) {
+                    float z[4][8];
 #pragma unroll
-                        for (int gte = 0; gte < 4; ++gte)
+                    for (int gte = 0; gte < 4; ++gte) {
+                        if (KX == 0) {
+#pragma unroll
+                            for (int ug = 0; ug < 2; ++ug)
+                                unpack24(zw[gte][ug][0], zw[gte][ug][1], zw[gte][ug][2], z[gte][ug * 4 + 0], z[gte][ug * 4 + 1],
+                                         z[gte][ug * 4 + 2], z[gte][ug * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) z[gte][u] = 0.0f;
+                        }
+                        if (has_acc) {
 #pragma unroll
                             for (int u = 0; u < 8; ++u) z[gte][u] += __uint_as_float(v[gte][u]);
+                        }
                     }
                     uint32_t cnew[8];
                     __align__(16) __half hh[8];
@@ -893,7 +920,7 @@ inline int tc_ensure(TcNet& t, int tiles, std::string* err) {
     if (t.abuf) cudaFree(t.abuf);
     t.abuf = nullptr;
     const size_t n_h1 = (size_t)tiles * NT * 4 * TC_IMG, n_h2 = (size_t)tiles * NT * 5 * TC_IMG;
-    const size_t n_zx = (size_t)tiles * NT * 10 * 128 * 128, n_l4 = (size_t)tiles * 128 * DENSE;
+    const size_t n_zx = (size_t)tiles * NT * 10 * ZX_CHUNK_WORDS, n_l4 = (size_t)tiles * 128 * DENSE;
     const size_t n_xop = (size_t)tiles * NT * 64 * TC_TILE;
     t.abytes = (n_h1 + n_h2) * 2 * 2 + n_xop * 2 + (n_zx + n_l4) * 4 + 1024;
     cudaError_t e = cudaMalloc(&t.abuf, t.abytes);
@@ -987,7 +1014,7 @@ struct TcSub { int t0, nt; int64_t s0, ns; };
 
 inline cudaError_t tc_lstm2(TcNet& t, const TcSub& b, cudaStream_t st) {
     LstmArgs a2;
-    a2.Wimg = t.img2; a2.xop = nullptr; a2.C = t.C; a2.zx = t.zx2 + (size_t)b.t0 * NT * 10 * 128 * 128;
+    a2.Wimg = t.img2; a2.xop = nullptr; a2.C = t.C; a2.zx = t.zx2 + (size_t)b.t0 * NT * 10 * ZX_CHUNK_WORDS;
     a2.hout = t.h2 + (size_t)b.t0 * NT * 5 * TC_IMG; a2.hout_lo = t.h2_lo + (size_t)b.t0 * NT * 5 * TC_IMG; a2.kb_out = 5;
     a2.n_sites = b.ns; a2.n_tiles = b.nt; a2.err = t.err; a2.trace = (t.trace && b.t0 == 0) ? t.trace + 2 * NT * 8 * 8 : nullptr;
     return launch_lstm<5, 0>(a2, t.sm_count, st);

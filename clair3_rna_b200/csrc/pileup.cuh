@@ -247,15 +247,25 @@ struct OpRows {
     __device__ int64_t size() const { return d.NW; }
     __device__ T load(int64_t w) const { return __popc(row_word(d, w)); }
     __device__ void store(int64_t w, const T& incl, const T& own) const {
-        uint32_t bits = own ? row_word(d, w) : 0u;
-        int32_t base = incl - own;
+        const uint32_t bits = own ? row_word(d, w) : 0u;
+        const int32_t base = incl - own;
         d.rowR[w] = bits;
         d.word_base[w] = base;
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (base < d.L_ub) d.row_pos[base] = d.R0 + (int32_t)(w << 5) + b;
-            ++base;
+        // row_pos of the word's rows: the lanes that are here together write one word's rows at a time
+        // (the k-th lane takes the k-th set bit), instead of every lane walking its own bits
+        const uint32_t act = __activemask();
+        const int lane = threadIdx.x & 31;
+        const int n_act = __popc(act), my = __popc(act & ((1u << lane) - 1u));
+        uint32_t pend = __ballot_sync(act, bits != 0u);
+        while (pend) {
+            const int src = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const uint32_t b = __shfl_sync(act, bits, src);
+            const int32_t bs = __shfl_sync(act, base, src);
+            const int32_t p0 = d.R0 + (int32_t)(__shfl_sync(act, (int32_t)w, src) << 5);
+            const int c = __popc(b);
+            for (int j = my; j < c; j += n_act)
+                if (bs + j < d.L_ub) d.row_pos[bs + j] = p0 + (int32_t)__fns(b, 0, j + 1);
         }
         if (w == d.NW - 1) {
             *d.n_rows = incl;

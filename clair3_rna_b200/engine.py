@@ -184,7 +184,7 @@ class Engine:
         0 -> h1 [n,33,256], 1 -> zx2 [n,33,2,640] (Keras gate columns), 2 -> h2 [n,33,320], 3 -> l4 [n,128]"""
         tiles = (n_sites + 127) // 128
         tiles += tiles & 1
-        sizes = {0: tiles * 33 * 4 * 8192 * 2, 1: tiles * 33 * 10 * 128 * 128 * 4, 2: tiles * 33 * 5 * 8192 * 2,
+        sizes = {0: tiles * 33 * 4 * 8192 * 2, 1: tiles * 33 * 10 * 32 * 3 * 128 * 4, 2: tiles * 33 * 5 * 8192 * 2,
                  3: tiles * 128 * 128 * 4}
         buf = np.empty(sizes[which], np.uint8)
         nb = C.c_int64(0)
@@ -195,7 +195,10 @@ class Engine:
             a = a.transpose(0, 4, 1, 2, 3, 5).reshape(tiles * 128, 33, kb * 64)
             return a[:n_sites].astype(np.float32)
         if which == 1:
-            a = buf.view(np.float32).reshape(tiles, 33, 2, 5, 4, 8, 128, 4)   # [tile][t][dir][chunk][gate][ug][row][4]
+            w = buf.view(np.uint32).reshape(tiles, 33, 2, 5, 4, 8, 3, 128)    # [tile][t][dir][chunk][gate][ug][plane][row]
+            w0, w1, w2 = w[..., 0, :], w[..., 1, :], w[..., 2, :]
+            d = (w0 >> 24) | ((w1 >> 24) << 8) | ((w2 >> 24) << 16)             # 24-bit floats, 4 values in 3 words
+            a = np.stack([w0 << 8, w1 << 8, w2 << 8, d << 8], axis=-1).astype(np.uint32).view(np.float32)
             a = a.transpose(0, 6, 1, 2, 4, 3, 5, 7).reshape(tiles * 128, 33, 2, 4 * 160)   # gate, chunk*32 + ug*4 + i
             return a[:n_sites]
         return buf.view(np.float32).reshape(tiles * 128, 128)[:n_sites]
