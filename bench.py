@@ -48,8 +48,8 @@ def measured_traffic(workload_name):
     if z.get("workload") != workload_name:
         return None, None
     d = z["dram_bytes_per_launch"]
-    k5 = sum(v for k, v in d.items() if k.startswith("k_lstm_tc") or k in ("k_gemm_zx", "k_heads", "k_gemm_tc"))
-    return k5, d.get("k_count<18>")
+    k5 = sum(v for k, v in d.items() if k.startswith("k_lstm_tc") or k.startswith("k_xop") or k in ("k_gemm_zx", "k_heads", "k_gemm_tc"))
+    return k5, d.get("count_path")
 
 
 def dataset(cfg_idx, scale, contig_slot, cache_dir="/tmp/c3r_bench_cache"):
@@ -303,7 +303,7 @@ def main():
                          "k3_filter": float(st[4]), "k4_window_alt(+host sync)": float(st[5]), "k5_network": k5_ms},
             "roofline": {"kernel": "k5 network (k_lstm_tc x2, k_gemm_tc x2, k_heads)", "bound": "tensor",
                          "achieved": ach_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sus"],
-                         "traffic": tr_k5, "traffic_source": "profiles/r1_traffic.json (ncu dram bytes, sum over the K5 kernels captured)" if tr_k5 else None,
+                         "traffic": tr_k5, "traffic_source": "profiles/r1_traffic.json (ncu dram bytes, sum over the K5 kernels)" if tr_k5 else None,
                          "peak_source": pk["src"] + " bf16 sustained"},
             "roofline_count": {"kernel": "K2 count path (k_cmp, event scan, k_scatter, k_cov_aggr, k_rows)", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                "frac": ach_gbs / pk["hbm"], "traffic": tr_k2, "algorithmic_bytes": k2_bytes,
