@@ -76,17 +76,22 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_flag = gpu, [], False
 
-    def run(self):
+    def sample(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            row = [x.strip() for x in out.strip().split(",")]
+            if len(row) >= 7:
+                self.rows.append(row)
+        except Exception:
+            pass
+
+    def run(self):
         while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
+            self.sample()
             time.sleep(0.2)
 
     def summary(self):
@@ -231,11 +236,11 @@ def main():
     res0 = eng.wait(ticket, release=False)
     n_cand, n_rows = res0.n_cand, res0.n_rows
     d2h = res0.pos.nbytes + res0.depth.nbytes + res0.probs.nbytes + res0.alt_off.nbytes + res0.alt_n.nbytes + res0.alt.nbytes
+    sampler = ClockSampler(local_rank)        # samples nvidia-smi through the warm-up, the timed steps and the e2e leg
+    sampler.start()
     for _ in range(args.warmup):
         flush.fill_(1)
         eng.rerun_resident(ticket)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     tot_ms, stage_acc, launches = 0.0, np.zeros(8), 0
     t_wall0 = time.time()
@@ -247,7 +252,6 @@ def main():
         stage_acc += np.array(st)
         launches += nl
     barrier()
-    sampler.stop_flag = True
     eng.release(ticket)
     t_dev = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
     n_all = torch.tensor([float(n_cand)], dtype=torch.float64, device="cuda")
@@ -277,6 +281,11 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e = float(n_all.item()) * args.steps / float(e2e_t.item())
+    if not sampler.rows:                     # very short runs: take one sample with the GPU still busy
+        tk = eng.submit(pbatch, None, 1, region[0], region[1])
+        sampler.sample()
+        eng.wait(tk)
+    sampler.stop_flag = True
 
     if rank == 0:
         pk = peaks()

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
             for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
                 const int m = tile / g.n_tiles, n = tile % g.n_tiles;
                 const size_t ao = (size_t)m * g.n_kb * TC_IMG, bo = (size_t)n * g.n_kb * TC_IMG;
-                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
+                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {       // same k order for every tile: a site's result does not
+                                                                  // depend on where in the batch it sits
                     const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
                     const uint32_t dst = s_base + s * GEMM_STAGE_BYTES;
                     ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 101);
@@ -205,7 +206,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
 // The activation images are re-loaded per k block as soon as the last n-tile has consumed that block
 // (a_free[kb] -> a_full[kb]), so switching m-tiles overlaps with the tail of the previous one.
 // Only the leader CTA issues MMAs; the peer relays "my stage / my A block has landed" with one
-// cluster-scope arrival each, commits are multicast to both CTAs.
+// cluster-scope arrival each, commits are multicast to both CTAs.  CTA pair p walks the n-tiles starting at
+// p mod n_tiles, so that the 74 pairs do not all pull the same weight block out of L2 at the same moment.
 constexpr int ZXG_KB = 4;                                   // K = 256 = 4 k blocks of 64
 constexpr int ZXG_STAGES = 3;
 constexpr int ZXG_THREADS = 224;                            // + warp 6: activation (A) loader
@@ -262,7 +264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                         ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 112);
                         ptx::mbar_arrive_expect_tx(b_full + 8 * s, 2 * IMG_B);
                         // weight images are [n256][rank half][kb64][128 x 64]
-                        const size_t off = ((((size_t)n * 2 + rank) * ZXG_KB) + kb) * TC_IMG;
+                        const size_t off = ((((size_t)((n + pair) % n_tiles) * 2 + rank) * ZXG_KB) + kb) * TC_IMG;
                         ptx::bulk_g2s(s_b + s * 2 * IMG_B, g.B + off, IMG_B, b_full + 8 * s);
                         ptx::bulk_g2s(s_b + s * 2 * IMG_B + IMG_B, g.B_lo + off, IMG_B, b_full + 8 * s);
                     }
@@ -360,8 +362,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
             for (int n = 0; n < n_tiles; ++n, ++tc) {
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's bias readers are done
-                bias_s[threadIdx.x - 64] = g.bias[(size_t)n * 256 + (threadIdx.x - 64)];
-                bias_s[threadIdx.x + 64] = g.bias[(size_t)n * 256 + (threadIdx.x + 64)];
+                const int nn = (n + pair) % n_tiles;            // same rotation as the weight loader
+                bias_s[threadIdx.x - 64] = g.bias[(size_t)nn * 256 + (threadIdx.x - 64)];
+                bias_s[threadIdx.x + 64] = g.bias[(size_t)nn * 256 + (threadIdx.x + 64)];
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const float* bias = bias_s;
                 ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 116);
@@ -375,7 +378,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                     ptx::tmem_ld16(taddr + j * 16, v);
                     ptx::tmem_wait_ld();
                     // ZX layout is per 128-column chunk: [m][n128][32 col-groups][3 planes][128 rows], 24-bit floats
-                    uint32_t* o = (uint32_t*)g.out + ((((size_t)m * (2 * n_tiles) + 2 * n + (j >> 3)) * 32 + (j & 7) * 4) * 3) * 128 + row;
+                    uint32_t* o = (uint32_t*)g.out + ((((size_t)m * (2 * n_tiles) + 2 * nn + (j >> 3)) * 32 + (j & 7) * 4) * 3) * 128 + row;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         uint32_t w0, w1, w2;
