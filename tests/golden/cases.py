@@ -24,6 +24,9 @@ CASES = {
                       platform="hifi", padding=True),
     "phased_noisy": dict(_BASE, cfg=4, scale=0.01, over=dict(genes_per_mb=100, depth=18, sub=0.04, ins=0.03, dele=0.04,
                                                              seed=777003), platform="hifi", phased=True),
+    # config 5 shape: a contig longer than one 5 Mb reference chunk, called chunk by chunk (--chunk_id i --chunk_num 2)
+    # so that the reference's own chunk geometry (create_tensor_pileup.py:380-418) is part of the pin
+    "cfg5_two_chunks": dict(_BASE, cfg=5, scale=0.0245, over=dict(genes_per_mb=6, seed=777052), platform="ont", chunks=2),
     "af_zero": dict(_BASE, cfg=1, scale=0.03, over=dict(genes_per_mb=70, depth=8, seed=777004), platform="ont",
                     snp_af=0.0, min_cov=2),
 }

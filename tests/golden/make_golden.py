@@ -84,11 +84,17 @@ def run_reference_batcher(text, platform):
 def make_case(name):
     case = golden_cases.CASES[name]
     batch, ref_bytes, contig = golden_cases.build(name)
+    n_chunks = case.get("chunks", 1)
+    texts = []
     with tempfile.TemporaryDirectory() as tmp:
         write_fasta(os.path.join(tmp, "ref.fa"), contig, ref_bytes)
         batch.save(os.path.join(tmp, "reads.npz"))
-        text = run_reference_producer(tmp, contig, case["platform"], case["phased"], case["padding"],
-                                      case["snp_af"], case["indel_af"], case["min_cov"], case["min_mq"])
+        for cid in range(1, n_chunks + 1):
+            texts.append(run_reference_producer(tmp, contig, case["platform"], case["phased"], case["padding"],
+                                                case["snp_af"], case["indel_af"], case["min_cov"], case["min_mq"],
+                                                chunk_id=cid, chunk_num=n_chunks))
+    chunk_of = np.concatenate([np.full(len(t.splitlines()), cid + 1, np.int32) for cid, t in enumerate(texts)])
+    text = "".join(texts)
     rows = [r.split("\t") for r in text.splitlines()]
     raw = np.array([[int(v) for v in r[3].split()] for r in rows], dtype=np.int32)
     X, pos, alt = run_reference_batcher(text, case["platform"])
@@ -100,7 +106,7 @@ def make_case(name):
     depth = np.array([int(a.split("-", 1)[0]) for a in alt], np.int64)
     out = os.path.join(HERE, name + ".npz")
     np.savez_compressed(out, pos=p, tensor=X.astype(np.int32), raw=raw.reshape(len(rows), 33, C) if len(rows) else raw,
-                        alt_info=np.array(alt), ref33=np.array(ref33), depth=depth)
+                        alt_info=np.array(alt), ref33=np.array(ref33), depth=depth, chunk=chunk_of)
     print("%-28s candidates=%6d  reads=%6d  rescaled=%d  -> %s (%d KB)" % (
         name, len(rows), batch.n_reads, int((depth > 216).sum()), os.path.basename(out), os.path.getsize(out) // 1024))
 

@@ -36,10 +36,32 @@ def run_case(name, nn_impl):
                  keep_tensor=True, keep_rows=True)
     w = weights.synthetic(C, sharpen=8.0)
     eng.set_weights(w)
-    res = eng.call_chunk(batch, ref, 1, 1, len(ref_bytes) + 33)
+    if case.get("chunks", 1) == 1:
+        res = eng.call_chunk(batch, ref, 1, 1, len(ref_bytes) + 33)
+    else:
+        res = run_chunked(eng, batch, ref, case["chunks"])
     eng.close()
     _cache[key] = (res, batch, ref, w)
     return _cache[key]
+
+
+def run_chunked(eng, batch, ref, n_chunks):
+    """chunk by chunk with the reference's geometry; candidate-space results concatenated in chunk order
+    (alt_info / flank strings are made per chunk against that chunk's read subset)"""
+    from clair3_rna_b200.engine import alt_info_strings, flank_strings
+    from clair3_rna_b200.synth import chunk_geometry
+    import types
+    pos, depth, tensor, probs, alts, flanks = [], [], [], [], [], []
+    for cid in range(1, n_chunks + 1):
+        _, _, s1, e1, rs1, re1 = chunk_geometry(len(ref), cid, n_chunks)
+        sub, r = batch.fetch(s1, e1), ref[rs1 - 1:re1]
+        res = eng.call_chunk(sub, r, rs1, s1, e1)
+        pos.append(res.pos); depth.append(res.depth); tensor.append(res.tensor); probs.append(res.probs)
+        alts += alt_info_strings(res, sub, r, rs1)
+        flanks += flank_strings(res, r, rs1)
+    return types.SimpleNamespace(pos=np.concatenate(pos), depth=np.concatenate(depth), tensor=np.concatenate(tensor),
+                                 probs=np.concatenate(probs), alt_strings=alts, flank_strings=flanks,
+                                 n_cand=sum(len(p) for p in pos))
 
 
 @pytest.mark.parametrize("name", sorted(golden_cases.CASES))
@@ -50,8 +72,10 @@ def test_candidates_and_tensors_match_reference_golden(name):
     assert res.pos.tolist() == g["pos"].tolist()
     assert res.depth.tolist() == g["depth"].tolist()
     assert np.array_equal(res.tensor, g["tensor"])
-    assert alt_info_strings(res, batch, ref, 1) == [str(s).rstrip("\n") for s in g["alt_info"]]
-    assert flank_strings(res, ref, 1) == [str(s) for s in g["ref33"]]
+    alts = res.alt_strings if hasattr(res, "alt_strings") else alt_info_strings(res, batch, ref, 1)
+    flanks = res.flank_strings if hasattr(res, "flank_strings") else flank_strings(res, ref, 1)
+    assert alts == [str(s).rstrip("\n") for s in g["alt_info"]]
+    assert flanks == [str(s) for s in g["ref33"]]
 
 
 @pytest.mark.parametrize("name", ["cfg1_ont_drna", "phased_noisy", "pad_dense"])

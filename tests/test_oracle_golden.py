@@ -21,10 +21,20 @@ def oracle_run(name):
     batch, ref_bytes, contig = golden_cases.build(name)
     ref_seq = ref_bytes.decode("ascii")
     n = len(ref_seq)
-    # one chunk covering the contig: reads [max(1, 0-33), n+33], reference from 1
-    return pileup_oracle.run_region(batch, ref_seq, 1, 1, n + 33, snp_min_af=case["snp_af"],
-                                    indel_min_af=case["indel_af"], min_coverage=case["min_cov"],
-                                    min_mq=case["min_mq"], padding=case["padding"], phased=case["phased"])
+    kw = dict(snp_min_af=case["snp_af"], indel_min_af=case["indel_af"], min_coverage=case["min_cov"],
+              min_mq=case["min_mq"], padding=case["padding"], phased=case["phased"])
+    if case.get("chunks", 1) == 1:
+        # one chunk covering the contig: reads [max(1, 0-33), n+33], reference from 1
+        return pileup_oracle.run_region(batch, ref_seq, 1, 1, n + 33, **kw)
+    # chunk by chunk with the reference's geometry (create_tensor_pileup.py:380-418), results concatenated
+    from clair3_rna_b200.synth import chunk_geometry
+    parts = []
+    for cid in range(1, case["chunks"] + 1):
+        _, _, s1, e1, rs1, re1 = chunk_geometry(n, cid, case["chunks"])
+        parts.append(pileup_oracle.run_region(batch.fetch(s1, e1), ref_seq[rs1 - 1:re1], rs1, s1, e1, **kw))
+    return dict(pos=np.concatenate([p["pos"] for p in parts]), depth=np.concatenate([p["depth"] for p in parts]),
+                tensor=np.concatenate([p["tensor"] for p in parts]), alt_info=sum((list(p["alt_info"]) for p in parts), []),
+                ref33=sum((list(p["ref33"]) for p in parts), []))
 
 
 @pytest.mark.parametrize("name", sorted(golden_cases.CASES))
