@@ -322,9 +322,10 @@ def main():
                                "peak_source": pk["src"]},
         }
         if not args.no_cpu_baseline:
-            n, dt = run_cpu(cfg, batch, ref, w, C, 1, 2)
+            n, dt = run_cpu(cfg, batch, ref, w, C, 1, 8)
             line["cpu_baseline"] = {"value": n / dt if dt > 0 else 0.0, "unit": "sites/s", "cores": 1, "kind": "port",
-                                    "sample": "2 gene regions of the workload (%d candidate sites), oracle port, 1 process" % n}
+                                    "sample": "8 gene regions of the workload (%d candidate sites, %.1f s), oracle port "
+                                              "(mpileup text -> generate_tensor -> fp32 network, batch 200), 1 process" % (n, dt)}
         print(json.dumps(line))
     eng.close()
     if world > 1:

@@ -112,3 +112,32 @@ def test_random_adversarial_inputs_match_oracle(seed, phased, padding):
     assert res.pos.tolist() == ora["pos"].tolist()
     assert np.array_equal(res.tensor, ora["tensor"])
     assert alt_info_strings(res, sub, ref, ref_start1) == ora["alt_info"]
+
+
+def test_all_n_reference_takes_the_capacity_retry():
+    """Against a reference of N every read base is a row event, far beyond the first-attempt event capacity
+    (ops + bases/4): the device flags the overflow and c3r_submit_chunk retries with the exact bound.  Rows
+    must still equal the oracle's columns (base counts by strand, no reference channel to fold them into)."""
+    from clair3_rna_b200 import weights
+    from clair3_rna_b200.engine import Engine
+    from oracle import mpileup, pileup_oracle
+    batch, ref_full = random_case(11, False)
+    ref = np.full_like(ref_full, ord('N'))
+    ref[1000:1400] = ref_full[1000:1400]                 # a stretch of real bases in the middle
+    eng = Engine(0, 18, min_coverage=2, nn_impl=0, keep_rows=True, keep_tensor=True)
+    eng.set_weights(weights.synthetic(18))
+    s1, e1 = 1, 3000
+    res = eng.call_chunk(batch, ref, 1, s1, e1)
+    eng.close()
+    ref_seq = ref.tobytes().decode("ascii")
+    rows = {int(p): i for i, p in enumerate(res.row_pos)}
+    n = 0
+    for pos1, _d, bases, _hps in mpileup.mpileup_rows(batch, s1, e1, 2316, 5):
+        vec, _alt, depth, _pass, _ms = pileup_oracle.column_vector(pos1, bases, ref_seq, 1, None, 0.08, 0.15)
+        if pos1 in rows:
+            assert res.row_counts[rows[pos1]].tolist() == vec, pos1
+            n += 1
+    assert n == len(rows) and n > 1500
+    ora = pileup_oracle.run_region(batch, ref_seq, 1, s1, e1, min_coverage=2)
+    assert res.pos.tolist() == ora["pos"].tolist() and np.array_equal(res.tensor, ora["tensor"])
+    assert all(1001 <= p <= 1400 for p in res.pos.tolist())
