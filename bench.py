@@ -313,10 +313,14 @@ def main():
             "clocks": sampler.summary(),
             "stage_ms": {"memset": float(st[0]), "k1_scan_rows": float(st[1]), "k2_compare_events": float(st[2]), "k2_rows": float(st[3]),
                          "k3_filter": float(st[4]), "k4_window_alt(+host sync)": float(st[5]), "k5_network": k5_ms},
-            "roofline": {"kernel": "k5 network (k_lstm_tc x2, k_gemm_tc x2, k_heads)", "bound": "tensor",
+            "roofline": {"kernel": "K5 network (k_xop, k_lstm_tc<4>, k_gemm_zx, k_lstm_tc<5>, k_gemm_tc, k_heads)", "bound": "tensor",
                          "achieved": ach_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sus"],
                          "traffic": tr_k5, "traffic_source": "profiles/r1_traffic.json (ncu dram bytes, sum over the K5 kernels)" if tr_k5 else None,
-                         "peak_source": pk["src"] + " bf16 sustained"},
+                         "peak_source": pk["src"] + " bf16 sustained",
+                         "hbm_gbs_of_traffic": (tr_k5 / (k5_ms * 1e-3) / 1e9) if (tr_k5 and k5_ms > 0) else None,
+                         "note": "useful flops (47.786 MFLOP/site) over the CUDA-event time of the six network kernels; the "
+                                 "two largest (k_gemm_zx, k_lstm_tc<5>) are limited by moving the hoisted LSTM2 projection "
+                                 "through HBM, see profiles/r1_summary.md"},
             "roofline_count": {"kernel": "K2 count path (k_cmp, event scan, k_scatter, k_cov_aggr, k_rows)", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                "frac": ach_gbs / pk["hbm"], "traffic": tr_k2, "algorithmic_bytes": k2_bytes,
                                "peak_source": pk["src"]},
