@@ -38,17 +38,19 @@ namespace c3r {
 //   [tile][t][dir*CH + chunk][32 col-groups][3 planes][128 rows] uint32
 constexpr int ZX_CHUNK_WORDS = 32 * 3 * 128;
 __device__ __forceinline__ uint32_t f24_bits(float v) { return (__float_as_uint(v) + 0x80u) >> 8; }
+// words: w0 = hi16(a) | hi16(b) << 16, w1 = hi16(c) | hi16(d) << 16, w2 = the four low bytes; one byte permute per
+// value on the way back (its lowest byte repeats the low byte instead of being zero: 2^-16 relative, immaterial)
 __device__ __forceinline__ void pack24(float a, float b, float c, float d, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
-    const uint32_t ud = f24_bits(d);
-    w0 = f24_bits(a) | (ud << 24);
-    w1 = f24_bits(b) | ((ud >> 8) << 24);
-    w2 = f24_bits(c) | ((ud >> 16) << 24);
+    const uint32_t ua = f24_bits(a), ub = f24_bits(b), uc = f24_bits(c), ud = f24_bits(d);
+    w0 = __byte_perm(ua, ub, 0x6521);
+    w1 = __byte_perm(uc, ud, 0x6521);
+    w2 = __byte_perm(__byte_perm(ua, ub, 0x0040), __byte_perm(uc, ud, 0x0040), 0x5410);
 }
 __device__ __forceinline__ void unpack24(uint32_t w0, uint32_t w1, uint32_t w2, float& a, float& b, float& c, float& d) {
-    a = __uint_as_float(w0 << 8);
-    b = __uint_as_float(w1 << 8);
-    c = __uint_as_float(w2 << 8);
-    d = __uint_as_float(((w0 >> 24) | ((w1 >> 24) << 8) | ((w2 >> 24) << 16)) << 8);
+    a = __uint_as_float(__byte_perm(w0, w2, 0x1044));
+    b = __uint_as_float(__byte_perm(w0, w2, 0x3255));
+    c = __uint_as_float(__byte_perm(w1, w2, 0x1066));
+    d = __uint_as_float(__byte_perm(w1, w2, 0x3277));
 }
 
 constexpr int TC_TILE = 128;                 // sites per CTA tile
@@ -445,7 +447,7 @@ constexpr int LSTM_GATE_WARPS = 16;          // 4 per TMEM lane quarter, 8 units
 constexpr int LSTM_THREADS = 64 + 32 * LSTM_GATE_WARPS;   // warp 0: MMA issue, warp 1: x loader, then the gate warps
 
 // Gate math on the SFU.  Default: tanh.approx.f32 (MUFU.TANH, max relative error 2^-11), sigmoid as
-// 0.5*tanh(0.5x)+0.5 - 5 SFU ops per (site, unit).  Its error is of the size of the fp16 rounding h
+// 0.5*tanh(0.5z)+0.5 with the 0.5z folded into the packed weights - 5 SFU ops per (site, unit).  Its error is of the size of the fp16 rounding h
 // already goes through as the next step's MMA operand; measured effect on the output probabilities
 // versus the ex2/rcp form: none (max |dp| 2.53e-4 vs 2.55e-4 on the stress weights, tools/prec_probe.py).
 // LSTM_EXACT_GATES = true selects ex2.approx / rcp.approx (<= 2 ulp each), 8 SFU ops per (site, unit):
@@ -466,7 +468,9 @@ __device__ __forceinline__ float sig_times_tanh(float zs, float zt) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-LOG2E * x)); }
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sigmoid_tanh(float x) { return fmaf(tanh_approx(0.5f * x), 0.5f, 0.5f); }
+// sigmoid(z) from the pre-halved pre-activation x = 0.5 z (the i, f, o columns of every LSTM weight, bias and of the
+// hoisted projection are packed times 0.5 - an exact scaling - so the gate stage saves three multiplies per unit)
+__device__ __forceinline__ float sigmoid_tanh(float x) { return fmaf(tanh_approx(x), 0.5f, 0.5f); }
 
 template <int CH, int KX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_lstm_tc(LstmArgs a) {
@@ -604,7 +608,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     ptx::bulk_prefetch_l2((const uint32_t*)a.zx + (((size_t)tile * NT + t) * (2 * CH) + dir * CH + c) * ZX_CHUNK_WORDS, ZX_CHUNK_WORDS * 4);
                     if (u >= 2) {                            // pace on the MMA commits: use u-2 is complete
                         const uint32_t use = base_use + u - 2;
-                        ptx::mbar_wait(b_accf + 8 * (use & 1), (use >> 1) & 1, a.err, 216);
+                        // best-effort pacing only: if this thread has fallen two uses behind the MMA thread the
+                        // parity test cannot tell (it would see "not yet" until the slot's next use), so give up
+                        // after a short spin instead of treating it as a protocol failure
+                        for (int spin = 0; spin < 2048; ++spin)
+                            if (ptx::mbar_try_wait(b_accf + 8 * (use & 1), (use >> 1) & 1)) break;
                     }
                 }
             }
@@ -634,6 +642,118 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
             const int sub = gw >> 2;                         // which 8 units of the chunk's 32
             const int row = q * 32 + lane;
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+            if (KX == 0) {
+                // ---- LSTM2: the hoisted projection comes from HBM.  A chunk is processed as two groups of 4 units and the
+                // packed values of the NEXT group (which may belong to the next chunk or step) are requested before the
+                // current group's gate math, so their latency hides behind it instead of sitting in front of every chunk.
+                auto zsrc = [&](int hstep) -> const uint32_t* {                  // hstep = (step * CH + c) * 2 + ug
+                    const int ug = hstep & 1, cc = (hstep >> 1) % CH, st = (hstep >> 1) / CH;
+                    const int tt = dir == 0 ? st : NT - 1 - st;
+                    return (const uint32_t*)a.zx + (((size_t)tile * NT + tt) * (2 * CH) + dir * CH + cc) * ZX_CHUNK_WORDS +
+                           (size_t)((sub * 2 + ug) * 3) * 128 + row;
+                };
+                uint32_t zn[4][3];
+                {
+                    const uint32_t* zp = zsrc(0);
+#pragma unroll
+                    for (int gte = 0; gte < 4; ++gte)
+#pragma unroll
+                        for (int pl = 0; pl < 3; ++pl) zn[gte][pl] = zp[(size_t)(gte * 8 * 3 + pl) * 128];
+                }
+                for (int step = 0; step < NT; ++step) {
+                    const uint32_t gstep = base_step + step;
+                    const uint32_t nbuf = (gstep + 1) & 1;       // h_t goes to the buffer step+1 reads
+                    const int t = dir == 0 ? step : NT - 1 - step;
+                    uint8_t* ah = smem + Cfg::B_BYTES + nbuf * Cfg::AH_BYTES;
+                    __half* hout_t = a.hout + ((size_t)tile * NT + t) * a.kb_out * TC_IMG;
+                    __half* hout_lo_t = a.hout_lo + ((size_t)tile * NT + t) * a.kb_out * TC_IMG;
+                    const bool has_acc = step > 0;
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const uint32_t use = base_use + step * CH + c;
+                        const uint32_t slot = use & 1;
+#pragma unroll
+                        for (int ug = 0; ug < 2; ++ug) {
+                            uint32_t zw[4][3];
+#pragma unroll
+                            for (int gte = 0; gte < 4; ++gte)
+#pragma unroll
+                                for (int pl = 0; pl < 3; ++pl) zw[gte][pl] = zn[gte][pl];
+                            const int hnext = (step * CH + c) * 2 + ug + 1;
+                            if (hnext < NT * CH * 2) {
+                                const uint32_t* zp = zsrc(hnext);
+#pragma unroll
+                                for (int gte = 0; gte < 4; ++gte)
+#pragma unroll
+                                    for (int pl = 0; pl < 3; ++pl) zn[gte][pl] = zp[(size_t)(gte * 8 * 3 + pl) * 128];
+                            }
+                            if (ug == 0) {
+                                ptx::mbar_wait(b_accf + 8 * slot, (use >> 1) & 1, a.err, 208);
+                                ptx::tc_fence_after();
+                                lstm_trace(a, tr && gw == 0, rank, step, c, 2);
+                            }
+                            uint32_t cprev[4];
+                            uint32_t v[4][4];
+                            if (has_acc) {
+#pragma unroll
+                                for (int gte = 0; gte < 4; ++gte)
+                                    ptx::tmem_ld4(tmem + lane_addr + slot * 128 + gte * 32 + sub * 8 + ug * 4, v[gte]);
+                                ptx::tmem_ld4(tmem + lane_addr + Cfg::C_COL + c * 32 + sub * 8 + ug * 4, cprev);
+                                ptx::tmem_wait_ld();
+                            }
+                            if (ug == 0) lstm_trace(a, tr && gw == 0, rank, step, c, 3);
+                            float z[4][4];
+#pragma unroll
+                            for (int gte = 0; gte < 4; ++gte) {
+                                unpack24(zw[gte][0], zw[gte][1], zw[gte][2], z[gte][0], z[gte][1], z[gte][2], z[gte][3]);
+                                if (has_acc) {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) z[gte][u] += __uint_as_float(v[gte][u]);
+                                }
+                            }
+                            uint32_t cnew[4];
+                            __align__(8) __half hh[4];
+                            __align__(8) __half hl[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float cp = has_acc ? __uint_as_float(cprev[u]) : 0.0f;
+                                float cn, hv;
+                                if (LSTM_EXACT_GATES) {
+                                    cn = fmaf(sigmoid_fast(2.0f * z[1][u]), cp, sig_times_tanh(2.0f * z[0][u], z[2][u]));
+                                    hv = sig_times_tanh(2.0f * z[3][u], cn);
+                                } else {
+                                    cn = fmaf(sigmoid_tanh(z[1][u]), cp, sigmoid_tanh(z[0][u]) * tanh_approx(z[2][u]));
+                                    hv = sigmoid_tanh(z[3][u]) * tanh_approx(cn);
+                                }
+                                cnew[u] = __float_as_uint(cn);
+                                hh[u] = __float2half(hv);
+                                hl[u] = __float2half(hv - __half2float(hh[u]));
+                            }
+                            ptx::tmem_st4(tmem + lane_addr + Cfg::C_COL + c * 32 + sub * 8 + ug * 4, cnew);
+                            // h_t: next step's A operand (k index = unit): this group's 4 halfs of the row's 16-byte k8 cell
+                            const uint2 pk = *(const uint2*)hh;
+                            const int k8 = c * 4 + sub;
+                            *(uint2*)(ah + (size_t)k8 * (TC_TILE * 16) + row * 16 + ug * 8) = pk;
+                            if (ug == 1) {
+                                ptx::tmem_wait_st();
+                                ptx::tc_fence_before();
+                                // the MMA of step+1 starts only after this warp's LAST arrival of the step, so one
+                                // generic->async proxy fence before that arrival covers all of its h writes
+                                if (c == CH - 1) ptx::fence_proxy_async();
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
+                                lstm_trace(a, tr && gw == 0, rank, step, c, 4);
+                            }
+                            {
+                                const int col8 = (dir * U) / 8 + k8;             // 8-column group in the concat [fwd | bwd]
+                                const size_t oo = (size_t)(col8 / 8) * TC_IMG + (size_t)(col8 % 8) * (TC_TILE * 8) + row * 8 + ug * 4;
+                                *(uint2*)(hout_t + oo) = pk;
+                                *(uint2*)(hout_lo_t + oo) = *(const uint2*)hl;
+                            }
+                        }
+                    }
+                }
+            } else {
             for (int step = 0; step < NT; ++step) {
                 const uint32_t gstep = base_step + step;
                 const uint32_t nbuf = (gstep + 1) & 1;       // h_t goes to the buffer step+1 reads
@@ -697,8 +817,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         const float cp = step > 0 ? __uint_as_float(cprev[u]) : 0.0f;
                         float cn, hv;
                         if (LSTM_EXACT_GATES) {
-                            cn = fmaf(sigmoid_fast(z[1][u]), cp, sig_times_tanh(z[0][u], z[2][u]));
-                            hv = sig_times_tanh(z[3][u], cn);
+                            cn = fmaf(sigmoid_fast(2.0f * z[1][u]), cp, sig_times_tanh(2.0f * z[0][u], z[2][u]));
+                            hv = sig_times_tanh(2.0f * z[3][u], cn);
                         } else {
                             cn = fmaf(sigmoid_tanh(z[1][u]), cp, sigmoid_tanh(z[0][u]) * tanh_approx(z[2][u]));
                             hv = sigmoid_tanh(z[3][u]) * tanh_approx(cn);
@@ -729,6 +849,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         *(uint4*)(hout_lo_t + oo) = *(const uint4*)hl;
                     }
                 }
+            }
             }
             // the step_done commits multicast to this CTA have landed before it may exit
             if (gw == 0) {
@@ -837,19 +958,20 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
                 for (int j = 0; j < 64; ++j) {
                     const int col = rank * 64 + j, gate = col / 32, ul = col % 32;
                     const int kc = gate * U1 + c * 32 + ul;                     // column in [.., 4u]
+                    const float gs = gate == 2 ? 1.0f : 0.5f;                   // i, f, o columns hold 0.5 * z (see the gate math)
                     for (int k = 0; k < KT1; ++k) {
                         __half v = __float2half(0.0f);
                         if (k < C || (k >= C && k < 2 * C)) {
                             const int ch = k < C ? k : k - C;
                             __half hi, lo;
-                            split(h[o_w1 + (size_t)ch * 2 * G1 + dir * G1 + kc], hi, lo);
+                            split(gs * h[o_w1 + (size_t)ch * 2 * G1 + dir * G1 + kc], hi, lo);
                             v = k < C ? hi : lo;
                         } else if (k == 2 * C || k == 2 * C + 1) {
                             __half hi, lo;
-                            split(h[o_b1 + dir * G1 + kc], hi, lo);
+                            split(gs * h[o_b1 + dir * G1 + kc], hi, lo);
                             v = k == 2 * C ? hi : lo;
                         } else if (k >= KX) {
-                            v = __float2half(h[o_u1 + (size_t)dir * U1 * G1 + (size_t)(k - KX) * G1 + kc]);
+                            v = __float2half(gs * h[o_u1 + (size_t)dir * U1 * G1 + (size_t)(k - KX) * G1 + kc]);
                         }
                         im[img_index(64, j, k)] = v;
                     }
@@ -861,8 +983,9 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
                 for (int j = 0; j < 64; ++j) {
                     const int col = rank * 64 + j, gate = col / 32, ul = col % 32;
                     const int kc = gate * U2 + c * 32 + ul;
+                    const float gs = gate == 2 ? 1.0f : 0.5f;
                     for (int k = 0; k < KT2; ++k)
-                        im[img_index(64, j, k)] = __float2half(h[o_u2 + (size_t)dir * U2 * G2 + (size_t)k * G2 + kc]);
+                        im[img_index(64, j, k)] = __float2half(gs * h[o_u2 + (size_t)dir * U2 * G2 + (size_t)k * G2 + kc]);
                 }
             }
         }
@@ -875,11 +998,12 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
                 const int gate = j / 32, ul = j % 32;
                 const int kc = gate * U2 + c * 32 + ul;
                 const int col = nt * 128 + j;
-                fb[col] = h[o_b2 + dir * G2 + kc];
+                const float gs = gate == 2 ? 1.0f : 0.5f;
+                fb[col] = gs * h[o_b2 + dir * G2 + kc];
                 for (int k = 0; k < H1W; ++k) {
                     const int n256 = col / 256, half = (col % 256) / 128, r = col % 128;
                     const size_t ix = (((size_t)n256 * 2 + half) * 4 + k / TC_KB) * TC_IMG + img_index(128, r, k % TC_KB);
-                    split(h[o_w2 + (size_t)k * 2 * G2 + dir * G2 + kc], w2p[ix], w2p_lo[ix]);
+                    split(gs * h[o_w2 + (size_t)k * 2 * G2 + dir * G2 + kc], w2p[ix], w2p_lo[ix]);
                 }
             }
         }

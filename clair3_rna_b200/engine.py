@@ -197,8 +197,11 @@ class Engine:
         if which == 1:
             w = buf.view(np.uint32).reshape(tiles, 33, 2, 5, 4, 8, 3, 128)    # [tile][t][dir][chunk][gate][ug][plane][row]
             w0, w1, w2 = w[..., 0, :], w[..., 1, :], w[..., 2, :]
-            d = (w0 >> 24) | ((w1 >> 24) << 8) | ((w2 >> 24) << 16)             # 24-bit floats, 4 values in 3 words
-            a = np.stack([w0 << 8, w1 << 8, w2 << 8, d << 8], axis=-1).astype(np.uint32).view(np.float32)
+            # 24-bit floats: w0 = hi16(a) | hi16(b) << 16, w1 = hi16(c) | hi16(d) << 16, w2 = the four low bytes
+            vals = [((w0 & 0xffff) << 16) | ((w2 & 0xff) << 8), (w0 & 0xffff0000) | (((w2 >> 8) & 0xff) << 8),
+                    ((w1 & 0xffff) << 16) | (((w2 >> 16) & 0xff) << 8), (w1 & 0xffff0000) | (((w2 >> 24) & 0xff) << 8)]
+            a = np.stack(vals, axis=-1).astype(np.uint32).view(np.float32).copy()
+            a[:, :, :, :, [0, 1, 3]] *= 2.0                                   # i, f, o columns are stored as 0.5 * z
             a = a.transpose(0, 6, 1, 2, 4, 3, 5, 7).reshape(tiles * 128, 33, 2, 4 * 160)   # gate, chunk*32 + ug*4 + i
             return a[:n_sites]
         return buf.view(np.float32).reshape(tiles * 128, 128)[:n_sites]
