@@ -488,7 +488,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
     const uint32_t b_w = b0, b_accf = b0 + 8, b_acce = b0 + 24, b_xr = b0 + 40, b_step = b0 + 56;
     const uint32_t b_accr = b0 + 72;
     const uint32_t b_xl = b0 + 88;                           // 11,12: this CTA's x tile landed (bulk copy tx)
-    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 14);
+    // 13: h_t complete in this CTA (its 16 gate warps, once per step) | 15: the peer's relay of the same (leader only).
+    // Accumulator slots are released as soon as the gate warps hold the values in registers (acc_empty), so the MMAs
+    // of the next chunks run under the gate math; only the first MMA of a step waits for h_t (these two barriers).
+    const uint32_t b_hrdy = b0 + 104, b_hrdy_r = b0 + 120;
+    uint32_t* tmem_ptr_s = (uint32_t*)(bars + 20);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     // clusters come in (forward, backward) pairs so a cluster keeps one direction's weights resident
@@ -504,6 +508,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
         ptx::mbar_init(b_xr, 1); ptx::mbar_init(b_xr + 8, 1);            // peer's x tile landed (relayed)
         ptx::mbar_init(b_xl, 1); ptx::mbar_init(b_xl + 8, 1);
         ptx::mbar_init(b_step, 1); ptx::mbar_init(b_step + 8, 1);
+        ptx::mbar_init(b_hrdy, LSTM_GATE_WARPS); ptx::mbar_init(b_hrdy_r, 1);
         ptx::fence_barrier_init();
         // this CTA's half of the direction's weights: resident for the whole kernel
         ptx::mbar_arrive_expect_tx(b_w, Cfg::B_BYTES);
@@ -534,8 +539,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
         const bool tr = a.trace != nullptr && cluster_id == 0 && work_it == 0 && lane == 0;
 
         if (warp == 0) {
-            // ------------------------------------------------ MMA issue (leader CTA, one thread)
-            if (rank == 0 && lane == 0) {
+            // ------------------------------------------------ MMA issue (leader CTA; the whole warp runs the loop
+            // converged, lane 0 is the one whose MMAs and commits take effect)
+            if (rank == 0) {
+                const uint32_t el = lane == 0 ? 1u : 0u;
                 for (int step = 0; step < NT; ++step) {
                     const uint32_t gstep = base_step + step;
                     const uint32_t buf = gstep & 1;
@@ -549,42 +556,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         // slot free (its previous use drained by both CTAs) ...
                         ptx::mbar_wait(b_acce + 8 * slot, ((use >> 1) & 1) ^ 1, a.err, 203);
                         ptx::mbar_wait_cluster(b_accr + 8 * slot, ((use >> 1) & 1) ^ 1, a.err, 213);
-                        // ... and, at the start of a step, every chunk of the previous step finished
-                        // (h complete): the other slot's latest use is use-1.
-                        if (c == 0 && use > 0) {
-                            const uint32_t prev = use - 1;
-                            ptx::mbar_wait(b_acce + 8 * (prev & 1), (prev >> 1) & 1, a.err, 204);
-                            ptx::mbar_wait_cluster(b_accr + 8 * (prev & 1), (prev >> 1) & 1, a.err, 214);
+                        // ... and, at the start of a step, h of the previous step is complete in both CTAs
+                        if (c == 0 && step > 0) {
+                            ptx::mbar_wait(b_hrdy, (gstep - 1) & 1, a.err, 204);
+                            ptx::mbar_wait_cluster(b_hrdy_r, (gstep - 1) & 1, a.err, 214);
                         }
                         ptx::tc_fence_after();
                         lstm_trace(a, tr, 0, step, c, 0);
-                        const uint32_t sb = s_B + c * (64 * KT * 2);
+                        // One thread issues every MMA, so the instructions between two issues are the critical path
+                        // of the whole CTA pair: descriptors are built once per chunk and advanced by constant adds
+                        // (the start-address field counts 16-byte units and cannot carry out of its 14 bits here).
+                        const uint64_t dB0 = ptx::make_smem_desc(s_B + c * (64 * KT * 2), 64 * 16, 128);
                         bool first = true;
                         if (KX > 0) {
-                            const uint32_t sx = s_AX + buf * Cfg::AX_BYTES;
+                            const uint64_t dX0 = ptx::make_smem_desc(s_AX + buf * Cfg::AX_BYTES, TC_TILE * 16, 128);
 #pragma unroll
                             for (int k = 0; k < KX / 16; ++k) {
-                                const uint64_t da = ptx::make_smem_desc(sx + k * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                                const uint64_t db = ptx::make_smem_desc(sb + k * 2 * (64 * 16), 64 * 16, 128);
-                                ptx::mma_f16<2>(tmem + slot * 128, da, db, IDESC, first ? 0u : 1u);
+                                ptx::mma_f16_2cta_elect(tmem + slot * 128, dX0 + (uint64_t)(k * ((2 * TC_TILE * 16) >> 4)),
+                                                        dB0 + (uint64_t)(k * ((2 * 64 * 16) >> 4)), IDESC, first ? 0u : 1u, el);
                                 first = false;
                             }
                         }
                         if (step > 0) {
-                            const uint32_t sh = s_AH + buf * Cfg::AH_BYTES;
+                            const uint64_t dH0 = ptx::make_smem_desc(s_AH + buf * Cfg::AH_BYTES, TC_TILE * 16, 128);
 #pragma unroll
                             for (int k = 0; k < U / 16; ++k) {
-                                const uint64_t da = ptx::make_smem_desc(sh + k * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                                const uint64_t db = ptx::make_smem_desc(sb + (KX / 8 + k * 2) * (64 * 16), 64 * 16, 128);
-                                ptx::mma_f16<2>(tmem + slot * 128, da, db, IDESC, first ? 0u : 1u);
+                                ptx::mma_f16_2cta_elect(tmem + slot * 128, dH0 + (uint64_t)(k * ((2 * TC_TILE * 16) >> 4)),
+                                                        dB0 + (uint64_t)(((KX / 8 + k * 2) * (64 * 16)) >> 4), IDESC, first ? 0u : 1u, el);
                                 first = false;
                             }
                         }
                         // (LSTM2, step 0: no MMA at all; the commit below still fires the barrier)
-                        ptx::mma_commit_2_mcast(b_accf + 8 * slot, 3);
+                        ptx::mma_commit_2_mcast_elect(b_accf + 8 * slot, 3, el);
                         lstm_trace(a, tr, 0, step, c, 1);
                     }
-                    ptx::mma_commit_2_mcast(b_step + 8 * buf, 3);
+                    ptx::mma_commit_2_mcast_elect(b_step + 8 * buf, 3, el);
                 }
             }
             if (rank == 1 && lane == 0) {
@@ -596,6 +602,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     ptx::mbar_wait(b_acce + 8 * slot, (use >> 1) & 1, a.err, 215);
                     ptx::mbar_arrive_cluster(b_accr + 8 * slot, 0);
                     lstm_trace(a, tr, 1, u / CH, u % CH, 5);
+                    if (u % CH == CH - 1) {                  // end of a step: h_t of this CTA is complete
+                        const uint32_t gstep = base_step + u / CH;
+                        ptx::mbar_wait(b_hrdy, gstep & 1, a.err, 217);
+                        ptx::mbar_arrive_cluster(b_hrdy_r, 0);
+                    }
                 }
             }
         } else if (warp == 1) {
@@ -702,6 +713,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                                 ptx::tmem_wait_ld();
                             }
                             if (ug == 0) lstm_trace(a, tr && gw == 0, rank, step, c, 3);
+                            if (ug == 1) {                       // the accumulator slot is in registers: hand it back
+                                ptx::tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
+                                lstm_trace(a, tr && gw == 0, rank, step, c, 4);
+                            }
                             float z[4][4];
 #pragma unroll
                             for (int gte = 0; gte < 4; ++gte) {
@@ -736,13 +753,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                             *(uint2*)(ah + (size_t)k8 * (TC_TILE * 16) + row * 16 + ug * 8) = pk;
                             if (ug == 1) {
                                 ptx::tmem_wait_st();
-                                ptx::tc_fence_before();
-                                // the MMA of step+1 starts only after this warp's LAST arrival of the step, so one
-                                // generic->async proxy fence before that arrival covers all of its h writes
-                                if (c == CH - 1) ptx::fence_proxy_async();
-                                __syncwarp();
-                                if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
-                                lstm_trace(a, tr && gw == 0, rank, step, c, 4);
+                                if (c == CH - 1) {               // this warp's part of h_t is in shared memory: one
+                                    ptx::tc_fence_before();      // generic->async proxy fence covers all of its writes
+                                    ptx::fence_proxy_async();
+                                    __syncwarp();
+                                    if (lane == 0) ptx::mbar_arrive(b_hrdy);
+                                }
                             }
                             {
                                 const int col8 = (dir * U) / 8 + k8;             // 8-column group in the concat [fwd | bwd]
@@ -792,6 +808,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     if (step > 0) ptx::tmem_ld8(tmem + lane_addr + Cfg::C_COL + c * 32 + sub * 8, cprev);
                     ptx::tmem_wait_ld();
                     lstm_trace(a, tr && gw == 0, rank, step, c, 3);
+                    ptx::tc_fence_before();                      // the accumulator slot is in registers: hand it back
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
+                    lstm_trace(a, tr && gw == 0, rank, step, c, 4);
                     float z[4][8];
 #pragma unroll
                     for (int gte = 0; gte < 4; ++gte) {
@@ -833,13 +853,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     const int k8 = c * 4 + sub;
                     *(uint4*)(ah + (size_t)k8 * (TC_TILE * 16) + row * 16) = pk;
                     ptx::tmem_wait_st();
-                    ptx::tc_fence_before();
-                    // the MMA of step+1 starts only after this warp's LAST arrival of the step, so one
-                    // generic->async proxy fence before that arrival covers all of its h writes
-                    if (c == CH - 1) ptx::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(b_acce + 8 * slot);
-                    lstm_trace(a, tr && gw == 0, rank, step, c, 4);
+                    if (c == CH - 1) {                           // this warp's part of h_t is in shared memory: one
+                        ptx::tc_fence_before();                  // generic->async proxy fence covers all of its writes
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(b_hrdy);
+                    }
                     // layer output (hi + lo fp16 terms) goes out AFTER the arrival: the release fence of
                     // the arrival would otherwise wait for these HBM stores on the recurrence's critical path
                     {

@@ -139,6 +139,22 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64
             ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
+// Same instruction, executed by the whole (converged) warp with only the lane whose `elected` is non-zero
+// issuing it.  Keeping the issue path warp-uniform lets the compiler feed the descriptors from uniform
+// registers directly; under a divergent `if (lane == 0)` it wraps every MMA in an elect/R2UR/branch loop.
+__device__ __forceinline__ void mma_f16_2cta_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred p, pe;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+}
+__device__ __forceinline__ void mma_commit_2_mcast_elect(uint32_t bar, uint16_t mask, uint32_t elected) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %2, 0;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(bar), "h"(mask), "r"(elected) : "memory");
+}
 // all previously issued MMAs of this thread arrive on the mbarrier when complete
 __device__ __forceinline__ void mma_commit_1(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
