@@ -322,13 +322,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                         ptx::mbar_wait_cluster(b_pfull + 8 * s, ph, g.err, 125);
                         ptx::tc_fence_after();
                         if (trm) g.trace[tc * 32 + 8 + kb] = clock64();
-                        const uint32_t sa = s_a + kb * 2 * IMG_B, sb = s_b + s * 2 * IMG_B;
-                        for (int term = 0; term < g.terms; ++term) {    // A_hi*B_hi, A_lo*B_hi, A_hi*B_lo
-                            const uint32_t ta = sa + (term == 1 ? IMG_B : 0), tb = sb + (term == 2 ? IMG_B : 0);
+                        // descriptors once per stage, then constant adds (the address field counts 16-byte units)
+                        const uint64_t dA0 = ptx::make_smem_desc(s_a + kb * 2 * IMG_B, TC_TILE * 16, 128);
+                        const uint64_t dB0 = ptx::make_smem_desc(s_b + s * 2 * IMG_B, TC_TILE * 16, 128);
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {          // A_hi*B_hi, A_lo*B_hi, A_hi*B_lo
 #pragma unroll
                             for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
-                                const uint64_t da = ptx::make_smem_desc(ta + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                                const uint64_t db = ptx::make_smem_desc(tb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
+                                const uint64_t da = dA0 + (uint64_t)(((term == 1 ? IMG_B : 0) + k4 * 2 * (TC_TILE * 16)) >> 4);
+                                const uint64_t db = dB0 + (uint64_t)(((term == 2 ? IMG_B : 0) + k4 * 2 * (TC_TILE * 16)) >> 4);
                                 ptx::mma_f16<2>(tmem + slot * 256, da, db, idesc, (kb > 0 || term > 0 || k4 > 0) ? 1u : 0u);
                             }
                         }
