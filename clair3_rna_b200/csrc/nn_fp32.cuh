@@ -160,27 +160,42 @@ __global__ void __launch_bounds__(256) k_lstm_step(const float* __restrict__ zx,
     }
 }
 
-// L5_1/L5_2 + the two SELU heads + softmax.  A block of 128 threads (one per hidden unit) takes
-// HS sites at a time so every weight is read once per HS sites.
+// L5_1/L5_2 + the two SELU heads + softmax.  Persistent blocks of 256 threads keep both 128x128 kernels in shared
+// memory (128 KB, read from L2 once per block instead of once per 16 sites); each half of the block (one thread per
+// hidden unit) takes HS sites at a time.
 constexpr int HS = 16;
-__global__ void __launch_bounds__(128) k_heads(NetF32 w, const float* __restrict__ l4, float* __restrict__ probs, int64_t n) {
-    __shared__ __align__(16) float x[HS][DENSE];
-    __shared__ float a1[HS][DENSE], a2[HS][DENSE], y[HS][24];
-    const int j = threadIdx.x;
-    for (int64_t s0 = (int64_t)blockIdx.x * HS; s0 < n; s0 += (int64_t)gridDim.x * HS) {
-        const int ns = (int)(n - s0 < HS ? n - s0 : HS);
-        for (int i = 0; i < HS; ++i) x[i][j] = i < ns ? l4[(s0 + i) * DENSE + j] : 0.0f;
+constexpr int HEADS_THREADS = 256;
+constexpr int HEADS_SMEM = (2 * DENSE * DENSE + 3 * 2 * HS * DENSE + 2 * HS * 24) * 4;
+__global__ void __launch_bounds__(HEADS_THREADS) k_heads(NetF32 w, const float* __restrict__ l4, float* __restrict__ probs, int64_t n) {
+    extern __shared__ __align__(16) float wsm[];             // [2][DENSE][DENSE]: k51, k52, then the activations
+    float (*x)[HS][DENSE] = (float (*)[HS][DENSE])(wsm + 2 * DENSE * DENSE);
+    float (*a1)[HS][DENSE] = x + 2;
+    float (*a2)[HS][DENSE] = x + 4;
+    float (*y)[HS][24] = (float (*)[HS][24])(wsm + 2 * DENSE * DENSE + 3 * 2 * HS * DENSE);
+    const int hf = threadIdx.x >> 7, j = threadIdx.x & 127;
+    for (int i = threadIdx.x; i < DENSE * DENSE / 4; i += HEADS_THREADS) {
+        ((float4*)wsm)[i] = ((const float4*)w.k51)[i];
+        ((float4*)wsm)[DENSE * DENSE / 4 + i] = ((const float4*)w.k52)[i];
+    }
+    const float* w1s = wsm;
+    const float* w2s = wsm + DENSE * DENSE;
+    const float b1 = w.b51[j], b2 = w.b52[j];
+    __syncthreads();
+    for (int64_t g0 = (int64_t)blockIdx.x * 2 * HS; g0 < n; g0 += (int64_t)gridDim.x * 2 * HS) {
+        const int64_t s0 = g0 + hf * HS;
+        const int ns = (int)(n - s0 < HS ? (n - s0 < 0 ? 0 : n - s0) : HS);
+        for (int i = 0; i < HS; ++i) x[hf][i][j] = i < ns ? l4[(s0 + i) * DENSE + j] : 0.0f;
         __syncthreads();
         float s1[HS], s2[HS];
 #pragma unroll
-        for (int i = 0; i < HS; ++i) { s1[i] = w.b51[j]; s2[i] = w.b52[j]; }
+        for (int i = 0; i < HS; ++i) { s1[i] = b1; s2[i] = b2; }
         for (int k = 0; k < DENSE; k += 4) {             // 4 k per step: one 16-byte shared load feeds 8 FMAs
             float w1[4], w2[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { w1[q] = w.k51[(k + q) * DENSE + j]; w2[q] = w.k52[(k + q) * DENSE + j]; }
+            for (int q = 0; q < 4; ++q) { w1[q] = w1s[(k + q) * DENSE + j]; w2[q] = w2s[(k + q) * DENSE + j]; }
 #pragma unroll
             for (int i = 0; i < HS; ++i) {
-                const float4 xv = *(const float4*)&x[i][k];
+                const float4 xv = *(const float4*)&x[hf][i][k];
                 s1[i] = fmaf(xv.x, w1[0], s1[i]); s2[i] = fmaf(xv.x, w2[0], s2[i]);
                 s1[i] = fmaf(xv.y, w1[1], s1[i]); s2[i] = fmaf(xv.y, w2[1], s2[i]);
                 s1[i] = fmaf(xv.z, w1[2], s1[i]); s2[i] = fmaf(xv.z, w2[2], s2[i]);
@@ -188,34 +203,47 @@ __global__ void __launch_bounds__(128) k_heads(NetF32 w, const float* __restrict
             }
         }
 #pragma unroll
-        for (int i = 0; i < HS; ++i) { a1[i][j] = seluf_(s1[i]); a2[i][j] = seluf_(s2[i]); }
+        for (int i = 0; i < HS; ++i) { a1[hf][i][j] = seluf_(s1[i]); a2[hf][i][j] = seluf_(s2[i]); }
         __syncthreads();
-        // 24 outputs x HS sites = 384 dot products over 128 threads
+        // 24 outputs x HS sites = 384 dot products over the half's 128 threads
         for (int e = j; e < 24 * HS; e += 128) {
             const int i = e / 24, o = e % 24;
             float v;
             if (o < 21) {
                 v = w.by1[o];
-                for (int k = 0; k < DENSE; ++k) v = fmaf(a1[i][k], w.ky1[k * 21 + o], v);
+                for (int k = 0; k < DENSE; ++k) v = fmaf(a1[hf][i][k], w.ky1[k * 21 + o], v);
             } else {
                 v = w.by2[o - 21];
-                for (int k = 0; k < DENSE; ++k) v = fmaf(a2[i][k], w.ky2[k * 3 + (o - 21)], v);
+                for (int k = 0; k < DENSE; ++k) v = fmaf(a2[hf][i][k], w.ky2[k * 3 + (o - 21)], v);
             }
-            y[i][o] = seluf_(v);
+            y[hf][i][o] = seluf_(v);
         }
         __syncthreads();
         for (int e = j; e < 24 * HS; e += 128) {
             const int i = e / 24, o = e % 24;
             if (i >= ns) continue;
             const int lo = o < 21 ? 0 : 21, hi = o < 21 ? 21 : 24;
-            float mx = y[i][lo];
-            for (int k = lo + 1; k < hi; ++k) mx = fmaxf(mx, y[i][k]);
+            float mx = y[hf][i][lo];
+            for (int k = lo + 1; k < hi; ++k) mx = fmaxf(mx, y[hf][i][k]);
             float sum = 0.0f;
-            for (int k = lo; k < hi; ++k) sum += expf(y[i][k] - mx);
-            probs[(s0 + i) * 24 + o] = expf(y[i][o] - mx) / sum;
+            for (int k = lo; k < hi; ++k) sum += expf(y[hf][i][k] - mx);
+            probs[(s0 + i) * 24 + o] = expf(y[hf][i][o] - mx) / sum;
         }
         __syncthreads();
     }
+}
+inline cudaError_t launch_heads(const NetF32& w, const float* l4, float* probs, int64_t n, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if (n <= 0) return cudaSuccess;
+    int64_t groups = (n + 2 * HS - 1) / (2 * HS);
+    const unsigned grid = (unsigned)(groups < sm_count ? groups : sm_count);
+    k_heads<<<grid, HEADS_THREADS, HEADS_SMEM, st>>>(w, l4, probs, n);
+    return cudaGetLastError();
 }
 
 struct NetF32Scratch {
@@ -261,7 +289,7 @@ inline int netf32_forward(const NetF32& w, const NetF32Scratch& s, const int32_t
     dim3 g4((DENSE + 63) / 64, (unsigned)((n + 63) / 64));
     k_sgemm<1><<<g4, 256, 0, st>>>(s.h2, w.k4, w.b4, s.l4, n, DENSE, L4_IN);
     ++launches;
-    k_heads<<<(unsigned)((n + HS - 1) / HS < 4096 ? (n + HS - 1) / HS : 4096), 128, 0, st>>>(w, s.l4, probs, n);
+    launch_heads(w, s.l4, probs, n, 148, st);
     ++launches;
     return launches;
 }

@@ -1174,9 +1174,8 @@ inline cudaError_t tc_l4_heads(TcNet& t, const NetF32& net, const TcSub& b, floa
     g4.mode = 1; g4.err = t.err; g4.dbg = 0; g4.trace = nullptr;
     cudaError_t e = launch_gemm(g4, t.sm_count, st);
     if (e != cudaSuccess) return e;
-    if (b.ns > 0)
-        k_heads<<<(unsigned)((b.ns + HS - 1) / HS < 4096 ? (b.ns + HS - 1) / HS : 4096), 128, 0, st>>>(
-            net, t.l4 + (size_t)b.t0 * 128 * DENSE, probs + b.s0 * 24, b.ns);
+    e = launch_heads(net, t.l4 + (size_t)b.t0 * 128 * DENSE, probs + b.s0 * 24, b.ns, t.sm_count, st);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
