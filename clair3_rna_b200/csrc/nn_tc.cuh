@@ -665,13 +665,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     return (const uint32_t*)a.zx + (((size_t)tile * NT + tt) * (2 * CH) + dir * CH + cc) * ZX_CHUNK_WORDS +
                            (size_t)((sub * 2 + ug) * 3) * 128 + row;
                 };
-                uint32_t zn[4][3];
+                uint32_t zz[2][4][3];                            // group ug uses zz[ug] while zz[ug ^ 1] is being filled
                 {
                     const uint32_t* zp = zsrc(0);
 #pragma unroll
                     for (int gte = 0; gte < 4; ++gte)
 #pragma unroll
-                        for (int pl = 0; pl < 3; ++pl) zn[gte][pl] = zp[(size_t)(gte * 8 * 3 + pl) * 128];
+                        for (int pl = 0; pl < 3; ++pl) zz[0][gte][pl] = zp[(size_t)(gte * 8 * 3 + pl) * 128];
                 }
                 for (int step = 0; step < NT; ++step) {
                     const uint32_t gstep = base_step + step;
@@ -687,18 +687,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         const uint32_t slot = use & 1;
 #pragma unroll
                         for (int ug = 0; ug < 2; ++ug) {
-                            uint32_t zw[4][3];
-#pragma unroll
-                            for (int gte = 0; gte < 4; ++gte)
-#pragma unroll
-                                for (int pl = 0; pl < 3; ++pl) zw[gte][pl] = zn[gte][pl];
                             const int hnext = (step * CH + c) * 2 + ug + 1;
                             if (hnext < NT * CH * 2) {
                                 const uint32_t* zp = zsrc(hnext);
 #pragma unroll
                                 for (int gte = 0; gte < 4; ++gte)
 #pragma unroll
-                                    for (int pl = 0; pl < 3; ++pl) zn[gte][pl] = zp[(size_t)(gte * 8 * 3 + pl) * 128];
+                                    for (int pl = 0; pl < 3; ++pl) zz[ug ^ 1][gte][pl] = zp[(size_t)(gte * 8 * 3 + pl) * 128];
                             }
                             if (ug == 0) {
                                 ptx::mbar_wait(b_accf + 8 * slot, (use >> 1) & 1, a.err, 208);
@@ -724,30 +719,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                             float z[4][4];
 #pragma unroll
                             for (int gte = 0; gte < 4; ++gte) {
-                                unpack24(zw[gte][0], zw[gte][1], zw[gte][2], z[gte][0], z[gte][1], z[gte][2], z[gte][3]);
+                                unpack24(zz[ug][gte][0], zz[ug][gte][1], zz[ug][gte][2], z[gte][0], z[gte][1], z[gte][2], z[gte][3]);
                                 if (has_acc) {
 #pragma unroll
                                     for (int u = 0; u < 4; ++u) z[gte][u] += __uint_as_float(v[gte][u]);
                                 }
                             }
                             uint32_t cnew[4];
-                            __align__(8) __half hh[4];
-                            __align__(8) __half hl[4];
+                            float hv4[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const float cp = has_acc ? __uint_as_float(cprev[u]) : 0.0f;
-                                float cn, hv;
+                                float cn;
                                 if (LSTM_EXACT_GATES) {
                                     cn = fmaf(sigmoid_fast(2.0f * z[1][u]), cp, sig_times_tanh(2.0f * z[0][u], z[2][u]));
-                                    hv = sig_times_tanh(2.0f * z[3][u], cn);
+                                    hv4[u] = sig_times_tanh(2.0f * z[3][u], cn);
                                 } else {
                                     cn = fmaf(sigmoid_tanh(z[1][u]), cp, sigmoid_tanh(z[0][u]) * tanh_approx(z[2][u]));
-                                    hv = sigmoid_tanh(z[3][u]) * tanh_approx(cn);
+                                    hv4[u] = sigmoid_tanh(z[3][u]) * tanh_approx(cn);
                                 }
                                 cnew[u] = __float_as_uint(cn);
-                                hh[u] = __float2half(hv);
-                                hl[u] = __float2half(hv - __half2float(hh[u]));
                             }
+                            // h as fp16 hi + lo terms, two values per conversion
+                            __half2 hh2[2], hl2[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                hh2[u] = __floats2half2_rn(hv4[2 * u], hv4[2 * u + 1]);
+                                const float2 back = __half22float2(hh2[u]);
+                                hl2[u] = __floats2half2_rn(hv4[2 * u] - back.x, hv4[2 * u + 1] - back.y);
+                            }
+                            const __half2* hh = hh2;
+                            const __half2* hl = hl2;
                             ptx::tmem_st4(tmem + lane_addr + Cfg::C_COL + c * 32 + sub * 8 + ug * 4, cnew);
                             // h_t: next step's A operand (k index = unit): this group's 4 halfs of the row's 16-byte k8 cell
                             const uint2 pk = *(const uint2*)hh;
