@@ -44,14 +44,14 @@ struct Slot {
     // inputs
     Buf pos, flag, mapq, hp, cigar_off, cigar, seq_off, seq, ref;
     // per read/op
-    Buf admit, read_end, op_head, op_x, op_y, op_rid;
+    Buf admit, read_end, op_head, op_x, op_y, op_rid, blockmax;
     // position space
     Buf covA, covE, rowR, wdiff, word_base;
     // row space
     Buf row_pos, counts, row_depth, row_flag, head_cnt, tail_cnt, skipdiff, max_skip, row_ins, row_del;
     Buf binc, bin_cur, events, raw, cov, cov_tile, refnib;
     Buf cand_row, cand_pos, cand_depth, tensor, alt_off, alt_n, alt, cur_ref, deleted, probs;
-    Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32) [4] max read span (i64) [5] raw row events (i64)
+    Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32) [5] raw row events (i64)
     Buf scan_scratch;
     // pinned results
     Pin h_scalars, h_pos, h_depth, h_probs, h_alt_off, h_alt_n, h_alt, h_tensor, h_row_pos, h_counts, h_row_depth;
@@ -143,6 +143,7 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     CK(cudaMemsetAsync(s.covE.p, 0, (size_t)(d.NW + 4) * 4, st));
     CK(cudaMemsetAsync(s.wdiff.p, 0, (size_t)(d.NW + 4) * 8, st));
     CK(cudaMemsetAsync(s.scalars.p, 0, 64, st));
+    CK(cudaMemsetAsync(s.blockmax.p, 0, (size_t)(d.n_reads / 256 + 2) * 4, st));
     CK(cudaEventRecord(s.ev[1], st));
     if (d.n_reads > 0) {
         k_read_prepare<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, st>>>(d);
@@ -349,7 +350,7 @@ void c3r_destroy(c3r_ctx* ctx) {
     for (int i = 0; i < N_SLOTS; ++i) {
         Slot& s = ctx->slots[i];
         Buf* bs[] = {&s.pos, &s.flag, &s.mapq, &s.hp, &s.cigar_off, &s.cigar, &s.seq_off, &s.seq, &s.ref, &s.admit,
-                     &s.read_end, &s.op_head, &s.op_x, &s.op_y, &s.op_rid, &s.covA, &s.covE, &s.rowR, &s.wdiff,
+                     &s.read_end, &s.op_head, &s.op_x, &s.op_y, &s.op_rid, &s.blockmax, &s.covA, &s.covE, &s.rowR, &s.wdiff,
                      &s.word_base, &s.row_pos, &s.counts, &s.row_depth, &s.row_flag, &s.head_cnt, &s.tail_cnt,
                      &s.skipdiff, &s.max_skip, &s.row_ins, &s.row_del, &s.binc, &s.bin_cur, &s.events, &s.raw, &s.cov, &s.cov_tile, &s.refnib,
                      &s.cand_row, &s.cand_pos, &s.cand_depth, &s.tensor, &s.alt_off, &s.alt_n, &s.alt, &s.cur_ref,
@@ -478,7 +479,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
 #define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
     EN(pos, R * 4); EN(flag, R * 2); EN(mapq, R); EN(hp, R); EN(cigar_off, (R + 1) * 4); EN(cigar, O * 4);
     EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 64); if (ref) { EN(ref, ref_len + 16); }
-    EN(admit, R); EN(read_end, R * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_rid, O * 4);
+    EN(admit, R); EN(read_end, R * 4); EN(blockmax, (R / 256 + 2) * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_rid, O * 4);
     EN(covA, (d.NW + 4) * 4); EN(covE, (d.NW + 4) * 4); EN(rowR, (d.NW + 4) * 4); EN(wdiff, (d.NW + 4) * 8);
     EN(word_base, (d.NW + 4) * 4);
     EN(row_pos, (L_ub + 2) * 4); EN(counts, ((L_ub + 32) * d.C) * 4); EN(row_depth, (L_ub + 2) * 4); EN(row_flag, L_ub + 2);
@@ -513,7 +514,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.n_raw = P<int64_t>(s.scalars) + 5;
     d.refnib = ref ? P<uint32_t>(s.refnib) : P<uint32_t>(ctx->refnib_res);
     d.n_ref_words = (ref_len + 7) / 8;
-    d.max_span = P<int64_t>(s.scalars) + 4;
+    d.blockmax = P<int32_t>(s.blockmax);
     d.cand_row = P<int32_t>(s.cand_row); d.cand_pos = P<int32_t>(s.cand_pos); d.cand_depth = P<int32_t>(s.cand_depth);
     d.cur_ref = P<Int2>(s.cur_ref); d.deleted = P<uint8_t>(s.deleted);
 

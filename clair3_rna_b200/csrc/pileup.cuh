@@ -83,7 +83,7 @@ struct Dev {
     int32_t* cov;                  // [L_ub+2][4 or 6]: Mf Mr Df Dr [M_hp1 M_hp2]
     int32_t* cov_tile;             // [L_ub/256+2][4 or 6]: sums of cov over tiles of 256 rows, then their exclusive prefix
     const uint32_t* refnib; int64_t n_ref_words;     // one-hot reference nibbles of the loaded window (k_refnib)
-    int64_t* max_span;             // device scalar: longest reference span of an admitted read
+    int32_t* blockmax;             // [n_reads/256+1]: largest end of the admitted reads of each block of 256 reads
     // ---- candidates
     int64_t* n_cand; int32_t* cand_row; int64_t cand_cap;
     int32_t* cand_pos; int32_t* cand_depth;
@@ -196,8 +196,7 @@ struct OpCigar {
         if (k + 1 == d.cigar_off[r + 1]) {          // last op: the read's whole span
             const int32_t end = d.pos[r] + (int32_t)(incl.v >> 32);
             d.read_end[r] = end;
-            if ((long long)(incl.v >> 32) > *(volatile long long*)d.max_span)      // few reads raise the maximum
-                atomicMax((unsigned long long*)d.max_span, (unsigned long long)(incl.v >> 32));
+            atomicMax(&d.blockmax[r >> 8], end);
             int64_t a = (int64_t)d.pos[r] - d.R0, b = (int64_t)end - d.R0;
             if (a < 0) a = 0;
             if (b > d.W) b = d.W;
@@ -574,16 +573,14 @@ __device__ __forceinline__ bool ins_equal(const Dev& d, const RowEvent& a, const
 }
 
 // first read (BAM order) that shows the reference base at position p, as key rid * 2.  Reference-relative
-// counting keeps no per-read record of matching bases, so this walks the reads that can reach p: those
-// starting within the longest read span before it.  Only count ties ask for it.
+// counting keeps no per-read record of matching bases, so this walks reads: it starts at the first block of 256 reads
+// whose running maximum of read ends passes p (no earlier read can reach p) and stops at the first read starting
+// after p.  Only count ties ask for it.
 __device__ uint32_t first_ref_read(const Dev& d, int32_t p, uint32_t ref_nib) {
-    const int64_t span = *d.max_span;
-    int64_t lo = 0, hi = d.n_reads;                      // first read with pos > p - span
-    while (lo < hi) {
-        const int64_t m = (lo + hi) >> 1;
-        if ((int64_t)d.pos[m] > (int64_t)p - span) hi = m; else lo = m + 1;
-    }
-    for (int64_t r = lo; r < d.n_reads && d.pos[r] <= p; ++r) {
+    const int64_t n_blocks = (d.n_reads + 255) >> 8;
+    int64_t b = 0;
+    while (b < n_blocks && d.blockmax[b] <= p) ++b;
+    for (int64_t r = b << 8; r < d.n_reads && d.pos[r] <= p; ++r) {
         if (!d.admit[r] || d.read_end[r] <= p) continue;
         int32_t x = d.pos[r];
         uint32_t y = (uint32_t)d.seq_off[r];
