@@ -679,17 +679,104 @@ __global__ void __launch_bounds__(1024) k_cov_aggr(Dev d) {
     }
 }
 
+// Distinct indel alleles among the n events of one row (mismatch events, len == 0, are skipped), enumerated by the
+// whole warp: the first unassigned token becomes the leader and every lane compares its own tokens with it at once.
+// An insertion compare is a chain of dependent sequence loads; done serially per pair it costs about a microsecond,
+// which a het insertion under 500x coverage used to pay tens of thousands of times.  `done` is the warp's bitmap
+// in shared memory (IND_WORDS words: rows of up to IND_MAX events; the callers walk longer rows serially).
+// FOLD merges the two strands of an allele (alt_info keys are case-folded) and tracks the earliest read; without
+// FOLD the strands stay apart (I1/D1 are per strand).
+// visit(leader event, count, first-occurrence key, base index of the first occurrence's inserted bases).
+constexpr int IND_WORDS = 128;
+constexpr int IND_MAX = IND_WORDS * 32;
+template <bool FOLD, class Visit>
+__device__ __forceinline__ void for_each_indel_allele(const Dev& d, const RowEvent* evs, int n, int lane, uint32_t* done,
+                                                      Visit visit) {
+    const int nw = (n + 31) >> 5;
+    for (int w = 0; w < nw; ++w) {
+        const int q = w * 32 + lane;
+        const uint32_t m = __ballot_sync(0xffffffffu, q >= n || evs[q < n ? q : n - 1].len == 0);
+        if (lane == 0) done[w] = m;
+    }
+    __syncwarp();
+    int w0 = 0;
+    for (;;) {
+        while (w0 < nw && done[w0] == 0xffffffffu) ++w0;
+        if (w0 >= nw) break;
+        const RowEvent ev = evs[w0 * 32 + __ffs(~done[w0]) - 1];
+        const bool is_del = ev.info & 2u;
+        int32_t cnt = 0;
+        uint32_t first = 0xffffffffu, first_y = ev.yb;
+        for (int w = w0; w < nw; ++w) {
+            const uint32_t dw = done[w];
+            if (dw == 0xffffffffu) continue;
+            bool match = false;
+            if (!((dw >> lane) & 1u)) {
+                const RowEvent o = evs[w * 32 + lane];
+                const bool same_kind = FOLD ? ((o.info ^ ev.info) & 2u) == 0 : ((o.info ^ ev.info) & 3u) == 0;
+                match = same_kind && (is_del ? o.len == ev.len : ins_equal(d, o, ev, FOLD));
+                if (match) {
+                    const uint32_t kk = (o.info >> 4) * 2u + 1u;
+                    if (kk < first) { first = kk; first_y = o.yb; }
+                }
+            }
+            const uint32_t mm = __ballot_sync(0xffffffffu, match);
+            cnt += __popc(mm);
+            if (lane == 0) done[w] = dw | mm;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t of = __shfl_xor_sync(0xffffffffu, first, o), oy = __shfl_xor_sync(0xffffffffu, first_y, o);
+            if (of < first) { first = of; first_y = oy; }
+        }
+        visit(ev, cnt, first, first_y);
+    }
+}
+
+// indel tokens of one row: per strand totals and the largest distinct allele per strand (I, I1, D, D1 and, phased,
+// IP/DP/IM/DM) into the row vector v.  evs[0..n) may also hold mismatch events (len == 0), which are skipped.
+template <int C>
+__device__ void row_indels(const Dev& d, const RowEvent* evs, int32_t n, int32_t* v, int32_t& ins_cnt, int32_t& del_cnt) {
+    for (int32_t s = 0; s < n; ++s) {
+        const RowEvent e = evs[s];
+        if (e.len == 0) continue;
+        const uint32_t rev = e.info & 1u;
+        const uint32_t hp = (e.info >> 2) & 3u;
+        const bool is_del = e.info & 2u;
+        if (is_del) { ++del_cnt; ++v[rev ? 15 : 6]; } else { ++ins_cnt; ++v[rev ? 13 : 4]; }
+        if (C == 30) {
+            if (hp == 1) ++v[is_del ? 23 : 22]; else if (hp == 2) ++v[is_del ? 29 : 28];
+        }
+        bool seen = false;
+        for (int32_t q = 0; q < s && !seen; ++q) {
+            const RowEvent o = evs[q];
+            if (o.len != 0 && ((o.info ^ e.info) & 3u) == 0 && (is_del ? o.len == e.len : ins_equal(d, o, e, false))) seen = true;
+        }
+        if (seen) continue;
+        int32_t same = 1;
+        for (int32_t q = s + 1; q < n; ++q) {
+            const RowEvent o = evs[q];
+            if (o.len != 0 && ((o.info ^ e.info) & 3u) == 0 && (is_del ? o.len == e.len : ins_equal(d, o, e, false))) ++same;
+        }
+        const int ch = is_del ? (rev ? 16 : 7) : (rev ? 14 : 5);
+        if (same > v[ch]) v[ch] = same;
+    }
+}
+
 // K2 proper.  Block = one coverage tile of 256 rows (grid-stride); thread = row, warp = 32 consecutive
 // rows.  Coverage = tile prefix + in-block prefix of the difference rows; the row's events give everything else:
 // mismatching bases, I/I1/D/D1, phased channels; then the candidate predicate (integer AF threshold
 // tables, first-occurrence tie-break) and the row leaves through shared memory as 16-byte coalesced stores.
 constexpr int ROWS_WARPS = 8;
+constexpr int ROWS_HEAVY = 32;               // rows with more events than this are walked by the whole warp
 template <int C>
 __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(Dev d) {
     constexpr int NC = C == 30 ? 6 : 4;
     static_assert(ROWS_WARPS * 32 == COV_TILE, "one block per coverage tile");
     __shared__ __align__(16) int32_t stage[ROWS_WARPS][TILE_ROWS * C];
     __shared__ int32_t wtot[ROWS_WARPS][NC];
+    __shared__ uint32_t done_s[ROWS_WARPS][IND_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t L = *d.n_rows;
     const int32_t ev_base = d.binc[0];
@@ -742,40 +829,90 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(Dev d) {
         int32_t* v = &stage[warp][lane * C];
 #pragma unroll
         for (int i = 0; i < C; ++i) v[i] = 0;
-        if (live) {
-            unsigned long long wf = 0, wr = 0, wp = 0, wm = 0;       // mismatching A,C,G,T as four 16-bit fields
-            int32_t mm_f = 0, mm_r = 0, mm_p = 0, mm_m = 0;          // all mismatch events incl. N / ambiguity codes
-            int32_t ins_cnt = 0, del_cnt = 0;
-            for (int32_t s = e0; s < e1; ++s) {
-                const RowEvent e = d.events[s];
-                const uint32_t rev = e.info & 1u;
+        unsigned long long wf = 0, wr = 0, wp = 0, wm = 0;           // mismatching A,C,G,T as four 16-bit fields
+        int32_t mm_f = 0, mm_r = 0, mm_p = 0, mm_m = 0;              // all mismatch events incl. N / ambiguity codes
+        int32_t ins_cnt = 0, del_cnt = 0;
+        const bool heavy_me = live && (e1 - e0) > ROWS_HEAVY;
+        // rows with many events (a het variant under deep coverage is hundreds of them): the whole warp walks one such
+        // row at a time - mismatch counters by warp reduction, its indel tokens compacted into shared memory
+        for (uint32_t heavy = __ballot_sync(0xffffffffu, heavy_me); heavy; heavy &= heavy - 1) {
+            const int src = __ffs(heavy) - 1;
+            const int32_t E0 = __shfl_sync(0xffffffffu, e0, src), E1 = __shfl_sync(0xffffffffu, e1, src);
+            unsigned long long af = 0, ar = 0, ap = 0, am = 0;
+            int32_t cf = 0, cr = 0, cp = 0, cm = 0;
+            int32_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};         // indel tokens: ins f, ins r, del f, del r, IP, DP, IM, DM (warp-uniform)
+            for (int32_t s0 = E0; s0 < E1; s0 += 32) {
+                const int32_t s = s0 + lane;
+                RowEvent e;
+                e.info = 0; e.len = 0; e.yb = 5u; e.row = 0;
+                if (s < E1) e = d.events[s];
                 const uint32_t hp = (e.info >> 2) & 3u;
-                if (e.len == 0) {
+                if (e.len == 0 && e.yb <= 4u) {
+                    const unsigned long long inc = e.yb < 4u ? 1ull << (16 * e.yb) : 0ull;
+                    if (e.info & 1u) { ar += inc; ++cr; } else { af += inc; ++cf; }
+                    if (C == 30) {
+                        if (hp == 1) { ap += inc; ++cp; } else if (hp == 2) { am += inc; ++cm; }
+                    }
+                }
+                if (__any_sync(0xffffffffu, e.len != 0)) {
+                    const int x = e.len != 0 ? (int)(e.info & 3u) : -1;       // is_del << 1 | rev
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) t[y] += __popc(__ballot_sync(0xffffffffu, x == y));
+                    if (C == 30) {
+#pragma unroll
+                        for (int y = 0; y < 4; ++y)          // (hp 1, ins) (hp 1, del) (hp 2, ins) (hp 2, del)
+                            t[4 + y] += __popc(__ballot_sync(0xffffffffu, x >= 0 && (int)hp == 1 + (y >> 1) && (x >> 1) == (y & 1)));
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                af += __shfl_xor_sync(0xffffffffu, af, o); ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                cf += __shfl_xor_sync(0xffffffffu, cf, o); cr += __shfl_xor_sync(0xffffffffu, cr, o);
+                if (C == 30) {
+                    ap += __shfl_xor_sync(0xffffffffu, ap, o); am += __shfl_xor_sync(0xffffffffu, am, o);
+                    cp += __shfl_xor_sync(0xffffffffu, cp, o); cm += __shfl_xor_sync(0xffffffffu, cm, o);
+                }
+            }
+            if (lane == src) {
+                wf = af; wr = ar; wp = ap; wm = am;
+                mm_f = cf; mm_r = cr; mm_p = cp; mm_m = cm;
+            }
+            const int32_t n_ind = t[0] + t[1] + t[2] + t[3];
+            if (n_ind > 0 && E1 - E0 > IND_MAX) {            // longer than the bitmap: serial walk of the list
+                if (lane == src) row_indels<C>(d, d.events + E0, E1 - E0, v, ins_cnt, del_cnt);
+            } else if (n_ind > 0) {
+                int32_t best[4] = {0, 0, 0, 0};              // largest distinct allele: I1, i1, D1, d1
+                for_each_indel_allele<false>(d, d.events + E0, E1 - E0, lane, done_s[warp],
+                                             [&](const RowEvent& ev, int32_t cnt, uint32_t, uint32_t) {
+                    const int x = (int)(ev.info & 3u);
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) if (y == x && cnt > best[y]) best[y] = cnt;
+                });
+                if (lane == src) {
+                    ins_cnt = t[0] + t[1]; del_cnt = t[2] + t[3];
+                    v[4] = t[0]; v[13] = t[1]; v[6] = t[2]; v[15] = t[3];
+                    v[5] = best[0]; v[14] = best[1]; v[7] = best[2]; v[16] = best[3];
+                    if (C == 30) { v[22] = t[4]; v[23] = t[5]; v[28] = t[6]; v[29] = t[7]; }
+                }
+            }
+            __syncwarp();
+        }
+        if (live) {
+            if (!heavy_me) {
+                bool any_indel = false;
+                for (int32_t s = e0; s < e1; ++s) {
+                    const RowEvent e = d.events[s];
+                    if (e.len != 0) { any_indel = true; continue; }
+                    const uint32_t rev = e.info & 1u;
+                    const uint32_t hp = (e.info >> 2) & 3u;
                     const unsigned long long inc = e.yb < 4u ? 1ull << (16 * e.yb) : 0ull;
                     if (rev) { wr += inc; ++mm_r; } else { wf += inc; ++mm_f; }
                     if (C == 30) {
                         if (hp == 1) { wp += inc; ++mm_p; } else if (hp == 2) { wm += inc; ++mm_m; }
                     }
-                    continue;
                 }
-                const bool is_del = e.info & 2u;
-                if (is_del) { ++del_cnt; ++v[rev ? 15 : 6]; } else { ++ins_cnt; ++v[rev ? 13 : 4]; }
-                if (C == 30) {
-                    if (hp == 1) ++v[is_del ? 23 : 22]; else if (hp == 2) ++v[is_del ? 29 : 28];
-                }
-                bool seen = false;
-                for (int32_t q = e0; q < s && !seen; ++q) {
-                    const RowEvent o = d.events[q];
-                    if (o.len != 0 && ((o.info ^ e.info) & 3u) == 0 && (is_del ? o.len == e.len : ins_equal(d, o, e, false))) seen = true;
-                }
-                if (seen) continue;
-                int32_t same = 1;
-                for (int32_t q = s + 1; q < e1; ++q) {
-                    const RowEvent o = d.events[q];
-                    if (o.len != 0 && ((o.info ^ e.info) & 3u) == 0 && (is_del ? o.len == e.len : ins_equal(d, o, e, false))) ++same;
-                }
-                const int ch = is_del ? (rev ? 16 : 7) : (rev ? 14 : 5);
-                if (same > v[ch]) v[ch] = same;
+                if (any_indel) row_indels<C>(d, d.events + e0, e1 - e0, v, ins_cnt, del_cnt);
             }
             if (rc >= 'a') rc -= 32;
             const int ri_raw = rc == 'A' ? 0 : rc == 'C' ? 1 : rc == 'G' ? 2 : rc == 'T' ? 3 : -1;
@@ -1011,7 +1148,7 @@ struct OpAltOff {
 // alleles in alt_dict insertion order (create_tensor_pileup.py:223,235,251,259-261): keys are
 // case-folded, so the two strands of one allele merge and keep the earlier first occurrence.
 // One warp per candidate: the lanes split the row's events to find the first read showing each
-// non-reference base; lane 0 then builds the (short) allele list.
+// non-reference base and to collect the indel tokens; lane 0 then builds the (short) allele list.
 __global__ void __launch_bounds__(256) k_altinfo(Dev d) {
     const int64_t n = *d.n_cand < d.cand_cap ? *d.n_cand : d.cand_cap;
     const int lane = threadIdx.x & 31;
@@ -1021,64 +1158,92 @@ __global__ void __launch_bounds__(256) k_altinfo(Dev d) {
     const int32_t p = d.row_pos[row];
     const int64_t off = d.alt_off[i];
     const int32_t e0 = d.binc[row] - d.binc[0], e1 = d.binc[row + 1] - d.binc[0];
-    // first-occurrence key of each non-reference base: the earliest read among the row's mismatch events
+    // One pass over the row's events by all lanes: first-occurrence key of each non-reference base (the earliest read
+    // among the mismatch events), and the indel tokens compacted into shared memory so that the allele loop below does
+    // not walk the whole event list with one dependent global load per event.
+    __shared__ uint32_t done_s[8][IND_WORDS];
+    const int wip = threadIdx.x >> 5;
     uint32_t key[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-    {
-        for (int32_t s = e0 + lane; s < e1; s += 32) {
-            const RowEvent e = d.events[s];
-            if (e.len != 0 || e.yb > 3u) continue;
+    bool any_ind = false;
+    for (int32_t s0 = e0; s0 < e1; s0 += 32) {
+        const int32_t s = s0 + lane;
+        RowEvent e;
+        e.info = 0; e.len = 0; e.yb = 4u; e.row = 0;
+        if (s < e1) e = d.events[s];
+        if (e.len == 0 && e.yb <= 3u) {
             const uint32_t kk = (e.info >> 4) * 2u;
 #pragma unroll
             for (int b = 0; b < 4; ++b) if (b == (int)e.yb && kk < key[b]) key[b] = kk;
         }
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) key[b] = min(key[b], __shfl_xor_sync(0xffffffffu, key[b], sft));
+        any_ind |= e.len != 0;
     }
-    if (lane != 0) return;
-    if (off + 4 + (e1 - e0) > d.alt_cap) { atomicExch(d.err, 4); d.alt_n[i] = 0; return; }
+    any_ind = __any_sync(0xffffffffu, any_ind);
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) key[b] = min(key[b], __shfl_xor_sync(0xffffffffu, key[b], sft));
+    __syncwarp();
+    if (off + 4 + (e1 - e0) > d.alt_cap) { if (lane == 0) { atomicExch(d.err, 4); d.alt_n[i] = 0; } return; }
     AltEntry* out = d.alt + off;
-    int m = 0;
+    int m = 0;                                       // lane 0's count of entries
     bool acgt;
     const int ri = ref_index(d, p, &acgt);
     const char L4[4] = {'A', 'C', 'G', 'T'};
     const int32_t* v = d.counts + (int64_t)row * d.C;
     int32_t alt_cnt = 0;
-    for (int b = 0; b < 4; ++b) {
-        if (b == ri) continue;
-        const int32_t c = v[b] + v[9 + b];
-        if (c <= 0) continue;
-        alt_cnt += c;
-        AltEntry e; e.kind = 'X'; e.base = L4[b]; e.len = 0; e.count = c; e.seq_off = 0; e.order = key[b];
-        out[m++] = e;
-    }
-    for (int32_t s = e0; s < e1; ++s) {
-        const RowEvent ev = d.events[s];
-        if (ev.len == 0) continue;
-        const bool is_del = ev.info & 2u;
-        bool seen = false;
-        for (int32_t q = e0; q < s && !seen; ++q) {
-            const RowEvent o = d.events[q];
-            if (o.len != 0 && ((o.info ^ ev.info) & 2u) == 0 && (is_del ? o.len == ev.len : ins_equal(d, o, ev, true))) seen = true;
+    if (lane == 0) {
+        for (int b = 0; b < 4; ++b) {
+            if (b == ri) continue;
+            const int32_t c = v[b] + v[9 + b];
+            if (c <= 0) continue;
+            alt_cnt += c;
+            AltEntry e; e.kind = 'X'; e.base = L4[b]; e.len = 0; e.count = c; e.seq_off = 0; e.order = key[b];
+            out[m++] = e;
         }
-        if (seen) continue;
-        int32_t cnt = 0;
-        uint32_t first = 0xffffffffu, first_y = ev.yb;
-        for (int32_t q = s; q < e1; ++q) {
-            const RowEvent o = d.events[q];
-            if (o.len != 0 && ((o.info ^ ev.info) & 2u) == 0 && (is_del ? o.len == ev.len : ins_equal(d, o, ev, true))) {
-                ++cnt;
-                const uint32_t kk = (o.info >> 4) * 2u + 1u;
-                if (kk < first) { first = kk; first_y = o.yb; }
+    }
+    // distinct indel alleles (strands folded), their counts and first occurrences
+    if (!any_ind) {
+    } else if (e1 - e0 <= IND_MAX) {
+        for_each_indel_allele<true>(d, d.events + e0, e1 - e0, lane, done_s[wip],
+                                    [&](const RowEvent& ev, int32_t cnt, uint32_t first, uint32_t first_y) {
+            if (lane != 0) return;
+            AltEntry e;
+            e.kind = (ev.info & 2u) ? 'D' : 'I'; e.base = L4[ri];
+            e.len = (uint16_t)(ev.len > 65535 ? 65535 : ev.len);
+            e.count = cnt; e.seq_off = first_y; e.order = first;
+            out[m++] = e;
+        });
+    } else if (lane == 0) {                          // longer than the bitmap: serial walk of the row's list
+        const RowEvent* evs = d.events + e0;
+        const int32_t n_ev = e1 - e0;
+        for (int32_t s = 0; s < n_ev; ++s) {
+            const RowEvent ev = evs[s];
+            if (ev.len == 0) continue;
+            const bool is_del = ev.info & 2u;
+            bool seen = false;
+            for (int32_t q = 0; q < s && !seen; ++q) {
+                const RowEvent o = evs[q];
+                if (o.len != 0 && ((o.info ^ ev.info) & 2u) == 0 && (is_del ? o.len == ev.len : ins_equal(d, o, ev, true))) seen = true;
             }
+            if (seen) continue;
+            int32_t cnt = 0;
+            uint32_t first = 0xffffffffu, first_y = ev.yb;
+            for (int32_t q = s; q < n_ev; ++q) {
+                const RowEvent o = evs[q];
+                if (o.len != 0 && ((o.info ^ ev.info) & 2u) == 0 && (is_del ? o.len == ev.len : ins_equal(d, o, ev, true))) {
+                    ++cnt;
+                    const uint32_t kk = (o.info >> 4) * 2u + 1u;
+                    if (kk < first) { first = kk; first_y = o.yb; }
+                }
+            }
+            AltEntry e;
+            e.kind = is_del ? 'D' : 'I'; e.base = L4[ri];
+            e.len = (uint16_t)(ev.len > 65535 ? 65535 : ev.len);
+            e.count = cnt; e.seq_off = first_y; e.order = first;
+            out[m++] = e;
         }
-        AltEntry e;
-        e.kind = is_del ? 'D' : 'I'; e.base = L4[ri];
-        e.len = (uint16_t)(ev.len > 65535 ? 65535 : ev.len);
-        e.count = cnt; e.seq_off = first_y; e.order = first;
-        out[m++] = e;
     }
+    if (lane != 0) return;
     // insertion sort by first occurrence
     for (int a = 1; a < m; ++a) {
         AltEntry e = out[a];
