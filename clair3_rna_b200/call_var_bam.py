@@ -22,7 +22,6 @@ import numpy as np
 from . import params as P
 from . import decoder, fasta, weights as W
 from .reads import ReadBatch
-from .synth import chunk_geometry
 
 
 def str2bool(v):
@@ -60,32 +59,40 @@ def build_parser():
     ap.add_argument('--enable_variant_calling_at_sequence_head_and_tail', type=str2bool, default=False)
     ap.add_argument('--cmd_fn', type=str, default=None)
     ap.add_argument('--device', type=int, default=0, help="CUDA device ordinal")
+    ap.add_argument('--bed_fn', type=str, default=None, help="confident regions: candidates must overlap them")
+    ap.add_argument('--extend_bed', type=str, default=None, help="BED of the columns to pile up (samtools mpileup -l)")
+    ap.add_argument('--vcf_fn', type=str, default=None, help="genotyping mode: call exactly the sites of this VCF")
     # accepted for argv compatibility, not used by this path
-    for name in ('--samtools', '--pypy', '--python', '--extend_bed', '--bed_fn', '--vcf_fn', '--temp_file_dir',
-                 '--tensorflow_threads'):
+    for name in ('--samtools', '--pypy', '--python', '--temp_file_dir', '--tensorflow_threads'):
         ap.add_argument(name, default=None)
     ap.add_argument('--gvcf', type=str2bool, default=False)
     ap.add_argument('--debug', action='store_true')
     return ap
 
 
-def chunk_region(args, contig_len):
-    """(read_start1, read_end1, ref_start1, ref_end1) as create_tensor_pileup.py:380-418."""
-    if args.chunk_id is not None and args.chunk_num is not None:
-        _, _, s, e, rs, re_ = chunk_geometry(contig_len, args.chunk_id, args.chunk_num)
-        return s, e, rs, re_
-    if args.ctgStart is not None and args.ctgEnd is not None:
-        s = max(1, args.ctgStart - P.NO_OF_POSITIONS)
-        e = args.ctgEnd + P.NO_OF_POSITIONS
-        return s, e, max(1, args.ctgStart - P.EXPAND_REFERENCE_REGION), args.ctgEnd + P.EXPAND_REFERENCE_REGION
-    return 1, contig_len + P.NO_OF_POSITIONS, 1, contig_len
+def chunk_plan(args, contig_len):
+    """regions.ChunkPlan of this call (geometry + site filters) as create_tensor_pileup.py:373-418, or None when the
+    reference would return without output (genotyping chunk without sites)."""
+    from . import regions
+
+    def existing(path):                              # file_path_from: a missing file reads as "option not given"
+        return path if path and os.path.exists(path) else None
+    bed_fn, extend_bed, vcf_fn = existing(args.bed_fn), existing(args.extend_bed), existing(args.vcf_fn)
+    chunked = args.chunk_id is not None and args.chunk_num is not None and args.chunk_id <= args.chunk_num
+    ranged = args.ctgStart is not None and args.ctgEnd is not None and args.ctgStart <= args.ctgEnd
+    return regions.plan_chunk(
+        contig_len, chunk_id=args.chunk_id if chunked else None, chunk_num=args.chunk_num if chunked else None,
+        ctg_start=args.ctgStart if ranged else None, ctg_end=args.ctgEnd if ranged else None,
+        extend_rows=regions.read_bed_rows(extend_bed, args.ctgName) if extend_bed else None,
+        confident_rows=regions.read_bed_rows(bed_fn, args.ctgName) if bed_fn else None,
+        known_positions=regions.read_known_positions(vcf_fn, args.ctgName) if vcf_fn else None)
 
 
-def call_chunk_to_rows(eng, batch, ref, ref_start1, start1, end1, contig, qual, native=True):
+def call_chunk_to_rows(eng, batch, ref, ref_start1, start1, end1, contig, qual, native=True, site_filter=None):
     """GPU pass + decode.  native=True decodes through c3r_decode_vcf (C++, all host cores); native=False is
     the per-candidate Python decoder the native one is checked against (tests/test_decode_native_cpu.py)."""
     from .engine import alt_info_strings, flank_strings, decode_vcf_rows
-    res = eng.call_chunk(batch, ref, ref_start1, start1, end1)
+    res = eng.call_chunk(batch, ref, ref_start1, start1, end1, site_filter)
     if native:
         return decode_vcf_rows(res, batch, ref, ref_start1, contig, qual=qual), res
     alts = alt_info_strings(res, batch, ref, ref_start1)
@@ -101,14 +108,22 @@ def call_chunk_to_rows(eng, batch, ref, ref_start1, start1, end1, contig, qual, 
 
 
 def run(args) -> int:
-    if args.gvcf or args.enable_variant_calling_at_sequence_head_and_tail or args.bed_fn or args.vcf_fn:
-        sys.exit("[ERROR] --gvcf / --bed_fn / --vcf_fn / head-and-tail calling are outside this path (SURVEY.md §8f)")
+    if args.gvcf or args.enable_variant_calling_at_sequence_head_and_tail:
+        sys.exit("[ERROR] --gvcf / head-and-tail calling are outside this path (SURVEY.md §8f)")
     from .engine import Engine
     fai = fasta.read_fai(args.ref_fn)
     if args.ctgName not in fai:
         sys.exit("[ERROR] contig %s not in %s.fai" % (args.ctgName, args.ref_fn))
     contig_len = fai[args.ctgName][0]
-    s1, e1, rs1, re1 = chunk_region(args, contig_len)
+    try:
+        plan = chunk_plan(args, contig_len)
+    except ValueError as e:
+        sys.exit(str(e))
+    if plan is None:                                 # genotyping chunk without sites: no output file, like the reference
+        if os.path.exists(args.call_fn):
+            os.remove(args.call_fn)
+        return 0
+    s1, e1, rs1, re1 = plan.start1, plan.end1, plan.ref_start1, plan.ref_end1
     ref = fasta.fetch(args.ref_fn, fai, args.ctgName, rs1, re1)
     if args.bam_fn.endswith(".npz"):
         batch = ReadBatch.load(args.bam_fn).fetch(s1, e1)
@@ -123,7 +138,7 @@ def run(args) -> int:
                  min_coverage=args.minCoverage, min_mq=args.minMQ,
                  enable_padding=bool(args.enable_padding_in_splice_junction_regions))
     eng.set_weights(W.load(args.chkpnt_fn))
-    rows, _ = call_chunk_to_rows(eng, batch, ref, rs1, s1, e1, args.ctgName, args.qual)
+    rows, _ = call_chunk_to_rows(eng, batch, ref, rs1, s1, e1, args.ctgName, args.qual, site_filter=plan.site_filter())
     eng.close()
     if os.path.exists(args.call_fn):
         os.remove(args.call_fn)

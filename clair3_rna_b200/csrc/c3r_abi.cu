@@ -50,6 +50,7 @@ struct Slot {
     // row space
     Buf row_pos, counts, row_depth, row_flag, head_cnt, tail_cnt, skipdiff, max_skip, row_ins, row_del;
     Buf binc, bin_cur, events, raw, cov, cov_tile, refnib;
+    Buf pbed, cbed, known;     // site filters of the chunk
     Buf cand_row, cand_pos, cand_depth, tensor, alt_off, alt_n, alt, cur_ref, deleted, probs;
     Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32) [5] raw row events (i64)
     Buf scan_scratch;
@@ -77,6 +78,7 @@ struct c3r_ctx {
     NetF32Scratch nscr;
     TcNet tc;                 // tensor-core path state (nn_tc.cuh)
     bool exact_bounds = false; // capacity bounds from an exact host pass over the CIGARs (retry path)
+    const c3r_site_filter* filter = nullptr;   // of the submit in progress
     bool tc_dirty = false;    // a tensor-core forward ran since the last device error check
     Buf thr;                  // allele-frequency threshold tables (k_thr_table)
     Buf ref_res;              // resident reference window (c3r_set_reference)
@@ -151,6 +153,7 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     }
     { OpCigar op; op.d = d; if (d.n_ops > 0) L += device_scan(op, d.n_ops, (ScanElem*)s.scan_scratch.p, (ScanElem*)nullptr, st); }
     { OpWords op; op.d = d; L += device_scan(op, d.NW, (Int2*)s.scan_scratch.p, (Int2*)nullptr, st); }
+    if (d.n_known > 0) { k_mark_known<<<(unsigned)((d.n_known + 255) / 256), 256, 0, st>>>(d); ++L; }
     { OpRows op; op.d = d; L += device_scan(op, d.NW, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
     k_clear_rows<<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[2], st));
@@ -404,9 +407,40 @@ int c3r_set_reference(c3r_ctx* ctx, const uint8_t* ref, int64_t ref_start1, int6
 static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
                        int64_t region_start1, int64_t region_end1, c3r_ticket* ticket);
 
+// sorted, disjoint, non-touching intervals / strictly increasing sites: the device searches them by bisection
+static int check_filter(c3r_ctx* ctx, const c3r_site_filter* f) {
+    if (!f) return 0;
+    const struct { const int32_t* iv; int64_t n; const char* what; } beds[2] = {
+        {f->pileup_bed, f->n_pileup_bed, "pileup_bed"}, {f->confident_bed, f->n_confident_bed, "confident_bed"}};
+    for (const auto& b : beds) {
+        if (b.n > 0 && !b.iv) return fail(ctx, C3R_ERR_ARG, "site filter: interval count without intervals");
+        if (b.n > 0x3fffffff) return fail(ctx, C3R_ERR_CAPACITY, "site filter: too many intervals");
+        for (int64_t k = 0; k < b.n; ++k) {
+            if (b.iv[2 * k] < 0 || b.iv[2 * k + 1] <= b.iv[2 * k] || (k && b.iv[2 * k] <= b.iv[2 * k - 1])) {
+                char m[128];
+                snprintf(m, sizeof m, "site filter: %s must be sorted, non-empty, disjoint and non-touching (interval %lld)", b.what, (long long)k);
+                return fail(ctx, C3R_ERR_ARG, m);
+            }
+        }
+    }
+    if (f->n_known_sites > 0 && !f->known_sites) return fail(ctx, C3R_ERR_ARG, "site filter: site count without sites");
+    if (f->n_known_sites > 0x7fffffff) return fail(ctx, C3R_ERR_CAPACITY, "site filter: too many sites");
+    for (int64_t k = 1; k < f->n_known_sites; ++k)
+        if (f->known_sites[k] <= f->known_sites[k - 1]) return fail(ctx, C3R_ERR_ARG, "site filter: known_sites must be strictly increasing");
+    return 0;
+}
+
 int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
                      int64_t region_start1, int64_t region_end1, c3r_ticket* ticket) {
+    return c3r_submit_chunk_filtered(ctx, rd, ref, ref_start1, ref_len, region_start1, region_end1, nullptr, ticket);
+}
+
+int c3r_submit_chunk_filtered(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
+                              int64_t region_start1, int64_t region_end1, const c3r_site_filter* filter,
+                              c3r_ticket* ticket) {
     if (!ctx || !rd || !ticket) return C3R_ERR_ARG;
+    if (int rc = check_filter(ctx, filter)) return rc;
+    ctx->filter = filter;
     ctx->exact_bounds = false;
     int rc = submit_once(ctx, rd, ref, ref_start1, ref_len, region_start1, region_end1, ticket);
     if (rc == C3R_ERR_CAPACITY && ctx->err.find("device capacity") != std::string::npos) {
@@ -414,6 +448,7 @@ int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int6
         rc = submit_once(ctx, rd, ref, ref_start1, ref_len, region_start1, region_end1, ticket);
         ctx->exact_bounds = false;
     }
+    ctx->filter = nullptr;
     return rc;
 }
 
@@ -470,6 +505,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
         ev_ub = rd->n_ops + rd->n_seq_bytes / 2;
     }
     int64_t L_ub = md_len + 32 * (n_skip + rd->n_reads) + 64;
+    if (ctx->filter && ctx->filter->n_known_sites > 0) L_ub += 33 * ctx->filter->n_known_sites;   // rows around known sites
     if (L_ub > d.W) L_ub = d.W;
     if (L_ub < 64) L_ub = 64;
     d.L_ub = L_ub;
@@ -489,6 +525,13 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     EN(events, d.events_ub * sizeof(RowEvent)); EN(raw, d.events_ub * sizeof(RowEvent));
     EN(cov, (L_ub + 4) * NCOV_MAX * 4); EN(cov_tile, (L_ub / COV_TILE + 4) * NCOV_MAX * 4);
     if (ref) { EN(refnib, ((ref_len + 7) / 8 + 1) * 4); }
+    const c3r_site_filter* flt = ctx->filter;
+    d.n_pbed = d.n_cbed = d.n_known = -1;
+    if (flt) {
+        if (flt->n_pileup_bed >= 0) { EN(pbed, (flt->n_pileup_bed + 1) * 8); d.n_pbed = (int32_t)flt->n_pileup_bed; }
+        if (flt->n_confident_bed >= 0) { EN(cbed, (flt->n_confident_bed + 1) * 8); d.n_cbed = (int32_t)flt->n_confident_bed; }
+        if (flt->n_known_sites >= 0) { EN(known, (flt->n_known_sites + 1) * 4); d.n_known = (int32_t)flt->n_known_sites; }
+    }
     EN(cand_row, (L_ub + 2) * 4); EN(cand_pos, (L_ub + 2) * 4); EN(cand_depth, (L_ub + 2) * 4);
     EN(cur_ref, (L_ub + 2) * 8); EN(deleted, L_ub + 2);
     {
@@ -515,6 +558,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.refnib = ref ? P<uint32_t>(s.refnib) : P<uint32_t>(ctx->refnib_res);
     d.n_ref_words = (ref_len + 7) / 8;
     d.blockmax = P<int32_t>(s.blockmax);
+    d.pbed = P<int32_t>(s.pbed); d.cbed = P<int32_t>(s.cbed); d.known = P<int32_t>(s.known);
     d.cand_row = P<int32_t>(s.cand_row); d.cand_pos = P<int32_t>(s.cand_pos); d.cand_depth = P<int32_t>(s.cand_depth);
     d.cur_ref = P<Int2>(s.cur_ref); d.deleted = P<uint8_t>(s.deleted);
 
@@ -528,6 +572,9 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
         CK(cudaMemcpyAsync(s.cigar_off.p, rd->cigar_off, (rd->n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(s.seq_off.p, rd->seq_off, (rd->n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     }
+    if (d.n_pbed > 0) CK(cudaMemcpyAsync(s.pbed.p, flt->pileup_bed, (size_t)d.n_pbed * 8, cudaMemcpyHostToDevice, st));
+    if (d.n_cbed > 0) CK(cudaMemcpyAsync(s.cbed.p, flt->confident_bed, (size_t)d.n_cbed * 8, cudaMemcpyHostToDevice, st));
+    if (d.n_known > 0) CK(cudaMemcpyAsync(s.known.p, flt->known_sites, (size_t)d.n_known * 4, cudaMemcpyHostToDevice, st));
     if (rd->n_ops > 0) CK(cudaMemcpyAsync(s.cigar.p, rd->cigar, rd->n_ops * 4, cudaMemcpyHostToDevice, st));
     if (rd->n_seq_bytes > 0) CK(cudaMemcpyAsync(s.seq.p, rd->seq, rd->n_seq_bytes, cudaMemcpyHostToDevice, st));
     if (ref && ref_len > 0) {

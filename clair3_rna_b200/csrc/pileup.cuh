@@ -65,6 +65,11 @@ struct Dev {
     int32_t C; int32_t min_cov; int32_t min_mq; uint32_t excl; double snp_af, indel_af;
     int32_t padding; int32_t max_depth; double skip_prop;
     const uint16_t* thr_snp; const uint16_t* thr_indel;     // THR_N entries each (k_thr_table)
+    // ---- optional site filters (create_tensor_pileup.py:446-451, 480-481, 551-556); n < 0: not given.
+    // Intervals: sorted, disjoint, non-touching (start0, end0) pairs; known: sorted 1-based positions.
+    const int32_t* pbed; int32_t n_pbed;                    // mpileup -l: rows exist only inside
+    const int32_t* cbed; int32_t n_cbed;                    // confident BED: [pos-1, pos+max_del+1) must overlap
+    const int32_t* known; int32_t n_known;                  // genotyping: candidates are exactly these sites
     // ---- per read / per op
     uint8_t* admit; int32_t* read_end; int32_t* op_head;
     int32_t* op_x; uint32_t* op_y; int32_t* op_rid;
@@ -218,6 +223,15 @@ struct OpWords {
         if (incl.b > 0) d.covE[w] = 0xffffffffu;
     }
 };
+
+// Genotyping mode: a known site is a candidate even in the middle of an intron, where the columns only carry
+// `>` / `<`; marking the site like an aligned base gives it and its 16 neighbours on each side count rows.
+__global__ void k_mark_known(Dev d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n_known) return;
+    const int64_t o = (int64_t)d.known[i] - 1 - d.R0;
+    if (o >= 0 && o < d.W) atomicOr(&d.covE[o >> 5], 1u << (o & 31));
+}
 
 // -------------------------------------------- S3: rows = dilate16(E) & A, rank
 __device__ __forceinline__ uint32_t row_word(const Dev& d, int64_t w) {
@@ -562,6 +576,29 @@ struct OpSkip {
         d.max_skip[i] = m;
     }
 };
+
+// ------------------------------------------------------------- site filters
+// index of the last interval whose start is <= q, or -1
+__device__ __forceinline__ int iv_last_start_le(const int32_t* iv, int n, int32_t q) {
+    int lo = 0, hi = n;                                  // first interval with start > q
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (iv[2 * mid] <= q) lo = mid + 1; else hi = mid; }
+    return lo - 1;
+}
+// [a, b) lies inside one interval (the intervals do not touch, so a gap-free run cannot span two)
+__device__ __forceinline__ bool iv_contains(const int32_t* iv, int n, int32_t a, int32_t b) {
+    const int k = iv_last_start_le(iv, n, a);
+    return k >= 0 && iv[2 * k + 1] >= b;
+}
+// some interval has start < b and end > a (IntervalTree.overlap, shared/interval_tree.py:80-89)
+__device__ __forceinline__ bool iv_overlaps(const int32_t* iv, int n, int32_t a, int32_t b) {
+    const int k = iv_last_start_le(iv, n, b - 1);
+    return k >= 0 && iv[2 * k + 1] > a;
+}
+__device__ __forceinline__ bool known_site(const int32_t* ks, int n, int32_t pos1) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks[mid] < pos1) lo = mid + 1; else hi = mid; }
+    return lo < n && ks[lo] == pos1;
+}
 
 // ------------------------------------------------------------- K2: rows
 __device__ __forceinline__ bool ins_equal(const Dev& d, const RowEvent& a, const RowEvent& b, bool fold_strand) {
@@ -980,7 +1017,19 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(Dev d) {
                 }
             }
             if (depth > 0 && (d.snp_af == 0.0 || d.indel_af == 0.0)) pass = true;
-            const uint8_t flag = (acgt && pass && depth >= d.min_cov) ? 1 : 0;
+            bool cand = acgt && pass && depth >= d.min_cov;
+            if (d.n_known >= 0) cand = known_site(d.known, d.n_known, p + 1);        // :555-556 - AF, depth and base ignored
+            else if (cand && d.n_cbed >= 0) {
+                // longest deleted reference string of the row, clipped where the loaded reference ends (:234-237)
+                int32_t max_del = 0;
+                const int32_t room = (int32_t)min((int64_t)0x7fffffff, d.ref_len - ((int64_t)p - d.ref_start0) - 1);
+                for (int32_t s = e0; s < e1; ++s) {
+                    const RowEvent e = d.events[s];
+                    if (e.len != 0 && (e.info & 2u)) max_del = max(max_del, min(e.len, max(room, 0)));
+                }
+                cand = iv_overlaps(d.cbed, d.n_cbed, p, p + max_del + 2);
+            }
+            const uint8_t flag = cand ? 1 : 0;
             v[ri] = -fsum;
             v[9 + ri] = -rsum;
             d.row_depth[row] = depth;
@@ -1018,6 +1067,8 @@ struct OpCand {
         if (!d.row_flag[row]) return 0;
         const int64_t o = (int64_t)d.row_pos[row] - d.R0;
         if (o - FLANK < 0 || o + FLANK >= d.W) return 0;
+        // mpileup -l: columns outside the BED are never printed, so the 33 columns must also lie inside it
+        if (d.n_pbed >= 0 && !iv_contains(d.pbed, d.n_pbed, d.row_pos[row] - FLANK, d.row_pos[row] + FLANK + 1)) return 0;
         // 33 consecutive bits of covA starting at o-16
         const int64_t s = o - FLANK;
         const int64_t w = s >> 5;

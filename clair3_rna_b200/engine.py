@@ -116,7 +116,10 @@ class Engine:
         self._check(self.lib.c3r_set_reference(self.ctx, ref.ctypes.data, ref_start1, int(ref.size)), "c3r_set_reference")
 
     # ------------------------------------------------------------------
-    def submit(self, batch: ReadBatch, ref, ref_start1: int, region_start1: int, region_end1: int) -> int:
+    def submit(self, batch: ReadBatch, ref, ref_start1: int, region_start1: int, region_end1: int,
+               site_filter=None) -> int:
+        """site_filter: None or dict(pileup_bed=, confident=, known=) as made by regions.ChunkPlan.site_filter():
+        merged int32 interval arrays [n,2] / sorted 1-based sites; a missing or None entry = option not given."""
         rd = L.Reads()
         rd.n_reads, rd.n_ops, rd.n_seq_bytes = batch.n_reads, batch.n_ops, int(batch.seq.size)
         arrs = dict(pos=np.ascontiguousarray(batch.pos, np.int32), flag=np.ascontiguousarray(batch.flag, np.uint16),
@@ -132,8 +135,23 @@ class Engine:
         else:
             ref = np.ascontiguousarray(ref, np.uint8)
             rp, rn = ref.ctypes.data, int(ref.size)
-        self._check(self.lib.c3r_submit_chunk(self.ctx, C.byref(rd), rp, ref_start1, rn,
-                                              region_start1, region_end1, C.byref(t)), "c3r_submit_chunk")
+        if site_filter is None:
+            self._check(self.lib.c3r_submit_chunk(self.ctx, C.byref(rd), rp, ref_start1, rn,
+                                                  region_start1, region_end1, C.byref(t)), "c3r_submit_chunk")
+            return int(t.value)
+        f = L.SiteFilter()
+        keep = []
+        for key, field, width in (("pileup_bed", "pileup_bed", 2), ("confident", "confident_bed", 2), ("known", "known_sites", 1)):
+            a = site_filter.get(key)
+            if a is None:
+                setattr(f, "n_" + field, -1)
+                continue
+            a = np.ascontiguousarray(a, np.int32).reshape(-1, width)
+            keep.append(a)
+            setattr(f, field, a.ctypes.data if a.size else None)
+            setattr(f, "n_" + field, a.shape[0])
+        self._check(self.lib.c3r_submit_chunk_filtered(self.ctx, C.byref(rd), rp, ref_start1, rn, region_start1,
+                                                       region_end1, C.byref(f), C.byref(t)), "c3r_submit_chunk_filtered")
         return int(t.value)
 
     def wait(self, ticket: int, release: bool = True) -> ChunkResult:
@@ -159,8 +177,8 @@ class Engine:
     def release(self, ticket: int):
         self.lib.c3r_release(self.ctx, ticket)
 
-    def call_chunk(self, batch, ref, ref_start1, region_start1, region_end1) -> ChunkResult:
-        return self.wait(self.submit(batch, ref, ref_start1, region_start1, region_end1))
+    def call_chunk(self, batch, ref, ref_start1, region_start1, region_end1, site_filter=None) -> ChunkResult:
+        return self.wait(self.submit(batch, ref, ref_start1, region_start1, region_end1, site_filter))
 
     def rerun_resident(self, ticket: int):
         """-> (total_ms, [8 stage ms], kernel launches) of one device-resident pass."""

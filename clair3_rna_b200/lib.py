@@ -41,8 +41,15 @@ class Result(C.Structure):
                 ("row_depth", C.c_void_p), ("stage_ms", C.c_float * 8), ("kernel_launches", C.c_int32)]
 
 
+class SiteFilter(C.Structure):
+    """c3r_site_filter (include/c3r_b200.h)"""
+    _fields_ = [("pileup_bed", C.c_void_p), ("n_pileup_bed", C.c_int64),
+                ("confident_bed", C.c_void_p), ("n_confident_bed", C.c_int64),
+                ("known_sites", C.c_void_p), ("n_known_sites", C.c_int64)]
+
+
 EXPORTS = ["c3r_abi_version", "c3r_default_params", "c3r_create", "c3r_destroy", "c3r_last_error",
-           "c3r_set_weights", "c3r_set_reference", "c3r_submit_chunk", "c3r_wait", "c3r_release", "c3r_rerun_resident", "c3r_forward", "c3r_debug_fetch",
+           "c3r_set_weights", "c3r_set_reference", "c3r_submit_chunk", "c3r_submit_chunk_filtered", "c3r_wait", "c3r_release", "c3r_rerun_resident", "c3r_forward", "c3r_debug_fetch",
            "c3r_bam_open", "c3r_bam_close", "c3r_bam_error", "c3r_bam_n_ref", "c3r_bam_ref_name", "c3r_bam_ref_len",
            "c3r_bam_header_text", "c3r_bam_idxstats", "c3r_bam_fetch", "c3r_bam_write",
            "c3r_decode_vcf", "c3r_free_text"]
@@ -71,6 +78,8 @@ def load():
     lib.c3r_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
     lib.c3r_submit_chunk.argtypes = [C.c_void_p, C.POINTER(Reads), C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                      C.c_int64, C.POINTER(C.c_int64)]
+    lib.c3r_submit_chunk_filtered.argtypes = [C.c_void_p, C.POINTER(Reads), C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                              C.c_int64, C.POINTER(SiteFilter), C.POINTER(C.c_int64)]
     lib.c3r_wait.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Result)]
     lib.c3r_release.argtypes = [C.c_void_p, C.c_int64]
     lib.c3r_rerun_resident.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float)]

@@ -13,6 +13,10 @@ gathered on rank 0 (gloo/nccl `gather_object`), merged with sort_vcf semantics (
 Inside a rank the stages of consecutive shards overlap: while the GPU runs shard i (c3r_submit_chunk returns
 once the work is queued), the host fetches + inflates the BAM blocks of shard i+1 and decodes the rows of
 shard i-1 (c3r_decode_vcf, all host cores).
+
+Region modes (`--bed_fn`, `--genotyping_mode_vcf_fn`, run_clair3_rna:319-345, 434-435): contigs are intersected
+with those of the BED / VCF, the per-contig "split BED" (rows widened by 33 bp) becomes the pileup filter of
+every chunk of the contig, and the chunk geometry follows the BED span / the site count (regions.plan_chunk).
 """
 from __future__ import annotations
 
@@ -22,8 +26,7 @@ import sys
 import time
 
 from . import params as P
-from . import decoder, fasta, sharder, weights as W
-from .synth import chunk_geometry
+from . import decoder, fasta, regions, sharder, weights as W
 
 
 def build_shards(contigs, mapped, chunk_size=P.CHUNK_SIZE):
@@ -42,13 +45,16 @@ def build_shards(contigs, mapped, chunk_size=P.CHUNK_SIZE):
 
 def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, world=1, phased=False, padding=False,
         snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF, min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ,
-        qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None):
+        qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None, bed_fn=None, vcf_fn=None):
     from .bam import BamFile
     from .engine import Engine, decode_vcf_rows
     fai = fasta.read_fai(ref_fn)
     bf = BamFile(bam_fn)
     idx = {n: m for n, _, m, _ in bf.idxstats()}
-    ctgs = [(n, l) for n, l in zip(bf.references, bf.lengths) if n in fai and (contigs is None or n in contigs)]
+    conf_rows = regions.read_bed_rows(bed_fn) if bed_fn else None          # {contig: rows}
+    known_pos = regions.read_known_positions(vcf_fn) if vcf_fn else None    # {contig: sites}
+    ctgs = [(n, l) for n, l in zip(bf.references, bf.lengths) if n in fai and (contigs is None or n in contigs)
+            and (conf_rows is None or n in conf_rows) and (known_pos is None or n in known_pos)]
     shards, costs = build_shards(ctgs, idx)
     owner = sharder.assign(costs, world)
     mine = [i for i in range(len(shards)) if owner[i] == rank]
@@ -62,17 +68,30 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
 
     def load(i):
         name, length, cid, num = shards[i]
-        _, _, s1, e1, rs1, re1 = chunk_geometry(length, cid, num)
-        batch = bf.fetch(name, s1, e1)
-        ref = fasta.fetch(ref_fn, fai, name, rs1, re1)
-        return name, batch, ref, rs1, s1, e1
+        conf = conf_rows.get(name) if conf_rows is not None else None
+        known = known_pos.get(name) if known_pos is not None else None
+        # the split BED of the contig (run_clair3_rna:231-289): the VCF one is written first, the BED one over it
+        ext = regions.extend_bed_rows(conf) if conf is not None else \
+            regions.extend_known_rows(known) if known is not None else None
+        plan = regions.plan_chunk(length, chunk_id=cid, chunk_num=num, extend_rows=ext, confident_rows=conf,
+                                  known_positions=known)
+        if plan is None:
+            return None
+        batch = bf.fetch(name, plan.start1, plan.end1)
+        ref = fasta.fetch(ref_fn, fai, name, plan.ref_start1, plan.ref_end1)
+        return name, batch, ref, plan
 
     pending = None                                   # (shard index, ticket, name, batch, ref, rs1)
     for i in mine + [None]:
         nxt = None
         if i is not None:
-            name, batch, ref, rs1, s1, e1 = load(i)
-            nxt = (i, eng.submit(batch, ref, rs1, s1, e1), name, batch, ref, rs1)
+            got = load(i)
+            if got is None:                          # genotyping chunk without sites
+                rows_of[i] = []
+                continue
+            name, batch, ref, plan = got
+            nxt = (i, eng.submit(batch, ref, plan.ref_start1, plan.start1, plan.end1, plan.site_filter()),
+                   name, batch, ref, plan.ref_start1)
         if pending is not None:
             j, ticket, pname, pbatch, pref, prs1 = pending
             res = eng.wait(ticket)
@@ -115,6 +134,8 @@ def main(argv=None):
     ap.add_argument("--chkpnt_fn", required=True)
     ap.add_argument("--output", required=True)
     ap.add_argument("--ctgName", default=None, help="comma separated contigs (default: all with mapped reads)")
+    ap.add_argument("--bed_fn", default=None, help="call only in these regions (BED, plain or gzip)")
+    ap.add_argument("--genotyping_mode_vcf_fn", default=None, help="call exactly the sites of this VCF (plain or gzip)")
     ap.add_argument("--sampleName", default="SAMPLE")
     ap.add_argument("--snp_min_af", type=float, default=P.SNP_MIN_AF)
     ap.add_argument("--indel_min_af", type=float, default=P.INDEL_MIN_AF)
@@ -134,7 +155,7 @@ def main(argv=None):
     run(a.bam_fn, a.ref_fn, a.chkpnt_fn, a.output, contigs=a.ctgName.split(",") if a.ctgName else None, device=local,
         rank=rank, world=world, phased=a.enable_phasing_model, padding=a.enable_padding_in_splice_junction_regions,
         snp_min_af=a.snp_min_af, indel_min_af=a.indel_min_af, min_coverage=a.minCoverage, min_mq=a.minMQ, qual=a.qual,
-        sample_name=a.sampleName, stats=stats)
+        sample_name=a.sampleName, stats=stats, bed_fn=a.bed_fn, vcf_fn=a.genotyping_mode_vcf_fn)
     print("[rank %d] %d shards, %d candidates in %.2f s" % (rank, stats["shards"], stats["candidates"], stats["seconds"]),
           file=sys.stderr)
     if world > 1:

@@ -138,6 +138,29 @@ int c3r_set_reference(c3r_ctx* ctx, const uint8_t* ref, int64_t ref_start1, int6
  *   region_start1..region_end1: the 1-based inclusive mpileup region (:412-415)          */
 int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* reads, const uint8_t* ref, int64_t ref_start1,
                      int64_t ref_len, int64_t region_start1, int64_t region_end1, c3r_ticket* ticket);
+
+/* Optional site filters of one chunk: the region modes of the producer.  Intervals are 0-based half-open BED
+ * intervals as (start, end) int32 pairs, sorted, non-empty, disjoint and non-touching (merge on the host);
+ * a count < 0 means "option not given", 0 means "given but empty for this contig".
+ *   pileup_bed     --extend_bed -> `samtools mpileup -l`: pileup columns exist only inside these intervals, so
+ *                  a candidate needs its 33 columns inside one of them   (create_tensor_pileup.py:446-451)
+ *   confident_bed  --bed_fn: a candidate needs [pos-1, pos+max_del_length+1) to overlap an interval, where
+ *                  max_del_length is the longest deletion starting at the site
+ *                  (create_tensor_pileup.py:480-481, 551-554; shared/interval_tree.py:80-89)
+ *   known_sites    --vcf_fn: strictly increasing 1-based positions; candidates are exactly these sites,
+ *                  whatever their allele fractions, depth or reference base    (create_tensor_pileup.py:397-405, 555-556)
+ * The arrays are host memory, read during the call.  Chunk geometry in these modes (BED span, site-count
+ * chunks) is host logic: clair3_rna_b200/regions.py restates create_tensor_pileup.py:373-418.            */
+typedef struct {
+    const int32_t* pileup_bed;    int64_t n_pileup_bed;
+    const int32_t* confident_bed; int64_t n_confident_bed;
+    const int32_t* known_sites;   int64_t n_known_sites;
+} c3r_site_filter;
+
+/* c3r_submit_chunk with site filters; filter == NULL is c3r_submit_chunk. */
+int c3r_submit_chunk_filtered(c3r_ctx* ctx, const c3r_reads* reads, const uint8_t* ref, int64_t ref_start1,
+                              int64_t ref_len, int64_t region_start1, int64_t region_end1,
+                              const c3r_site_filter* filter, c3r_ticket* ticket);
 int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* result);
 int c3r_release(c3r_ctx* ctx, c3r_ticket ticket);
 

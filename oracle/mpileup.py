@@ -139,10 +139,29 @@ class _Cursor:
         return t + ('$' if last else '')
 
 
-def mpileup_rows(batch, start1: int, end1: int, excl_flags: int = 2316, min_mq: int = 5):
+def mpileup_rows(batch, start1: int, end1: int, excl_flags: int = 2316, min_mq: int = 5, bed=None):
     """yield (pos1, depth, bases, hp_csv) for every printed column of ctg:start1-end1.
 
-    `batch` is a clair3_rna_b200.reads.ReadBatch in coordinate order."""
+    `batch` is a clair3_rna_b200.reads.ReadBatch in coordinate order.  `bed` = [(start0, end0)] restates
+    `samtools mpileup -l file.bed`: only columns whose 0-based position lies in an interval are printed
+    (bam_plcmd.c: `if (conf->bed && !bed_overlap(conf->bed, name, pos, pos + 1)) continue`)."""
+    import bisect
+    if bed is not None:
+        bed = sorted((int(a), int(b)) for a, b in bed if b > a)
+        merged = []
+        for a, b in bed:
+            if merged and a <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], b)
+            else:
+                merged.append([a, b])
+        bed_starts = [a for a, _ in merged]
+        bed_ends = [b for _, b in merged]
+
+    def in_bed(q):
+        if bed is None:
+            return True
+        k = bisect.bisect_right(bed_starts, q) - 1
+        return k >= 0 and q < bed_ends[k]
     n = batch.n_reads
     pos = batch.pos
     order_ok = np.all(pos[1:] >= pos[:-1]) if n > 1 else True
@@ -174,16 +193,16 @@ def mpileup_rows(batch, start1: int, end1: int, excl_flags: int = 2316, min_mq: 
             p = max(p + 1, int(pos[nxt]))           # jump over the uncovered gap
             continue
         active = [c for c in active if c.end > p]
-        if active:
+        if active and in_bed(p):
             toks = [c.token(p) for c in active]
             hps = ",".join(str(c.hp) if c.hp else '*' for c in active)
             yield p + 1, len(active), "".join(toks), hps
         p += 1
 
 
-def mpileup_text(batch, contig: str, start1: int, end1: int, excl_flags=2316, min_mq=5, with_hp=False):
+def mpileup_text(batch, contig: str, start1: int, end1: int, excl_flags=2316, min_mq=5, with_hp=False, bed=None):
     """iterator over the text lines samtools would print."""
-    for pos1, depth, bases, hps in mpileup_rows(batch, start1, end1, excl_flags, min_mq):
+    for pos1, depth, bases, hps in mpileup_rows(batch, start1, end1, excl_flags, min_mq, bed=bed):
         line = "%s\t%d\tN\t%d\t%s\t%s" % (contig, pos1, depth, bases, "I" * depth)
         if with_hp:
             line += "\t" + hps

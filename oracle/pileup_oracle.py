@@ -180,6 +180,38 @@ def column_vector(pos1, bases, ref_seq, ref_start1, hp_list, snp_min_af, indel_m
     return vec, list(alt.items()), depth, pass_af, max_skip
 
 
+def max_del_length(pos1, bases, ref_seq, ref_start1):
+    """longest deleted reference string among the column's deletion tokens (create_tensor_pileup.py:220,234-237):
+    the slice of the loaded reference is what is measured, so it is clipped where the reference ends."""
+    entries = tokenize(bases)[0]
+    off = pos1 - ref_start1
+    best = 0
+    for t in entries:
+        if t[0] == '-':
+            best = max(best, len(ref_seq[off + 1: off + len(t)]))
+    return best
+
+
+def confident_tree(bed_rows, extend_start1, extend_end1):
+    """bed_tree_from(bed_file_path, contig_name, bed_ctg_start, bed_ctg_end) of shared/interval_tree.py:8-77 for
+    one contig: rows (start0, end0) in file order -> the intervals the tree holds."""
+    out = []
+    for a, b in bed_rows:
+        if extend_start1 and extend_end1:
+            if b < extend_start1 or a > extend_end1:
+                continue
+        if a == b:
+            b += 1
+        out.append((a, b))
+    return out
+
+
+def region_in(intervals, begin, end):
+    """is_region_in(tree, ctg, begin, end) (shared/interval_tree.py:80-89): any interval with iv.begin < end and
+    iv.end > begin."""
+    return any(a < end and b > begin for a, b in intervals)
+
+
 def flank_seq(ref_seq, center1, ref_start1):
     lo = center1 - FLANK - ref_start1
     hi = center1 + FLANK + 1 - ref_start1
@@ -192,13 +224,14 @@ def flank_seq(ref_seq, center1, ref_start1):
 
 
 def candidate_rows(columns, ref_seq, ref_start1, snp_min_af=0.08, indel_min_af=0.15, min_coverage=4,
-                   padding=False, phased=False):
+                   padding=False, phased=False, confident=None, known=None):
     """columns: iterable of (pos1, depth_col, bases, hp_csv).  Yields per emitted
     candidate (pos1, ref33, window[list of 33 lists], alt_info_str, depth).
 
     Mirrors the ring buffer, the >=33-contiguous-rows rule, the in-place
     splice-junction padding on shared rows and the `del depth_dict[center]`
-    side effect of create_tensor_pileup.py:463-611."""
+    side effect of create_tensor_pileup.py:463-611.  `confident` = intervals of the --bed_fn tree (see
+    confident_tree) or None; `known` = set of 1-based --vcf_fn positions of this chunk or None (:551-556)."""
     ring = [None] * WIN
     slot = 0
     prev = -1
@@ -219,7 +252,10 @@ def candidate_rows(columns, ref_seq, ref_start1, snp_min_af=0.08, indel_min_af=0
             depth_of[pos1] = depth
         if depth > 0 and (snp_min_af == 0.0 or indel_min_af == 0.0):
             pass_af = True
-        if rb in "ACGT" and pass_af and depth >= min_coverage:
+        pass_bed = confident is None or region_in(confident, pos1 - 1,
+                                                  pos1 + max_del_length(pos1, bases, ref_seq, ref_start1) + 1)
+        if (pass_bed and rb in "ACGT" and pass_af and depth >= min_coverage and known is None) or (
+                known is not None and pos1 in known):
             pending.append(pos1)
             alt_of[pos1] = alt_items
             depth_of[pos1] = depth
@@ -265,13 +301,19 @@ def batch_tensor(window, depth):
 
 
 def run_region(batch, ref_seq, ref_start1, start1, end1, *, snp_min_af=0.08, indel_min_af=0.15,
-               min_coverage=4, min_mq=5, excl_flags=2316, padding=False, phased=False):
-    """flat reads -> dict of arrays for every emitted candidate of the region."""
+               min_coverage=4, min_mq=5, excl_flags=2316, padding=False, phased=False,
+               pileup_bed=None, confident_bed=None, known=None):
+    """flat reads -> dict of arrays for every emitted candidate of the region.
+
+    pileup_bed: rows (start0, end0) of --extend_bed (mpileup -l); confident_bed: rows of --bed_fn in file order;
+    known: iterable of 1-based --vcf_fn positions of this chunk."""
     from .mpileup import mpileup_rows
     pos, ref33, tens, alt, depth = [], [], [], [], []
-    cols = mpileup_rows(batch, start1, end1, excl_flags, min_mq)
+    cols = mpileup_rows(batch, start1, end1, excl_flags, min_mq, bed=pileup_bed)
+    confident = None if confident_bed is None else confident_tree(confident_bed, start1, end1)
     for c, r33, win, ai, d in candidate_rows(cols, ref_seq, ref_start1, snp_min_af, indel_min_af,
-                                             min_coverage, padding, phased):
+                                             min_coverage, padding, phased, confident=confident,
+                                             known=None if known is None else set(known)):
         pos.append(c)
         ref33.append(r33)
         tens.append(batch_tensor(win, d))

@@ -52,7 +52,7 @@ def mpileup(argv):
     from clair3_rna_b200.reads import ReadBatch
     from oracle.mpileup import mpileup_text
     bam, region = None, None
-    min_mq, excl, extra = 0, 0x704, None
+    min_mq, excl, extra, bed_fn = 0, 0x704, None, None
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -60,7 +60,9 @@ def mpileup(argv):
             region = argv[i + 1]; i += 2
         elif a == "--min-MQ":
             min_mq = int(argv[i + 1]); i += 2
-        elif a in ("--min-BQ", "--max-depth", "-l"):
+        elif a == "-l":
+            bed_fn = argv[i + 1]; i += 2
+        elif a in ("--min-BQ", "--max-depth"):
             i += 2
         elif a == "--excl-flags":
             excl = int(argv[i + 1]); i += 2
@@ -76,8 +78,16 @@ def mpileup(argv):
     name, a, b = parse_region(region)
     if a is None:
         a, b = 1, int(batch.end().max()) if batch.n_reads else 1
+    bed = None
+    if bed_fn is not None:                      # BED rows of this contig, whitespace separated like samtools' reader
+        bed = []
+        with open(bed_fn) as fp:
+            for row in fp:
+                c = row.split()
+                if len(c) >= 3 and c[0] == name and not row.startswith("#"):
+                    bed.append((int(c[1]), int(c[2])))
     out = sys.stdout
-    for line in mpileup_text(batch.fetch(a, b), name, a, b, excl, min_mq, with_hp=(extra == "HP")):
+    for line in mpileup_text(batch.fetch(a, b), name, a, b, excl, min_mq, with_hp=(extra == "HP"), bed=bed):
         out.write(line)
         out.write("\n")
 

@@ -42,7 +42,7 @@ def write_fasta(path, name, seq: bytes):
 
 
 def run_reference_producer(tmp, contig, platform, phased, padding, snp_af, indel_af, min_cov, min_mq,
-                           chunk_id=1, chunk_num=1):
+                           chunk_id=1, chunk_num=1, bed_fn=None, extend_bed=None, vcf_fn=None):
     shim = "%s %s" % (sys.executable, os.path.join(ROOT, "oracle", "samtools_shim.py"))
     cmd = [sys.executable, os.path.join(REF_ROOT, "clair3_rna.py"), "create_tensor_pileup",
            "--bam_fn", os.path.join(tmp, "reads.npz"), "--ref_fn", os.path.join(tmp, "ref.fa"),
@@ -54,6 +54,12 @@ def run_reference_producer(tmp, contig, platform, phased, padding, snp_af, indel
         cmd += ["--add_phasing_feature", "True"]
     if padding:
         cmd += ["--enable_padding_in_splice_junction_regions", "True"]
+    if bed_fn:
+        cmd += ["--bed_fn", bed_fn]
+    if extend_bed:
+        cmd += ["--extend_bed", extend_bed]
+    if vcf_fn:
+        cmd += ["--vcf_fn", vcf_fn]
     env = dict(os.environ, PYTHONPATH=REF_ROOT)
     out = subprocess.run(cmd, cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
     return out.stdout.decode("ascii")
@@ -89,10 +95,29 @@ def make_case(name):
     with tempfile.TemporaryDirectory() as tmp:
         write_fasta(os.path.join(tmp, "ref.fa"), contig, ref_bytes)
         batch.save(os.path.join(tmp, "reads.npz"))
+        # region modes: the files run_clair3_rna would hand to the producer (--bed_fn as given by the user, the
+        # per-contig split BED with space separated rows widened by 33 bp, the genotyping VCF)
+        from clair3_rna_b200 import regions
+        conf, known = golden_cases.bed_rows(name), golden_cases.known_positions(name)
+        files = {}
+        if conf is not None:
+            files["bed_fn"] = os.path.join(tmp, "confident.bed")
+            with open(files["bed_fn"], "w") as fp:
+                fp.write("# confident regions\n" + "".join("%s\t%d\t%d\n" % (contig, a, b) for a, b in conf))
+            ext = regions.extend_bed_rows(conf)
+        if known is not None:
+            files["vcf_fn"] = os.path.join(tmp, "known.vcf")
+            with open(files["vcf_fn"], "w") as fp:
+                fp.write("##fileformat=VCFv4.2\n" + "".join("%s\t%d\t.\tA\tC\t.\tPASS\t.\n" % (contig, p) for p in known))
+            ext = regions.extend_known_rows(known)
+        if files:
+            files["extend_bed"] = os.path.join(tmp, contig)
+            with open(files["extend_bed"], "w") as fp:
+                fp.write("\n".join("%s %d %d" % (contig, a, b) for a, b in ext))
         for cid in range(1, n_chunks + 1):
             texts.append(run_reference_producer(tmp, contig, case["platform"], case["phased"], case["padding"],
                                                 case["snp_af"], case["indel_af"], case["min_cov"], case["min_mq"],
-                                                chunk_id=cid, chunk_num=n_chunks))
+                                                chunk_id=cid, chunk_num=n_chunks, **files))
     chunk_of = np.concatenate([np.full(len(t.splitlines()), cid + 1, np.int32) for cid, t in enumerate(texts)])
     text = "".join(texts)
     rows = [r.split("\t") for r in text.splitlines()]

@@ -36,26 +36,29 @@ def run_case(name, nn_impl):
                  keep_tensor=True, keep_rows=True)
     w = weights.synthetic(C, sharpen=8.0)
     eng.set_weights(w)
-    if case.get("chunks", 1) == 1:
+    plans = golden_cases.chunk_plans(name)
+    if len(plans) == 1 and plans[0].site_filter() is None:
         res = eng.call_chunk(batch, ref, 1, 1, len(ref_bytes) + 33)
     else:
-        res = run_chunked(eng, batch, ref, case["chunks"])
+        res = run_chunked(eng, batch, ref, plans)
     eng.close()
     _cache[key] = (res, batch, ref, w)
     return _cache[key]
 
 
-def run_chunked(eng, batch, ref, n_chunks):
-    """chunk by chunk with the reference's geometry; candidate-space results concatenated in chunk order
-    (alt_info / flank strings are made per chunk against that chunk's read subset)"""
+def run_chunked(eng, batch, ref, plans):
+    """producer call by producer call with the reference's geometry and site filters (regions.ChunkPlan);
+    candidate-space results concatenated in chunk order (alt_info / flank strings are made per chunk against that
+    chunk's read subset)"""
     from clair3_rna_b200.engine import alt_info_strings, flank_strings
-    from clair3_rna_b200.synth import chunk_geometry
     import types
     pos, depth, tensor, probs, alts, flanks = [], [], [], [], [], []
-    for cid in range(1, n_chunks + 1):
-        _, _, s1, e1, rs1, re1 = chunk_geometry(len(ref), cid, n_chunks)
+    for plan in plans:
+        if plan is None:                             # the reference returns without output (no known site in the chunk)
+            continue
+        s1, e1, rs1, re1 = plan.start1, plan.end1, plan.ref_start1, plan.ref_end1
         sub, r = batch.fetch(s1, e1), ref[rs1 - 1:re1]
-        res = eng.call_chunk(sub, r, rs1, s1, e1)
+        res = eng.call_chunk(sub, r, rs1, s1, e1, plan.site_filter())
         pos.append(res.pos); depth.append(res.depth); tensor.append(res.tensor); probs.append(res.probs)
         alts += alt_info_strings(res, sub, r, rs1)
         flanks += flank_strings(res, r, rs1)

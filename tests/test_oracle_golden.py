@@ -23,15 +23,18 @@ def oracle_run(name):
     n = len(ref_seq)
     kw = dict(snp_min_af=case["snp_af"], indel_min_af=case["indel_af"], min_coverage=case["min_cov"],
               min_mq=case["min_mq"], padding=case["padding"], phased=case["phased"])
-    if case.get("chunks", 1) == 1:
-        # one chunk covering the contig: reads [max(1, 0-33), n+33], reference from 1
-        return pileup_oracle.run_region(batch, ref_seq, 1, 1, n + 33, **kw)
-    # chunk by chunk with the reference's geometry (create_tensor_pileup.py:380-418), results concatenated
-    from clair3_rna_b200.synth import chunk_geometry
+    # producer call by producer call with the reference's geometry (create_tensor_pileup.py:373-418), results
+    # concatenated; region-mode cases carry their BED / known-site filters in the plan
     parts = []
-    for cid in range(1, case["chunks"] + 1):
-        _, _, s1, e1, rs1, re1 = chunk_geometry(n, cid, case["chunks"])
-        parts.append(pileup_oracle.run_region(batch.fetch(s1, e1), ref_seq[rs1 - 1:re1], rs1, s1, e1, **kw))
+    conf = golden_cases.bed_rows(name)
+    for plan in golden_cases.chunk_plans(name):
+        if plan is None:
+            continue
+        s1, e1, rs1, re1 = plan.start1, plan.end1, plan.ref_start1, plan.ref_end1
+        parts.append(pileup_oracle.run_region(
+            batch.fetch(s1, e1), ref_seq[rs1 - 1:re1], rs1, s1, e1,
+            pileup_bed=None if plan.pileup_bed is None else plan.pileup_bed.tolist(),
+            confident_bed=conf, known=None if plan.known is None else plan.known.tolist(), **kw))
     return dict(pos=np.concatenate([p["pos"] for p in parts]), depth=np.concatenate([p["depth"] for p in parts]),
                 tensor=np.concatenate([p["tensor"] for p in parts]), alt_info=sum((list(p["alt_info"]) for p in parts), []),
                 ref33=sum((list(p["ref33"]) for p in parts), []))
