@@ -108,8 +108,8 @@ def call_chunk_to_rows(eng, batch, ref, ref_start1, start1, end1, contig, qual, 
 
 
 def run(args) -> int:
-    if args.gvcf or args.enable_variant_calling_at_sequence_head_and_tail:
-        sys.exit("[ERROR] --gvcf / head-and-tail calling are outside this path (SURVEY.md §8f)")
+    if args.gvcf:
+        sys.exit("[ERROR] --gvcf is outside this path (SURVEY.md §8f)")
     from .engine import Engine
     fai = fasta.read_fai(args.ref_fn)
     if args.ctgName not in fai:
@@ -136,7 +136,8 @@ def run(args) -> int:
     C = P.CHANNEL_SIZE + (P.PHASED_CHANNEL_SIZE if args.enable_phasing_model else 0)
     eng = Engine(args.device, C, snp_min_af=args.snp_min_af, indel_min_af=args.indel_min_af,
                  min_coverage=args.minCoverage, min_mq=args.minMQ,
-                 enable_padding=bool(args.enable_padding_in_splice_junction_regions))
+                 enable_padding=bool(args.enable_padding_in_splice_junction_regions),
+                 enable_head_tail=bool(args.enable_variant_calling_at_sequence_head_and_tail))
     eng.set_weights(W.load(args.chkpnt_fn))
     rows, _ = call_chunk_to_rows(eng, batch, ref, rs1, s1, e1, args.ctgName, args.qual, site_filter=plan.site_filter())
     eng.close()

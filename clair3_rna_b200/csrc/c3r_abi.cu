@@ -50,9 +50,9 @@ struct Slot {
     // row space
     Buf row_pos, counts, row_depth, row_flag, head_cnt, tail_cnt, skipdiff, max_skip, row_ins, row_del;
     Buf binc, bin_cur, events, raw, cov, cov_tile, refnib;
-    Buf pbed, cbed, known;     // site filters of the chunk
+    Buf pbed, cbed, known, covP;   // site filters of the chunk; printed columns (covA inside the pileup BED)
     Buf cand_row, cand_pos, cand_depth, tensor, alt_off, alt_n, alt, cur_ref, deleted, probs;
-    Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32) [5] raw row events (i64)
+    Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32) [4] tail columns (2 x i32) [5] raw row events (i64)
     Buf scan_scratch;
     // pinned results
     Pin h_scalars, h_pos, h_depth, h_probs, h_alt_off, h_alt_n, h_alt, h_tensor, h_row_pos, h_counts, h_row_depth;
@@ -154,6 +154,12 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     { OpCigar op; op.d = d; if (d.n_ops > 0) L += device_scan(op, d.n_ops, (ScanElem*)s.scan_scratch.p, (ScanElem*)nullptr, st); }
     { OpWords op; op.d = d; L += device_scan(op, d.NW, (Int2*)s.scan_scratch.p, (Int2*)nullptr, st); }
     if (d.n_known > 0) { k_mark_known<<<(unsigned)((d.n_known + 255) / 256), 256, 0, st>>>(d); ++L; }
+    if (d.n_pbed >= 0) { k_bed_mask<<<(unsigned)((d.NW + 4 + 255) / 256), 256, 0, st>>>(d, (uint32_t*)s.covP.p); ++L; }
+    if (d.head_tail) {
+        k_last_col<<<(unsigned)((d.NW + 255) / 256), 256, 0, st>>>(d);
+        k_last_gap<<<(unsigned)((d.NW + 255) / 256), 256, 0, st>>>(d);
+        L += 2;
+    }
     { OpRows op; op.d = d; L += device_scan(op, d.NW, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
     k_clear_rows<<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[2], st));
@@ -309,6 +315,7 @@ void c3r_default_params(c3r_params* p) {
     p->nn_impl = 1;
     p->keep_tensor = 0;
     p->keep_rows = 0;
+    p->enable_head_tail = 0;
 }
 
 int c3r_create(c3r_ctx** out, int device_ordinal, const c3r_params* params) {
@@ -528,7 +535,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     const c3r_site_filter* flt = ctx->filter;
     d.n_pbed = d.n_cbed = d.n_known = -1;
     if (flt) {
-        if (flt->n_pileup_bed >= 0) { EN(pbed, (flt->n_pileup_bed + 1) * 8); d.n_pbed = (int32_t)flt->n_pileup_bed; }
+        if (flt->n_pileup_bed >= 0) { EN(pbed, (flt->n_pileup_bed + 1) * 8); EN(covP, (d.NW + 4) * 4); d.n_pbed = (int32_t)flt->n_pileup_bed; }
         if (flt->n_confident_bed >= 0) { EN(cbed, (flt->n_confident_bed + 1) * 8); d.n_cbed = (int32_t)flt->n_confident_bed; }
         if (flt->n_known_sites >= 0) { EN(known, (flt->n_known_sites + 1) * 4); d.n_known = (int32_t)flt->n_known_sites; }
     }
@@ -559,6 +566,9 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.n_ref_words = (ref_len + 7) / 8;
     d.blockmax = P<int32_t>(s.blockmax);
     d.pbed = P<int32_t>(s.pbed); d.cbed = P<int32_t>(s.cbed); d.known = P<int32_t>(s.known);
+    d.covP = d.n_pbed >= 0 ? P<uint32_t>(s.covP) : d.covA;
+    d.head_tail = pr.enable_head_tail;
+    d.tail = P<int32_t>(s.scalars) + 8;
     d.cand_row = P<int32_t>(s.cand_row); d.cand_pos = P<int32_t>(s.cand_pos); d.cand_depth = P<int32_t>(s.cand_depth);
     d.cur_ref = P<Int2>(s.cur_ref); d.deleted = P<uint8_t>(s.deleted);
 

@@ -70,6 +70,9 @@ struct Dev {
     const int32_t* pbed; int32_t n_pbed;                    // mpileup -l: rows exist only inside
     const int32_t* cbed; int32_t n_cbed;                    // confident BED: [pos-1, pos+max_del+1) must overlap
     const int32_t* known; int32_t n_known;                  // genotyping: candidates are exactly these sites
+    // printed columns = covA inside the pileup BED (covA itself without one); head/tail mode: zero rows around runs
+    const uint32_t* covP; int32_t head_tail;
+    int32_t* tail;              // [0] offset of the last printed column + 1, [1] offset of the last gap below it + 1
     // ---- per read / per op
     uint8_t* admit; int32_t* read_end; int32_t* op_head;
     int32_t* op_x; uint32_t* op_y; int32_t* op_rid;
@@ -600,6 +603,56 @@ __device__ __forceinline__ bool known_site(const int32_t* ks, int n, int32_t pos
     return lo < n && ks[lo] == pos1;
 }
 
+// printed columns of word w: covA restricted to the pileup BED (mpileup -l)
+__global__ void k_bed_mask(Dev d, uint32_t* out) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= d.NW + 4) return;
+    uint32_t bits = 0u;
+    const uint32_t a = w < d.NW ? d.covA[w] : 0u;
+    if (a) {
+        const int64_t lo = (int64_t)d.R0 + (w << 5), hi = lo + 32;           // genome positions of the word
+        for (int k = iv_last_start_le(d.pbed, d.n_pbed, (int32_t)(hi - 1)); k >= 0 && d.pbed[2 * k + 1] > lo; --k) {
+            const int64_t x = d.pbed[2 * k] > lo ? d.pbed[2 * k] - lo : 0, y = d.pbed[2 * k + 1] < hi ? d.pbed[2 * k + 1] - lo : 32;
+            bits |= (y >= 32 ? 0xffffffffu : (1u << y) - 1u) & (0xffffffffu << x);
+        }
+    }
+    out[w] = a & bits;
+}
+// head/tail mode: the last printed column of the stream and the last gap below it (the final run starts after it)
+__global__ void k_last_col(Dev d) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= d.NW) return;
+    const uint32_t b = d.covP[w];
+    if (b) atomicMax(&d.tail[0], (int32_t)(w << 5) + 32 - __clz(b));
+}
+__global__ void k_last_gap(Dev d) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t last = d.tail[0] - 1;
+    if (last < 0 || w > (last >> 5)) return;
+    uint32_t m = ~d.covP[w];
+    if (w == (last >> 5)) m &= (1u << (last & 31)) - 1u;
+    if (m) atomicMax(&d.tail[1], (int32_t)(w << 5) + 32 - __clz(m));
+}
+// printed columns right below / above region offset o, up to 16 each (the part of the 33-column window that lies in
+// the candidate's own run)
+__device__ __forceinline__ void printed_run(const Dev& d, int64_t o, int* n_before, int* n_after) {
+    const int64_t w = o >> 5;
+    const unsigned long long up = (d.covP[w] | ((unsigned long long)d.covP[w + 1] << 32)) >> (o & 31);   // bit 0 = o
+    const int na = __ffsll((long long)~(up >> 1)) - 1;
+    *n_after = na > FLANK ? FLANK : na;
+    const int64_t s = o - FLANK < 0 ? 0 : o - FLANK;
+    const int wb = (int)(o - s);                                                                         // columns s .. o-1
+    int nb = 0;
+    if (wb > 0) {
+        const int64_t ws = s >> 5;
+        const unsigned long long dn = (d.covP[ws] | ((unsigned long long)d.covP[ws + 1] << 32)) >> (s & 31);   // bit 0 = s
+        const unsigned long long x = ~dn << (64 - wb);                    // bit 63 = column o-1
+        nb = x ? __clzll((long long)x) : wb;
+        if (nb > wb) nb = wb;
+    }
+    *n_before = nb;
+}
+
 // ------------------------------------------------------------- K2: rows
 __device__ __forceinline__ bool ins_equal(const Dev& d, const RowEvent& a, const RowEvent& b, bool fold_strand) {
     if (a.len != b.len) return false;
@@ -1066,14 +1119,21 @@ struct OpCand {
     __device__ T load(int64_t row) const {
         if (!d.row_flag[row]) return 0;
         const int64_t o = (int64_t)d.row_pos[row] - d.R0;
+        if (d.head_tail) {
+            // zero rows stand in for the columns before the run; the columns after it are only supplied when the
+            // stream ends, i.e. for the final run (create_tensor_pileup.py:508-511, 613-637)
+            if (!bit_at(d.covP, o)) return 0;
+            int nb, na;
+            printed_run(d, o, &nb, &na);
+            return (na == FLANK || o >= d.tail[1]) ? 1 : 0;
+        }
         if (o - FLANK < 0 || o + FLANK >= d.W) return 0;
-        // mpileup -l: columns outside the BED are never printed, so the 33 columns must also lie inside it
-        if (d.n_pbed >= 0 && !iv_contains(d.pbed, d.n_pbed, d.row_pos[row] - FLANK, d.row_pos[row] + FLANK + 1)) return 0;
-        // 33 consecutive bits of covA starting at o-16
+        // 33 consecutive printed columns starting at o-16 (covP = covA inside the pileup BED: mpileup -l never prints
+        // the others, so the ring buffer restarts there)
         const int64_t s = o - FLANK;
         const int64_t w = s >> 5;
         const int sh = (int)(s & 31);
-        unsigned long long lo = d.covA[w] | ((unsigned long long)d.covA[w + 1] << 32);
+        unsigned long long lo = d.covP[w] | ((unsigned long long)d.covP[w + 1] << 32);
         const unsigned long long bits = lo >> sh;          // 64 - sh >= 33 bits are valid
         const unsigned long long need = (1ull << 33) - 1ull;
         return (bits & need) == need ? 1 : 0;
@@ -1106,10 +1166,17 @@ __global__ void k_window(Dev d, int apply_scale) {
         const int32_t row = d.cand_row[i];
         const int32_t depth = d.cand_depth[i];
         const bool sc = apply_scale && depth > 0 && (double)depth > (double)d.max_depth * 1.5;
+        int k0 = 0, k1 = WIN - 1;                          // window rows that are columns of the candidate's run
+        if (d.head_tail) {
+            int nb, na;
+            printed_run(d, (int64_t)d.cand_pos[i] - 1 - d.R0, &nb, &na);
+            k0 = FLANK - nb; k1 = FLANK + na;
+        }
         const int32_t* src = d.counts + ((int64_t)row - FLANK) * d.C;
         int32_t* dst = d.tensor + i * per;
         for (int j = threadIdx.x; j < per; j += blockDim.x) {
-            int32_t v = src[j];
+            const int k = j / d.C;
+            int32_t v = (k >= k0 && k <= k1) ? src[j] : 0;
             if (sc) v = rescale(v, depth, d.max_depth);
             dst[j] = v;
         }
@@ -1133,51 +1200,89 @@ __global__ void k_padding(Dev d) {
     const int64_t n = *d.n_cand < d.cand_cap ? *d.n_cand : d.cand_cap;
     const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= n) return;
-    if (h > 0 && d.cand_pos[h] - d.cand_pos[h - 1] <= 2 * FLANK && d.cand_row[h] - d.cand_row[h - 1] == d.cand_pos[h] - d.cand_pos[h - 1])
-        return;                                      // not a chain head
+    // chains: consecutive candidates of one run <= 32 bp apart.  In head/tail mode a window also looks at the depth
+    // of columns of neighbouring runs (and at whether their centres were emitted), so there the chain is by distance only.
+    auto linked = [&](int64_t i) {
+        const int32_t dp = d.cand_pos[i] - d.cand_pos[i - 1];
+        return dp <= 2 * FLANK && (d.head_tail || d.cand_row[i] - d.cand_row[i - 1] == dp);
+    };
+    if (h > 0 && linked(h)) return;                  // not a chain head
     const int per = WIN * d.C;
+    // head/tail mode: the slots of the ring that no column of the run has overwritten yet all reference ONE zero row
+    // (`[[0] * C] * 33`), so a padding write into such a slot shows in all of them until the run has 33 columns
+    int32_t zf[4] = {0, 0, 0, 0}, zr[4] = {0, 0, 0, 0};
+    int32_t z_run = -1;
     for (int64_t i = h; i < n; ++i) {
-        if (i > h && !(d.cand_pos[i] - d.cand_pos[i - 1] <= 2 * FLANK &&
-                       d.cand_row[i] - d.cand_row[i - 1] == d.cand_pos[i] - d.cand_pos[i - 1])) break;
+        if (i > h && !linked(i)) break;
         const int32_t row = d.cand_row[i];
         const int32_t depth = d.cand_depth[i];
-        int32_t mx_depth = 0, mx_skip = 0;
-        bool any = false;
-        for (int k = 0; k < WIN; ++k) {
-            const int32_t r = row - FLANK + k;
-            if (!d.deleted[r]) { const int32_t dd = d.row_depth[r]; if (!any || dd > mx_depth) mx_depth = dd; any = true; }
-            const int32_t ms = d.max_skip[r];
-            mx_skip = ms > mx_skip ? ms : mx_skip;
+        const int32_t p = d.cand_pos[i] - 1;
+        int nb = FLANK, na = FLANK;
+        if (d.head_tail) {
+            printed_run(d, (int64_t)p - d.R0, &nb, &na);
+            if (nb < FLANK && z_run != p - nb) {         // a new run: a new shared zero row
+                z_run = p - nb;
+                for (int b = 0; b < 4; ++b) zf[b] = zr[b] = 0;
+            }
         }
-        if (any && mx_depth > 0 && __ddiv_rn((double)mx_skip, (double)mx_depth) > d.skip_prop) {
-            const Int2 c = d.cur_ref[row];
-            const int32_t sf = c.a < 0 ? -c.a : c.a, sr = c.b < 0 ? -c.b : c.b;
-            const double pf = sf + sr > 0 ? __ddiv_rn((double)sf, (double)(sf + sr)) : 0.0;
-            const double pr = 1.0 - pf;
-            const int32_t vf = -(int32_t)__dmul_rn((double)depth, pf);
-            const int32_t vr = -(int32_t)__dmul_rn((double)depth, pr);
-            const double thr = __dmul_rn((double)depth, d.skip_prop);
+        // row of window slot k: the run's own column, else (head/tail mode) a column of another run if one is
+        // printed there - such a column has its depth in depth_dict but is a zero row in this window
+        auto slot_row = [&](int k, bool* own) -> int32_t {
+            *own = k >= FLANK - nb && k <= FLANK + na;
+            if (*own) return row - FLANK + k;
+            const int64_t o = (int64_t)p - FLANK + k - d.R0;
+            if (o < 0 || o >= d.W || !bit_at(d.covP, o)) return -1;
+            return row_lower_bound(d, p - FLANK + k);
+        };
+        const bool flushed = d.head_tail && na < FLANK;   // emitted when the stream ends: no padding step (:613-637)
+        if (!flushed) {
+            int32_t mx_depth = 0, mx_skip = 0;
+            bool any = false;
             for (int k = 0; k < WIN; ++k) {
-                if (k == FLANK) continue;
-                const int32_t r = row - FLANK + k;
-                const int32_t cd = d.deleted[r] ? 0 : d.row_depth[r];
-                if ((double)cd < thr) {
-                    bool acgt;
-                    ref_index(d, d.row_pos[r], &acgt);
-                    if (acgt) { Int2 nv; nv.a = vf; nv.b = vr; d.cur_ref[r] = nv; }
+                bool own;
+                const int32_t r = slot_row(k, &own);
+                if (r < 0) continue;
+                if (!d.deleted[r]) { const int32_t dd = d.row_depth[r]; if (!any || dd > mx_depth) mx_depth = dd; any = true; }
+                const int32_t ms = d.max_skip[r];
+                mx_skip = ms > mx_skip ? ms : mx_skip;
+            }
+            if (any && mx_depth > 0 && __ddiv_rn((double)mx_skip, (double)mx_depth) > d.skip_prop) {
+                const Int2 c = d.cur_ref[row];
+                const int32_t sf = c.a < 0 ? -c.a : c.a, sr = c.b < 0 ? -c.b : c.b;
+                const double pf = sf + sr > 0 ? __ddiv_rn((double)sf, (double)(sf + sr)) : 0.0;
+                const double pr = 1.0 - pf;
+                const int32_t vf = -(int32_t)__dmul_rn((double)depth, pf);
+                const int32_t vr = -(int32_t)__dmul_rn((double)depth, pr);
+                const double thr = __dmul_rn((double)depth, d.skip_prop);
+                for (int k = 0; k < WIN; ++k) {
+                    if (k == FLANK) continue;
+                    bool own;
+                    const int32_t r = slot_row(k, &own);
+                    const int32_t cd = (r < 0 || d.deleted[r]) ? 0 : d.row_depth[r];
+                    if ((double)cd < thr) {
+                        bool acgt;
+                        const int ri = ref_index(d, p - FLANK + k, &acgt);
+                        if (!acgt) continue;
+                        if (own) { Int2 nv; nv.a = vf; nv.b = vr; d.cur_ref[r] = nv; }
+                        else { zf[ri] = vf; zr[ri] = vr; }
+                    }
                 }
             }
         }
         int32_t* dst = d.tensor + i * per;
         for (int k = 0; k < WIN; ++k) {
-            const int32_t r = row - FLANK + k;
-            bool acgt;
-            const int ri = ref_index(d, d.row_pos[r], &acgt);
-            const Int2 c = d.cur_ref[r];
-            dst[k * d.C + ri] = c.a;
-            dst[k * d.C + 9 + ri] = c.b;
+            if (k >= FLANK - nb && k <= FLANK + na) {
+                const int32_t r = row - FLANK + k;
+                bool acgt;
+                const int ri = ref_index(d, d.row_pos[r], &acgt);
+                const Int2 c = d.cur_ref[r];
+                dst[k * d.C + ri] = c.a;
+                dst[k * d.C + 9 + ri] = c.b;
+            } else if (k < FLANK) {                      // not yet overwritten slots: the shared zero row
+                for (int b = 0; b < 4; ++b) { dst[k * d.C + b] = zf[b]; dst[k * d.C + 9 + b] = zr[b]; }
+            }                                            // slots after the end of the stream: fresh zero rows
         }
-        d.deleted[row] = 1;
+        if (!flushed) d.deleted[row] = 1;
     }
 }
 

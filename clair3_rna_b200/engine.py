@@ -57,9 +57,9 @@ def _view(ptr, n, dtype):
 class Engine:
     def __init__(self, device: int = 0, channels: int = 18, *, snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF,
                  min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ, enable_padding=False, nn_impl=1,
-                 keep_tensor=False, keep_rows=False):
+                 keep_tensor=False, keep_rows=False, enable_head_tail=False):
         self.lib = L.load()
-        if self.lib.c3r_abi_version() != 1:
+        if self.lib.c3r_abi_version() != 2:
             raise C3RError("ABI version mismatch")
         prm = L.Params()
         self.lib.c3r_default_params(C.byref(prm))
@@ -72,6 +72,7 @@ class Engine:
         prm.nn_impl = nn_impl
         prm.keep_tensor = int(keep_tensor)
         prm.keep_rows = int(keep_rows)
+        prm.enable_head_tail = int(enable_head_tail)
         self.params = prm
         self.channels = channels
         self.ctx = C.c_void_p()

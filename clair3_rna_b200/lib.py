@@ -15,7 +15,8 @@ class Params(C.Structure):
     _fields_ = [("channels", C.c_int32), ("min_coverage", C.c_int32), ("min_mq", C.c_int32),
                 ("excl_flags", C.c_uint32), ("snp_min_af", C.c_double), ("indel_min_af", C.c_double),
                 ("enable_padding", C.c_int32), ("max_depth", C.c_int32), ("skip_proportion", C.c_double),
-                ("nn_impl", C.c_int32), ("keep_tensor", C.c_int32), ("keep_rows", C.c_int32)]
+                ("nn_impl", C.c_int32), ("keep_tensor", C.c_int32), ("keep_rows", C.c_int32),
+                ("enable_head_tail", C.c_int32)]
 
 
 class Reads(C.Structure):

@@ -45,7 +45,7 @@ def build_shards(contigs, mapped, chunk_size=P.CHUNK_SIZE):
 
 def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, world=1, phased=False, padding=False,
         snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF, min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ,
-        qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None, bed_fn=None, vcf_fn=None):
+        qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None, bed_fn=None, vcf_fn=None, head_tail=False):
     from .bam import BamFile
     from .engine import Engine, decode_vcf_rows
     fai = fasta.read_fai(ref_fn)
@@ -60,7 +60,7 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
     mine = [i for i in range(len(shards)) if owner[i] == rank]
     C = P.CHANNEL_SIZE + (P.PHASED_CHANNEL_SIZE if phased else 0)
     eng = Engine(device, C, snp_min_af=snp_min_af, indel_min_af=indel_min_af, min_coverage=min_coverage,
-                 min_mq=min_mq, enable_padding=padding)
+                 min_mq=min_mq, enable_padding=padding, enable_head_tail=head_tail)
     eng.set_weights(W.load(chkpnt_fn))
     t0 = time.time()
     rows_of = {}
@@ -144,6 +144,7 @@ def main(argv=None):
     ap.add_argument("--qual", type=int, default=P.QUAL_CUT_OFF)
     ap.add_argument("--enable_phasing_model", action="store_true")
     ap.add_argument("--enable_padding_in_splice_junction_regions", action="store_true")
+    ap.add_argument("--enable_variant_calling_at_sequence_head_and_tail", action="store_true")
     a = ap.parse_args(argv)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -155,7 +156,8 @@ def main(argv=None):
     run(a.bam_fn, a.ref_fn, a.chkpnt_fn, a.output, contigs=a.ctgName.split(",") if a.ctgName else None, device=local,
         rank=rank, world=world, phased=a.enable_phasing_model, padding=a.enable_padding_in_splice_junction_regions,
         snp_min_af=a.snp_min_af, indel_min_af=a.indel_min_af, min_coverage=a.minCoverage, min_mq=a.minMQ, qual=a.qual,
-        sample_name=a.sampleName, stats=stats, bed_fn=a.bed_fn, vcf_fn=a.genotyping_mode_vcf_fn)
+        sample_name=a.sampleName, stats=stats, bed_fn=a.bed_fn, vcf_fn=a.genotyping_mode_vcf_fn,
+        head_tail=a.enable_variant_calling_at_sequence_head_and_tail)
     print("[rank %d] %d shards, %d candidates in %.2f s" % (rank, stats["shards"], stats["candidates"], stats["seconds"]),
           file=sys.stderr)
     if world > 1:

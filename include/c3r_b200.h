@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define C3R_ABI_VERSION 1
+#define C3R_ABI_VERSION 2
 #define C3R_WINDOW 33        /* shared/param_p.py:34-35  no_of_positions */
 #define C3R_N_OUT 24         /* 21 gt21 + 3 genotype, shared/param_p.py:37 */
 
@@ -56,6 +56,9 @@ typedef struct {
     int32_t nn_impl;         /* 0 = fp32 CUDA-core network, 1 = tcgen05 fp16/fp32-accumulate network */
     int32_t keep_tensor;     /* also return the int32 windows (parity / debug) */
     int32_t keep_rows;       /* also return the per-position count matrix (parity / debug) */
+    int32_t enable_head_tail;/* --enable_variant_calling_at_sequence_head_and_tail: zero rows stand in for the columns
+                                before a run of pileup columns and after the end of the stream
+                                (create_tensor_pileup.py:467, 508-514, 613-637) */
 } c3r_params;
 
 /* Flat alignment records of one region, BAM record order (coordinate sorted).

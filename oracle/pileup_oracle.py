@@ -224,15 +224,23 @@ def flank_seq(ref_seq, center1, ref_start1):
 
 
 def candidate_rows(columns, ref_seq, ref_start1, snp_min_af=0.08, indel_min_af=0.15, min_coverage=4,
-                   padding=False, phased=False, confident=None, known=None):
+                   padding=False, phased=False, confident=None, known=None, head_tail=False):
     """columns: iterable of (pos1, depth_col, bases, hp_csv).  Yields per emitted
     candidate (pos1, ref33, window[list of 33 lists], alt_info_str, depth).
 
     Mirrors the ring buffer, the >=33-contiguous-rows rule, the in-place
     splice-junction padding on shared rows and the `del depth_dict[center]`
     side effect of create_tensor_pileup.py:463-611.  `confident` = intervals of the --bed_fn tree (see
-    confident_tree) or None; `known` = set of 1-based --vcf_fn positions of this chunk or None (:551-556)."""
-    ring = [None] * WIN
+    confident_tree) or None; `known` = set of 1-based --vcf_fn positions of this chunk or None (:551-556).
+    head_tail = --enable_variant_calling_at_sequence_head_and_tail (:467,508-511,613-637): the ring starts (and
+    restarts at every gap) as 33 references to ONE all-zero row, so no window is ever incomplete, a padding write
+    into a not-yet-overwritten slot lands in that shared row, and the candidates still pending when the stream
+    ends are flushed over fresh zero rows without the padding step."""
+    n_ch = 30 if phased else 18
+
+    def fresh_ring():
+        return [[0] * n_ch] * WIN if head_tail else [None] * WIN
+    ring = fresh_ring()
     slot = 0
     prev = -1
     pending = []
@@ -241,7 +249,7 @@ def candidate_rows(columns, ref_seq, ref_start1, snp_min_af=0.08, indel_min_af=0
         hp_list = hps.split(',') if phased else None
         rb = ref_seq[pos1 - ref_start1].upper()
         if prev + 1 != pos1:
-            ring = [None] * WIN
+            ring = fresh_ring()
             slot = 0
             pending = []
         prev = pos1
@@ -287,6 +295,16 @@ def candidate_rows(columns, ref_seq, ref_start1, snp_min_af=0.08, indel_min_af=0
                 yield (center, flank_seq(ref_seq, center, ref_start1),
                        [list(r) for r in window], alt_info, cdepth)
                 del alt_of[center], depth_of[center]
+    if head_tail:
+        for pos1 in range(prev + 1, prev + FLANK + 1):
+            ring[slot] = [0] * n_ch
+            slot = (slot + 1) % WIN
+            center = pos1 - FLANK
+            if center in pending:
+                window = ring[slot:] + ring[:slot]
+                alt_info = str(depth_of[center]) + '-' + ' '.join('%s %d' % kv for kv in alt_of[center])
+                yield (center, flank_seq(ref_seq, center, ref_start1),
+                       [list(r) for r in window], alt_info, depth_of[center])
 
 
 def batch_tensor(window, depth):
@@ -302,7 +320,7 @@ def batch_tensor(window, depth):
 
 def run_region(batch, ref_seq, ref_start1, start1, end1, *, snp_min_af=0.08, indel_min_af=0.15,
                min_coverage=4, min_mq=5, excl_flags=2316, padding=False, phased=False,
-               pileup_bed=None, confident_bed=None, known=None):
+               pileup_bed=None, confident_bed=None, known=None, head_tail=False):
     """flat reads -> dict of arrays for every emitted candidate of the region.
 
     pileup_bed: rows (start0, end0) of --extend_bed (mpileup -l); confident_bed: rows of --bed_fn in file order;
@@ -313,7 +331,7 @@ def run_region(batch, ref_seq, ref_start1, start1, end1, *, snp_min_af=0.08, ind
     confident = None if confident_bed is None else confident_tree(confident_bed, start1, end1)
     for c, r33, win, ai, d in candidate_rows(cols, ref_seq, ref_start1, snp_min_af, indel_min_af,
                                              min_coverage, padding, phased, confident=confident,
-                                             known=None if known is None else set(known)):
+                                             known=None if known is None else set(known), head_tail=head_tail):
         pos.append(c)
         ref33.append(r33)
         tens.append(batch_tensor(win, d))

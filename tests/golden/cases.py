@@ -37,6 +37,16 @@ CASES = {
                          platform="hifi", padding=True, chunks=1, bed=dict(n=60, seed=13)),
     "known_sites": dict(_BASE, cfg=1, scale=0.05, over=dict(genes_per_mb=70, depth=10, seed=777062), platform="ont",
                         chunks=3, known=dict(n=400, seed=12)),
+    # --enable_variant_calling_at_sequence_head_and_tail: zero rows before a run starts and
+    # after the stream ends; with the padding rule the shared zero row collects the padding writes
+    "headtail_ont": dict(_BASE, cfg=1, scale=0.05, over=dict(genes_per_mb=80, depth=9, sub=0.06, ins=0.03, dele=0.06,
+                                                             seed=777071), platform="ont", head_tail=True),
+    "headtail_pad": dict(_BASE, cfg=3, scale=0.012, over=dict(genes_per_mb=100, hi_depth_genes=1, hi_depth=200, depth=20,
+                                                              sub=0.03, ins=0.01, dele=0.03, seed=777072),
+                         platform="hifi", padding=True, head_tail=True),
+    "headtail_phased_bed": dict(_BASE, cfg=4, scale=0.01, over=dict(genes_per_mb=100, depth=15, sub=0.04, ins=0.03,
+                                                                    dele=0.04, seed=777073),
+                                platform="hifi", phased=True, head_tail=True, chunks=2, bed=dict(n=60, seed=14)),
     "af_zero": dict(_BASE, cfg=1, scale=0.03, over=dict(genes_per_mb=70, depth=8, seed=777004), platform="ont",
                     snp_af=0.0, min_cov=2),
 }

@@ -42,7 +42,7 @@ def write_fasta(path, name, seq: bytes):
 
 
 def run_reference_producer(tmp, contig, platform, phased, padding, snp_af, indel_af, min_cov, min_mq,
-                           chunk_id=1, chunk_num=1, bed_fn=None, extend_bed=None, vcf_fn=None):
+                           chunk_id=1, chunk_num=1, bed_fn=None, extend_bed=None, vcf_fn=None, head_tail=False):
     shim = "%s %s" % (sys.executable, os.path.join(ROOT, "oracle", "samtools_shim.py"))
     cmd = [sys.executable, os.path.join(REF_ROOT, "clair3_rna.py"), "create_tensor_pileup",
            "--bam_fn", os.path.join(tmp, "reads.npz"), "--ref_fn", os.path.join(tmp, "ref.fa"),
@@ -54,6 +54,8 @@ def run_reference_producer(tmp, contig, platform, phased, padding, snp_af, indel
         cmd += ["--add_phasing_feature", "True"]
     if padding:
         cmd += ["--enable_padding_in_splice_junction_regions", "True"]
+    if head_tail:
+        cmd += ["--enable_variant_calling_at_sequence_head_and_tail", "True"]
     if bed_fn:
         cmd += ["--bed_fn", bed_fn]
     if extend_bed:
@@ -117,7 +119,7 @@ def make_case(name):
         for cid in range(1, n_chunks + 1):
             texts.append(run_reference_producer(tmp, contig, case["platform"], case["phased"], case["padding"],
                                                 case["snp_af"], case["indel_af"], case["min_cov"], case["min_mq"],
-                                                chunk_id=cid, chunk_num=n_chunks, **files))
+                                                chunk_id=cid, chunk_num=n_chunks, head_tail=case.get("head_tail", False), **files))
     chunk_of = np.concatenate([np.full(len(t.splitlines()), cid + 1, np.int32) for cid, t in enumerate(texts)])
     text = "".join(texts)
     rows = [r.split("\t") for r in text.splitlines()]

@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib):
 
 def test_abi_version_and_defaults(lib):
     from clair3_rna_b200 import lib as L
-    assert lib.c3r_abi_version() == 1
+    assert lib.c3r_abi_version() == 2
     p = L.Params()
     lib.c3r_default_params(C.byref(p))
     assert (p.channels, p.min_coverage, p.min_mq, p.excl_flags, p.max_depth) == (18, 4, 5, 2316, 144)

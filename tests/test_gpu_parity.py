@@ -33,7 +33,7 @@ def run_case(name, nn_impl):
     C = 30 if case["phased"] else 18
     eng = Engine(0, C, snp_min_af=case["snp_af"], indel_min_af=case["indel_af"], min_coverage=case["min_cov"],
                  min_mq=case["min_mq"], enable_padding=case["padding"], nn_impl=nn_impl,
-                 keep_tensor=True, keep_rows=True)
+                 keep_tensor=True, keep_rows=True, enable_head_tail=case.get("head_tail", False))
     w = weights.synthetic(C, sharpen=8.0)
     eng.set_weights(w)
     plans = golden_cases.chunk_plans(name)

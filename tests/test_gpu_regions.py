@@ -17,7 +17,8 @@ def _engine(case, **kw):
     from clair3_rna_b200.engine import Engine
     C = 30 if case["phased"] else 18
     eng = Engine(0, C, snp_min_af=case["snp_af"], indel_min_af=case["indel_af"], min_coverage=case["min_cov"],
-                 min_mq=case["min_mq"], enable_padding=case["padding"], nn_impl=0, keep_tensor=True, **kw)
+                 min_mq=case["min_mq"], enable_padding=case["padding"], nn_impl=0, keep_tensor=True,
+                 enable_head_tail=case.get("head_tail", False), **kw)
     eng.set_weights(weights.synthetic(C, sharpen=8.0))
     return eng
 
@@ -30,7 +31,8 @@ def _random_rows(batch, n_ref, rng, n):
     return rows
 
 
-@pytest.mark.parametrize("name,seed", [("phased_noisy", 1), ("pad_dense", 2), ("ties_lowdepth", 3)])
+@pytest.mark.parametrize("name,seed", [("phased_noisy", 1), ("pad_dense", 2), ("ties_lowdepth", 3),
+                                       ("headtail_ont", 4), ("headtail_pad", 5), ("headtail_phased_bed", 6)])
 def test_random_filters_match_oracle(name, seed):
     from oracle import pileup_oracle
     from clair3_rna_b200 import regions
@@ -49,7 +51,8 @@ def test_random_filters_match_oracle(name, seed):
     known = sorted({int(batch.pos[int(rng.integers(batch.n_reads))]) + 1 + int(rng.integers(0, span)) for _ in range(150)})
     known = [p for p in known if p <= n]
     kw = dict(snp_min_af=case["snp_af"], indel_min_af=case["indel_af"], min_coverage=case["min_cov"],
-              min_mq=case["min_mq"], padding=case["padding"], phased=case["phased"])
+              min_mq=case["min_mq"], padding=case["padding"], phased=case["phased"],
+              head_tail=case.get("head_tail", False))
     eng = _engine(case)
     combos = [dict(pileup_bed=ext, confident_bed=conf), dict(pileup_bed=ext), dict(confident_bed=conf),
               dict(pileup_bed=regions.extend_known_rows(known), known=known), dict(known=known),

@@ -22,7 +22,8 @@ def oracle_run(name):
     ref_seq = ref_bytes.decode("ascii")
     n = len(ref_seq)
     kw = dict(snp_min_af=case["snp_af"], indel_min_af=case["indel_af"], min_coverage=case["min_cov"],
-              min_mq=case["min_mq"], padding=case["padding"], phased=case["phased"])
+              min_mq=case["min_mq"], padding=case["padding"], phased=case["phased"],
+              head_tail=case.get("head_tail", False))
     # producer call by producer call with the reference's geometry (create_tensor_pileup.py:373-418), results
     # concatenated; region-mode cases carry their BED / known-site filters in the plan
     parts = []
