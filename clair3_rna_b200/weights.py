@@ -1,9 +1,9 @@
 """Network weights in Keras layout (what clair3_rna/model.py:126-156 creates).
 
-Real checkpoints are TF TensorBundles that need TensorFlow to read and are not on
-disk here, so tests and benches use seeded synthetic weights with Keras' default
-initialisers (Glorot-uniform kernels, orthogonal recurrent kernels, zero bias with
-forget-gate bias 1).  The neutral on-disk format is an .npz of the arrays below.
+Real checkpoints are TF TensorBundles (read by tf_bundle.py; none is on disk here), so tests
+and benches use seeded synthetic weights with Keras' default initialisers (Glorot-uniform
+kernels, orthogonal recurrent kernels, zero bias with forget-gate bias 1).  The neutral
+on-disk format is an .npz of the arrays below.
 """
 import numpy as np
 
@@ -67,5 +67,10 @@ def save(path: str, w: dict) -> None:
 
 
 def load(path: str) -> dict:
+    """.npz in the layout above, or the prefix of a Keras TF-format checkpoint (`<prefix>.index` +
+    `<prefix>.data-*`, what the reference's --chkpnt_fn points at) read by tf_bundle.py without TensorFlow."""
+    from . import tf_bundle
+    if not path.endswith(".npz") and tf_bundle.is_checkpoint_prefix(path):
+        return tf_bundle.load_keras_checkpoint(path)
     z = np.load(path)
     return {k.replace("__", "/"): np.ascontiguousarray(z[k], dtype=np.float32) for k in z.files}
