@@ -861,7 +861,7 @@ __device__ void row_indels(const Dev& d, const RowEvent* evs, int32_t n, int32_t
 constexpr int ROWS_WARPS = 8;
 constexpr int ROWS_HEAVY = 32;               // rows with more events than this are walked by the whole warp
 template <int C>
-__global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(Dev d) {
+__global__ void __launch_bounds__(ROWS_WARPS * 32, 5) k_rows(Dev d) {
     constexpr int NC = C == 30 ? 6 : 4;
     static_assert(ROWS_WARPS * 32 == COV_TILE, "one block per coverage tile");
     __shared__ __align__(16) int32_t stage[ROWS_WARPS][TILE_ROWS * C];
@@ -1166,17 +1166,21 @@ __global__ void k_window(Dev d, int apply_scale) {
         const int32_t row = d.cand_row[i];
         const int32_t depth = d.cand_depth[i];
         const bool sc = apply_scale && depth > 0 && (double)depth > (double)d.max_depth * 1.5;
-        int k0 = 0, k1 = WIN - 1;                          // window rows that are columns of the candidate's run
-        if (d.head_tail) {
-            int nb, na;
-            printed_run(d, (int64_t)d.cand_pos[i] - 1 - d.R0, &nb, &na);
-            k0 = FLANK - nb; k1 = FLANK + na;
-        }
         const int32_t* src = d.counts + ((int64_t)row - FLANK) * d.C;
         int32_t* dst = d.tensor + i * per;
+        if (!d.head_tail) {
+            for (int j = threadIdx.x; j < per; j += blockDim.x) {
+                int32_t v = src[j];
+                if (sc) v = rescale(v, depth, d.max_depth);
+                dst[j] = v;
+            }
+            continue;
+        }
+        int nb, na;                                        // window rows that are columns of the candidate's run
+        printed_run(d, (int64_t)d.cand_pos[i] - 1 - d.R0, &nb, &na);
+        const int j0 = (FLANK - nb) * d.C, j1 = (FLANK + na + 1) * d.C;
         for (int j = threadIdx.x; j < per; j += blockDim.x) {
-            const int k = j / d.C;
-            int32_t v = (k >= k0 && k <= k1) ? src[j] : 0;
+            int32_t v = (j >= j0 && j < j1) ? src[j] : 0;
             if (sc) v = rescale(v, depth, d.max_depth);
             dst[j] = v;
         }
