@@ -45,7 +45,10 @@ def build_shards(contigs, mapped, chunk_size=P.CHUNK_SIZE):
 
 def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, world=1, phased=False, padding=False,
         snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF, min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ,
-        qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None, bed_fn=None, vcf_fn=None, head_tail=False):
+        qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None, bed_fn=None, vcf_fn=None, head_tail=False,
+        merge_qual=None, show_ref=True, rediportal_fn=None, rediportal_tags=None, output_no_tagging=None):
+    """merge_qual / show_ref / rediportal_*: the options of the merge stage (sharder.sort_vcf = sort_vcf_from of the
+    reference); the defaults keep every row as the chunks produced it."""
     from .bam import BamFile
     from .engine import Engine, decode_vcf_rows
     fai = fasta.read_fai(ref_fn)
@@ -116,14 +119,20 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
         rows_of = {}
         for p in parts:
             rows_of.update(p)
-    merged = sharder.merge_rows([rows_of[i] for i in range(len(shards))], [n for n, _ in ctgs])
-    if os.path.exists(output):
-        os.remove(output)
-    if merged:                                       # like the reference: no file when there is no record
-        header = decoder.vcf_header([(n, fai[n][0]) for n in fai], sample_name, ref_fn)
-        with open(output, "w") as fp:
-            fp.write(header + "\n")
-            fp.write("\n".join(merged) + "\n")
+    names = [n for n, _ in ctgs]
+    redi = sharder.read_rediportal(rediportal_fn, names, rediportal_tags) if rediportal_fn else None
+    merged, untagged = sharder.sort_vcf([rows_of[i] for i in range(len(shards))], names, qual=merge_qual,
+                                        show_ref=show_ref, rediportal=redi)
+    for path, rows in ((output, merged), (output_no_tagging, untagged)):
+        if path is None or rows is None:
+            continue
+        if os.path.exists(path):
+            os.remove(path)
+        if rows:                                     # like the reference: no file when there is no record
+            header = decoder.vcf_header([(n, fai[n][0]) for n in fai], sample_name, ref_fn)
+            with open(path, "w") as fp:
+                fp.write(header + "\n")
+                fp.write("\n".join(rows) + "\n")
     return merged
 
 
@@ -141,7 +150,13 @@ def main(argv=None):
     ap.add_argument("--indel_min_af", type=float, default=P.INDEL_MIN_AF)
     ap.add_argument("--minCoverage", type=int, default=P.MIN_COVERAGE)
     ap.add_argument("--minMQ", type=int, default=P.MIN_MQ)
-    ap.add_argument("--qual", type=int, default=P.QUAL_CUT_OFF)
+    ap.add_argument("--platform", default="ont", help="ont* / hifi*: sets the default of --qual like run_clair3_rna:535-539")
+    ap.add_argument("--qual", type=int, default=None, help="variants with QUAL <= qual are marked LowQual at the merge")
+    ap.add_argument("--print_ref_calls", action="store_true", help="keep reference calls in the merged VCF")
+    ap.add_argument("--tag_variant_using_readiportal", action="store_true")
+    ap.add_argument("--readiportal_source_fn", default=None, help="REDIportal TABLE1 (plain or gzip)")
+    ap.add_argument("--readiportal_database_filter_tag", default="A,D:A,R:A,R,D")
+    ap.add_argument("--output_no_tagging_fn", default=None)
     ap.add_argument("--enable_phasing_model", action="store_true")
     ap.add_argument("--enable_padding_in_splice_junction_regions", action="store_true")
     ap.add_argument("--enable_variant_calling_at_sequence_head_and_tail", action="store_true")
@@ -152,10 +167,16 @@ def main(argv=None):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("gloo")              # only VCF rows travel: no device collective on the data path
+    merge_qual = a.qual                              # param_p.py: qual_cut_off 2, min_thred_qual {ont: 8, hifi: 2}
+    if merge_qual is None:
+        merge_qual = 8 if a.platform.startswith("ont") else 2
     stats = {}
     run(a.bam_fn, a.ref_fn, a.chkpnt_fn, a.output, contigs=a.ctgName.split(",") if a.ctgName else None, device=local,
         rank=rank, world=world, phased=a.enable_phasing_model, padding=a.enable_padding_in_splice_junction_regions,
-        snp_min_af=a.snp_min_af, indel_min_af=a.indel_min_af, min_coverage=a.minCoverage, min_mq=a.minMQ, qual=a.qual,
+        snp_min_af=a.snp_min_af, indel_min_af=a.indel_min_af, min_coverage=a.minCoverage, min_mq=a.minMQ,
+        merge_qual=merge_qual, show_ref=a.print_ref_calls,
+        rediportal_fn=a.readiportal_source_fn if a.tag_variant_using_readiportal else None,
+        rediportal_tags=a.readiportal_database_filter_tag, output_no_tagging=a.output_no_tagging_fn,
         sample_name=a.sampleName, stats=stats, bed_fn=a.bed_fn, vcf_fn=a.genotyping_mode_vcf_fn,
         head_tail=a.enable_variant_calling_at_sequence_head_and_tail)
     print("[rank %d] %d shards, %d candidates in %.2f s" % (rank, stats["shards"], stats["candidates"], stats["seconds"]),
