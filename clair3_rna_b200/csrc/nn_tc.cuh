@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
 // p mod n_tiles, so that the 74 pairs do not all pull the same weight block out of L2 at the same moment.
 constexpr int ZXG_KB = 4;                                   // K = 256 = 4 k blocks of 64
 constexpr int ZXG_STAGES = 3;
-constexpr int ZXG_THREADS = 224;                            // + warp 6: activation (A) loader
+constexpr int ZXG_EPI_WARPS = 8;                            // two per TMEM lane quarter, 128 of the 256 columns each
+constexpr int ZXG_THREADS = 64 + 32 * ZXG_EPI_WARPS + 32;   // warp 0: weight ring, 1: MMA / relay, 2-9: epilogue, 10: activation loader
 constexpr int ZXG_SMEM = (2 * ZXG_KB + 2 * ZXG_STAGES) * TC_IMG * 2 + 1024 + 512;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_gemm_zx(GemmArgs g) {
@@ -238,7 +239,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
         for (int i = 0; i < ZXG_STAGES; ++i) {
             ptx::mbar_init(b_full + 8 * i, 1); ptx::mbar_init(b_empty + 8 * i, 1); ptx::mbar_init(b_pfull + 8 * i, 1);
         }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(b_accf + 8 * i, 1); ptx::mbar_init(b_acce + 8 * i, 8); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(b_accf + 8 * i, 1); ptx::mbar_init(b_acce + 8 * i, 2 * ZXG_EPI_WARPS); }
         for (int i = 0; i < ZXG_KB; ++i) {
             ptx::mbar_init(b_afull + 8 * i, 1); ptx::mbar_init(b_afree + 8 * i, 1); ptx::mbar_init(b_pafull + 8 * i, 1);
         }
@@ -264,6 +265,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                     for (int kb = 0; kb < ZXG_KB; ++kb, ++it) {
                         const uint32_t s = it % ZXG_STAGES, ph = (it / ZXG_STAGES) & 1;
                         ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 112);
+                        if (g.dbg == 2 && it >= ZXG_STAGES) { ptx::mbar_arrive(b_full + 8 * s); continue; }   // experiment: no weight traffic
                         ptx::mbar_arrive_expect_tx(b_full + 8 * s, 2 * IMG_B);
                         // weight images are [n256][rank half][kb64][128 x 64]
                         const size_t off = ((((size_t)((n + pair) % n_tiles) * 2 + rank) * ZXG_KB) + kb) * TC_IMG;
@@ -271,7 +273,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                         ptx::bulk_g2s(s_b + s * 2 * IMG_B + IMG_B, g.B_lo + off, IMG_B, b_full + 8 * s);
                     }
         }
-    } else if (warp == 6) {
+    } else if (warp == 2 + ZXG_EPI_WARPS) {
         if (lane == 0) {
             // ---------------------------------------------------- activation loader (both CTAs, own tile)
             uint32_t mi = 0;
@@ -279,9 +281,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                 const int m = 2 * mp + (int)rank;
                 for (int kb = 0; kb < ZXG_KB; ++kb) {
                     ptx::mbar_wait(b_afree + 8 * kb, (mi & 1) ^ 1, g.err, 111);    // last n-tile of the previous pair used it
-                    ptx::mbar_arrive_expect_tx(b_afull + 8 * kb, 2 * IMG_B);
+                    const bool lo = g.terms & 2;                    // the low-order activation image is only read by term 2
+                    ptx::mbar_arrive_expect_tx(b_afull + 8 * kb, lo ? 2 * IMG_B : IMG_B);
                     ptx::bulk_g2s(s_a + kb * 2 * IMG_B, g.A + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull + 8 * kb);
-                    ptx::bulk_g2s(s_a + kb * 2 * IMG_B + IMG_B, g.A_lo + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull + 8 * kb);
+                    if (lo) ptx::bulk_g2s(s_a + kb * 2 * IMG_B + IMG_B, g.A_lo + ((size_t)m * ZXG_KB + kb) * TC_IMG, IMG_B, b_afull + 8 * kb);
                 }
                 if (rank == 1)
                     for (int kb = 0; kb < ZXG_KB; ++kb) {
@@ -327,6 +330,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                         const uint64_t dB0 = ptx::make_smem_desc(s_b + s * 2 * IMG_B, TC_TILE * 16, 128);
 #pragma unroll
                         for (int term = 0; term < 3; ++term) {          // A_hi*B_hi, A_lo*B_hi, A_hi*B_lo
+                            if (!((g.terms >> term) & 1)) continue;
 #pragma unroll
                             for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
                                 const uint64_t da = dA0 + (uint64_t)(((term == 1 ? IMG_B : 0) + k4 * 2 * (TC_TILE * 16)) >> 4);
@@ -344,45 +348,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
         }
     } else {
         // -------------------------------------------------------- epilogue (both CTAs, own rows)
+        // warp -> TMEM lane quarter (warp & 3) and one of the two 128-column chunks of the tile
+        constexpr int EPI_T = 32 * ZXG_EPI_WARPS;
+        const int et = threadIdx.x - 64;                        // 0 .. EPI_T-1
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         uint32_t tc = 0;
         for (int mp = pair; mp < m_pairs; mp += n_pairs) {
             const int m = 2 * mp + (int)rank;
             {
                 // pull the NEXT pair-tile's activation images (2 x 64 KB, read once from HBM) towards L2 now,
-                // one 128-byte line per prefetch over the 128 epilogue threads: the bulk copies that re-load
+                // one 128-byte line per prefetch over the epilogue threads: the bulk copies that re-load
                 // them later are then L2 hits and do not stall the (in-order) copy queue of the weight ring
                 const int mn = m + 2 * n_pairs;
                 if (mn < g.m_tiles) {
                     const uint8_t* ph = (const uint8_t*)(g.A + (size_t)mn * ZXG_KB * TC_IMG);
                     const uint8_t* pl = (const uint8_t*)(g.A_lo + (size_t)mn * ZXG_KB * TC_IMG);
-                    for (uint32_t o = (threadIdx.x - 64) * 128; o < ZXG_KB * IMG_B; o += 128 * 128) {
+                    for (uint32_t o = et * 128; o < ZXG_KB * IMG_B; o += EPI_T * 128) {
                         ptx::prefetch_l2(ph + o);
-                        ptx::prefetch_l2(pl + o);
+                        if (g.terms & 2) ptx::prefetch_l2(pl + o);
                     }
                 }
             }
             for (int n = 0; n < n_tiles; ++n, ++tc) {
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // previous tile's bias readers are done
+                asm volatile("bar.sync 1, %0;" :: "n"(EPI_T) : "memory");      // previous tile's bias readers are done
                 const int nn = (n + pair) % n_tiles;            // same rotation as the weight loader
-                bias_s[threadIdx.x - 64] = g.bias[(size_t)nn * 256 + (threadIdx.x - 64)];
-                bias_s[threadIdx.x + 64] = g.bias[(size_t)nn * 256 + (threadIdx.x + 64)];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const float* bias = bias_s;
+                bias_s[et] = g.bias[(size_t)nn * 256 + et];
+                asm volatile("bar.sync 1, %0;" :: "n"(EPI_T) : "memory");
+                const float* bias = bias_s + half * 128;
                 ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 116);
                 ptx::tc_fence_after();
                 const bool tre = g.trace && blockIdx.x == 0 && tc < 64 && warp == 2 && lane == 0;
                 if (tre) g.trace[tc * 32 + 18] = clock64();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 256;
-#pragma unroll 2
-                for (int j = 0; j < 16; ++j) {
-                    uint32_t v[16];
-                    ptx::tmem_ld16(taddr + j * 16, v);
-                    ptx::tmem_wait_ld();
-                    // ZX layout is per 128-column chunk: [m][n128][32 col-groups][3 planes][128 rows], 24-bit floats
-                    uint32_t* o = (uint32_t*)g.out + ((((size_t)m * (2 * n_tiles) + 2 * nn + (j >> 3)) * 32 + (j & 7) * 4) * 3) * 128 + row;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + slot * 256 + half * 128;
+                // ZX layout is per 128-column chunk: [m][n128][32 col-groups][3 planes][128 rows], 24-bit floats
+                uint32_t* o0 = (uint32_t*)g.out + (((size_t)m * (2 * n_tiles) + 2 * nn + half) * 32 * 3) * 128 + row;
+                // the TMEM load of the next 16 columns is in flight while the current 16 are packed and stored
+                uint32_t va[16], vb[16];
+                ptx::tmem_ld16(taddr, va);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t (&v)[16] = (j & 1) ? vb : va;
+                    uint32_t (&vn)[16] = (j & 1) ? va : vb;
+                    ptx::tmem_wait_ld(v);
+                    if (j + 1 < 8) ptx::tmem_ld16(taddr + (j + 1) * 16, vn);
+                    uint32_t* o = o0 + (size_t)(j * 4 * 3) * 128;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         uint32_t w0, w1, w2;
@@ -390,6 +402,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ZXG_THREADS, 1) k_ge
                                __uint_as_float(v[c4 * 4 + 1]) + bias[j * 16 + c4 * 4 + 1],
                                __uint_as_float(v[c4 * 4 + 2]) + bias[j * 16 + c4 * 4 + 2],
                                __uint_as_float(v[c4 * 4 + 3]) + bias[j * 16 + c4 * 4 + 3], w0, w1, w2);
+                        if (g.dbg == 1 && w0 != 0x12345u) continue;    // experiment: no output traffic
                         o[(size_t)(c4 * 3 + 0) * 128] = w0;
                         o[(size_t)(c4 * 3 + 1) * 128] = w1;
                         o[(size_t)(c4 * 3 + 2) * 128] = w2;
@@ -433,7 +446,7 @@ struct LstmArgs {
     int C;
     const float* zx;        // LSTM2: hoisted projection, 24-bit ZX layout [tile][33][2*CH][32][3][128] (words)
     __half* hout;           // packed output [tile][33][KB_OUT][TC_IMG], high-order fp16 term
-    __half* hout_lo;        // low-order term: h - fp16(h), same layout
+    __half* hout_lo;        // low-order term: h - fp16(h), same layout; nullptr: the consumer does not use it
     int kb_out;             // 64-column blocks per time step in hout (LSTM1: 4, LSTM2: 5)
     int64_t n_sites;        // valid sites (tensor rows); tiles beyond are zero
     int n_tiles;            // 128-site tiles (even)
@@ -768,7 +781,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                                 const int col8 = (dir * U) / 8 + k8;             // 8-column group in the concat [fwd | bwd]
                                 const size_t oo = (size_t)(col8 / 8) * TC_IMG + (size_t)(col8 % 8) * (TC_TILE * 8) + row * 8 + ug * 4;
                                 *(uint2*)(hout_t + oo) = pk;
-                                *(uint2*)(hout_lo_t + oo) = *(const uint2*)hl;
+                                if (a.hout_lo) *(uint2*)(hout_lo_t + oo) = *(const uint2*)hl;
                             }
                         }
                     }
@@ -869,7 +882,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         const int col8 = (dir * U) / 8 + k8;                 // 8-column group in the concat [fwd | bwd]
                         const size_t oo = (size_t)(col8 / 8) * TC_IMG + (size_t)(col8 % 8) * (TC_TILE * 8) + row * 8;
                         *(uint4*)(hout_t + oo) = pk;
-                        *(uint4*)(hout_lo_t + oo) = *(const uint4*)hl;
+                        if (a.hout_lo) *(uint4*)(hout_lo_t + oo) = *(const uint4*)hl;
                     }
                 }
             }
@@ -1105,6 +1118,18 @@ inline cudaError_t launch_lstm(const LstmArgs& a, int sm_count, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// split-precision products of the hoisted LSTM2 projection as a bit mask: 1 = A_hi*B_hi, 2 = A_lo*B_hi,
+// 4 = A_hi*B_lo.  C3R_ZX_TERMS overrides for experiments (tools/zx_terms_probe.sh).
+inline int zx_terms() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("C3R_ZX_TERMS");
+        v = e ? atoi(e) : 5;
+        if (v < 1 || v > 7 || !(v & 1)) v = 5;
+    }
+    return v;
+}
+
 inline cudaError_t launch_gemm_zx(const GemmArgs& g, int sm_count, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
@@ -1198,15 +1223,15 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         else k_xop<30, 64><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
         ++launches;
         LstmArgs a1;
-        a1.Wimg = t.img1; a1.xop = t.xop; a1.C = t.C; a1.zx = nullptr; a1.hout = t.h1; a1.hout_lo = t.h1_lo; a1.kb_out = 4;
+        a1.Wimg = t.img1; a1.xop = t.xop; a1.C = t.C; a1.zx = nullptr; a1.hout = t.h1; a1.hout_lo = (zx_terms() & 2) ? t.h1_lo : nullptr; a1.kb_out = 4;
         a1.n_sites = m; a1.n_tiles = tiles; a1.err = t.err; a1.trace = t.trace;
         const cudaError_t e1 = t.C == 18 ? launch_lstm<4, 48>(a1, t.sm_count, st) : launch_lstm<4, 64>(a1, t.sm_count, st);
         TCK(e1, "lstm1");
         ++launches;
         GemmArgs g2;
-        g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = 3; g2.bias = t.b2p; g2.out = t.zx2;
+        g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = zx_terms(); g2.bias = t.b2p; g2.out = t.zx2;
         g2.m_tiles = tiles * NT; g2.n_tiles = 5; g2.n_kb = 4;
-        g2.mode = 0; g2.err = t.err; g2.dbg = 0; g2.trace = t.trace ? t.trace + 2 * 2 * NT * 8 * 8 : nullptr;
+        g2.mode = 0; g2.err = t.err; g2.dbg = getenv("C3R_ZX_DBG") ? atoi(getenv("C3R_ZX_DBG")) : 0; g2.trace = t.trace ? t.trace + 2 * 2 * NT * 8 * 8 : nullptr;
         TCK(launch_gemm_zx(g2, t.sm_count, st), "zx2 gemm");
         ++launches;
         // A = the tile pairs that fill whole rounds of the recurrent kernel, B = the rest

@@ -280,8 +280,9 @@ struct OpRows {
             const int32_t bs = __shfl_sync(act, base, src);
             const int32_t p0 = d.R0 + (int32_t)(__shfl_sync(act, (int32_t)w, src) << 5);
             const int c = __popc(b);
+            const bool full = b == 0xffffffffu;          // the usual case inside an exon: bit j is position j
             for (int j = my; j < c; j += n_act)
-                if (bs + j < d.L_ub) d.row_pos[bs + j] = p0 + (int32_t)__fns(b, 0, j + 1);
+                if (bs + j < d.L_ub) d.row_pos[bs + j] = p0 + (full ? j : (int32_t)__fns(b, 0, j + 1));
         }
         if (w == d.NW - 1) {
             *d.n_rows = incl;
