@@ -65,7 +65,7 @@ struct GemmArgs {
     const __half* B;      // [n_tiles][n_kb][TC_IMG]
     const __half* A_lo;   // same layouts, low-order terms (terms == 3)
     const __half* B_lo;
-    int terms;
+    int terms;            // split-precision products as a bit mask: 1 = A_hi*B_hi, 2 = A_lo*B_hi, 4 = A_hi*B_lo
     const float* bias;    // [n_tiles*128], GEMM column order
     float* out;
     int m_tiles, n_tiles, n_kb;
@@ -118,9 +118,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
                     const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
                     const uint32_t dst = s_base + s * GEMM_STAGE_BYTES;
                     ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 101);
-                    ptx::mbar_arrive_expect_tx(b_full + 8 * s, GEMM_STAGE_BYTES);
+                    const bool a_lo = g.terms & 2;                // the low-order activation image is only read by term 2
+                    ptx::mbar_arrive_expect_tx(b_full + 8 * s, a_lo ? GEMM_STAGE_BYTES : GEMM_STAGE_BYTES - TC_IMG * 2);
                     ptx::bulk_g2s(dst, g.A + ao + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
-                    ptx::bulk_g2s(dst + TC_IMG * 2, g.A_lo + ao + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
+                    if (a_lo) ptx::bulk_g2s(dst + TC_IMG * 2, g.A_lo + ao + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
                     ptx::bulk_g2s(dst + 2 * TC_IMG * 2, g.B + bo + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
                     ptx::bulk_g2s(dst + 3 * TC_IMG * 2, g.B_lo + bo + (size_t)kb * TC_IMG, TC_IMG * 2, b_full + 8 * s);
                 }
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
                     const uint32_t st0 = s_base + s * GEMM_STAGE_BYTES;
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {              // A_hi*B_hi, A_lo*B_hi, A_hi*B_lo
+                        if (!((g.terms >> term) & 1)) continue;
                         const uint32_t sa = st0 + (term == 1 ? TC_IMG * 2 : 0), sb = st0 + (term == 2 ? 3 : 2) * TC_IMG * 2;
 #pragma unroll
                         for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
@@ -1130,6 +1132,16 @@ inline int zx_terms() {
     return v;
 }
 
+inline int l4_terms() {                      // same mask for the L4 GEMM (C3R_L4_TERMS)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("C3R_L4_TERMS");
+        v = e ? atoi(e) : 7;
+        if (v < 1 || v > 7 || !(v & 1)) v = 7;
+    }
+    return v;
+}
+
 inline cudaError_t launch_gemm_zx(const GemmArgs& g, int sm_count, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
@@ -1190,14 +1202,14 @@ struct TcSub { int t0, nt; int64_t s0, ns; };
 inline cudaError_t tc_lstm2(TcNet& t, const TcSub& b, cudaStream_t st) {
     LstmArgs a2;
     a2.Wimg = t.img2; a2.xop = nullptr; a2.C = t.C; a2.zx = t.zx2 + (size_t)b.t0 * NT * 10 * ZX_CHUNK_WORDS;
-    a2.hout = t.h2 + (size_t)b.t0 * NT * 5 * TC_IMG; a2.hout_lo = t.h2_lo + (size_t)b.t0 * NT * 5 * TC_IMG; a2.kb_out = 5;
+    a2.hout = t.h2 + (size_t)b.t0 * NT * 5 * TC_IMG; a2.hout_lo = (l4_terms() & 2) ? t.h2_lo + (size_t)b.t0 * NT * 5 * TC_IMG : nullptr; a2.kb_out = 5;
     a2.n_sites = b.ns; a2.n_tiles = b.nt; a2.err = t.err; a2.trace = (t.trace && b.t0 == 0) ? t.trace + 2 * NT * 8 * 8 : nullptr;
     return launch_lstm<5, 0>(a2, t.sm_count, st);
 }
 inline cudaError_t tc_l4_heads(TcNet& t, const NetF32& net, const TcSub& b, float* probs, cudaStream_t st) {
     GemmArgs g4;
     g4.A = t.h2 + (size_t)b.t0 * NT * 5 * TC_IMG; g4.B = t.k4p; g4.A_lo = t.h2_lo + (size_t)b.t0 * NT * 5 * TC_IMG; g4.B_lo = t.k4p_lo;
-    g4.terms = 3; g4.bias = t.b4; g4.out = t.l4 + (size_t)b.t0 * 128 * DENSE; g4.m_tiles = b.nt; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
+    g4.terms = l4_terms(); g4.bias = t.b4; g4.out = t.l4 + (size_t)b.t0 * 128 * DENSE; g4.m_tiles = b.nt; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
     g4.mode = 1; g4.err = t.err; g4.dbg = 0; g4.trace = nullptr;
     cudaError_t e = launch_gemm(g4, t.sm_count, st);
     if (e != cudaSuccess) return e;
