@@ -80,6 +80,7 @@ struct c3r_ctx {
     bool exact_bounds = false; // capacity bounds from an exact host pass over the CIGARs (retry path)
     const c3r_site_filter* filter = nullptr;   // of the submit in progress
     bool tc_dirty = false;    // a tensor-core forward ran since the last device error check
+    cudaEvent_t nn_done = nullptr;   // end of the last network pass: the scratch (h1, zx2, h2 ...) is shared by all tickets
     Buf thr;                  // allele-frequency threshold tables (k_thr_table)
     Buf ref_res;              // resident reference window (c3r_set_reference)
     Buf refnib_res;           // its one-hot nibble form (k_refnib)
@@ -357,6 +358,7 @@ void c3r_destroy(c3r_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->nn_done) cudaEventDestroy(ctx->nn_done);
     for (int i = 0; i < N_SLOTS; ++i) {
         Slot& s = ctx->slots[i];
         Buf* bs[] = {&s.pos, &s.flag, &s.mapq, &s.hp, &s.cigar_off, &s.cigar, &s.seq_off, &s.seq, &s.ref, &s.admit,
@@ -364,7 +366,7 @@ void c3r_destroy(c3r_ctx* ctx) {
                      &s.word_base, &s.row_pos, &s.counts, &s.row_depth, &s.row_flag, &s.head_cnt, &s.tail_cnt,
                      &s.skipdiff, &s.max_skip, &s.row_ins, &s.row_del, &s.binc, &s.bin_cur, &s.events, &s.raw, &s.cov, &s.cov_tile, &s.refnib,
                      &s.cand_row, &s.cand_pos, &s.cand_depth, &s.tensor, &s.alt_off, &s.alt_n, &s.alt, &s.cur_ref,
-                     &s.deleted, &s.probs, &s.scalars, &s.scan_scratch};
+                     &s.deleted, &s.probs, &s.scalars, &s.scan_scratch, &s.pbed, &s.cbed, &s.known, &s.covP};
         for (Buf* b : bs) release(*b);
         Pin* ps[] = {&s.h_scalars, &s.h_pos, &s.h_depth, &s.h_probs, &s.h_alt_off, &s.h_alt_n, &s.h_alt, &s.h_tensor,
                      &s.h_row_pos, &s.h_counts, &s.h_row_depth};
@@ -594,6 +596,11 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
         ++s.launches;
     }
     s.in_use = true;
+    // The copies above overlap the network pass of the ticket before this one; the position / row stages do not
+    // start under it: their ~25 short kernels would only get SMs at the boundaries of the persistent network
+    // kernels, delaying both (measured: 2.62 ms per pass interleaved, against 2.35 ms of device work).
+    if (ctx->prm.nn_impl == 1 && getenv("C3R_INTERLEAVE") == nullptr)
+        if (cudaEvent_t done = tc_pass_done(ctx->tc)) CK(cudaStreamWaitEvent(st, done, 0));
     int rc = run_stage_a(ctx, s);
     if (!rc) rc = read_scalars(ctx, s);
     if (!rc) rc = ensure_stage_b(ctx, s);
@@ -812,7 +819,20 @@ int build_net(c3r_ctx* ctx, const std::map<std::string, std::pair<const float*, 
     return C3R_OK;
 }
 
+static int nn_forward_impl(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches);
+
+// Tickets run on their own streams but share the network's scratch buffers: passes are ordered by events.
 int nn_forward(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches) {
+    if (ctx->prm.nn_impl == 1)                       // the tensor-core pass orders itself buffer by buffer (TcPipe)
+        return nn_forward_impl(ctx, tensor_dev, n, probs_dev, st, launches);
+    if (!ctx->nn_done) CK(cudaEventCreateWithFlags(&ctx->nn_done, cudaEventDisableTiming));
+    else CK(cudaStreamWaitEvent(st, ctx->nn_done, 0));
+    const int rc = nn_forward_impl(ctx, tensor_dev, n, probs_dev, st, launches);
+    CK(cudaEventRecord(ctx->nn_done, st));
+    return rc;
+}
+
+static int nn_forward_impl(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches) {
     *launches = 0;
     if (ctx->prm.nn_impl == 1) {
         std::string terr;

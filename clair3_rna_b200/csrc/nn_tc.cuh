@@ -1132,6 +1132,16 @@ inline int zx_terms() {
     return v;
 }
 
+inline int zx_overlap_tiles() {              // projection tile pairs per idle SM pair under LSTM1's remainder round
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("C3R_ZX_OVERLAP");
+        v = e ? atoi(e) : 7;
+        if (v < 0 || v > 64) v = 7;
+    }
+    return v;
+}
+
 inline int l4_terms() {                      // same mask for the L4 GEMM (C3R_L4_TERMS)
     static int v = -1;
     if (v < 0) {
@@ -1142,7 +1152,7 @@ inline int l4_terms() {                      // same mask for the L4 GEMM (C3R_L
     return v;
 }
 
-inline cudaError_t launch_gemm_zx(const GemmArgs& g, int sm_count, cudaStream_t st) {
+inline cudaError_t launch_gemm_zx(const GemmArgs& g, int sm_count, cudaStream_t st, int max_pairs = 1 << 30) {
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_zx, cudaFuncAttributeMaxDynamicSharedMemorySize, ZXG_SMEM);
@@ -1150,6 +1160,7 @@ inline cudaError_t launch_gemm_zx(const GemmArgs& g, int sm_count, cudaStream_t 
         attr = true;
     }
     int pairs = g.m_tiles / 2 < sm_count / 2 ? g.m_tiles / 2 : sm_count / 2;
+    if (pairs > max_pairs) pairs = max_pairs;
     if (pairs < 1) pairs = 1;
     k_gemm_zx<<<pairs * 2, ZXG_THREADS, ZXG_SMEM, st>>>(g);
     return cudaGetLastError();
@@ -1180,12 +1191,18 @@ inline cudaError_t launch_gemm(const GemmArgs& g, int sm_count, cudaStream_t st)
 struct TcPipe {
     cudaStream_t s2 = nullptr;
     cudaEvent_t ev[2] = {};
+    // Passes of different tickets run on different streams but share the scratch buffers.  A pass may start
+    // (xop, LSTM1: they write xop and h1) once the previous pass's projection GEMM has read h1; it may write zx2 /
+    // h2 / l4 once the previous pass has ended.  (An event that was never recorded does not block.)
+    cudaEvent_t h1_free = nullptr, pass_done = nullptr;
     bool ok = false;
 };
 inline int tc_pipe_init(TcPipe& p, std::string* err) {
     if (p.ok) return 0;
     cudaError_t e = cudaStreamCreateWithFlags(&p.s2, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p.ev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.h1_free, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.pass_done, cudaEventDisableTiming);
     if (e != cudaSuccess) { *err = std::string("pipeline streams: ") + cudaGetErrorString(e); return -1; }
     p.ok = true;
     return 0;
@@ -1193,8 +1210,13 @@ inline int tc_pipe_init(TcPipe& p, std::string* err) {
 inline void tc_pipe_release(TcPipe* p) {
     if (p->s2) cudaStreamDestroy(p->s2);
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->h1_free) cudaEventDestroy(p->h1_free);
+    if (p->pass_done) cudaEventDestroy(p->pass_done);
     delete p;
 }
+
+// end of the last network pass (nullptr before the first one)
+inline cudaEvent_t tc_pass_done(const TcNet& t) { return t.pipe && t.pipe->ok ? t.pipe->pass_done : nullptr; }
 
 // tiles [t0, t0 + nt) of the pass, sites [s0, s0 + ns)
 struct TcSub { int t0, nt; int64_t s0, ns; };
@@ -1231,34 +1253,70 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         int tiles = (int)((m + TC_TILE - 1) / TC_TILE);
         tiles += tiles & 1;                  // CTA pairs
         if (tc_ensure(t, tiles, err)) return -1;
+        TCK(cudaStreamWaitEvent(st, P.h1_free, 0), "wait");         // the previous pass no longer reads xop / h1
         if (t.C == 18) k_xop<18, 48><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
         else k_xop<30, 64><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
         ++launches;
-        LstmArgs a1;
-        a1.Wimg = t.img1; a1.xop = t.xop; a1.C = t.C; a1.zx = nullptr; a1.hout = t.h1; a1.hout_lo = (zx_terms() & 2) ? t.h1_lo : nullptr; a1.kb_out = 4;
-        a1.n_sites = m; a1.n_tiles = tiles; a1.err = t.err; a1.trace = t.trace;
-        const cudaError_t e1 = t.C == 18 ? launch_lstm<4, 48>(a1, t.sm_count, st) : launch_lstm<4, 64>(a1, t.sm_count, st);
-        TCK(e1, "lstm1");
-        ++launches;
-        GemmArgs g2;
-        g2.A = t.h1; g2.B = t.w2p; g2.A_lo = t.h1_lo; g2.B_lo = t.w2p_lo; g2.terms = zx_terms(); g2.bias = t.b2p; g2.out = t.zx2;
-        g2.m_tiles = tiles * NT; g2.n_tiles = 5; g2.n_kb = 4;
-        g2.mode = 0; g2.err = t.err; g2.dbg = getenv("C3R_ZX_DBG") ? atoi(getenv("C3R_ZX_DBG")) : 0; g2.trace = t.trace ? t.trace + 2 * 2 * NT * 8 * 8 : nullptr;
-        TCK(launch_gemm_zx(g2, t.sm_count, st), "zx2 gemm");
-        ++launches;
-        // A = the tile pairs that fill whole rounds of the recurrent kernel, B = the rest
+        // A = the tile pairs that fill whole rounds of the recurrent kernels, B = the rest
         const int pairs = tiles / 2, per_round = t.sm_count / 4;
         int pa = pairs;
         if (pairs > per_round && pairs % per_round != 0) pa = (pairs / per_round) * per_round;
         TcSub A, B;
         A.t0 = 0; A.nt = 2 * pa; A.s0 = 0; A.ns = m < (int64_t)A.nt * TC_TILE ? m : (int64_t)A.nt * TC_TILE;
         B.t0 = A.nt; B.nt = tiles - A.nt; B.s0 = A.ns; B.ns = m - A.ns;
+        auto lstm1 = [&](const TcSub& b, cudaStream_t s) -> cudaError_t {
+            LstmArgs a1;
+            const int kx = t.C == 18 ? 48 : 64;
+            a1.Wimg = t.img1; a1.xop = t.xop + (size_t)b.t0 * NT * kx * TC_TILE; a1.C = t.C; a1.zx = nullptr;
+            a1.hout = t.h1 + (size_t)b.t0 * NT * 4 * TC_IMG;
+            a1.hout_lo = (zx_terms() & 2) ? t.h1_lo + (size_t)b.t0 * NT * 4 * TC_IMG : nullptr; a1.kb_out = 4;
+            a1.n_sites = b.ns; a1.n_tiles = b.nt; a1.err = t.err; a1.trace = b.t0 == 0 ? t.trace : nullptr;
+            return t.C == 18 ? launch_lstm<4, 48>(a1, t.sm_count, s) : launch_lstm<4, 64>(a1, t.sm_count, s);
+        };
+        // hoisted LSTM2 projection of the 128-row tiles [m0, m0 + mt) (tile = site tile * 33 + time step)
+        auto zx = [&](int m0, int mt, int max_pairs, cudaStream_t s) -> cudaError_t {
+            GemmArgs g2;
+            g2.A = t.h1 + (size_t)m0 * ZXG_KB * TC_IMG; g2.A_lo = t.h1_lo + (size_t)m0 * ZXG_KB * TC_IMG;
+            g2.B = t.w2p; g2.B_lo = t.w2p_lo; g2.terms = zx_terms(); g2.bias = t.b2p;
+            g2.out = t.zx2 + (size_t)m0 * 10 * ZX_CHUNK_WORDS;
+            g2.m_tiles = mt; g2.n_tiles = 5; g2.n_kb = 4;
+            g2.mode = 0; g2.err = t.err; g2.dbg = getenv("C3R_ZX_DBG") ? atoi(getenv("C3R_ZX_DBG")) : 0;
+            g2.trace = (t.trace && m0 == 0) ? t.trace + 2 * 2 * NT * 8 * 8 : nullptr;
+            return launch_gemm_zx(g2, t.sm_count, s, max_pairs);
+        };
+        // While LSTM1's remainder round leaves SMs idle, the projection of the first tiles of A runs on them
+        // (second stream); each idle SM pair gets as many tile pairs as fit in the remainder round's ~190 us.
+        const int busy_b = 4 * (B.nt / 2 < per_round ? B.nt / 2 : per_round);
+        const int idle_pairs = (t.sm_count - busy_b) / 2;
+        int m_early = 2 * idle_pairs * zx_overlap_tiles();
+        if (m_early > A.nt * NT) m_early = A.nt * NT;
+        if (B.nt == 0 || A.nt == 0 || idle_pairs < 8 || m_early <= 0) {
+            TcSub all; all.t0 = 0; all.nt = tiles; all.s0 = 0; all.ns = m;
+            TCK(lstm1(all, st), "lstm1");
+            TCK(cudaStreamWaitEvent(st, P.pass_done, 0), "wait");   // the previous pass no longer reads zx2 / h2 / l4
+            TCK(zx(0, tiles * NT, 1 << 30, st), "zx2 gemm");
+            launches += 2;
+        } else {
+            TCK(lstm1(A, st), "lstm1");
+            TCK(cudaEventRecord(P.ev[0], st), "event");
+            TCK(lstm1(B, st), "lstm1");
+            TCK(cudaStreamWaitEvent(P.s2, P.ev[0], 0), "wait");
+            TCK(cudaStreamWaitEvent(P.s2, P.pass_done, 0), "wait");
+            TCK(zx(0, m_early, idle_pairs, P.s2), "zx2 gemm");
+            TCK(cudaEventRecord(P.ev[1], P.s2), "event");
+            TCK(cudaStreamWaitEvent(st, P.ev[1], 0), "wait");
+            TCK(cudaStreamWaitEvent(st, P.pass_done, 0), "wait");
+            TCK(zx(m_early, tiles * NT - m_early, 1 << 30, st), "zx2 gemm");
+            launches += 4;
+        }
+        TCK(cudaEventRecord(P.h1_free, st), "event");
         float* pr = probs + o * 24;
         TCK(tc_lstm2(t, A, st), "lstm2");
         ++launches;
         if (B.nt == 0) {
             TCK(tc_l4_heads(t, net, A, pr, st), "l4/heads");
             launches += 2;
+            TCK(cudaEventRecord(P.pass_done, st), "event");
             continue;
         }
         TCK(cudaEventRecord(P.ev[0], st), "event");
@@ -1269,6 +1327,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         TCK(tc_l4_heads(t, net, B, pr, st), "l4/heads");
         TCK(cudaStreamWaitEvent(st, P.ev[1], 0), "wait");       // the caller's stream ends after everything
         launches += 5;
+        TCK(cudaEventRecord(P.pass_done, st), "event");
     }
 #undef TCK
     return launches;

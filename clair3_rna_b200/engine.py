@@ -46,12 +46,14 @@ ALT_DTYPE = np.dtype([("kind", "u1"), ("base", "u1"), ("len", "<u2"), ("count", 
                       ("seq_off", "<u4"), ("order", "<u4")])
 
 
-def _view(ptr, n, dtype):
+def _view(ptr, n, dtype, copy=True):
+    """numpy array over library-owned host memory; copy=False aliases it (valid until the ticket is released)"""
     if not ptr or n <= 0:
         return np.zeros(0, dtype)
     nbytes = int(n) * np.dtype(dtype).itemsize
     buf = (C.c_char * nbytes).from_address(ptr)
-    return np.frombuffer(buf, dtype=dtype, count=int(n)).copy()
+    a = np.frombuffer(buf, dtype=dtype, count=int(n))
+    return a.copy() if copy else a
 
 
 class Engine:
@@ -155,23 +157,28 @@ class Engine:
                                                        region_end1, C.byref(f), C.byref(t)), "c3r_submit_chunk_filtered")
         return int(t.value)
 
-    def wait(self, ticket: int, release: bool = True) -> ChunkResult:
+    def wait(self, ticket: int, release: bool = True, copy: bool = True) -> ChunkResult:
+        """Result of a ticket.  copy=True (default) returns private numpy copies and, with release=True, frees the
+        ticket.  copy=False returns arrays that alias the library's pinned result buffers - no allocation, no page
+        faults (copying 3-4 MB into fresh memory costs ~1.5 ms per chunk, more than half a device pass) - which
+        stay valid until release(ticket); the ticket is then NOT released here."""
         r = L.Result()
         self._check(self.lib.c3r_wait(self.ctx, ticket, C.byref(r)), "c3r_wait")
         n, Ct = int(r.n_cand), self.channels
-        alt_off = _view(r.alt_off, n, np.int64)
-        alt_n = _view(r.alt_n, n, np.int32)
+        v = lambda ptr, cnt, dt: _view(ptr, cnt, dt, copy)
+        alt_off = v(r.alt_off, n, np.int64)
+        alt_n = v(r.alt_n, n, np.int32)
         total = int((alt_off + alt_n).max()) if n else 0
         out = ChunkResult(
-            n_rows=int(r.n_rows), pos=_view(r.pos, n, np.int32), depth=_view(r.depth, n, np.int32),
-            probs=_view(r.probs, n * 24, np.float32).reshape(n, 24), alt_off=alt_off, alt_n=alt_n,
-            alt=_view(r.alt, total, ALT_DTYPE),
-            tensor=_view(r.tensor, n * 33 * Ct, np.int32).reshape(n, 33, Ct) if r.tensor else None,
-            row_pos=_view(r.row_pos, r.n_rows, np.int32) if r.row_pos else None,
-            row_counts=_view(r.row_counts, r.n_rows * Ct, np.int32).reshape(-1, Ct) if r.row_counts else None,
-            row_depth=_view(r.row_depth, r.n_rows, np.int32) if r.row_depth else None,
+            n_rows=int(r.n_rows), pos=v(r.pos, n, np.int32), depth=v(r.depth, n, np.int32),
+            probs=v(r.probs, n * 24, np.float32).reshape(n, 24), alt_off=alt_off, alt_n=alt_n,
+            alt=v(r.alt, total, ALT_DTYPE),
+            tensor=v(r.tensor, n * 33 * Ct, np.int32).reshape(n, 33, Ct) if r.tensor else None,
+            row_pos=v(r.row_pos, r.n_rows, np.int32) if r.row_pos else None,
+            row_counts=v(r.row_counts, r.n_rows * Ct, np.int32).reshape(-1, Ct) if r.row_counts else None,
+            row_depth=v(r.row_depth, r.n_rows, np.int32) if r.row_depth else None,
             stage_ms=[float(x) for x in r.stage_ms], launches=int(r.kernel_launches))
-        if release:
+        if release and copy:
             self.lib.c3r_release(self.ctx, ticket)
         return out
 

@@ -82,3 +82,29 @@ def test_no_record_means_no_file(tmp_path):
                               "--ref_fn", fa, "--call_fn", out, "--ctgName", "chr1", "--chunk_id", "1",
                               "--chunk_num", "1", "--pileup"]) == 0
     assert not os.path.exists(out)
+
+
+def test_tickets_in_flight_equal_sequential_calls():
+    """three tickets submitted back to back (their device work overlaps as far as the GPU allows; the network
+    scratch is shared, so passes are ordered by an event) give the results of one-at-a-time calls, bit for bit"""
+    import numpy as np
+    from clair3_rna_b200 import weights
+    from clair3_rna_b200.engine import Engine
+    from tests.golden import cases as golden_cases
+    names = ["cfg1_ont_drna", "ties_lowdepth", "cfg2_ont_cdna"]
+    data = [golden_cases.build(n) for n in names]
+    eng = Engine(0, 18, keep_tensor=True)
+    eng.set_weights(weights.synthetic(18, sharpen=8.0))
+    want = []
+    for batch, ref_bytes, _ in data:
+        ref = np.frombuffer(ref_bytes, np.uint8)
+        r = eng.call_chunk(batch, ref, 1, 1, len(ref_bytes) + 33)
+        want.append((r.pos.copy(), r.probs.copy(), r.tensor.copy()))
+    for _round in range(3):
+        tickets = [eng.submit(batch, np.frombuffer(ref_bytes, np.uint8), 1, 1, len(ref_bytes) + 33)
+                   for batch, ref_bytes, _ in data]
+        for t, (pos, probs, tensor) in zip(tickets, want):
+            r = eng.wait(t)
+            assert np.array_equal(r.pos, pos) and np.array_equal(r.tensor, tensor)
+            assert np.array_equal(r.probs, probs)
+    eng.close()
