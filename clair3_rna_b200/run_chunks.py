@@ -97,9 +97,10 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
                    name, batch, ref, plan.ref_start1)
         if pending is not None:
             j, ticket, pname, pbatch, pref, prs1 = pending
-            res = eng.wait(ticket)
+            res = eng.wait(ticket, copy=False)       # arrays over the library's pinned buffers, no copies
             n_cand += res.n_cand
             rows_of[j] = decode_vcf_rows(res, pbatch, pref, prs1, pname, qual=qual)
+            eng.release(ticket)
         pending = nxt
     eng.close()
     bf.close()
