@@ -703,4 +703,105 @@ int c3r_bam_write(const char* path, int n_ref, const char* const* names, const i
     return iok ? C3R_OK : C3R_ERR_ARG;
 }
 
+// bgzip + tabix of a VCF text (what `sort_vcf --compress_vcf True` does through the external tools,
+// src/sort_vcf.py:70-76): writes `path` as BGZF and `path`.tbi (tabix index, VCF preset: sequence column 1, begin
+// column 2, meta '#'; 16 kb linear index and the UCSC binning scheme like BAI; interval of a record =
+// [POS-1, POS-1+len(REF))).  The text must be header lines ('#') followed by position-sorted data lines.
+int c3r_vcf_write_bgzf(const char* path, const char* text, int64_t n_bytes, int level) {
+    if (!path || (!text && n_bytes) || n_bytes < 0) return C3R_ERR_ARG;
+    BgzfWriter w;
+    w.level = level <= 0 ? 6 : level;
+    w.fp = fopen(path, "wb");
+    if (!w.fp) return C3R_ERR_ARG;
+    std::vector<std::string> names;
+    std::vector<RefIndex> index;
+    std::vector<std::vector<std::pair<uint32_t, Chunk>>> chunks;
+    int cur = -1;
+    int64_t last_beg = -1;
+    bool sorted = true;
+    const char* p = text;
+    const char* const e = text + n_bytes;
+    while (p < e) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+        const char* le = nl ? nl + 1 : e;                       // line incl. its newline
+        const uint64_t v0 = w.tell();
+        w.write((const uint8_t*)p, (size_t)(le - p));
+        const uint64_t v1 = w.tell();
+        if (*p != '#' && le - p > 1) {
+            // CHROM \t POS \t ID \t REF
+            const char* t1 = (const char*)memchr(p, '\t', (size_t)(le - p));
+            const char* t2 = t1 ? (const char*)memchr(t1 + 1, '\t', (size_t)(le - t1 - 1)) : nullptr;
+            const char* t3 = t2 ? (const char*)memchr(t2 + 1, '\t', (size_t)(le - t2 - 1)) : nullptr;
+            const char* t4 = t3 ? (const char*)memchr(t3 + 1, '\t', (size_t)(le - t3 - 1)) : nullptr;
+            if (!t4) { fclose(w.fp); return C3R_ERR_ARG; }
+            const std::string chrom(p, t1);
+            const int64_t beg = strtoll(t1 + 1, nullptr, 10) - 1;
+            const int64_t end = beg + (t4 - t3 - 1 > 0 ? (int64_t)(t4 - t3 - 1) : 1);
+            if (beg < 0) { fclose(w.fp); return C3R_ERR_ARG; }
+            if (cur < 0 || names[cur] != chrom) {
+                for (const std::string& nm : names) if (nm == chrom) sorted = false;   // a contig must be one block
+                names.push_back(chrom);
+                index.emplace_back();
+                chunks.emplace_back();
+                cur = (int)names.size() - 1;
+                last_beg = -1;
+            }
+            if (beg < last_beg) sorted = false;
+            last_beg = beg;
+            RefIndex& ri = index[cur];
+            auto& bc = chunks[cur];
+            const uint32_t bin = (uint32_t)reg2bin(beg, end);
+            if (!bc.empty() && bc.back().first == bin && bc.back().second.end == v0) bc.back().second.end = v1;
+            else bc.push_back({bin, {v0, v1}});
+            const size_t w0 = (size_t)(beg >> 14), w1 = (size_t)((end - 1) >> 14);
+            if (ri.linear.size() <= w1) ri.linear.resize(w1 + 1, 0);
+            for (size_t k = w0; k <= w1; ++k) if (ri.linear[k] == 0) ri.linear[k] = v0;
+            ++ri.n_mapped;
+        }
+        p = le;
+    }
+    w.finish();
+    const bool ok = w.ok;
+    fclose(w.fp);
+    if (!ok || !sorted) return C3R_ERR_ARG;
+    std::vector<uint8_t> ix;
+    ix.insert(ix.end(), {'T', 'B', 'I', 1});
+    wr32(ix, (uint32_t)names.size());
+    wr32(ix, 2); wr32(ix, 1); wr32(ix, 2); wr32(ix, 0); wr32(ix, (uint32_t)'#'); wr32(ix, 0);
+    uint32_t l_nm = 0;
+    for (const std::string& nm : names) l_nm += (uint32_t)nm.size() + 1;
+    wr32(ix, l_nm);
+    for (const std::string& nm : names) { ix.insert(ix.end(), nm.begin(), nm.end()); ix.push_back(0); }
+    for (size_t r = 0; r < names.size(); ++r) {
+        RefIndex& ri = index[r];
+        uint64_t last = 0;
+        for (uint64_t& v : ri.linear) { if (v == 0) v = last; else last = v; }
+        auto& bc = chunks[r];
+        std::stable_sort(bc.begin(), bc.end(), [](const auto& a, const auto& c) {
+            return a.first != c.first ? a.first < c.first : a.second.beg < c.second.beg; });
+        std::vector<std::pair<uint32_t, std::vector<Chunk>>> bins;
+        for (const auto& x : bc) {
+            if (bins.empty() || bins.back().first != x.first) bins.emplace_back(x.first, std::vector<Chunk>());
+            bins.back().second.push_back(x.second);
+        }
+        wr32(ix, (uint32_t)bins.size());
+        for (const auto& bn : bins) {
+            wr32(ix, bn.first);
+            wr32(ix, (uint32_t)bn.second.size());
+            for (const Chunk& c : bn.second) { wr64(ix, c.beg); wr64(ix, c.end); }
+        }
+        wr32(ix, (uint32_t)ri.linear.size());
+        for (uint64_t v : ri.linear) wr64(ix, v);
+    }
+    BgzfWriter wi;
+    const std::string ip = std::string(path) + ".tbi";
+    wi.fp = fopen(ip.c_str(), "wb");
+    if (!wi.fp) return C3R_ERR_ARG;
+    wi.write(ix.data(), ix.size());
+    wi.finish();
+    const bool iok = wi.ok;
+    fclose(wi.fp);
+    return iok ? C3R_OK : C3R_ERR_ARG;
+}
+
 }  // extern "C"

@@ -46,7 +46,8 @@ def build_shards(contigs, mapped, chunk_size=P.CHUNK_SIZE):
 def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, world=1, phased=False, padding=False,
         snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF, min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ,
         qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None, bed_fn=None, vcf_fn=None, head_tail=False,
-        merge_qual=None, show_ref=True, rediportal_fn=None, rediportal_tags=None, output_no_tagging=None):
+        merge_qual=None, show_ref=True, rediportal_fn=None, rediportal_tags=None, output_no_tagging=None,
+        compress_vcf=False):
     """merge_qual / show_ref / rediportal_*: the options of the merge stage (sharder.sort_vcf = sort_vcf_from of the
     reference); the defaults keep every row as the chunks produced it."""
     from .bam import BamFile
@@ -129,8 +130,15 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
             continue
         if os.path.exists(path):
             os.remove(path)
+        for stale in (path + ".gz", path + ".gz.tbi"):
+            if os.path.exists(stale):
+                os.remove(stale)
         if rows:                                     # like the reference: no file when there is no record
             header = decoder.vcf_header([(n, fai[n][0]) for n in fai], sample_name, ref_fn)
+            if compress_vcf:                         # bgzip -f + tabix -p vcf (sort_vcf.py:70-76): path.gz, path.gz.tbi
+                from . import vcf_io
+                vcf_io.write_vcf_gz(path + ".gz", header, rows)
+                continue
             with open(path, "w") as fp:
                 fp.write(header + "\n")
                 fp.write("\n".join(rows) + "\n")
@@ -158,6 +166,7 @@ def main(argv=None):
     ap.add_argument("--readiportal_source_fn", default=None, help="REDIportal TABLE1 (plain or gzip)")
     ap.add_argument("--readiportal_database_filter_tag", default="A,D:A,R:A,R,D")
     ap.add_argument("--output_no_tagging_fn", default=None)
+    ap.add_argument("--compress_vcf", action="store_true", help="write <output>.gz (BGZF) and <output>.gz.tbi instead of plain text")
     ap.add_argument("--enable_phasing_model", action="store_true")
     ap.add_argument("--enable_padding_in_splice_junction_regions", action="store_true")
     ap.add_argument("--enable_variant_calling_at_sequence_head_and_tail", action="store_true")
@@ -178,6 +187,7 @@ def main(argv=None):
         merge_qual=merge_qual, show_ref=a.print_ref_calls,
         rediportal_fn=a.readiportal_source_fn if a.tag_variant_using_readiportal else None,
         rediportal_tags=a.readiportal_database_filter_tag, output_no_tagging=a.output_no_tagging_fn,
+        compress_vcf=a.compress_vcf,
         sample_name=a.sampleName, stats=stats, bed_fn=a.bed_fn, vcf_fn=a.genotyping_mode_vcf_fn,
         head_tail=a.enable_variant_calling_at_sequence_head_and_tail)
     print("[rank %d] %d shards, %d candidates in %.2f s" % (rank, stats["shards"], stats["candidates"], stats["seconds"]),

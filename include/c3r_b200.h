@@ -226,6 +226,11 @@ int c3r_bam_fetch(c3r_bam* bam, int tid, int64_t start1, int64_t end1, c3r_reads
 int c3r_bam_write(const char* path, int n_ref, const char* const* names, const int64_t* lens,
                   const c3r_reads* const* batches, int level, const char* header_text);
 
+/* bgzip + tabix of the merged VCF: what `sort_vcf --compress_vcf True` does through the external `bgzip` and
+ * `tabix -p vcf` (src/sort_vcf.py:70-76, run_clair3_rna:722).  Writes `path` (BGZF) and `path`.tbi from the VCF
+ * text (header lines, then data lines sorted by position within each contig).  level <= 0: zlib default.      */
+int c3r_vcf_write_bgzf(const char* path, const char* text, int64_t n_bytes, int level);
+
 #ifdef __cplusplus
 }
 #endif
