@@ -47,6 +47,12 @@ CASES = {
     "headtail_phased_bed": dict(_BASE, cfg=4, scale=0.01, over=dict(genes_per_mb=100, depth=15, sub=0.04, ins=0.03,
                                                                     dele=0.04, seed=777073),
                                 platform="hifi", phased=True, head_tail=True, chunks=2, bed=dict(n=60, seed=14)),
+    # --ctgStart/--ctgEnd instead of a chunk (create_tensor_pileup.py:407-415), and head/tail calling at known sites
+    "range_mode": dict(_BASE, cfg=1, scale=0.06, over=dict(genes_per_mb=70, depth=9, seed=777081), platform="ont",
+                       ctg_range=(9000, 41000)),
+    "headtail_known": dict(_BASE, cfg=1, scale=0.05, over=dict(genes_per_mb=70, depth=9, sub=0.05, ins=0.03, dele=0.05,
+                                                               seed=777082), platform="ont", head_tail=True, chunks=2,
+                           known=dict(n=300, seed=15)),
     "af_zero": dict(_BASE, cfg=1, scale=0.03, over=dict(genes_per_mb=70, depth=8, seed=777004), platform="ont",
                     snp_af=0.0, min_cov=2),
 }
@@ -111,6 +117,10 @@ def chunk_plans(name):
     n = case.get("chunks", 1)
     conf, known = bed_rows(name), known_positions(name)
     ext = regions.extend_bed_rows(conf) if conf is not None else regions.extend_known_rows(known) if known is not None else None
+    if "ctg_range" in case:
+        a, b = case["ctg_range"]
+        return [regions.plan_chunk(len(ref), ctg_start=a, ctg_end=b, extend_rows=ext, confident_rows=conf,
+                                   known_positions=known)]
     if n == 1 and conf is None and known is None:
         return [regions.ChunkPlan(1, len(ref) + 33, 1, len(ref))]
     return [regions.plan_chunk(len(ref), chunk_id=cid, chunk_num=n, extend_rows=ext, confident_rows=conf,

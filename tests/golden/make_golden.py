@@ -42,14 +42,18 @@ def write_fasta(path, name, seq: bytes):
 
 
 def run_reference_producer(tmp, contig, platform, phased, padding, snp_af, indel_af, min_cov, min_mq,
-                           chunk_id=1, chunk_num=1, bed_fn=None, extend_bed=None, vcf_fn=None, head_tail=False):
+                           chunk_id=1, chunk_num=1, bed_fn=None, extend_bed=None, vcf_fn=None, head_tail=False,
+                           ctg_range=None):
     shim = "%s %s" % (sys.executable, os.path.join(ROOT, "oracle", "samtools_shim.py"))
     cmd = [sys.executable, os.path.join(REF_ROOT, "clair3_rna.py"), "create_tensor_pileup",
            "--bam_fn", os.path.join(tmp, "reads.npz"), "--ref_fn", os.path.join(tmp, "ref.fa"),
            "--ctgName", contig, "--platform", platform, "--samtools", shim,
            "--minCoverage", str(min_cov), "--minMQ", str(min_mq),
-           "--snp_min_af", str(snp_af), "--indel_min_af", str(indel_af),
-           "--chunk_id", str(chunk_id), "--chunk_num", str(chunk_num)]
+           "--snp_min_af", str(snp_af), "--indel_min_af", str(indel_af)]
+    if ctg_range is not None:
+        cmd += ["--ctgStart", str(ctg_range[0]), "--ctgEnd", str(ctg_range[1])]
+    else:
+        cmd += ["--chunk_id", str(chunk_id), "--chunk_num", str(chunk_num)]
     if phased:
         cmd += ["--add_phasing_feature", "True"]
     if padding:
@@ -119,7 +123,8 @@ def make_case(name):
         for cid in range(1, n_chunks + 1):
             texts.append(run_reference_producer(tmp, contig, case["platform"], case["phased"], case["padding"],
                                                 case["snp_af"], case["indel_af"], case["min_cov"], case["min_mq"],
-                                                chunk_id=cid, chunk_num=n_chunks, head_tail=case.get("head_tail", False), **files))
+                                                chunk_id=cid, chunk_num=n_chunks, head_tail=case.get("head_tail", False),
+                                                ctg_range=case.get("ctg_range"), **files))
     chunk_of = np.concatenate([np.full(len(t.splitlines()), cid + 1, np.int32) for cid, t in enumerate(texts)])
     text = "".join(texts)
     rows = [r.split("\t") for r in text.splitlines()]

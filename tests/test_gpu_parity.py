@@ -37,7 +37,9 @@ def run_case(name, nn_impl):
     w = weights.synthetic(C, sharpen=8.0)
     eng.set_weights(w)
     plans = golden_cases.chunk_plans(name)
-    if len(plans) == 1 and plans[0].site_filter() is None:
+    whole = len(plans) == 1 and plans[0].site_filter() is None and \
+        (plans[0].start1, plans[0].end1, plans[0].ref_start1) == (1, len(ref_bytes) + 33, 1)
+    if whole:
         res = eng.call_chunk(batch, ref, 1, 1, len(ref_bytes) + 33)
     else:
         res = run_chunked(eng, batch, ref, plans)
