@@ -1102,7 +1102,7 @@ inline int tc_ensure(TcNet& t, int tiles, std::string* err) {
     return 0;
 }
 
-constexpr int TC_SUB_TILES = 256;            // 32768 sites per pass: bounds the hoisted-projection scratch (5.5 GB)
+constexpr int TC_SUB_TILES = 320;            // at most 40960 sites per sub-pass: bounds the hoisted-projection scratch (7 GB)
 
 template <int CH, int KX>
 inline cudaError_t launch_lstm(const LstmArgs& a, int sm_count, cudaStream_t st) {
@@ -1248,8 +1248,12 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
     TcPipe& P = *t.pipe;
     int launches = 0;
 #define TCK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { *err = std::string(what) + ": " + cudaGetErrorString(e__); return -1; } } while (0)
-    for (int64_t o = 0; o < n; o += (int64_t)TC_SUB_TILES * TC_TILE) {
-        const int64_t m = n - o < (int64_t)TC_SUB_TILES * TC_TILE ? n - o : (int64_t)TC_SUB_TILES * TC_TILE;
+    // a batch larger than the scratch goes through in sub-passes of whole rounds of the recurrent kernels
+    // (sm_count / 4 cluster pairs x 2 tiles each), so that only the last sub-pass has a partly filled round
+    const int round_tiles = 2 * (t.sm_count / 4) > 0 ? 2 * (t.sm_count / 4) : 2;
+    const int sub_tiles = TC_SUB_TILES >= round_tiles ? (TC_SUB_TILES / round_tiles) * round_tiles : TC_SUB_TILES;
+    for (int64_t o = 0; o < n; o += (int64_t)sub_tiles * TC_TILE) {
+        const int64_t m = n - o < (int64_t)sub_tiles * TC_TILE ? n - o : (int64_t)sub_tiles * TC_TILE;
         int tiles = (int)((m + TC_TILE - 1) / TC_TILE);
         tiles += tiles & 1;                  // CTA pairs
         if (tc_ensure(t, tiles, err)) return -1;

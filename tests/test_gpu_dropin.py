@@ -108,3 +108,23 @@ def test_tickets_in_flight_equal_sequential_calls():
             assert np.array_equal(r.pos, pos) and np.array_equal(r.tensor, tensor)
             assert np.array_equal(r.probs, probs)
     eng.close()
+
+
+def test_large_batch_sub_passes_equal_small_batches():
+    """a batch that needs several sub-passes of the network (more sites than the scratch holds at once) gives, site
+    by site, the bits of the same sites sent in small batches"""
+    import numpy as np
+    from clair3_rna_b200 import weights
+    from clair3_rna_b200.engine import Engine
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_ont_drna.npz"))
+    base = g["tensor"]
+    rng = np.random.default_rng(5)
+    n = 45000
+    x = base[rng.integers(0, len(base), n)]
+    eng = Engine(0, 18)
+    eng.set_weights(weights.synthetic(18, sharpen=8.0))
+    big, _ = eng.forward(x)
+    for a, b in ((0, 3000), (37000, 39500), (n - 2100, n)):
+        small, _ = eng.forward(x[a:b])
+        assert np.array_equal(big[a:b], small)
+    eng.close()
