@@ -34,10 +34,6 @@ const char* const GT21_LABELS[21] = {"AA", "AC", "AG", "AT", "CC", "CG", "CT", "
 const char ACGT[5] = "ACGT";
 const char NT16[17] = "=ACMGRSVTWYHKDBN";
 
-int gt21_index(const std::string& lab) {
-    for (int i = 0; i < 21; ++i) if (lab == GT21_LABELS[i]) return i;
-    return -1;
-}
 char base2acgt(char c) {                            // shared/utils.py:41-44; 0 when the base is not in the table
     static const char* K = "ACGTURYSWKMBDHVN";
     static const char* V = "ACGTTACCAGACAAAA";
@@ -103,6 +99,12 @@ std::vector<std::string> two_indels(const std::vector<Allele>& alt, char kind) {
     return r;
 }
 
+struct FamV {                                       // probabilities of one outcome family (at most 6 members)
+    float v[6];
+    int n = 0;
+    void push_back(float x) { v[n++] = x; }
+};
+
 struct Decision {
     bool flags[N_FAM];
     bool has_ref = false, has_alt = false;
@@ -117,8 +119,10 @@ Decision decide(char center, const float* probs, const std::vector<Allele>& alt)
     const char ref_acgt = base2acgt(center);
     const float* gt21 = probs;
     const float p00 = probs[21], p11 = probs[22], p01 = probs[23];
-    const std::string rr_lab = std::string(1, ref_acgt) + ref_acgt;
-    const float rr = gt21[gt21_index(rr_lab)];
+    // GT21_LABELS indices: AA 0, CC 4, GG 7, TT 9; AC 1, AG 2, AT 3, CG 5, CT 6, GT 8
+    static const int HOMO_IX[4] = {0, 4, 7, 9};
+    static const int HET_IX[6] = {1, 2, 3, 5, 6, 8};
+    const float rr = gt21[HOMO_IX[ref_acgt == 'A' ? 0 : ref_acgt == 'C' ? 1 : ref_acgt == 'G' ? 2 : 3]];
     const float p_ref = p00 * rr;
     auto as_ref = [&](float p) {
         for (bool& f : D.flags) f = false;
@@ -130,9 +134,9 @@ Decision decide(char center, const float* probs, const std::vector<Allele>& alt)
     if (p00 >= 0.5f && rr >= 0.5f) { as_ref(p_ref); return D; }
     static const char* HOMO[4] = {"AA", "CC", "GG", "TT"};
     static const char* HET[6] = {"AC", "AG", "AT", "CG", "CT", "GT"};
-    std::vector<float> fam[N_FAM];
-    for (int i = 0; i < 4; ++i) fam[HOMO_SNP].push_back(p11 * gt21[gt21_index(HOMO[i])]);
-    for (int i = 0; i < 6; ++i) fam[HET_SNP].push_back(p01 * gt21[gt21_index(HET[i])]);
+    FamV fam[N_FAM];
+    for (int i = 0; i < 4; ++i) fam[HOMO_SNP].push_back(p11 * gt21[HOMO_IX[i]]);
+    for (int i = 0; i < 6; ++i) fam[HET_SNP].push_back(p01 * gt21[HET_IX[i]]);
     fam[HOMO_INS].push_back(p11 * gt21[15]);
     fam[HET_INSINS].push_back(p01 * gt21[15]);
     for (int i = 0; i < 4; ++i) fam[HET_ACGT_INS].push_back(gt21[16 + i] * p01);
@@ -141,97 +145,97 @@ Decision decide(char center, const float* probs, const std::vector<Allele>& alt)
     for (int i = 0; i < 4; ++i) fam[HET_ACGT_DEL].push_back(gt21[11 + i] * p01);
     fam[INSDEL].push_back(p01 * gt21[20]);
     const std::string ctr(1, center);
-    auto index_of = [](const std::vector<float>& v, float x) { for (size_t i = 0; i < v.size(); ++i) if (v[i] == x) return (int)i; return -1; };
-    auto argmax = [](const std::vector<float>& v) { int b = 0; for (size_t i = 1; i < v.size(); ++i) if (v[i] > v[b]) b = (int)i; return b; };
+    auto index_of = [](const FamV& v, float x) { for (int i = 0; i < v.n; ++i) if (v.v[i] == x) return i; return -1; };
+    auto argmax = [](const FamV& v) { int b = 0; for (int i = 1; i < v.n; ++i) if (v.v[i] > v.v[b]) b = i; return b; };
     float best = 0.f;
     // A failed family zeroes its probability and `continue`s WITHOUT clearing ref_base/alt_base, exactly like the
     // reference: the loop ends as soon as both happen to be set.
     for (int guard = 0; (!D.has_ref || !D.has_alt) && guard < 64; ++guard) {
         best = p_ref;
-        for (int f = HOMO_SNP; f < N_FAM; ++f) for (float x : fam[f]) if (x > best) best = x;
+        for (int f = HOMO_SNP; f < N_FAM; ++f) for (int i = 0; i < fam[f].n; ++i) if (fam[f].v[i] > best) best = fam[f].v[i];
         if (best == p_ref) { as_ref(best); return D; }
         for (int f = HOMO_SNP; f < N_FAM; ++f) D.flags[f] = index_of(fam[f], best) >= 0;
         D.flags[REF] = false;
         if (D.flags[HOMO_SNP]) {
-            std::vector<float>& v = fam[HOMO_SNP];
+            FamV& v = fam[HOMO_SNP];
             D.ref_base = ctr; D.has_ref = true;
             const int i = index_of(v, best);
             const char* lab = HOMO[argmax(v)];
             char chosen;
             snp_alts(alt, lab[0] != center ? lab[0] : lab[1], &chosen);
             if (chosen) { D.alt_base = std::string(1, chosen); D.has_alt = true; } else { D.has_alt = false; D.alt_base.clear(); }
-            if (!chosen || D.alt_base == D.ref_base) { v[i] = 0; continue; }
+            if (!chosen || D.alt_base == D.ref_base) { v.v[i] = 0; continue; }
         } else if (D.flags[HET_SNP]) {
-            std::vector<float>& v = fam[HET_SNP];
+            FamV& v = fam[HET_SNP];
             const char* lab = HET[argmax(v)];
             const int i = index_of(v, best);
             D.ref_base = ctr; D.has_ref = true;
             if (lab[0] != center && lab[1] != center) {
                 char chosen;
                 const std::vector<char> ranked = snp_alts(alt, 0, &chosen);
-                if (ranked.size() < 2) { v[i] = 0; continue; }
+                if (ranked.size() < 2) { v.v[i] = 0; continue; }
                 D.alt_base = std::string(1, ranked[0]) + "," + std::string(1, ranked[1]); D.has_alt = true;
             } else {
                 char chosen;
                 snp_alts(alt, lab[0] != center ? lab[0] : lab[1], &chosen);
                 if (chosen) { D.alt_base = std::string(1, chosen); D.has_alt = true; } else { D.has_alt = false; D.alt_base.clear(); }
-                if (!chosen || D.alt_base == D.ref_base) { v[i] = 0; continue; }
+                if (!chosen || D.alt_base == D.ref_base) { v.v[i] = 0; continue; }
             }
         } else if (D.flags[HOMO_INS]) {
-            std::vector<float>& v = fam[HOMO_INS];
+            FamV& v = fam[HOMO_INS];
             const int i = index_of(v, best);
             const std::string ins = best_indel(alt, 'I');
-            if (ins.empty()) { v[i] = 0; continue; }
+            if (ins.empty()) { v.v[i] = 0; continue; }
             D.ref_base = ctr; D.alt_base = ins; D.has_ref = D.has_alt = true;
         } else if (D.flags[HET_ACGT_INS]) {
-            std::vector<float>& v = fam[HET_ACGT_INS];
+            FamV& v = fam[HET_ACGT_INS];
             const int i = index_of(v, best);
             const std::string ins = best_indel(alt, 'I');
-            if (ins.empty()) { v[i] = 0; continue; }
+            if (ins.empty()) { v.v[i] = 0; continue; }
             D.ref_base = ctr; D.alt_base = ins; D.has_ref = D.has_alt = true;
             if (ACGT[i] != center) {
                 char chosen;
                 const std::vector<char> ranked = snp_alts(alt, 0, &chosen);
-                if (ranked.empty()) { v[i] = 0; continue; }
+                if (ranked.empty()) { v.v[i] = 0; continue; }
                 D.alt_base = std::string(1, ranked[0]) + "," + D.alt_base;
             }
         } else if (D.flags[HET_INSINS]) {
-            std::vector<float>& v = fam[HET_INSINS];
+            FamV& v = fam[HET_INSINS];
             const int i = index_of(v, best);
             const std::vector<std::string> two = two_indels(alt, 'I');
-            if (two.size() < 2) { v[i] = 0; continue; }
+            if (two.size() < 2) { v.v[i] = 0; continue; }
             D.ref_base = ctr; D.alt_base = two[0]; D.has_ref = D.has_alt = true;
             if (two[1] != two[0]) D.alt_base = two[1] + "," + two[0];
-            else { v[i] = 0; continue; }
+            else { v.v[i] = 0; continue; }
         } else if (D.flags[HOMO_DEL]) {
-            std::vector<float>& v = fam[HOMO_DEL];
+            FamV& v = fam[HOMO_DEL];
             const int i = index_of(v, best);
             const std::string dele = best_indel(alt, 'D');
-            if (dele.empty()) { v[i] = 0; continue; }
+            if (dele.empty()) { v.v[i] = 0; continue; }
             D.ref_base = ctr + dele; D.alt_base = D.ref_base.substr(0, 1); D.has_ref = D.has_alt = true;
         } else if (D.flags[HET_ACGT_DEL]) {
-            std::vector<float>& v = fam[HET_ACGT_DEL];
+            FamV& v = fam[HET_ACGT_DEL];
             const int i = index_of(v, best);
             const std::string dele = best_indel(alt, 'D');
-            if (dele.empty()) { v[i] = 0; continue; }
+            if (dele.empty()) { v.v[i] = 0; continue; }
             D.ref_base = ctr + dele; D.alt_base = D.ref_base.substr(0, 1); D.has_ref = D.has_alt = true;
             if (ACGT[i] != D.ref_base[0]) D.alt_base = D.alt_base + "," + std::string(1, ACGT[i]) + D.ref_base.substr(1);
         } else if (D.flags[HET_DELDEL]) {
-            std::vector<float>& v = fam[HET_DELDEL];
+            FamV& v = fam[HET_DELDEL];
             const int i = index_of(v, best);
             const std::vector<std::string> two = two_indels(alt, 'D');
-            if (two.size() < 2) { v[i] = 0; continue; }
+            if (two.size() < 2) { v.v[i] = 0; continue; }
             const std::string &longer = two[0], &other = two[1];
             D.ref_base = ctr + longer; D.alt_base = D.ref_base.substr(0, 1); D.has_ref = D.has_alt = true;
             const std::string a1 = D.alt_base;
             const std::string a2 = D.ref_base.substr(0, 1) + (other.size() + 1 <= D.ref_base.size() ? D.ref_base.substr(other.size() + 1) : "");
             if (a1 != a2 && D.ref_base != a1 && D.ref_base != a2) D.alt_base = a1 + "," + a2;
-            else { v[i] = 0; continue; }
+            else { v.v[i] = 0; continue; }
         } else if (D.flags[INSDEL]) {
-            std::vector<float>& v = fam[INSDEL];
+            FamV& v = fam[INSDEL];
             const int i = index_of(v, best);
             const std::string ins = best_indel(alt, 'I'), dele = best_indel(alt, 'D');
-            if (ins.empty() || dele.empty()) { v[i] = 0; continue; }
+            if (ins.empty() || dele.empty()) { v.v[i] = 0; continue; }
             D.ref_base = ctr + dele;
             D.alt_base = D.ref_base.substr(0, 1) + "," + ins + D.ref_base.substr(1);
             D.has_ref = D.has_alt = true;
@@ -243,11 +247,50 @@ Decision decide(char center, const float* probs, const std::vector<Allele>& alt)
 
 const double PHRED_TRANS = -10.0 * (std::log(M_E) / std::log(10.0));      // call_variants.py:58
 
+// x (0 <= x < 2^40) rounded to `scale` = 10^decimals units, to nearest with ties to even ON THE EXACT BINARY VALUE -
+// what printf("%.*f") and Python's '%.*f' print.  x * scale = hi + lo exactly (fused multiply-add), so the comparison
+// with one half is exact: a non-zero distance of the quotient's fraction from 0.5 is at least one ulp of hi and lo is
+// below half an ulp.
+inline uint64_t round_scaled(double x, double scale) {
+    const double hi = x * scale;
+    const double lo = std::fma(x, scale, -hi);
+    const double fl = std::floor(hi);
+    uint64_t q = (uint64_t)fl;
+    const double d = (hi - fl) - 0.5;
+    if (d > 0 || (d == 0 && (lo > 0 || (lo == 0 && (q & 1))))) ++q;
+    return q;
+}
+inline char* put_uint(char* p, uint64_t v) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+inline char* put_int(char* p, long v) {
+    if (v < 0) { *p++ = '-'; return put_uint(p, (uint64_t)(-(v + 1)) + 1); }
+    return put_uint(p, (uint64_t)v);
+}
+// "%.<decimals>f" of x >= 0 (decimals = 2 or 4); returns the end of the text (not NUL terminated)
+inline char* put_fixed(char* p, double x, int decimals) {
+    const uint64_t unit = decimals == 2 ? 100 : 10000;
+    const uint64_t q = round_scaled(x, (double)unit);
+    p = put_uint(p, q / unit);
+    *p++ = '.';
+    uint64_t f = q % unit;
+    for (uint64_t u = unit / 10; u; u /= 10) { *p++ = (char)('0' + f / u); f %= u; }
+    return p;
+}
+
 // round(max(x, 0), 2) as a double, through the correctly rounded 2-decimal text (Python's round() and "%.2f")
 double round2(double x, char* text, size_t n) {
+    (void)n;
     if (!(x > 0)) x = 0;
-    snprintf(text, n, "%.2f", x);
-    return strtod(text, nullptr);
+    if (!(x < 1e12)) { snprintf(text, n, "%.2f", x); return strtod(text, nullptr); }   // never reached by a QUAL
+    const uint64_t q = round_scaled(x, 100.0);
+    char* e = put_fixed(text, x, 2);
+    *e = 0;
+    return (double)q / 100.0;                        // == strtod(text): both are the correctly rounded q / 100
 }
 
 std::string iupac_to_n(const std::string& s) {
@@ -377,26 +420,30 @@ bool vcf_row(const char* contig, int pos, const std::string& ref33, int depth, c
     const char* filt = is_ref ? "RefCall" : ((qual_cut < 0 || qual >= qual_cut) ? "PASS" : "LowQual");
     ref_base = iupac_to_n(ref_base);
     alt_base = iupac_to_n(alt_base);
-    char buf[96];
+    char buf[160];
+    char* b = buf;
     out += contig;
-    snprintf(buf, sizeof buf, "\t%d\t.\t", pos);
-    out += buf;
+    *b++ = '\t'; b = put_int(b, pos); *b++ = '\t'; *b++ = '.'; *b++ = '\t';
+    out.append(buf, (size_t)(b - buf));
     out += ref_base; out += '\t'; out += alt_base; out += '\t'; out += qtxt; out += '\t'; out += filt;
     out += "\t.\tGT:GQ:DP:AD:AF\t";
     out += gt;
-    snprintf(buf, sizeof buf, ":%d:%d:%d", (int)qual, depth, ref_count);
-    out += buf;
-    for (long c : counts) { snprintf(buf, sizeof buf, ",%ld", c); out += buf; }
+    b = buf;
+    *b++ = ':'; b = put_int(b, (long)(int)qual); *b++ = ':'; b = put_int(b, depth); *b++ = ':'; b = put_int(b, ref_count);
+    out.append(buf, (size_t)(b - buf));
+    for (long c : counts) { b = buf; *b++ = ','; b = put_int(b, c); out.append(buf, (size_t)(b - buf)); }
     out += ':';
     if (counts.size() <= 1) {
-        snprintf(buf, sizeof buf, "%.4f", af);
-        out += buf;
+        b = af >= 0 ? put_fixed(buf, af, 4) : buf + snprintf(buf, sizeof buf, "%.4f", af);
+        out.append(buf, (size_t)(b - buf));
     } else {
         for (size_t i = 0; i < counts.size(); ++i) {
             double a = 1.0 * (double)counts[i] / (double)depth;
             if (a > 1.0) a = 1.0;
-            snprintf(buf, sizeof buf, i ? ",%.4f" : "%.4f", a);
-            out += buf;
+            b = buf;
+            if (i) *b++ = ',';
+            b = (a >= 0) ? put_fixed(b, a, 4) : b + snprintf(b, 64, "%.4f", a);       // nan / negative: libc's text
+            out.append(buf, (size_t)(b - buf));
         }
     }
     out += '\n';
@@ -477,5 +524,12 @@ int c3r_decode_vcf(const c3r_result* res, const c3r_reads* reads, const uint8_t*
 }
 
 void c3r_free_text(char* text) { free(text); }
+
+// test hook: the decoder's "%.2f" / "%.4f" (exact round-half-even without libc) into out (>= 32 bytes, NUL terminated)
+int c3r_debug_format_fixed(double x, int decimals, char* out) {
+    if (!out || (decimals != 2 && decimals != 4) || !(x >= 0) || !(x < 1e12)) return C3R_ERR_ARG;
+    *put_fixed(out, x, decimals) = 0;
+    return C3R_OK;
+}
 
 }  // extern "C"

@@ -195,6 +195,9 @@ int c3r_decode_vcf(const c3r_result* res, const c3r_reads* reads, const uint8_t*
                    int64_t ref_len, const char* contig, double qual_cut, int show_ref, int n_threads,
                    char** text, int64_t* n_bytes, int64_t* n_rows);
 void c3r_free_text(char* text);
+/* test hook: the decoder's own "%.2f" / "%.4f" formatting (exact, ties to even on the binary value) of
+ * 0 <= x < 1e12 into out (>= 32 bytes) */
+int c3r_debug_format_fixed(double x, int decimals, char* out);
 
 /* ------------------------------------------------------------------------------------------
  * BAM / BGZF / BAI input (host side, zlib; csrc/bam_io.cpp).  The reference reads the BAM only

@@ -108,3 +108,33 @@ def test_reference_window_offsets_and_padding():
         want.append(decoder.vcf_row("chrT", int(p), r33, ai, probs[i]))
     assert got == want
     assert got[1].split("\t")[3] == refs[19:23] and got[1].split("\t")[4] == refs[19]
+
+
+def test_fixed_point_formatting_equals_printf():
+    """the decoder prints QUAL and AF without libc: every value must read like '%.2f' / '%.4f' (correct rounding of
+    the exact binary value, ties to even) - exact ties, near-ties one ulp either side, count ratios, random values"""
+    import ctypes as C
+    from clair3_rna_b200 import lib as L
+    lib = L.load()
+    buf = C.create_string_buffer(64)
+
+    def fmt(x, d):
+        assert lib.c3r_debug_format_fixed(float(x), d, buf) == 0
+        return buf.value.decode()
+    rng = np.random.default_rng(11)
+    vals = [0.0, 0.005, 0.015, 0.025, 0.125, 0.375, 0.00005, 0.00015, 0.03125, 0.09375, 1.0, 0.5, 2.675, 1.005, 109.99499999,
+            99.995, 0.99995, 0.99994999999, 1e-300, 5e-324, 123456.785, 33.335, 8.0, 7.9949999999999, 1e11]
+    vals += [k / 2.0 ** m for m in range(1, 20) for k in (1, 3, 5, 7, 9, 11, 13, 15)]            # exactly representable ties and non-ties
+    vals += [s / d for d in range(1, 400) for s in range(0, d + 1, max(1, d // 7))]             # allele fractions
+    vals += list(rng.uniform(0, 1, 20000)) + list(rng.uniform(0, 120, 20000))
+    vals += [(k + 0.5) / 10000.0 for k in range(0, 3000, 7)] + [(k + 0.5) / 100.0 for k in range(0, 12000, 37)]
+    more = []
+    for v in vals:
+        more += [np.nextafter(v, 0.0), np.nextafter(v, 1e300)]
+    for v in vals + more:
+        v = float(v)
+        if not (0 <= v < 1e12):
+            continue
+        assert fmt(v, 2) == "%.2f" % v, repr(v)
+        assert fmt(v, 4) == "%.4f" % v, repr(v)
+    assert lib.c3r_debug_format_fixed(-1.0, 2, buf) != 0 and lib.c3r_debug_format_fixed(float("nan"), 4, buf) != 0
