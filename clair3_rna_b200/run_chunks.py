@@ -151,7 +151,9 @@ def main(argv=None):
     ap.add_argument("--ref_fn", required=True)
     ap.add_argument("--chkpnt_fn", required=True)
     ap.add_argument("--output", required=True)
-    ap.add_argument("--ctgName", default=None, help="comma separated contigs (default: all with mapped reads)")
+    ap.add_argument("--ctgName", default=None, help="comma separated contigs")
+    ap.add_argument("--include_all_ctgs", action="store_true",
+                    help="call every contig with mapped reads; default like run_clair3_rna:331-334: chr{1..22,X,Y} and {1..22,X,Y}")
     ap.add_argument("--bed_fn", default=None, help="call only in these regions (BED, plain or gzip)")
     ap.add_argument("--genotyping_mode_vcf_fn", default=None, help="call exactly the sites of this VCF (plain or gzip)")
     ap.add_argument("--sampleName", default="SAMPLE")
@@ -181,7 +183,10 @@ def main(argv=None):
     if merge_qual is None:
         merge_qual = 8 if a.platform.startswith("ont") else 2
     stats = {}
-    run(a.bam_fn, a.ref_fn, a.chkpnt_fn, a.output, contigs=a.ctgName.split(",") if a.ctgName else None, device=local,
+    # run_clair3_rna:364-368: without --ctg_name / --bed_fn / a genotyping VCF only the major contigs are called
+    restrict = not (a.include_all_ctgs or a.ctgName or a.bed_fn or a.genotyping_mode_vcf_fn)
+    contigs = a.ctgName.split(",") if a.ctgName else (list(sharder.MAJOR_CONTIGS) if restrict else None)
+    run(a.bam_fn, a.ref_fn, a.chkpnt_fn, a.output, contigs=contigs, device=local,
         rank=rank, world=world, phased=a.enable_phasing_model, padding=a.enable_padding_in_splice_junction_regions,
         snp_min_af=a.snp_min_af, indel_min_af=a.indel_min_af, min_coverage=a.minCoverage, min_mq=a.minMQ,
         merge_qual=merge_qual, show_ref=a.print_ref_calls,
