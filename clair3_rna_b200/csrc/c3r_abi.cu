@@ -732,7 +732,9 @@ int c3r_debug_fetch(c3r_ctx* ctx, int which, void* dst, int64_t max_bytes, int64
     size_t bytes = 0;
     switch (which) {
         case 0: src = t.h1; bytes = tiles * NT * 4 * TC_IMG * 2; break;
-        case 1: src = t.zx2; bytes = tiles * NT * 10 * ZX_CHUNK_WORDS * 4; break;
+        case 1:
+            if (lstm2_fused()) return fail(ctx, C3R_ERR_STATE, "zx2 does not exist: LSTM2 runs fused (C3R_LSTM2=hoisted keeps it)");
+            src = t.zx2; bytes = tiles * NT * 10 * ZX_CHUNK_WORDS * 4; break;
         case 2: src = t.h2; bytes = tiles * NT * 5 * TC_IMG * 2; break;
         case 3: src = t.l4; bytes = tiles * 128 * DENSE * 4; break;
         case 4: src = t.trace; bytes = t.trace ? (2 * 2 * NT * 8 * 8 + 64 * 32) * sizeof(long long) : 0; break;

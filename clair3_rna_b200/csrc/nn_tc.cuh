@@ -929,7 +929,22 @@ __global__ void __launch_bounds__(TC_TILE) k_xop(const int32_t* __restrict__ ten
     for (int k8 = 0; k8 < KX / 8; ++k8) *(uint4*)(dst + (size_t)k8 * (TC_TILE * 8)) = *(const uint4*)(&hv[k8 * 8]);
 }
 
+}  // namespace c3r
+#include "nn_lstm2f.cuh"
+namespace c3r {
+
 // ================================================================== host side
+// LSTM2 as one fused kernel (projection inside the recurrent step, nn_lstm2f.cuh) or, with C3R_LSTM2=hoisted, as the
+// projection GEMM + recurrent kernel pair that moves zx2 through HBM.
+inline bool lstm2_fused() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("C3R_LSTM2");
+        v = (e && std::string(e) == "hoisted") ? 0 : 1;
+    }
+    return v != 0;
+}
+
 struct TcNet {
     int ready = 0;
     int C = 18, KX = 48, sm_count = 148;
@@ -937,6 +952,7 @@ struct TcNet {
     size_t wbytes = 0;
     const __half *img1 = nullptr, *img2 = nullptr, *w2p = nullptr, *k4p = nullptr, *w2p_lo = nullptr, *k4p_lo = nullptr;
     const float *b2p = nullptr, *b4 = nullptr;
+    const uint8_t* wstream2 = nullptr;   // fused LSTM2: weight stream [2 dirs][2 halves][L2F_STREAM_BYTES]
     // activation scratch (sized for cap_tiles 128-site tiles)
     void* abuf = nullptr;
     size_t abytes = 0;
@@ -1053,12 +1069,17 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
         }
     for (int j = 0; j < DENSE; ++j) fb[2 * G2 + j] = h[o_b4 + j];
 
-    t.wbytes = hb.size() * 2 + fb.size() * 4 + 256;
+    std::vector<uint8_t> ws;
+    lstm2f_pack(ws, h, o_w2, o_b2, o_u2);
+    const size_t foff = ((hb.size() * 2 + 255) / 256) * 256;
+    const size_t soff = ((foff + fb.size() * 4 + 1023) / 1024) * 1024;
+    t.wbytes = soff + ws.size() + 256;
     cudaError_t e = cudaMalloc(&t.wbuf, t.wbytes);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     uint8_t* d = (uint8_t*)t.wbuf;
     cudaMemcpy(d, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
-    const size_t foff = ((hb.size() * 2 + 255) / 256) * 256;
+    cudaMemcpy(d + soff, ws.data(), ws.size(), cudaMemcpyHostToDevice);
+    t.wstream2 = d + soff;
     e = cudaMemcpy(d + foff, fb.data(), fb.size() * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     t.img1 = (const __half*)d;
@@ -1085,7 +1106,7 @@ inline int tc_ensure(TcNet& t, int tiles, std::string* err) {
     if (t.abuf) cudaFree(t.abuf);
     t.abuf = nullptr;
     const size_t n_h1 = (size_t)tiles * NT * 4 * TC_IMG, n_h2 = (size_t)tiles * NT * 5 * TC_IMG;
-    const size_t n_zx = (size_t)tiles * NT * 10 * ZX_CHUNK_WORDS, n_l4 = (size_t)tiles * 128 * DENSE;
+    const size_t n_zx = lstm2_fused() ? 64 : (size_t)tiles * NT * 10 * ZX_CHUNK_WORDS, n_l4 = (size_t)tiles * 128 * DENSE;
     const size_t n_xop = (size_t)tiles * NT * 64 * TC_TILE;
     t.abytes = (n_h1 + n_h2) * 2 * 2 + n_xop * 2 + (n_zx + n_l4) * 4 + 1024;
     cudaError_t e = cudaMalloc(&t.abuf, t.abytes);
@@ -1222,6 +1243,15 @@ inline cudaEvent_t tc_pass_done(const TcNet& t) { return t.pipe && t.pipe->ok ? 
 struct TcSub { int t0, nt; int64_t s0, ns; };
 
 inline cudaError_t tc_lstm2(TcNet& t, const TcSub& b, cudaStream_t st) {
+    if (lstm2_fused()) {
+        Lstm2fArgs f;
+        f.wstream = t.wstream2; f.h1 = t.h1 + (size_t)b.t0 * NT * 4 * TC_IMG;
+        f.hout = t.h2 + (size_t)b.t0 * NT * 5 * TC_IMG;
+        f.hout_lo = (l4_terms() & 2) ? t.h2_lo + (size_t)b.t0 * NT * 5 * TC_IMG : nullptr;
+        f.n_tiles = b.nt; f.err = t.err;
+        f.prof = (t.trace && b.t0 == 0) ? t.trace : nullptr;       // C3R_TRACE: wait-time totals of cluster 0
+        return launch_lstm2f(f, t.sm_count, st);
+    }
     LstmArgs a2;
     a2.Wimg = t.img2; a2.xop = nullptr; a2.C = t.C; a2.zx = t.zx2 + (size_t)b.t0 * NT * 10 * ZX_CHUNK_WORDS;
     a2.hout = t.h2 + (size_t)b.t0 * NT * 5 * TC_IMG; a2.hout_lo = (l4_terms() & 2) ? t.h2_lo + (size_t)b.t0 * NT * 5 * TC_IMG : nullptr; a2.kb_out = 5;
@@ -1262,7 +1292,9 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         else k_xop<30, 64><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
         ++launches;
         // A = the tile pairs that fill whole rounds of the recurrent kernels, B = the rest
-        const int pairs = tiles / 2, per_round = t.sm_count / 4;
+        // tile pairs one round of the LSTM2 kernel takes (fused: clusters of 2*NP CTAs, half of them per direction)
+        const int pairs = tiles / 2;
+        const int per_round = lstm2_fused() ? (t.sm_count / (2 * lstm2f_np()) / 2) * lstm2f_np() : t.sm_count / 4;
         int pa = pairs;
         if (pairs > per_round && pairs % per_round != 0) pa = (pairs / per_round) * per_round;
         TcSub A, B;
@@ -1294,7 +1326,12 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         const int idle_pairs = (t.sm_count - busy_b) / 2;
         int m_early = 2 * idle_pairs * zx_overlap_tiles();
         if (m_early > A.nt * NT) m_early = A.nt * NT;
-        if (B.nt == 0 || A.nt == 0 || idle_pairs < 8 || m_early <= 0) {
+        if (lstm2_fused()) {                                        // no projection GEMM: LSTM2 reads h1 itself
+            TcSub all; all.t0 = 0; all.nt = tiles; all.s0 = 0; all.ns = m;
+            TCK(lstm1(all, st), "lstm1");
+            TCK(cudaStreamWaitEvent(st, P.pass_done, 0), "wait");   // the previous pass no longer reads h2 / l4
+            ++launches;
+        } else if (B.nt == 0 || A.nt == 0 || idle_pairs < 8 || m_early <= 0) {
             TcSub all; all.t0 = 0; all.nt = tiles; all.s0 = 0; all.ns = m;
             TCK(lstm1(all, st), "lstm1");
             TCK(cudaStreamWaitEvent(st, P.pass_done, 0), "wait");   // the previous pass no longer reads zx2 / h2 / l4
@@ -1313,11 +1350,12 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
             TCK(zx(m_early, tiles * NT - m_early, 1 << 30, st), "zx2 gemm");
             launches += 4;
         }
-        TCK(cudaEventRecord(P.h1_free, st), "event");
+        if (!lstm2_fused()) TCK(cudaEventRecord(P.h1_free, st), "event");
         float* pr = probs + o * 24;
         TCK(tc_lstm2(t, A, st), "lstm2");
         ++launches;
         if (B.nt == 0) {
+            if (lstm2_fused()) TCK(cudaEventRecord(P.h1_free, st), "event");
             TCK(tc_l4_heads(t, net, A, pr, st), "l4/heads");
             launches += 2;
             TCK(cudaEventRecord(P.pass_done, st), "event");
@@ -1325,6 +1363,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         }
         TCK(cudaEventRecord(P.ev[0], st), "event");
         TCK(tc_lstm2(t, B, st), "lstm2");
+        if (lstm2_fused()) TCK(cudaEventRecord(P.h1_free, st), "event");
         TCK(cudaStreamWaitEvent(P.s2, P.ev[0], 0), "wait");
         TCK(tc_l4_heads(t, net, A, pr, P.s2), "l4/heads");
         TCK(cudaEventRecord(P.ev[1], P.s2), "event");

@@ -32,6 +32,17 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(rank) : "memory");
 }
+// The same without the release fence (MEMBAR.ALL.GPU + error barriers, ~0.5 us): for relays of events whose data
+// moved through the async proxy or TMEM and was already ordered by the producers' own fences (a bulk copy has landed,
+// an accumulator slot is drained, h is in shared memory behind fence.proxy.async) - the relaying thread itself has
+// written nothing the receiver reads.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(rank) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -53,15 +64,24 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
 // Bounded wait: a protocol bug must not hang the GPU.  On timeout the error word is set and
 // the caller carries on (results are garbage, the host reports the failure).
 constexpr uint32_t WAIT_SPINS = 1u << 24;
+// Once any wait of the grid has timed out every later wait gives up after a few polls, so a broken protocol
+// costs one time-out, not one per remaining wait.
+__device__ __forceinline__ bool wait_abandoned(const int* err, uint32_t i) {
+    return err && (i & 1023u) == 1023u && *(const volatile int*)err != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-    for (uint32_t i = 0; i < WAIT_SPINS; ++i)
+    for (uint32_t i = 0; i < WAIT_SPINS; ++i) {
         if (mbar_try_wait(bar, parity)) return;
-    if (err) atomicExch(err, code);
+        if (wait_abandoned(err, i)) return;
+    }
+    if (err) atomicCAS(err, 0, code);
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* err, int code) {
-    for (uint32_t i = 0; i < WAIT_SPINS; ++i)
+    for (uint32_t i = 0; i < WAIT_SPINS; ++i) {
         if (mbar_try_wait_cluster(bar, parity)) return;
-    if (err) atomicExch(err, code);
+        if (wait_abandoned(err, i)) return;
+    }
+    if (err) atomicCAS(err, 0, code);
 }
 
 // --------------------------------------------------------------- async proxy

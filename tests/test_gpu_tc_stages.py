@@ -23,8 +23,15 @@ def test_tc_intermediates(name, C):
     ref = model.forward(w, x, intermediates=inter)
     n = x.shape[0]
     report = {}
+    from clair3_rna_b200.engine import C3RError
     for which, key in ((0, "h1"), (1, "zx2"), (2, "h2"), (3, "l4")):
-        got = eng.debug_fetch(which, n)
+        try:
+            got = eng.debug_fetch(which, n)
+        except C3RError:
+            # zx2 only exists with C3R_LSTM2=hoisted: the fused LSTM2 keeps the projection in tensor memory
+            assert key == "zx2" and os.environ.get("C3R_LSTM2") != "hoisted"
+            report[key] = 0.0
+            continue
         report[key] = float(np.abs(got - inter[key]).max())
     report["probs"] = float(np.abs(p - ref).max())
     print(name, report, "ms", ms)
