@@ -556,28 +556,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
         const bool tr = a.trace != nullptr && cluster_id == 0 && work_it == 0 && lane == 0;
 
         if (warp == 0) {
-            // ------------------------------------------------ MMA issue (leader CTA; the whole warp runs the loop
-            // converged, lane 0 is the one whose MMAs and commits take effect)
+            // ------------------------------------------------ MMA issue (leader CTA): one thread chosen by elect.sync, so that
+            // ptxas emits straight-line UTCHMMA fed from uniform registers (a `lane == 0` test or a converged warp with
+            // a per-lane predicate gets an ELECT / R2UR loop around every MMA, ~100 cycles each)
             if (rank == 0) {
-                const uint32_t el = lane == 0 ? 1u : 0u;
+                if (ptx::elect_one()) {
                 for (int step = 0; step < NT; ++step) {
                     const uint32_t gstep = base_step + step;
                     const uint32_t buf = gstep & 1;
                     if (KX > 0) {
                         ptx::mbar_wait(b_xl + 8 * buf, (gstep >> 1) & 1, a.err, 202);
-                        ptx::mbar_wait_cluster(b_xr + 8 * buf, (gstep >> 1) & 1, a.err, 212);
+                        ptx::mbar_wait(b_xr + 8 * buf, (gstep >> 1) & 1, a.err, 212);
                     }
                     for (int c = 0; c < CH; ++c) {
                         const uint32_t use = base_use + step * CH + c;
                         const uint32_t slot = use & 1;
-                        // slot free (its previous use drained by both CTAs) ...
+                        // slot free (its previous use drained by both CTAs)
                         ptx::mbar_wait(b_acce + 8 * slot, ((use >> 1) & 1) ^ 1, a.err, 203);
-                        ptx::mbar_wait_cluster(b_accr + 8 * slot, ((use >> 1) & 1) ^ 1, a.err, 213);
-                        // ... and, at the start of a step, h of the previous step is complete in both CTAs
-                        if (c == 0 && step > 0) {
-                            ptx::mbar_wait(b_hrdy, (gstep - 1) & 1, a.err, 204);
-                            ptx::mbar_wait_cluster(b_hrdy_r, (gstep - 1) & 1, a.err, 214);
-                        }
+                        ptx::mbar_wait(b_accr + 8 * slot, ((use >> 1) & 1) ^ 1, a.err, 213);
                         ptx::tc_fence_after();
                         lstm_trace(a, tr, 0, step, c, 0);
                         // One thread issues every MMA, so the instructions between two issues are the critical path
@@ -585,30 +581,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                         // (the start-address field counts 16-byte units and cannot carry out of its 14 bits here).
                         const uint64_t dB0 = ptx::make_smem_desc(s_B + c * (64 * KT * 2), 64 * 16, 128);
                         bool first = true;
-                        if (KX > 0) {
+                        if (KX > 0) {                              // the input part does not need h_{t-1}: it goes first
                             const uint64_t dX0 = ptx::make_smem_desc(s_AX + buf * Cfg::AX_BYTES, TC_TILE * 16, 128);
 #pragma unroll
                             for (int k = 0; k < KX / 16; ++k) {
-                                ptx::mma_f16_2cta_elect(tmem + slot * 128, dX0 + (uint64_t)(k * ((2 * TC_TILE * 16) >> 4)),
-                                                        dB0 + (uint64_t)(k * ((2 * 64 * 16) >> 4)), IDESC, first ? 0u : 1u, el);
+                                ptx::mma_f16<2>(tmem + slot * 128, dX0 + (uint64_t)(k * ((2 * TC_TILE * 16) >> 4)),
+                                                dB0 + (uint64_t)(k * ((2 * 64 * 16) >> 4)), IDESC, first ? 0u : 1u);
                                 first = false;
                             }
+                        }
+                        // at the start of a step, h of the previous step must be complete in both CTAs
+                        if (c == 0 && step > 0) {
+                            ptx::mbar_wait(b_hrdy, (gstep - 1) & 1, a.err, 204);
+                            ptx::mbar_wait(b_hrdy_r, (gstep - 1) & 1, a.err, 214);
+                            ptx::tc_fence_after();
                         }
                         if (step > 0) {
                             const uint64_t dH0 = ptx::make_smem_desc(s_AH + buf * Cfg::AH_BYTES, TC_TILE * 16, 128);
 #pragma unroll
                             for (int k = 0; k < U / 16; ++k) {
-                                ptx::mma_f16_2cta_elect(tmem + slot * 128, dH0 + (uint64_t)(k * ((2 * TC_TILE * 16) >> 4)),
-                                                        dB0 + (uint64_t)(((KX / 8 + k * 2) * (64 * 16)) >> 4), IDESC, first ? 0u : 1u, el);
+                                ptx::mma_f16<2>(tmem + slot * 128, dH0 + (uint64_t)(k * ((2 * TC_TILE * 16) >> 4)),
+                                                dB0 + (uint64_t)(((KX / 8 + k * 2) * (64 * 16)) >> 4), IDESC, first ? 0u : 1u);
                                 first = false;
                             }
                         }
                         // (LSTM2, step 0: no MMA at all; the commit below still fires the barrier)
-                        ptx::mma_commit_2_mcast_elect(b_accf + 8 * slot, 3, el);
+                        ptx::mma_commit_2_mcast(b_accf + 8 * slot, 3);
                         lstm_trace(a, tr, 0, step, c, 1);
                     }
-                    ptx::mma_commit_2_mcast_elect(b_step + 8 * buf, 3, el);
+                    ptx::mma_commit_2_mcast(b_step + 8 * buf, 3);
                 }
+                }
+                __syncwarp();
             }
             if (rank == 1 && lane == 0) {
                 // relay: one cluster-scope arrival per accumulator use on behalf of this CTA's 16 gate
@@ -617,12 +621,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     const uint32_t use = base_use + u;
                     const uint32_t slot = use & 1;
                     ptx::mbar_wait(b_acce + 8 * slot, (use >> 1) & 1, a.err, 215);
-                    ptx::mbar_arrive_cluster(b_accr + 8 * slot, 0);
+                    ptx::mbar_arrive_cluster_relaxed(b_accr + 8 * slot, 0);
                     lstm_trace(a, tr, 1, u / CH, u % CH, 5);
                     if (u % CH == CH - 1) {                  // end of a step: h_t of this CTA is complete
                         const uint32_t gstep = base_step + u / CH;
                         ptx::mbar_wait(b_hrdy, gstep & 1, a.err, 217);
-                        ptx::mbar_arrive_cluster(b_hrdy_r, 0);
+                        ptx::mbar_arrive_cluster_relaxed(b_hrdy_r, 0);
                     }
                 }
             }
@@ -658,7 +662,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                                   a.xop + ((size_t)tile * NT + t) * (size_t)(KX * TC_TILE), Cfg::AX_BYTES, b_xl + 8 * buf);
                     if (rank == 1) {                         // tell the leader this CTA's tile has landed
                         ptx::mbar_wait(b_xl + 8 * buf, (gstep >> 1) & 1, a.err, 206);
-                        ptx::mbar_arrive_cluster(b_xr + 8 * buf, 0);
+                        ptx::mbar_arrive_cluster_relaxed(b_xr + 8 * buf, 0);
                     }
                     lstm_trace(a, tr, rank, step, 0, 7);
                 }
@@ -1249,7 +1253,7 @@ inline cudaError_t tc_lstm2(TcNet& t, const TcSub& b, cudaStream_t st) {
         f.hout = t.h2 + (size_t)b.t0 * NT * 5 * TC_IMG;
         f.hout_lo = (l4_terms() & 2) ? t.h2_lo + (size_t)b.t0 * NT * 5 * TC_IMG : nullptr;
         f.n_tiles = b.nt; f.err = t.err;
-        f.prof = (t.trace && b.t0 == 0) ? t.trace : nullptr;       // C3R_TRACE: wait-time totals of cluster 0
+        f.prof = (t.trace && b.t0 == 0) ? t.trace + 2 * NT * 8 * 8 : nullptr;   // C3R_TRACE: wait-time totals of cluster 0 (LSTM2's part of the trace buffer)
         return launch_lstm2f(f, t.sm_count, st);
     }
     LstmArgs a2;

@@ -62,6 +62,22 @@ def synthetic(channels: int = 18, seed: int = 20260, sharpen: float = 1.0, input
     return w
 
 
+def adversarial(channels: int = 18, seed: int = 7, sharpen: float = 8.0) -> dict:
+    """A second, harsher weight set for tolerance tests: recurrent kernels x3, forget bias around 3, random non-zero
+    LSTM biases - gates saturate and the cell state grows, unlike anything Keras' initialisers produce."""
+    w = synthetic(channels, seed=seed, sharpen=sharpen)
+    rng = np.random.default_rng(seed + 1)
+    for k in list(w):
+        if k.endswith("recurrent_kernel"):
+            w[k] = (w[k] * 3.0).astype(np.float32)
+        elif k.startswith("LSTM") and k.endswith("bias"):
+            u = w[k].shape[0] // 4
+            b = rng.uniform(-0.5, 0.5, w[k].shape).astype(np.float32)
+            b[u:2 * u] += 3.0
+            w[k] = b
+    return w
+
+
 def save(path: str, w: dict) -> None:
     np.savez(path, **{k.replace("/", "__"): v for k, v in w.items()})
 

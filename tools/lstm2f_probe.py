@@ -27,6 +27,7 @@ if os.environ.get("C3R_TRACE"):
     import ctypes as C
     buf = np.zeros(2 * 2 * 33 * 8 * 8 + 64 * 32, np.int64); nb = C.c_int64(0)
     eng.lib.c3r_debug_fetch(eng.ctx, 4, buf.ctypes.data, buf.nbytes, C.byref(nb))
+    buf = buf[2 * 33 * 8 * 8:]
     names = ["acc_empty", "acc_empty_peer", "x", "h_ready", "w_full", "w_peer_full", "total", "steps", "producer_wait_empty", "gate0_wait_acc"]
     tot, steps = float(buf[6]), float(buf[7])
     print(tag, "MMA thread cycles/step %.0f;" % (tot / max(steps, 1)), " ".join("%s %.0f" % (nm, buf[i] / max(steps, 1)) for i, nm in enumerate(names) if i not in (6, 7)), flush=True)
