@@ -815,7 +815,7 @@ int build_net(c3r_ctx* ctx, const std::map<std::string, std::pair<const float*, 
     n.ky1 = b + o_ky1; n.by1 = b + o_by1; n.ky2 = b + o_ky2; n.by2 = b + o_by2;
     // tensor-core path: repack into fp16 operand images
     std::string terr;
-    if (tc_build(ctx->tc, n, h.data(), o_w1, o_b1, o_u1, o_w2, o_b2, o_u2, o_k4, o_b4, ctx->sm_count, &terr))
+    if (tc_build(ctx->tc, n, h.data(), o_w1, o_b1, o_u1, o_w2, o_b2, o_u2, o_k4, o_b4, o_k51, o_b51, o_k52, o_b52, ctx->sm_count, &terr))
         return fail(ctx, C3R_ERR_CUDA, "tensor-core weight repack failed: " + terr);
     ctx->have_weights = true;
     return C3R_OK;

@@ -165,8 +165,11 @@ __global__ void __launch_bounds__(256) k_lstm_step(const float* __restrict__ zx,
 // hidden unit) takes HS sites at a time.
 constexpr int HS = 16;
 constexpr int HEADS_THREADS = 256;
-constexpr int HEADS_SMEM = (2 * DENSE * DENSE + 3 * 2 * HS * DENSE + 2 * HS * 24) * 4;
-__global__ void __launch_bounds__(HEADS_THREADS) k_heads(NetF32 w, const float* __restrict__ l4, float* __restrict__ probs, int64_t n) {
+constexpr int HEADS_SMEM = (2 * DENSE * DENSE + 3 * 2 * HS * DENSE + 2 * HS * 24 + DENSE * 24) * 4;
+// l4: SELU'd L4 activations [n][128] (n_part == 0), or n_part planes of raw partial sums `stride` floats apart
+// (split-K GEMM): then x = selu(sum + b4) is formed here and, if l4_out is given, stored for inspection.
+__global__ void __launch_bounds__(HEADS_THREADS) k_heads(NetF32 w, const float* __restrict__ l4, int n_part, size_t stride,
+                                                         float* __restrict__ l4_out, float* __restrict__ probs, int64_t n) {
     extern __shared__ __align__(16) float wsm[];             // [2][DENSE][DENSE]: k51, k52, then the activations
     float (*x)[HS][DENSE] = (float (*)[HS][DENSE])(wsm + 2 * DENSE * DENSE);
     float (*a1)[HS][DENSE] = x + 2;
@@ -180,11 +183,31 @@ __global__ void __launch_bounds__(HEADS_THREADS) k_heads(NetF32 w, const float* 
     const float* w1s = wsm;
     const float* w2s = wsm + DENSE * DENSE;
     const float b1 = w.b51[j], b2 = w.b52[j];
+    const float b4j = n_part > 0 ? w.b4[j] : 0.0f;
+    // the two small head kernels [128][21] and [128][3] side by side as [128][24]
+    float (*wy)[24] = (float (*)[24])(wsm + 2 * DENSE * DENSE + 3 * 2 * HS * DENSE + 2 * HS * 24);
+    for (int i = threadIdx.x; i < DENSE * 24; i += HEADS_THREADS) {
+        const int k = i / 24, o = i % 24;
+        wy[k][o] = o < 21 ? w.ky1[k * 21 + o] : w.ky2[k * 3 + (o - 21)];
+    }
     __syncthreads();
     for (int64_t g0 = (int64_t)blockIdx.x * 2 * HS; g0 < n; g0 += (int64_t)gridDim.x * 2 * HS) {
         const int64_t s0 = g0 + hf * HS;
         const int ns = (int)(n - s0 < HS ? (n - s0 < 0 ? 0 : n - s0) : HS);
-        for (int i = 0; i < HS; ++i) x[hf][i][j] = i < ns ? l4[(s0 + i) * DENSE + j] : 0.0f;
+        if (n_part > 0) {
+            for (int i = 0; i < HS; ++i) {
+                float v = 0.0f;
+                if (i < ns) {
+                    v = b4j;
+                    for (int q = 0; q < n_part; ++q) v += l4[(size_t)q * stride + (s0 + i) * DENSE + j];
+                    v = seluf_(v);
+                    if (l4_out) l4_out[(s0 + i) * DENSE + j] = v;
+                }
+                x[hf][i][j] = v;
+            }
+        } else {
+            for (int i = 0; i < HS; ++i) x[hf][i][j] = i < ns ? l4[(s0 + i) * DENSE + j] : 0.0f;
+        }
         __syncthreads();
         float s1[HS], s2[HS];
 #pragma unroll
@@ -208,15 +231,14 @@ __global__ void __launch_bounds__(HEADS_THREADS) k_heads(NetF32 w, const float* 
         // 24 outputs x HS sites = 384 dot products over the half's 128 threads
         for (int e = j; e < 24 * HS; e += 128) {
             const int i = e / 24, o = e % 24;
-            float v;
-            if (o < 21) {
-                v = w.by1[o];
-                for (int k = 0; k < DENSE; ++k) v = fmaf(a1[hf][i][k], w.ky1[k * 21 + o], v);
-            } else {
-                v = w.by2[o - 21];
-                for (int k = 0; k < DENSE; ++k) v = fmaf(a2[hf][i][k], w.ky2[k * 3 + (o - 21)], v);
+            const float* av = o < 21 ? a1[hf][i] : a2[hf][i];
+            float v0 = o < 21 ? w.by1[o] : w.by2[o - 21], v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;   // four chains in flight
+            for (int k = 0; k < DENSE; k += 4) {
+                const float4 a4 = *(const float4*)&av[k];
+                v0 = fmaf(a4.x, wy[k][o], v0); v1 = fmaf(a4.y, wy[k + 1][o], v1);
+                v2 = fmaf(a4.z, wy[k + 2][o], v2); v3 = fmaf(a4.w, wy[k + 3][o], v3);
             }
-            y[hf][i][o] = seluf_(v);
+            y[hf][i][o] = seluf_((v0 + v1) + (v2 + v3));
         }
         __syncthreads();
         for (int e = j; e < 24 * HS; e += 128) {
@@ -232,7 +254,8 @@ __global__ void __launch_bounds__(HEADS_THREADS) k_heads(NetF32 w, const float* 
         __syncthreads();
     }
 }
-inline cudaError_t launch_heads(const NetF32& w, const float* l4, float* probs, int64_t n, int sm_count, cudaStream_t st) {
+inline cudaError_t launch_heads(const NetF32& w, const float* l4, int n_part, size_t stride, float* l4_out, float* probs,
+                                int64_t n, int sm_count, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM);
@@ -242,7 +265,7 @@ inline cudaError_t launch_heads(const NetF32& w, const float* l4, float* probs, 
     if (n <= 0) return cudaSuccess;
     int64_t groups = (n + 2 * HS - 1) / (2 * HS);
     const unsigned grid = (unsigned)(groups < sm_count ? groups : sm_count);
-    k_heads<<<grid, HEADS_THREADS, HEADS_SMEM, st>>>(w, l4, probs, n);
+    k_heads<<<grid, HEADS_THREADS, HEADS_SMEM, st>>>(w, l4, n_part, stride, l4_out, probs, n);
     return cudaGetLastError();
 }
 
@@ -289,7 +312,7 @@ inline int netf32_forward(const NetF32& w, const NetF32Scratch& s, const int32_t
     dim3 g4((DENSE + 63) / 64, (unsigned)((n + 63) / 64));
     k_sgemm<1><<<g4, 256, 0, st>>>(s.h2, w.k4, w.b4, s.l4, n, DENSE, L4_IN);
     ++launches;
-    launch_heads(w, s.l4, probs, n, 148, st);
+    launch_heads(w, s.l4, 0, 0, nullptr, probs, n, 148, st);
     ++launches;
     return launches;
 }

@@ -321,13 +321,7 @@ __global__ void __launch_bounds__(L2F_THREADS, 1) k_lstm2_fused(Lstm2fArgs a) {
                     const float zg = __uint_as_float(v[2][u]), zo = __uint_as_float(v[3][u]);
                     const float cp = step > 0 ? __uint_as_float(cprev[u]) : 0.0f;
                     float cn, hv;
-                    if (LSTM_EXACT_GATES) {
-                        cn = fmaf(sigmoid_fast(2.0f * zf), cp, sig_times_tanh(2.0f * zi, zg));
-                        hv = sig_times_tanh(2.0f * zo, cn);
-                    } else {
-                        cn = fmaf(sigmoid_tanh(zf), cp, sigmoid_tanh(zi) * tanh_approx(zg));
-                        hv = sigmoid_tanh(zo) * tanh_approx(cn);
-                    }
+                    lstm_cell(zi, zf, zg, zo, cp, cn, hv);
                     cnew[u] = __float_as_uint(cn);
                     hh[u] = __float2half(hv);
                     hl[u] = __float2half(hv - __half2float(hh[u]));

@@ -70,6 +70,8 @@ struct GemmArgs {
     float* out;
     int m_tiles, n_tiles, n_kb;
     int mode;             // 0: 24-bit ZX layout [m][n][32 col-groups][3][128 rows]   1: row-major [m*128+r][n_tiles*128] + SELU
+    int ksplit;           // mode 1: K cut into ksplit ranges, one work item each; > 1: raw partial sums (no bias, no SELU)
+    size_t split_stride;  //         go to out + range * split_stride and the consumer adds them up (k_heads)
     int dbg;              // experiments: 1 = skip the output stores, 2 = hi*hi term only
     long long* trace;     // optional [64 tiles][32 events] SM-clock stamps of CTA 0
     int* err;
@@ -105,16 +107,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_ptr_s;
     const int n_tiles_total = g.m_tiles * g.n_tiles;
+    const int ksplit = g.ksplit > 1 ? g.ksplit : 1;
+    const int n_items = n_tiles_total * ksplit;
     const uint32_t idesc = ptx::make_idesc_f16(128, 128);
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int tile = item % n_tiles_total, ks = item / n_tiles_total;
                 const int m = tile / g.n_tiles, n = tile % g.n_tiles;
                 const size_t ao = (size_t)m * g.n_kb * TC_IMG, bo = (size_t)n * g.n_kb * TC_IMG;
-                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {       // same k order for every tile: a site's result does not
-                                                                  // depend on where in the batch it sits
+                const int kb0 = ks * g.n_kb / ksplit, kb1 = (ks + 1) * g.n_kb / ksplit;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {        // same k order and ranges for every tile: a site's result
+                                                                  // does not depend on where in the batch it sits
                     const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
                     const uint32_t dst = s_base + s * GEMM_STAGE_BYTES;
                     ptx::mbar_wait(b_empty + 8 * s, ph ^ 1, g.err, 101);
@@ -130,11 +136,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
     } else if (warp == 1) {
         if (lane == 0) {
             uint32_t it = 0, tc = 0;
-            for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tc) {
+                const int ks = item / n_tiles_total;
+                const int kb0 = ks * g.n_kb / ksplit, kb1 = (ks + 1) * g.n_kb / ksplit;
                 const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
                 ptx::mbar_wait(b_acce + 8 * slot, aph ^ 1, g.err, 102);
                 ptx::tc_fence_after();
-                for (int kb = 0; kb < g.n_kb; ++kb, ++it) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const uint32_t s = it % GEMM_STAGES, ph = (it / GEMM_STAGES) & 1;
                     ptx::mbar_wait(b_full + 8 * s, ph, g.err, 103);
                     ptx::tc_fence_after();
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
                         for (int k4 = 0; k4 < TC_KB / 16; ++k4) {
                             const uint64_t da = ptx::make_smem_desc(sa + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
                             const uint64_t db = ptx::make_smem_desc(sb + k4 * 2 * (TC_TILE * 16), TC_TILE * 16, 128);
-                            ptx::mma_f16<1>(tmem + slot * 128, da, db, idesc, (kb > 0 || term > 0 || k4 > 0) ? 1u : 0u);
+                            ptx::mma_f16<1>(tmem + slot * 128, da, db, idesc, (kb > kb0 || term > 0 || k4 > 0) ? 1u : 0u);
                         }
                     }
                     ptx::mma_commit_1(b_empty + 8 * s);
@@ -159,7 +167,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint32_t tc = 0;
-        for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tc) {
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tc) {
+            const int tile = item % n_tiles_total, ks = item / n_tiles_total;
             const int m = tile / g.n_tiles, n = tile % g.n_tiles;
             const uint32_t slot = tc & 1, aph = (tc >> 1) & 1;
             ptx::mbar_wait(b_accf + 8 * slot, aph, g.err, 104);
@@ -187,8 +196,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(GemmArgs g) {
                     }
                 } else {
                     float* o = g.out + ((size_t)m * 128 + row) * ((size_t)g.n_tiles * 128) + (size_t)n * 128 + j * 16;
+                    if (ksplit > 1) {
+                        float4* o4 = (float4*)(o + (size_t)ks * g.split_stride);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) o[c] = seluf_(__uint_as_float(v[c]) + bias[j * 16 + c]);
+                        for (int c = 0; c < 4; ++c)
+                            o4[c] = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) o[c] = seluf_(__uint_as_float(v[c]) + bias[j * 16 + c]);
+                    }
                 }
             }
             ptx::tc_fence_before();
@@ -489,6 +505,27 @@ __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.appro
 // hoisted projection are packed times 0.5 - an exact scaling - so the gate stage saves three multiplies per unit)
 __device__ __forceinline__ float sigmoid_tanh(float x) { return fmaf(tanh_approx(x), 0.5f, 0.5f); }
 
+// One LSTM cell update from the pre-activations (zi, zf, zo pre-halved, see above).
+//   C3R_GATE_MODE 0: five tanh.approx                      2: ex2/rcp everywhere (8 SFU ops)
+//                 1: as 0 but the forget gate by ex2/rcp (6 SFU ops): the absolute error of tanh.approx (2^-11)
+//                    in f multiplies the cell state, which is not bounded by 1 - with a forget bias of 3 the state
+//                    reaches ~20 and a 2.4e-4 error in f becomes 5e-3 in c per step
+#ifndef C3R_GATE_MODE
+#define C3R_GATE_MODE (C3R_EXACT_GATES ? 2 : 0)
+#endif
+__device__ __forceinline__ void lstm_cell(float zi, float zf, float zg, float zo, float cp, float& cn, float& hv) {
+    if (C3R_GATE_MODE == 2) {
+        cn = fmaf(sigmoid_fast(2.0f * zf), cp, sig_times_tanh(2.0f * zi, zg));
+        hv = sig_times_tanh(2.0f * zo, cn);
+    } else if (C3R_GATE_MODE == 1) {
+        cn = fmaf(sigmoid_fast(2.0f * zf), cp, sigmoid_tanh(zi) * tanh_approx(zg));
+        hv = sigmoid_tanh(zo) * tanh_approx(cn);
+    } else {
+        cn = fmaf(sigmoid_tanh(zf), cp, sigmoid_tanh(zi) * tanh_approx(zg));
+        hv = sigmoid_tanh(zo) * tanh_approx(cn);
+    }
+}
+
 template <int CH, int KX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_lstm_tc(LstmArgs a) {
     typedef LstmCfg<CH, KX> Cfg;
@@ -750,13 +787,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                             for (int u = 0; u < 4; ++u) {
                                 const float cp = has_acc ? __uint_as_float(cprev[u]) : 0.0f;
                                 float cn;
-                                if (LSTM_EXACT_GATES) {
-                                    cn = fmaf(sigmoid_fast(2.0f * z[1][u]), cp, sig_times_tanh(2.0f * z[0][u], z[2][u]));
-                                    hv4[u] = sig_times_tanh(2.0f * z[3][u], cn);
-                                } else {
-                                    cn = fmaf(sigmoid_tanh(z[1][u]), cp, sigmoid_tanh(z[0][u]) * tanh_approx(z[2][u]));
-                                    hv4[u] = sigmoid_tanh(z[3][u]) * tanh_approx(cn);
-                                }
+                                lstm_cell(z[0][u], z[1][u], z[2][u], z[3][u], cp, cn, hv4[u]);
                                 cnew[u] = __float_as_uint(cn);
                             }
                             // h as fp16 hi + lo terms, two values per conversion
@@ -859,13 +890,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSTM_THREADS, 1) k_l
                     for (int u = 0; u < 8; ++u) {
                         const float cp = step > 0 ? __uint_as_float(cprev[u]) : 0.0f;
                         float cn, hv;
-                        if (LSTM_EXACT_GATES) {
-                            cn = fmaf(sigmoid_fast(2.0f * z[1][u]), cp, sig_times_tanh(2.0f * z[0][u], z[2][u]));
-                            hv = sig_times_tanh(2.0f * z[3][u], cn);
-                        } else {
-                            cn = fmaf(sigmoid_tanh(z[1][u]), cp, sigmoid_tanh(z[0][u]) * tanh_approx(z[2][u]));
-                            hv = sigmoid_tanh(z[3][u]) * tanh_approx(cn);
-                        }
+                        lstm_cell(z[0][u], z[1][u], z[2][u], z[3][u], cp, cn, hv);
                         cnew[u] = __float_as_uint(cn);
                         hh[u] = __float2half(hv);
                         hl[u] = __float2half(hv - __half2float(hh[u]));
@@ -937,7 +962,79 @@ __global__ void __launch_bounds__(TC_TILE) k_xop(const int32_t* __restrict__ ten
 #include "nn_lstm2f.cuh"
 namespace c3r {
 
+// L4's partial sums -> l4 = selu(sum + bias): fp32 [site][128] (inspection) and the fp16 hi / lo operand images
+// [tile][2 kb][128 x 64] of the L5 GEMM.  Block = 32 rows of a 128-site tile, thread = (row, 8-column cell), 4 cells each.
+__global__ void __launch_bounds__(128) k_l4_finish(const float* __restrict__ part, int n_part, size_t stride,
+                                                   const float* __restrict__ bias, float* __restrict__ l4,
+                                                   __half* __restrict__ img, __half* __restrict__ img_lo) {
+    const int tile = blockIdx.x >> 2;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int e = ((blockIdx.x & 3) * 4 + it) * 128 + threadIdx.x, row = e >> 4, cell = e & 15;
+        const size_t src = ((size_t)tile * 128 + row) * DENSE + cell * 8;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = bias[cell * 8 + c];
+        for (int q = 0; q < n_part; ++q) {
+            const float4 a = *(const float4*)(part + (size_t)q * stride + src), b = *(const float4*)(part + (size_t)q * stride + src + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            v[c] = seluf_(v[c]);
+            hi[c] = __float2half(v[c]);
+            lo[c] = __float2half(v[c] - __half2float(hi[c]));
+        }
+        *(float4*)(l4 + src) = make_float4(v[0], v[1], v[2], v[3]);
+        *(float4*)(l4 + src + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        const size_t dst = ((size_t)tile * 2 + cell / 8) * TC_IMG + (size_t)(cell % 8) * (TC_TILE * 8) + row * 8;
+        *(uint4*)(img + dst) = *(const uint4*)hi;
+        *(uint4*)(img_lo + dst) = *(const uint4*)lo;
+    }
+}
+
+// The two output layers on a5 = [selu(L5_1) | selu(L5_2)] (fp32 [site][256]): Y_gt21 (21) and Y_genotype (3), SELU,
+// softmax (model.py:154-156,195-197, 213-214).  One warp per site, lane = output.
+constexpr int HOUT_WARPS = 8;
+__global__ void __launch_bounds__(HOUT_WARPS * 32) k_heads_out(NetF32 w, const float* __restrict__ a5, float* __restrict__ probs, int64_t n) {
+    __shared__ float wy[DENSE][24];
+    __shared__ float by[24];
+    for (int i = threadIdx.x; i < DENSE * 24; i += blockDim.x) {
+        const int k = i / 24, o = i % 24;
+        wy[k][o] = o < 21 ? w.ky1[k * 21 + o] : w.ky2[k * 3 + (o - 21)];
+    }
+    if (threadIdx.x < 24) by[threadIdx.x] = threadIdx.x < 21 ? w.by1[threadIdx.x] : w.by2[threadIdx.x - 21];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = lane < 24 ? lane : 23;
+    for (int64_t s = (int64_t)blockIdx.x * HOUT_WARPS + warp; s < n; s += (int64_t)gridDim.x * HOUT_WARPS) {
+        const float* av = a5 + s * 256 + (o < 21 ? 0 : DENSE);
+        float v0 = by[o], v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+#pragma unroll 8
+        for (int k = 0; k < DENSE; k += 4) {
+            const float4 a4 = *(const float4*)(av + k);
+            v0 = fmaf(a4.x, wy[k][o], v0); v1 = fmaf(a4.y, wy[k + 1][o], v1);
+            v2 = fmaf(a4.z, wy[k + 2][o], v2); v3 = fmaf(a4.w, wy[k + 3][o], v3);
+        }
+        const float y = seluf_((v0 + v1) + (v2 + v3));
+        // softmax within lanes 0..20 and within lanes 21..23
+        const bool g1 = lane < 21, g2 = lane >= 21 && lane < 24;
+        float m1 = g1 ? y : -INFINITY, m2 = g2 ? y : -INFINITY;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, d)); m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, d)); }
+        const float e = g1 ? expf(y - m1) : (g2 ? expf(y - m2) : 0.0f);
+        float s1 = g1 ? e : 0.0f, s2 = g2 ? e : 0.0f;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, d); s2 += __shfl_xor_sync(0xffffffffu, s2, d); }
+        if (lane < 24) probs[s * 24 + lane] = e / (g1 ? s1 : s2);
+    }
+}
+
 // ================================================================== host side
+constexpr int L4_KSPLIT = 3;                 // L4's K = 165 k blocks goes in 3 ranges of 55 (see tc_l4_heads)
+
 // LSTM2 as one fused kernel (projection inside the recurrent step, nn_lstm2f.cuh) or, with C3R_LSTM2=hoisted, as the
 // projection GEMM + recurrent kernel pair that moves zx2 through HBM.
 inline bool lstm2_fused() {
@@ -957,12 +1054,17 @@ struct TcNet {
     const __half *img1 = nullptr, *img2 = nullptr, *w2p = nullptr, *k4p = nullptr, *w2p_lo = nullptr, *k4p_lo = nullptr;
     const float *b2p = nullptr, *b4 = nullptr;
     const uint8_t* wstream2 = nullptr;   // fused LSTM2: weight stream [2 dirs][2 halves][L2F_STREAM_BYTES]
+    const __half *k5p = nullptr, *k5p_lo = nullptr;   // [L5_1 | L5_2] as one N = 256 GEMM: [2 n tiles][2 kb][TC_IMG]
+    const float* b5p = nullptr;                        // [256]
     // activation scratch (sized for cap_tiles 128-site tiles)
     void* abuf = nullptr;
     size_t abytes = 0;
     int cap_tiles = 0;
     __half *h1 = nullptr, *h2 = nullptr, *h1_lo = nullptr, *h2_lo = nullptr, *xop = nullptr;
-    float *zx2 = nullptr, *l4 = nullptr;
+    float *zx2 = nullptr, *l4 = nullptr, *l4p = nullptr;   // l4p: L4's partial sums [L4_KSPLIT][tiles*128][128]
+    size_t l4_stride = 0;
+    __half *l4h = nullptr, *l4h_lo = nullptr;              // l4 as fp16 operand images [tile][2 kb][TC_IMG] (hi, lo)
+    float* a5 = nullptr;                                   // selu(L5_1) | selu(L5_2): [tiles*128][256]
     int* err = nullptr;
     long long* trace = nullptr;    // [2 layers][2][33][8][8], filled when C3R_TRACE is set
     bool attr_set = false;
@@ -983,7 +1085,8 @@ inline void tc_release(TcNet& t) {
 inline size_t img_index(int R, int r, int k) { return (size_t)(k / 8) * R * 8 + (size_t)r * 8 + (k % 8); }
 
 inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, size_t o_b1, size_t o_u1, size_t o_w2,
-                    size_t o_b2, size_t o_u2, size_t o_k4, size_t o_b4, int sm_count, std::string* err) {
+                    size_t o_b2, size_t o_u2, size_t o_k4, size_t o_b4, size_t o_k51, size_t o_b51, size_t o_k52, size_t o_b52,
+                    int sm_count, std::string* err) {
     tc_release(t);
     const int C = net.C;
     t.C = C;
@@ -995,14 +1098,17 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
     const size_t n_img2 = (size_t)2 * 2 * 5 * 64 * KT2;
     const size_t n_w2p = (size_t)10 * 4 * TC_IMG;                 // [n_tile][kb][128x64]
     const size_t n_k4p = (size_t)(L4_IN / TC_KB) * TC_IMG;
-    std::vector<__half> hb(n_img1 + n_img2 + 2 * n_w2p + 2 * n_k4p);
-    std::vector<float> fb(2 * G2 + DENSE);
+    const size_t n_k5p = (size_t)2 * 2 * TC_IMG;
+    std::vector<__half> hb(n_img1 + n_img2 + 2 * n_w2p + 2 * n_k4p + 2 * n_k5p);
+    std::vector<float> fb(2 * G2 + DENSE + 2 * DENSE);
     __half* img1 = hb.data();
     __half* img2 = img1 + n_img1;
     __half* w2p = img2 + n_img2;
     __half* k4p = w2p + n_w2p;
     __half* w2p_lo = k4p + n_k4p;
     __half* k4p_lo = w2p_lo + n_w2p;
+    __half* k5p = k4p_lo + n_k4p;
+    __half* k5p_lo = k5p + n_k5p;
     auto split = [](float w, __half& hi, __half& lo) {
         hi = __float2half(w);
         lo = __float2half(w - __half2float(hi));
@@ -1072,6 +1178,14 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
             split(h[o_k4 + (size_t)k * DENSE + j], k4p[ix], k4p_lo[ix]);
         }
     for (int j = 0; j < DENSE; ++j) fb[2 * G2 + j] = h[o_b4 + j];
+    // L5_1 and L5_2 side by side: GEMM column n*128 + j = unit j of layer n; B image row = output unit, k = input
+    for (int n = 0; n < 2; ++n)
+        for (int k = 0; k < DENSE; ++k)
+            for (int j = 0; j < DENSE; ++j) {
+                const size_t ix = ((size_t)n * 2 + k / TC_KB) * TC_IMG + img_index(128, j, k % TC_KB);
+                split(h[(n == 0 ? o_k51 : o_k52) + (size_t)k * DENSE + j], k5p[ix], k5p_lo[ix]);
+            }
+    for (int j = 0; j < DENSE; ++j) { fb[2 * G2 + DENSE + j] = h[o_b51 + j]; fb[2 * G2 + 2 * DENSE + j] = h[o_b52 + j]; }
 
     std::vector<uint8_t> ws;
     lstm2f_pack(ws, h, o_w2, o_b2, o_u2);
@@ -1092,8 +1206,11 @@ inline int tc_build(TcNet& t, const NetF32& net, const float* h, size_t o_w1, si
     t.k4p = t.w2p + n_w2p;
     t.w2p_lo = t.k4p + n_k4p;
     t.k4p_lo = t.w2p_lo + n_w2p;
+    t.k5p = t.k4p_lo + n_k4p;
+    t.k5p_lo = t.k5p + n_k5p;
     t.b2p = (const float*)(d + foff);
     t.b4 = t.b2p + 2 * G2;
+    t.b5p = t.b4 + DENSE;
     e = cudaMalloc((void**)&t.err, 64);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     cudaMemset(t.err, 0, 64);
@@ -1112,12 +1229,17 @@ inline int tc_ensure(TcNet& t, int tiles, std::string* err) {
     const size_t n_h1 = (size_t)tiles * NT * 4 * TC_IMG, n_h2 = (size_t)tiles * NT * 5 * TC_IMG;
     const size_t n_zx = lstm2_fused() ? 64 : (size_t)tiles * NT * 10 * ZX_CHUNK_WORDS, n_l4 = (size_t)tiles * 128 * DENSE;
     const size_t n_xop = (size_t)tiles * NT * 64 * TC_TILE;
-    t.abytes = (n_h1 + n_h2) * 2 * 2 + n_xop * 2 + (n_zx + n_l4) * 4 + 1024;
+    t.abytes = (n_h1 + n_h2) * 2 * 2 + n_xop * 2 + (n_zx + n_l4 * (1 + L4_KSPLIT)) * 4 + n_l4 * 2 * 2 + n_l4 * 2 * 4 + 1024;
     cudaError_t e = cudaMalloc(&t.abuf, t.abytes);
     if (e != cudaSuccess) { *err = std::string("activation scratch: ") + cudaGetErrorString(e); t.cap_tiles = 0; return -1; }
     uint8_t* p = (uint8_t*)t.abuf;
     t.zx2 = (float*)p; p += n_zx * 4;
     t.l4 = (float*)p; p += n_l4 * 4;
+    t.l4p = (float*)p; p += n_l4 * 4 * L4_KSPLIT;
+    t.l4_stride = n_l4;
+    t.a5 = (float*)p; p += n_l4 * 2 * 4;
+    t.l4h = (__half*)p; p += n_l4 * 2;
+    t.l4h_lo = (__half*)p; p += n_l4 * 2;
     t.h1 = (__half*)p; p += n_h1 * 2;
     t.h1_lo = (__half*)p; p += n_h1 * 2;
     t.h2 = (__half*)p; p += n_h2 * 2;
@@ -1198,7 +1320,7 @@ inline cudaError_t launch_gemm(const GemmArgs& g, int sm_count, cudaStream_t st)
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    int grid = g.m_tiles * g.n_tiles;
+    int grid = g.m_tiles * g.n_tiles * (g.ksplit > 1 ? g.ksplit : 1);
     if (grid > sm_count) grid = sm_count;
     k_gemm_tc<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(g);
     return cudaGetLastError();
@@ -1265,12 +1387,27 @@ inline cudaError_t tc_lstm2(TcNet& t, const TcSub& b, cudaStream_t st) {
 inline cudaError_t tc_l4_heads(TcNet& t, const NetF32& net, const TcSub& b, float* probs, cudaStream_t st) {
     GemmArgs g4;
     g4.A = t.h2 + (size_t)b.t0 * NT * 5 * TC_IMG; g4.B = t.k4p; g4.A_lo = t.h2_lo + (size_t)b.t0 * NT * 5 * TC_IMG; g4.B_lo = t.k4p_lo;
-    g4.terms = l4_terms(); g4.bias = t.b4; g4.out = t.l4 + (size_t)b.t0 * 128 * DENSE; g4.m_tiles = b.nt; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
-    g4.mode = 1; g4.err = t.err; g4.dbg = 0; g4.trace = nullptr;
+    // K = 10560 always goes in L4_KSPLIT ranges (partial sums added up by k_l4_finish): a remainder launch of a few dozen
+    // tiles still fills the SMs, and the summation order is the same whatever the batch size
+    g4.terms = l4_terms(); g4.bias = t.b4; g4.out = t.l4p + (size_t)b.t0 * 128 * DENSE; g4.m_tiles = b.nt; g4.n_tiles = 1; g4.n_kb = L4_IN / TC_KB;
+    g4.mode = 1; g4.ksplit = L4_KSPLIT; g4.split_stride = t.l4_stride; g4.err = t.err; g4.dbg = 0; g4.trace = nullptr;
     cudaError_t e = launch_gemm(g4, t.sm_count, st);
     if (e != cudaSuccess) return e;
-    e = launch_heads(net, t.l4 + (size_t)b.t0 * 128 * DENSE, probs + b.s0 * 24, b.ns, t.sm_count, st);
+    // l4 = selu(sum of the partial sums + bias) as fp16 operand images; [L5_1 | L5_2] as one tensor-core GEMM
+    // (N = 256, K = 128, split precision, + bias + SELU); the two small output layers and the softmax per site
+    k_l4_finish<<<b.nt * 4, 128, 0, st>>>(t.l4p + (size_t)b.t0 * 128 * DENSE, L4_KSPLIT, t.l4_stride, t.b4,
+                                      t.l4 + (size_t)b.t0 * 128 * DENSE, t.l4h + (size_t)b.t0 * 2 * TC_IMG, t.l4h_lo + (size_t)b.t0 * 2 * TC_IMG);
+    GemmArgs g5;
+    g5.A = t.l4h + (size_t)b.t0 * 2 * TC_IMG; g5.A_lo = t.l4h_lo + (size_t)b.t0 * 2 * TC_IMG; g5.B = t.k5p; g5.B_lo = t.k5p_lo;
+    g5.terms = 7; g5.bias = t.b5p; g5.out = t.a5 + (size_t)b.t0 * 128 * 256; g5.m_tiles = b.nt; g5.n_tiles = 2; g5.n_kb = 2;
+    g5.mode = 1; g5.ksplit = 1; g5.split_stride = 0; g5.err = t.err; g5.dbg = 0; g5.trace = nullptr;
+    e = launch_gemm(g5, t.sm_count, st);
     if (e != cudaSuccess) return e;
+    {
+        int64_t blocks = (b.ns + HOUT_WARPS - 1) / HOUT_WARPS;
+        if (blocks > (int64_t)t.sm_count * 4) blocks = (int64_t)t.sm_count * 4;
+        if (blocks > 0) k_heads_out<<<(unsigned)blocks, HOUT_WARPS * 32, 0, st>>>(net, t.a5 + (size_t)b.t0 * 128 * 256, probs + b.s0 * 24, b.ns);
+    }
     return cudaGetLastError();
 }
 
@@ -1320,7 +1457,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
             g2.B = t.w2p; g2.B_lo = t.w2p_lo; g2.terms = zx_terms(); g2.bias = t.b2p;
             g2.out = t.zx2 + (size_t)m0 * 10 * ZX_CHUNK_WORDS;
             g2.m_tiles = mt; g2.n_tiles = 5; g2.n_kb = 4;
-            g2.mode = 0; g2.err = t.err; g2.dbg = getenv("C3R_ZX_DBG") ? atoi(getenv("C3R_ZX_DBG")) : 0;
+            g2.mode = 0; g2.ksplit = 1; g2.split_stride = 0; g2.err = t.err; g2.dbg = getenv("C3R_ZX_DBG") ? atoi(getenv("C3R_ZX_DBG")) : 0;
             g2.trace = (t.trace && m0 == 0) ? t.trace + 2 * 2 * NT * 8 * 8 : nullptr;
             return launch_gemm_zx(g2, t.sm_count, s, max_pairs);
         };
@@ -1361,7 +1498,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         if (B.nt == 0) {
             if (lstm2_fused()) TCK(cudaEventRecord(P.h1_free, st), "event");
             TCK(tc_l4_heads(t, net, A, pr, st), "l4/heads");
-            launches += 2;
+            launches += 4;
             TCK(cudaEventRecord(P.pass_done, st), "event");
             continue;
         }
@@ -1373,7 +1510,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         TCK(cudaEventRecord(P.ev[1], P.s2), "event");
         TCK(tc_l4_heads(t, net, B, pr, st), "l4/heads");
         TCK(cudaStreamWaitEvent(st, P.ev[1], 0), "wait");       // the caller's stream ends after everything
-        launches += 5;
+        launches += 9;
         TCK(cudaEventRecord(P.pass_done, st), "event");
     }
 #undef TCK

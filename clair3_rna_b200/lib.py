@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libc3r_b200.so")
+LIB_PATH = os.environ.get("C3R_LIB") or os.path.join(HERE, "libc3r_b200.so")   # C3R_LIB: an experimental build
 
 WINDOW = 33
 N_OUT = 24

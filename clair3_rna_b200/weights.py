@@ -62,18 +62,20 @@ def synthetic(channels: int = 18, seed: int = 20260, sharpen: float = 1.0, input
     return w
 
 
-def adversarial(channels: int = 18, seed: int = 7, sharpen: float = 8.0) -> dict:
-    """A second, harsher weight set for tolerance tests: recurrent kernels x3, forget bias around 3, random non-zero
+def adversarial(channels: int = 18, seed: int = 7, sharpen: float = 8.0, recurrent_scale: float = 3.0,
+                forget_bias: float = 3.0) -> dict:
+    """A second, harsher weight set for tolerance tests: recurrent kernels scaled up (orthogonal x recurrent_scale, so
+    every step amplifies a perturbation of h by up to that factor), forget bias around forget_bias, random non-zero
     LSTM biases - gates saturate and the cell state grows, unlike anything Keras' initialisers produce."""
     w = synthetic(channels, seed=seed, sharpen=sharpen)
     rng = np.random.default_rng(seed + 1)
     for k in list(w):
         if k.endswith("recurrent_kernel"):
-            w[k] = (w[k] * 3.0).astype(np.float32)
+            w[k] = (w[k] * recurrent_scale).astype(np.float32)
         elif k.startswith("LSTM") and k.endswith("bias"):
             u = w[k].shape[0] // 4
             b = rng.uniform(-0.5, 0.5, w[k].shape).astype(np.float32)
-            b[u:2 * u] += 3.0
+            b[u:2 * u] += forget_bias
             w[k] = b
     return w
 
