@@ -121,47 +121,223 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------ CPU oracle legs
-def _cpu_worker(args):
-    """oracle port of the reference pipeline on one region: mpileup text -> tensors -> fp32 network"""
+# The reference pipeline on the host cores, stage by stage: mpileup text -> generate_tensor windows
+# (producer, oracle/pileup_oracle.py), then batches of 200 through the fp32 network (oracle/model.py, one torch
+# thread like call_variants.py:200-206) and every candidate through the decoder (output_with restated in
+# clair3_rna_b200/decoder.py:vcf_row) - the consumer.  The reference itself (Python + samtools + TensorFlow) cannot
+# travel to the GPU box, so this is the port (kind "port").
+_W = {}
+
+
+def _cpu_init(w):
     import torch
     torch.set_num_threads(1)                 # call_variants.py:200-206
+    _W["w"] = w                              # weights once per worker, not once per job
+
+
+def _cpu_worker(args):
+    """one job = one region: -> (candidates, producer seconds, consumer seconds)"""
     from oracle import pileup_oracle, model
-    batch, ref_seq, ref_start1, s1, e1, C, w, phased, padding = args
+    from clair3_rna_b200 import decoder
+    batch, ref_seq, ref_start1, s1, e1, contig, phased, padding = args
+    t0 = time.time()
     out = pileup_oracle.run_region(batch, ref_seq, ref_start1, s1, e1, phased=phased, padding=padding)
+    t1 = time.time()
     n = len(out["pos"])
     for i in range(0, n, 200):               # predictBatchSize, param_p.py:51
-        model.forward(w, out["tensor"][i:i + 200])
-    return n
+        p = model.forward(_W["w"], out["tensor"][i:i + 200])
+        for k in range(p.shape[0]):
+            decoder.vcf_row(contig, int(out["pos"][i + k]), out["ref33"][i + k], out["alt_info"][i + k], p[k])
+    return n, t1 - t0, time.time() - t1
 
 
-def cpu_sample_regions(cfg, batch, ref, n_regions, span=60000):
-    """regions around the first read clusters of the contig (bounded sample)"""
+def cpu_jobs(cfg, batch, ref, n_jobs, span=4000):
+    """n_jobs regions of about equal cost: the first `span` bp of the read clusters of the contig's genes, largest
+    first (the pool hands them out one at a time, so the workers finish together)"""
     from clair3_rna_b200 import synth
     genes = synth.make_genes(cfg, 0, ref)
-    regs = []
     contig = cfg.contigs[0][0]
-    for g in genes[:n_regions]:
-        s0, e0 = g.exons[0][0], g.exons[-1][1]
-        s1, e1 = max(1, s0 - 100), e0 + 100
+    jobs = []
+    for g in genes:
+        s1 = max(1, g.exons[0][0] - 100)
+        e1 = min(g.exons[-1][1] + 100, s1 + span)
         sub = batch.fetch(s1, e1)
+        if sub.n_reads < 8:
+            continue
         rs1 = max(1, s1 - 1000)
-        ref_seq = ref.fetch_str(contig, rs1 - 1, e1 + 1000)
-        regs.append((sub, ref_seq, rs1, s1, e1))
-    return regs
+        jobs.append((sub, ref.fetch_str(contig, rs1 - 1, e1 + 1000), rs1, s1, e1, contig, cfg.phased, cfg.padding))
+        if len(jobs) >= n_jobs:
+            break
+    jobs.sort(key=lambda j: -j[0].n_reads)
+    return jobs
 
 
-def run_cpu(cfg, batch, ref, w, C, cores, n_regions):
+class CpuPipeline:
+    """persistent pool of worker processes over a fixed job list"""
+
+    def __init__(self, cfg, batch, ref, w, cores, n_jobs):
+        import multiprocessing as mp
+        self.jobs = cpu_jobs(cfg, batch, ref, n_jobs)
+        self.cores = cores
+        self.w = w
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(w,)) if cores > 1 else None
+        if self.pool is None:
+            _cpu_init(w)
+
+    def step(self):
+        t0 = time.time()
+        if self.pool is not None:
+            out = list(self.pool.imap_unordered(_cpu_worker, self.jobs, chunksize=1))
+        else:
+            out = [_cpu_worker(j) for j in self.jobs]
+        dt = time.time() - t0
+        return sum(o[0] for o in out), dt, sum(o[1] for o in out), sum(o[2] for o in out)
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
+def run_cpu(cfg, batch, ref, w, C, cores, n_jobs):
+    cp = CpuPipeline(cfg, batch, ref, w, cores, n_jobs)
+    try:
+        return cp.step()
+    finally:
+        cp.close()
+
+
+# ------------------------------------------------------------------ config 5: the sharded whole-genome leg
+# BASELINE.json configs[4]: 24 contigs with GRCh38 lengths, ont_dorado_drna004, partitioned by (contig, 5 Mb chunk)
+# exactly like the reference's CHUNK_LIST (run_clair3_rna:441-449, 681-706); rank r takes its greedy-LPT share
+# (sharder.assign), reads its chunks from a real BAM + FASTA (native BGZF/BAI reader), runs them through
+# Engine.submit / wait with one ticket ahead, decodes VCF rows natively and leaves them to rank 0, which merges with
+# sort_vcf semantics.  Strong scaling: the genome is fixed, the ranks share it.
+def _cfg5_make_contig(args):
+    scale, ci, path = args
+    from clair3_rna_b200 import synth
+    cfg = synth.config(5, scale=scale)
+    b = synth.make_contig_reads(cfg, ci, synth.Reference(cfg))
+    b.save(path)
+    return ci
+
+
+def cfg5_dataset(scale, rank, world, cores, barrier, cache_dir="/tmp/c3r_bench_cache"):
+    """reads.bam (+ .bai), genome.fa (+ .fai), weights.npz of the config-5 genome at `scale`, made once per box:
+    the ranks generate the contigs between them (process pools), rank 0 then writes the BAM, the last rank the FASTA"""
     import multiprocessing as mp
-    regs = cpu_sample_regions(cfg, batch, ref, n_regions)
-    jobs = [(b, r, rs, s, e, C, w, cfg.phased, cfg.padding) for (b, r, rs, s, e) in regs]
+    from clair3_rna_b200 import synth, weights
+    from clair3_rna_b200.reads import ReadBatch
+    from clair3_rna_b200.bam import write_bam
+    cfg = synth.config(5, scale=scale)
+    d = os.path.join(cache_dir, "cfg5_s%g" % scale)
+    os.makedirs(d, exist_ok=True)
+    bam, fa, wnpz = os.path.join(d, "reads.bam"), os.path.join(d, "genome.fa"), os.path.join(d, "weights.npz")
+    done = os.path.join(d, "done")
     t0 = time.time()
-    if cores > 1:
-        with mp.get_context("fork").Pool(cores) as pool:
-            ns = pool.map(_cpu_worker, jobs)
+    if not os.path.exists(done):
+        mine = [(scale, ci, os.path.join(d, "c%d.npz" % ci)) for ci in range(len(cfg.contigs))
+                if ci % world == rank and not os.path.exists(os.path.join(d, "c%d.npz" % ci))]
+        if mine:
+            # largest contigs first; the pool is sized to this rank's share of the host cores
+            with mp.get_context("fork").Pool(max(1, min(len(mine), cores // world))) as pool:
+                list(pool.imap_unordered(_cfg5_make_contig, sorted(mine, key=lambda a: -cfg.contigs[a[1]][1]), chunksize=1))
+        barrier()
+        if rank == 0:
+            batches = {cfg.contigs[ci][0]: ReadBatch.load(os.path.join(d, "c%d.npz" % ci)) for ci in range(len(cfg.contigs))}
+            write_bam(bam, cfg.contigs, batches, level=1)
+            weights.save(wnpz, weights.synthetic(18, sharpen=8.0))
+        if rank == world - 1:
+            ref = synth.Reference(cfg)
+            off = 0
+            with open(fa, "wb") as fp, open(fa + ".fai", "w") as fi:
+                for name, length in cfg.contigs:
+                    hdr = (">%s\n" % name).encode()
+                    fp.write(hdr)
+                    off += len(hdr)
+                    fi.write("%s\t%d\t%d\t60\t61\n" % (name, length, off))
+                    for s0 in range(0, length, 60 * (1 << 16)):
+                        a = ref.fetch(name, s0, min(length, s0 + 60 * (1 << 16)))
+                        full = (a.size // 60) * 60
+                        lines = np.empty((full // 60, 61), np.uint8)
+                        lines[:, :60] = a[:full].reshape(-1, 60)
+                        lines[:, 60] = 10
+                        fp.write(lines.tobytes())
+                        off += lines.size
+                        if a.size > full:
+                            fp.write(a[full:].tobytes() + b"\n")
+                            off += a.size - full + 1
+        barrier()
+        if rank == 0:
+            open(done, "w").write("ok\n")
+    barrier()
+    return cfg, bam, fa, wnpz, time.time() - t0
+
+
+def shard_cfg5_leg(scale, rank, world, local_rank, cores, barrier, gloo, eng):
+    """-> dict for the bench line (rank 0) or None"""
+    import pickle
+    import torch.distributed as dist
+    from clair3_rna_b200 import run_chunks
+    cfg, bam, fa, wnpz, prep_s = cfg5_dataset(scale, rank, world, cores, barrier)
+    tmp = os.path.join(os.path.dirname(bam), "rows_w%d" % world)
+    os.makedirs(tmp, exist_ok=True)
+
+    def gather(rows_of):
+        # per-shard VCF rows are left on the node's file system, like the reference's tmp/pileup_output/*.vcf
+        with open(os.path.join(tmp, "rank%d.pkl" % rank), "wb") as fp:
+            pickle.dump(rows_of, fp, protocol=4)
+        barrier()
+        if rank != 0:
+            return None
+        return [pickle.load(open(os.path.join(tmp, "rank%d.pkl" % r), "rb")) for r in range(world)]
+
+    cold = {}
+    barrier()
+    # first pass: cold (BAM handles and their indexes opened, file cache and buffers touched for the first time)
+    run_chunks.run(bam, fa, wnpz, None, device=local_rank, rank=rank, world=world, merge=False, stats=cold,
+                   engine=eng, loader_threads=max(1, min(4, cores // (2 * world))), native_threads=max(1, cores // (2 * world)))
+    stats = {}
+    barrier()
+    t0 = time.time()
+    merged = run_chunks.run(bam, fa, wnpz, os.path.join(tmp, "merged.vcf") if rank == 0 else None, device=local_rank,
+                            rank=rank, world=world, gather=gather if world > 1 else None, stats=stats, engine=eng,
+                            loader_threads=max(1, min(4, cores // (2 * world))), native_threads=max(1, cores // (2 * world)))
+    t_all = time.time() - t0
+    mine = dict(rank=rank, shards=stats["shards"], candidates=stats["candidates"], loop_s=stats["seconds"], cold_loop_s=cold["seconds"],
+                host_s=stats["host_seconds"], cost=stats["cost"], total_s=t_all)
+    if world > 1:
+        allst = [None] * world
+        dist.all_gather_object(allst, mine, group=gloo)
     else:
-        ns = [_cpu_worker(j) for j in jobs]
-    dt = time.time() - t0
-    return sum(ns), dt
+        allst = [mine]
+    if rank != 0:
+        return None
+    n = sum(a["candidates"] for a in allst)
+    t_max = max(a["loop_s"] for a in allst)
+    t_mean = sum(a["loop_s"] for a in allst) / world
+    cost = [a["cost"] for a in allst]
+    return {
+        "workload": "%s at scale %g: %d contigs, %d bp, %d (contig, chunk) shards, %d reads in one BAM" % (
+            cfg.name, scale, len(cfg.contigs), sum(l for _, l in cfg.contigs), stats["total_shards"],
+            int(sum(c for c in cost))),
+        "scaling": "strong", "n_gpus": world,
+        "value": n / t_max if t_max > 0 else 0.0, "unit": "sites/s",
+        "note": "candidates of the whole genome / slowest rank's loop (BAM fetch -> submit -> wait -> native decode, one "
+                "ticket ahead, loader and decoder threads beside the submitting thread), second pass over the genome in "
+                "the same process (the first, cold pass is reported beside it); the rank-0 merge (Python sort_vcf "
+                "restatement) is timed apart",
+        "candidates": n, "merged_rows": len(merged) if merged is not None else None,
+        "slowest_rank_s": t_max, "mean_rank_s": t_mean, "imbalance": t_max / t_mean if t_mean > 0 else None,
+        "cold_pass_slowest_rank_s": max(a["cold_loop_s"] for a in allst),
+        "lpt_cost_imbalance": max(cost) / (sum(cost) / world) if sum(cost) > 0 else None,
+        "merge_and_write_s": t_all - stats["seconds"],
+        "per_rank": [{"rank": a["rank"], "shards": a["shards"], "candidates": a["candidates"], "loop_s": round(a["loop_s"], 3),
+                      "host_s": {k: round(v, 3) for k, v in a["host_s"].items()}} for a in allst],
+        "host_feed": "host seconds of the slowest rank: " + ", ".join(
+            "%s %.2f" % (k, v) for k, v in max(allst, key=lambda a: a["loop_s"])["host_s"].items()),
+        "dataset_prep_s": prep_s,
+    }
 
 
 # ------------------------------------------------------------------ main
@@ -175,6 +351,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--nn_impl", type=int, default=1)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--cfg5_scale", type=float, default=1.0,
+                    help="genome scale of the sharded config-5 leg (1.0 = GRCh38 lengths, 631 chunks; 0 = skip the leg)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,32 +369,46 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample per step so that W+K steps end within minutes
-        n_regions = max(cores, 8)
+        # a bounded sample per step (the same >= 4 jobs per worker every step) so that W+K steps end within minutes
+        n_jobs = 4 * cores
+        cp = CpuPipeline(cfg, batch, ref, w, cores, n_jobs)
         vals = []
         for i in range(args.warmup + args.steps):
-            n, dt = run_cpu(cfg, batch, ref, w, C, cores, n_regions)
+            r = cp.step()
             if i >= args.warmup:
-                vals.append((n, dt))
+                vals.append(r)
+        cp.close()
+        one = CpuPipeline(cfg, batch, ref, w, 1, max(4, n_jobs // cores))       # the same pipeline in one process
+        n1, dt1, _, _ = one.step()
         n = sum(v[0] for v in vals)
         dt = sum(v[1] for v in vals)
+        prod, cons = sum(v[2] for v in vals), sum(v[3] for v in vals)
         v = n / dt if dt > 0 else 0.0
-        sample = "%d gene regions of the workload per step (%d candidate sites/step), oracle port, %d worker processes" % (
-            n_regions, vals[0][0] if vals else 0, cores)
+        v1 = n1 / dt1 if dt1 > 0 else 0.0
+        sample = ("%d regions of <= 4 kb around the first exons of the workload's genes per step (%d candidate sites/step), "
+                  "oracle port: mpileup text -> generate_tensor -> fp32 network (batch 200, 1 torch thread) -> VCF row decode; "
+                  "%d persistent worker processes, jobs handed out largest first; the full workload is %d reads - a sample, "
+                  "hence not the same config as the GPU arm" % (len(cp.jobs), vals[0][0] if vals else 0, cores, batch.n_reads))
         print(json.dumps({
             "impl": "reference", "metric": "candidate sites/sec (tensor+inference)", "value": v, "unit": "sites/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / max(1, len(vals)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
             "config": {"workload": workload, "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "sites/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "sites/s", "cores": cores, "kind": "port", "sample": sample,
+                             "sites_per_s_per_core": v / cores, "one_process_sites_per_s": v1,
+                             "parallel_speedup": (v / v1) if v1 > 0 else None,
+                             "producer_share": prod / (prod + cons) if prod + cons > 0 else None,
+                             "consumer_share": cons / (prod + cons) if prod + cons > 0 else None},
             "e2e": {"value": v, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
     import torch
     import torch.distributed as dist
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        gloo = dist.new_group(backend="gloo")           # python objects (per-rank statistics) travel over gloo
     torch.cuda.set_device(local_rank)
     from clair3_rna_b200.engine import Engine
     eng = Engine(local_rank, C, enable_padding=cfg.padding, nn_impl=args.nn_impl)
@@ -311,6 +503,11 @@ def main():
         sampler.sample()
         eng.wait(tk)
     sampler.stop_flag = True
+    shard5 = None
+    if args.cfg5_scale > 0 and C == 18 and not cfg.padding:
+        # the same engine (its buffers are warm, like in a process that has been running for a while)
+        shard5 = shard_cfg5_leg(args.cfg5_scale, rank, world, local_rank, cores, barrier, gloo, eng)
+    eng.close()
 
     if rank == 0:
         pk = peaks()
@@ -348,12 +545,15 @@ def main():
                                "peak_source": pk["src"]},
         }
         if not args.no_cpu_baseline:
-            n, dt = run_cpu(cfg, batch, ref, w, C, 1, 8)
+            n, dt, prod, cons = run_cpu(cfg, batch, ref, w, C, 1, 12)
             line["cpu_baseline"] = {"value": n / dt if dt > 0 else 0.0, "unit": "sites/s", "cores": 1, "kind": "port",
-                                    "sample": "8 gene regions of the workload (%d candidate sites, %.1f s), oracle port "
-                                              "(mpileup text -> generate_tensor -> fp32 network, batch 200), 1 process" % (n, dt)}
+                                    "sample": "12 regions of <= 4 kb of the workload (%d candidate sites, %.1f s), oracle port "
+                                              "(mpileup text -> generate_tensor -> fp32 network, batch 200 -> VCF row decode), "
+                                              "1 process; producer %.0f %% / consumer %.0f %% of the time" % (
+                                                  n, dt, 100 * prod / max(prod + cons, 1e-9), 100 * cons / max(prod + cons, 1e-9))}
+        if shard5 is not None:
+            line["shard_cfg5"] = shard5
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -22,9 +22,18 @@ def fetch(path: str, fai: dict, contig: str, start1: int, end1: int) -> np.ndarr
         fp.seek(offset + first_line * linewidth)
         raw = fp.read((last_line - first_line + 1) * linewidth)
     a = np.frombuffer(raw, np.uint8)
-    a = a[(a != 10) & (a != 13)]
+    n_lines = last_line - first_line + 1
+    if a.size == n_lines * linewidth:
+        # every line complete: drop the line terminators with one strided copy
+        a = a.reshape(n_lines, linewidth)[:, :linebases].reshape(-1)
+    else:
+        # the last line of the contig may be short (and may lack a terminator)
+        full = (a.size // linewidth) * linewidth
+        tail = a[full:]
+        a = np.concatenate([a[:full].reshape(-1, linewidth)[:, :linebases].reshape(-1), tail[(tail != 10) & (tail != 13)]])
     lo = (start1 - 1) - first_line * linebases
     a = a[lo: lo + (end1 - start1 + 1)].copy()
-    lower = (a >= 97) & (a <= 122)
-    a[lower] -= 32
+    if a.size and a.max() >= 97:
+        lower = (a >= 97) & (a <= 122)
+        a[lower] -= 32
     return a

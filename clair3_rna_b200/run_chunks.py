@@ -47,9 +47,12 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
         snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF, min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ,
         qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None, bed_fn=None, vcf_fn=None, head_tail=False,
         merge_qual=None, show_ref=True, rediportal_fn=None, rediportal_tags=None, output_no_tagging=None,
-        compress_vcf=False):
+        compress_vcf=False, engine=None, loader_threads=2, native_threads=0, merge=True):
     """merge_qual / show_ref / rediportal_*: the options of the merge stage (sharder.sort_vcf = sort_vcf_from of the
-    reference); the defaults keep every row as the chunks produced it."""
+    reference); the defaults keep every row as the chunks produced it.  engine: an Engine to reuse (its parameters and
+    weights are then the caller's business); loader_threads: BAM / FASTA readers working ahead of the GPU;
+    native_threads: threads of each BGZF inflate and of the row decoder (0 = all cores - give every rank its share
+    when several ranks run on one host)."""
     from .bam import BamFile
     from .engine import Engine, decode_vcf_rows
     fai = fasta.read_fai(ref_fn)
@@ -63,12 +66,27 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
     owner = sharder.assign(costs, world)
     mine = [i for i in range(len(shards)) if owner[i] == rank]
     C = P.CHANNEL_SIZE + (P.PHASED_CHANNEL_SIZE if phased else 0)
-    eng = Engine(device, C, snp_min_af=snp_min_af, indel_min_af=indel_min_af, min_coverage=min_coverage,
-                 min_mq=min_mq, enable_padding=padding, enable_head_tail=head_tail)
-    eng.set_weights(W.load(chkpnt_fn))
+    eng = engine
+    if eng is None:
+        eng = Engine(device, C, snp_min_af=snp_min_af, indel_min_af=indel_min_af, min_coverage=min_coverage,
+                     min_mq=min_mq, enable_padding=padding, enable_head_tail=head_tail)
+        eng.set_weights(W.load(chkpnt_fn))
     t0 = time.time()
     rows_of = {}
     n_cand = 0
+    # host seconds per stage of this rank's loop (the GPU works under all of them but `wait`)
+    tm = dict(fetch=0.0, ref=0.0, submit=0.0, wait=0.0, decode=0.0)
+
+    import threading
+    tls = threading.local()
+    readers = []
+
+    def reader():
+        # one BAM handle per loader thread (a handle serves one fetch at a time)
+        if getattr(tls, "bf", None) is None:
+            tls.bf = BamFile(bam_fn, threads=native_threads)
+            readers.append(tls.bf)
+        return tls.bf
 
     def load(i):
         name, length, cid, num = shards[i]
@@ -81,32 +99,89 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
                                   known_positions=known)
         if plan is None:
             return None
-        batch = bf.fetch(name, plan.start1, plan.end1)
+        t = time.time()
+        batch = reader().fetch(name, plan.start1, plan.end1)
+        tm["fetch"] += time.time() - t
+        t = time.time()
         ref = fasta.fetch(ref_fn, fai, name, plan.ref_start1, plan.ref_end1)
+        tm["ref"] += time.time() - t
         return name, batch, ref, plan
 
-    pending = None                                   # (shard index, ticket, name, batch, ref, rs1)
-    for i in mine + [None]:
-        nxt = None
+    # Three host stages run side by side (the native calls release the GIL): a loader thread fetches + inflates the
+    # BAM blocks and reads the reference of the shards ahead, this thread submits shard i+1 and waits for shard i,
+    # a decoder thread turns finished results into VCF rows.  Tickets: one running, one queued, two being decoded.
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    loader, dec = ThreadPoolExecutor(max(1, loader_threads)), ThreadPoolExecutor(1)
+    tm.update(load_wait=0.0, decode_wait=0.0)
+    submit_ms = []
+    it = iter(mine)
+    loads, decoding = deque(), deque()               # (shard, future) / (shard, ticket, future)
+
+    def prefetch():
+        i = next(it, None)
         if i is not None:
-            got = load(i)
+            loads.append((i, loader.submit(load, i)))
+
+    def decode(res, pbatch, pref, prs1, pname):
+        t = time.time()
+        rows = decode_vcf_rows(res, pbatch, pref, prs1, pname, qual=qual, threads=native_threads)
+        tm["decode"] += time.time() - t
+        return rows
+
+    def retire(block):
+        while decoding and (block or decoding[0][2].done()):
+            j, tk, f = decoding.popleft()
+            t = time.time()
+            rows_of[j] = f.result()
+            tm["decode_wait"] += time.time() - t
+            eng.release(tk)
+            block = False
+
+    for _ in range(2 + max(1, loader_threads)):
+        prefetch()
+    pending = None                                   # (shard index, ticket, name, batch, ref, rs1)
+    while loads or pending is not None:
+        nxt = None
+        if loads:
+            i, fut = loads.popleft()
+            prefetch()
+            t = time.time()
+            got = fut.result()
+            tm["load_wait"] += time.time() - t
             if got is None:                          # genotyping chunk without sites
                 rows_of[i] = []
-                continue
-            name, batch, ref, plan = got
-            nxt = (i, eng.submit(batch, ref, plan.ref_start1, plan.start1, plan.end1, plan.site_filter()),
-                   name, batch, ref, plan.ref_start1)
+            else:
+                name, batch, ref, plan = got
+                retire(len(decoding) >= 2)           # keep a ticket free for this submit
+                t = time.time()
+                nxt = (i, eng.submit(batch, ref, plan.ref_start1, plan.start1, plan.end1, plan.site_filter()),
+                       name, batch, ref, plan.ref_start1)
+                tm["submit"] += time.time() - t
+                submit_ms.append(1e3 * (time.time() - t))
         if pending is not None:
             j, ticket, pname, pbatch, pref, prs1 = pending
+            t = time.time()
             res = eng.wait(ticket, copy=False)       # arrays over the library's pinned buffers, no copies
+            tm["wait"] += time.time() - t
             n_cand += res.n_cand
-            rows_of[j] = decode_vcf_rows(res, pbatch, pref, prs1, pname, qual=qual)
-            eng.release(ticket)
+            decoding.append((j, ticket, dec.submit(decode, res, pbatch, pref, prs1, pname)))
+        retire(False)
         pending = nxt
-    eng.close()
+    while decoding:
+        retire(True)
+    loader.shutdown()
+    dec.shutdown()
+    if engine is None:
+        eng.close()
     bf.close()
+    for r in readers:
+        r.close()
     if stats is not None:
-        stats.update(shards=len(mine), candidates=n_cand, seconds=time.time() - t0)
+        stats.update(shards=len(mine), candidates=n_cand, seconds=time.time() - t0, host_seconds=tm, submit_ms=submit_ms,
+                     cost=sum(costs[i] for i in mine), total_shards=len(shards))
+    if not merge:                                    # the caller only wants this rank's loop (timing passes)
+        return None
     if world > 1:
         if gather is None:
             import torch.distributed as dist
@@ -116,7 +191,7 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
                 dist.gather_object(obj, out, dst=0)
                 return out
         parts = gather(rows_of)
-        if rank != 0:
+        if rank != 0 or parts is None:
             return None
         rows_of = {}
         for p in parts:
