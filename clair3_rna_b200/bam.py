@@ -62,7 +62,12 @@ class BamFile:
         out = []
         for i, (n, l) in enumerate(zip(self.references, self.lengths)):
             m, u = C.c_int64(0), C.c_int64(0)
-            self.lib.c3r_bam_idxstats(self.h, i, C.byref(m), C.byref(u))
+            rc = self.lib.c3r_bam_idxstats(self.h, i, C.byref(m), C.byref(u))
+            if rc != 0:
+                # an index without the metadata pseudo-bin carries no counts (samtools idxstats then counts records):
+                # treat the contig as having reads when a fetch over it finds any, instead of silently skipping it
+                probe = self.fetch(n, 1, int(l)) if l > 0 else None
+                m = C.c_int64(probe.n_reads if probe is not None else 0)
             out.append((n, l, int(m.value), int(u.value)))
         return out
 

@@ -9,7 +9,7 @@ call_variants it hands the chunk's flat alignment records to libc3r_b200.so.
 Inputs: --bam_fn is an indexed BAM (read by csrc/bam_io.cpp: BGZF inflate + BAI region fetch,
 the part of `samtools mpileup -r` that touches the file) or a flat-read .npz
 (clair3_rna_b200.reads.ReadBatch.save).  --chkpnt_fn is an .npz of Keras-layout weights
-(clair3_rna_b200.weights); TF checkpoints need TensorFlow to read and are converted offline.
+(clair3_rna_b200.weights) or the prefix of a Keras TF-format checkpoint, read natively by tf_bundle.py.
 """
 from __future__ import annotations
 
@@ -48,7 +48,7 @@ def build_parser():
     ap.add_argument('--chunk_num', type=int, default=None)
     ap.add_argument('--sampleName', type=str, default="SAMPLE")
     ap.add_argument('--snp_min_af', type=float, default=P.SNP_MIN_AF)
-    ap.add_argument('--indel_min_af', type=float, default=P.INDEL_MIN_AF)
+    ap.add_argument('--indel_min_af', type=float, default=0.08)      # call_var_bam.py:378 (0.15 is the WORKFLOW's default, run_clair3_rna)
     ap.add_argument('--min_af', type=float, default=None)
     ap.add_argument('--minCoverage', type=int, default=P.MIN_COVERAGE)
     ap.add_argument('--minMQ', type=int, default=P.MIN_MQ)

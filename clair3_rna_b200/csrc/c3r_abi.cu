@@ -53,7 +53,9 @@ struct Slot {
     Buf pbed, cbed, known, covP;   // site filters of the chunk; printed columns (covA inside the pileup BED)
     Buf cand_row, cand_pos, cand_depth, tensor, alt_off, alt_n, alt, cur_ref, deleted, probs;
     Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32) [4] tail columns (2 x i32) [5] raw row events (i64)
-    Buf scan_scratch;
+    Buf scan_scratch;     // look-back scan state: ticket counters, tile status words, tile aggregates / prefixes
+    ScanState scan = {};
+    uint32_t scan_epoch = 0;
     // pinned results
     Pin h_scalars, h_pos, h_depth, h_probs, h_alt_off, h_alt_n, h_alt, h_tensor, h_row_pos, h_counts, h_row_depth;
     Dev d;
@@ -152,8 +154,8 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
         k_read_prepare<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, st>>>(d);
         ++L;
     }
-    { OpCigar op; op.d = d; if (d.n_ops > 0) L += device_scan(op, d.n_ops, (ScanElem*)s.scan_scratch.p, (ScanElem*)nullptr, st); }
-    { OpWords op; op.d = d; L += device_scan(op, d.NW, (Int2*)s.scan_scratch.p, (Int2*)nullptr, st); }
+    { OpCigar op; op.d = d; if (d.n_ops > 0) L += device_scan(op, d.n_ops, s.scan, s.scan_epoch, (ScanElem*)nullptr, st); }
+    { OpWords op; op.d = d; L += device_scan(op, d.NW, s.scan, s.scan_epoch, (Int2*)nullptr, st); }
     if (d.n_known > 0) { k_mark_known<<<(unsigned)((d.n_known + 255) / 256), 256, 0, st>>>(d); ++L; }
     if (d.n_pbed >= 0) { k_bed_mask<<<(unsigned)((d.NW + 4 + 255) / 256), 256, 0, st>>>(d, (uint32_t*)s.covP.p); ++L; }
     if (d.head_tail) {
@@ -161,12 +163,12 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
         k_last_gap<<<(unsigned)((d.NW + 255) / 256), 256, 0, st>>>(d);
         L += 2;
     }
-    { OpRows op; op.d = d; L += device_scan(op, d.NW, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
+    { OpRows op; op.d = d; L += device_scan(op, d.NW, s.scan, s.scan_epoch, (int32_t*)nullptr, st); }
     k_clear_rows<<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[2], st));
     if (d.n_ops > 0) { k_cmp<<<(unsigned)((d.n_ops + CMP_THREADS - 1) / CMP_THREADS), CMP_THREADS, 0, st>>>(d); ++L; }
-    if (d.padding) { OpSkip op; op.d = d; L += device_scan(op, d.L_ub, (Int2*)s.scan_scratch.p, (Int2*)nullptr, st); }
-    { OpEvents op; op.d = d; L += device_scan(op, d.L_ub + 1, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
+    if (d.padding) { OpSkip op; op.d = d; L += device_scan(op, d.L_ub, s.scan, s.scan_epoch, (Int2*)nullptr, st); }
+    { OpEvents op; op.d = d; L += device_scan(op, d.L_ub + 1, s.scan, s.scan_epoch, (int32_t*)nullptr, st); }
     k_scatter<<<(unsigned)(ctx->sm_count * 32), 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[3], st));
     {
@@ -177,7 +179,7 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
         L += 2;
     }
     CK(cudaEventRecord(s.ev[4], st));
-    { OpCand op; op.d = d; L += device_scan(op, d.L_ub, (int32_t*)s.scan_scratch.p, (int32_t*)nullptr, st); }
+    { OpCand op; op.d = d; L += device_scan(op, d.L_ub, s.scan, s.scan_epoch, (int32_t*)nullptr, st); }
     CK(cudaEventRecord(s.ev[5], st));
     CK(cudaGetLastError());
     return 0;
@@ -190,6 +192,10 @@ int read_scalars(c3r_ctx* ctx, Slot& s) {
     s.n_rows = hs[0];
     s.n_cand = hs[1];
     const int32_t err = ((const int32_t*)s.h_scalars.p)[6];
+    if (err == 7)
+        return fail(ctx, C3R_ERR_CAPACITY, "a position is covered by more than 8000 reads: samtools mpileup (the reference's "
+                                           "column source) caps the depth there and drops reads; this chunk is refused "
+                                           "rather than called on different counts");
     if (err) {
         char b[128];
         snprintf(b, sizeof b, "device capacity check failed (code %d): rows=%lld cand=%lld", err, (long long)s.n_rows, (long long)s.n_cand);
@@ -232,7 +238,7 @@ int run_stage_b(c3r_ctx* ctx, Slot& s) {
             k_padding<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d); ++L;
             k_rescale<<<grid, 128, 0, st>>>(d); ++L;
         }
-        { OpAltOff op; op.d = d; L += device_scan(op, n, (long long*)s.scan_scratch.p, ((long long*)s.scalars.p) + 2, st); }
+        { OpAltOff op; op.d = d; L += device_scan(op, n, s.scan, s.scan_epoch, ((long long*)s.scalars.p) + 2, st); }
         k_altinfo<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(d); ++L;
     }
     CK(cudaEventRecord(s.ev[6], st));
@@ -546,7 +552,20 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     {
         int64_t mx = d.n_ops > d.NW ? d.n_ops : d.NW;
         if (L_ub + 4 > mx) mx = L_ub + 4;
-        EN(scan_scratch, (mx / SCAN_TILE + 2) * sizeof(ScanElem));
+        // scan state: 256 B of counters, then per tile a status word, an aggregate and an inclusive prefix
+        const size_t tiles = (size_t)(mx / SCAN_TILE + 2);
+        const size_t need = 256 + tiles * 4 + 2 * tiles * sizeof(ScanElem) + 64;
+        if (s.scan_scratch.cap < need) {
+            EN(scan_scratch, need);
+            CK(cudaMemsetAsync(s.scan_scratch.p, 0, s.scan_scratch.cap, s.st));     // status words of epoch 0, ticket 0
+        }
+        uint8_t* sp = (uint8_t*)s.scan_scratch.p;
+        const size_t cap_tiles = (s.scan_scratch.cap - 256 - 64) / (4 + 2 * sizeof(ScanElem));
+        s.scan.ctrl = (unsigned int*)sp;
+        s.scan.status = (uint32_t*)(sp + 256);
+        s.scan.aggr = sp + 256 + ((cap_tiles * 4 + 15) / 16) * 16;
+        s.scan.incl = (uint8_t*)s.scan.aggr + cap_tiles * sizeof(ScanElem);
+        s.scan.err = P<int32_t>(s.scalars) + 6;
     }
 #undef EN
     d.pos = P<int32_t>(s.pos); d.flag = P<uint16_t>(s.flag); d.mapq = P<uint8_t>(s.mapq); d.hp = P<uint8_t>(s.hp);
@@ -595,12 +614,12 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
         k_refnib<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>((const uint8_t*)s.ref.p, ref_len, (uint32_t*)s.refnib.p, nw);
         ++s.launches;
     }
-    s.in_use = true;
     // The copies above overlap the network pass of the ticket before this one; the position / row stages do not
     // start under it: their ~25 short kernels would only get SMs at the boundaries of the persistent network
     // kernels, delaying both (measured: 2.62 ms per pass interleaved, against 2.35 ms of device work).
     if (ctx->prm.nn_impl == 1 && getenv("C3R_INTERLEAVE") == nullptr)
         if (cudaEvent_t done = tc_pass_done(ctx->tc)) CK(cudaStreamWaitEvent(st, done, 0));
+    s.in_use = true;                                 // from here on every error path releases the slot (below)
     int rc = run_stage_a(ctx, s);
     if (!rc) rc = read_scalars(ctx, s);
     if (!rc) rc = ensure_stage_b(ctx, s);

@@ -25,6 +25,7 @@
 
 namespace c3r {
 
+constexpr int MPILEUP_MAX_DEPTH = 8000;      // htslib bam_plp maxcnt as samtools mpileup sets it by default
 constexpr int WIN = 33;
 constexpr int FLANK = 16;
 constexpr int TILE_ROWS = 32;
@@ -1087,6 +1088,10 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, 5) k_rows(Dev d) {
             v[ri] = -fsum;
             v[9 + ri] = -rsum;
             d.row_depth[row] = depth;
+            // samtools mpileup keeps at most 8000 reads per position (-d default; the reference never passes
+            // --max-depth, create_tensor_pileup.py:442) and drops the reads beyond - in a read-order dependent way
+            // that is not reproduced here: such a chunk is refused instead of being called differently
+            if (depth > MPILEUP_MAX_DEPTH) atomicExch(d.err, 7);
             d.row_flag[row] = flag;
             d.row_inscnt[row] = ins_cnt;
             d.row_delcnt[row] = del_cnt + star_f + star_r;

@@ -47,7 +47,7 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
         snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF, min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ,
         qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None, bed_fn=None, vcf_fn=None, head_tail=False,
         merge_qual=None, show_ref=True, rediportal_fn=None, rediportal_tags=None, output_no_tagging=None,
-        compress_vcf=False, engine=None, loader_threads=2, native_threads=0, merge=True):
+        compress_vcf=False, engine=None, loader_threads=2, native_threads=0, merge=True, cmdline=None):
     """merge_qual / show_ref / rediportal_*: the options of the merge stage (sharder.sort_vcf = sort_vcf_from of the
     reference); the defaults keep every row as the chunks produced it.  engine: an Engine to reuse (its parameters and
     weights are then the caller's business); loader_threads: BAM / FASTA readers working ahead of the GPU;
@@ -208,15 +208,22 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
         for stale in (path + ".gz", path + ".gz.tbi"):
             if os.path.exists(stale):
                 os.remove(stale)
-        if rows:                                     # like the reference: no file when there is no record
-            header = decoder.vcf_header([(n, fai[n][0]) for n in fai], sample_name, ref_fn)
-            if compress_vcf:                         # bgzip -f + tabix -p vcf (sort_vcf.py:70-76): path.gz, path.gz.tbi
-                from . import vcf_io
-                vcf_io.write_vcf_gz(path + ".gz", header, rows)
-                continue
-            with open(path, "w") as fp:
-                fp.write(header + "\n")
-                fp.write("\n".join(rows) + "\n")
+        if not rows:
+            # sort_vcf_from always opens output_fn for writing: without a record it leaves an EMPTY file (and its
+            # bgzip'ed twin under --compress_vcf) for the steps that follow (sort_vcf.py:123-292)
+            open(path, "w").close()
+            if compress_vcf:                         # `bgzip -f` of an empty file: the 28-byte BGZF end-of-file block
+                with open(path + ".gz", "wb") as fp:
+                    fp.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+            continue
+        header = decoder.vcf_header([(n, fai[n][0]) for n in fai], sample_name, ref_fn, cmdline=cmdline)
+        if compress_vcf:                             # bgzip -f + tabix -p vcf (sort_vcf.py:70-76): path.gz, path.gz.tbi
+            from . import vcf_io
+            vcf_io.write_vcf_gz(path + ".gz", header, rows)
+            continue
+        with open(path, "w") as fp:
+            fp.write(header + "\n")
+            fp.write("\n".join(rows) + "\n")
     return merged
 
 
@@ -268,6 +275,7 @@ def main(argv=None):
         rediportal_fn=a.readiportal_source_fn if a.tag_variant_using_readiportal else None,
         rediportal_tags=a.readiportal_database_filter_tag, output_no_tagging=a.output_no_tagging_fn,
         compress_vcf=a.compress_vcf,
+        cmdline=" ".join(sys.argv) if argv is None else " ".join(["run_chunks"] + list(argv)),
         sample_name=a.sampleName, stats=stats, bed_fn=a.bed_fn, vcf_fn=a.genotyping_mode_vcf_fn,
         head_tail=a.enable_variant_calling_at_sequence_head_and_tail)
     print("[rank %d] %d shards, %d candidates in %.2f s" % (rank, stats["shards"], stats["candidates"], stats["seconds"]),

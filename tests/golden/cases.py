@@ -14,9 +14,9 @@ CASES = {
     # name: config index, scale, SynthConfig overrides, caller options
     "cfg1_ont_drna": dict(_BASE, cfg=1, scale=0.08, over=dict(genes_per_mb=60), platform="ont"),
     "cfg2_ont_cdna": dict(_BASE, cfg=2, scale=0.0015, over=dict(genes_per_mb=50), platform="ont"),
-    "cfg3_hifi_pad": dict(_BASE, cfg=3, scale=0.02, over=dict(genes_per_mb=50, hi_depth_genes=2, hi_depth=400),
+    "cfg3_hifi_pad": dict(_BASE, cfg=3, scale=0.2, over=dict(genes_per_mb=50, hi_depth_genes=3, hi_depth=400),
                           platform="hifi", padding=True),
-    "cfg4_hifi_phased": dict(_BASE, cfg=4, scale=0.02, over=dict(genes_per_mb=50), platform="hifi", phased=True),
+    "cfg4_hifi_phased": dict(_BASE, cfg=4, scale=0.4, over=dict(genes_per_mb=50), platform="hifi", phased=True),
     "ties_lowdepth": dict(_BASE, cfg=1, scale=0.05, over=dict(genes_per_mb=80, depth=5, sub=0.12, ins=0.06, dele=0.12,
                                                               seed=777001), platform="ont"),
     "pad_dense": dict(_BASE, cfg=3, scale=0.012, over=dict(genes_per_mb=100, hi_depth_genes=1, hi_depth=260, depth=25,

@@ -141,3 +141,28 @@ def test_all_n_reference_takes_the_capacity_retry():
     ora = pileup_oracle.run_region(batch, ref_seq, 1, s1, e1, min_coverage=2)
     assert res.pos.tolist() == ora["pos"].tolist() and np.array_equal(res.tensor, ora["tensor"])
     assert all(1001 <= p <= 1400 for p in res.pos.tolist())
+
+
+def test_depth_above_the_mpileup_cap_is_refused():
+    """samtools mpileup reads at most 8000 reads per position (-d default; the reference never passes --max-depth,
+    create_tensor_pileup.py:442) and drops the rest in read order.  That is not reproduced: the chunk is refused
+    (C3R_ERR_CAPACITY with a message that says why) instead of being called on counts the reference never saw."""
+    import numpy as np
+    import pytest as _pytest
+    from clair3_rna_b200 import weights
+    from clair3_rna_b200.engine import Engine, C3RError
+    from clair3_rna_b200.reads import ReadBatch, encode_seq
+    rng = np.random.default_rng(3)
+    ref = rng.choice(np.frombuffer(b"ACGT", np.uint8), 400)
+    seq = ref[100:200].tobytes().decode()
+    def batch(n):
+        return ReadBatch.from_records("c", [(100, 16 * (i & 1), 60, 0, [(100, 0)], encode_seq(seq)) for i in range(n)])
+    eng = Engine(0, 18)
+    eng.set_weights(weights.synthetic(18))
+    ok = eng.call_chunk(batch(8000), ref, 1, 1, 433)            # exactly at the cap: called
+    assert ok.n_rows == 100
+    with _pytest.raises(C3RError, match="8000 reads"):
+        eng.call_chunk(batch(8001), ref, 1, 1, 433)
+    again = eng.call_chunk(batch(50), ref, 1, 1, 433)           # the context keeps working after the refusal
+    assert again.n_rows == 100
+    eng.close()

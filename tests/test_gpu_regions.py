@@ -165,6 +165,7 @@ def test_drivers_call_the_golden_sites(tmp_path, name):
         out = os.path.join(str(tmp_path), "c%d.vcf" % cid)
         argv = ["--bam_fn", f["bam"], "--ref_fn", f["fa"], "--chkpnt_fn", f["w"], "--ctgName", f["contig"],
                 "--chunk_id", str(cid), "--chunk_num", str(n_chunks), "--call_fn", out, "--pileup",
+                "--snp_min_af", "0.08", "--indel_min_af", "0.15",          # what run_clair3_rna passes (its own defaults)
                 "--extend_bed", f["split"]]
         argv += ["--bed_fn", f["bed"]] if "bed" in f else ["--vcf_fn", f["vcf"]]
         assert call_var_bam.main(argv) == 0
