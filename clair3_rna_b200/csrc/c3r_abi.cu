@@ -52,6 +52,8 @@ struct Slot {
     Buf binc, bin_cur, events, raw, cov, cov_tile, refnib;
     Buf pbed, cbed, known, covP;   // site filters of the chunk; printed columns (covA inside the pileup BED)
     Buf cand_row, cand_pos, cand_depth, tensor, alt_off, alt_n, alt, cur_ref, deleted, probs;
+    Buf xop;              // LSTM1 operand images written by k_window_xop (fused K4 -> K5 path)
+    bool fused_window = false;
     Buf scalars;          // [0] n_rows (i64) [1] n_cand (i64) [2] alt_total (i64) [3] err (i32) [4] tail columns (2 x i32) [5] raw row events (i64)
     Buf scan_scratch;     // look-back scan state: ticket counters, tile status words, tile aggregates / prefixes
     ScanState scan = {};
@@ -166,7 +168,12 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     { OpRows op; op.d = d; L += device_scan(op, d.NW, s.scan, s.scan_epoch, (int32_t*)nullptr, st); }
     k_clear_rows<<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[2], st));
-    if (d.n_ops > 0) { k_cmp<<<(unsigned)((d.n_ops + CMP_THREADS - 1) / CMP_THREADS), CMP_THREADS, 0, st>>>(d); ++L; }
+    if (d.n_ops > 0) {
+        const int64_t chunks = (d.n_ops + CMP_THREADS - 1) / CMP_THREADS;
+        const int64_t cap = (int64_t)ctx->sm_count * 6;
+        k_cmp<<<(unsigned)(chunks < cap ? chunks : cap), CMP_THREADS, 0, st>>>(d);
+        ++L;
+    }
     if (d.padding) { OpSkip op; op.d = d; L += device_scan(op, d.L_ub, s.scan, s.scan_epoch, (Int2*)nullptr, st); }
     { OpEvents op; op.d = d; L += device_scan(op, d.L_ub + 1, s.scan, s.scan_epoch, (int32_t*)nullptr, st); }
     k_scatter<<<(unsigned)(ctx->sm_count * 32), 256, 0, st>>>(d); ++L;
@@ -209,7 +216,13 @@ int ensure_stage_b(c3r_ctx* ctx, Slot& s) {
     Dev& d = s.d;
     const int64_t n = s.n_cand > 0 ? s.n_cand : 1;
     const int per = WIN * d.C;
-    if (ensure(ctx, s.tensor, (size_t)n * per * 4)) return C3R_ERR_CUDA;
+    // the window goes straight into the network's operand images unless the tensor itself is wanted (keep_tensor),
+    // the padding pass has to patch it first, or the fp32 network (which reads the int32 tensor) runs
+    s.fused_window = ctx->prm.nn_impl == 1 && !ctx->prm.keep_tensor && !d.padding && getenv("C3R_NO_FUSED_WINDOW") == nullptr;
+    if (s.fused_window) {
+        const size_t tiles = (size_t)((n + 255) / 256) * 2;
+        if (ensure(ctx, s.xop, tiles * WIN * (size_t)((d.C == 18 ? 48 : 64) * 128) * 2)) return C3R_ERR_CUDA;
+    } else if (ensure(ctx, s.tensor, (size_t)n * per * 4)) return C3R_ERR_CUDA;
     if (ensure(ctx, s.alt_off, (size_t)(n + 1) * 8)) return C3R_ERR_CUDA;
     if (ensure(ctx, s.alt_n, (size_t)n * 4)) return C3R_ERR_CUDA;
     d.alt_cap = 4 * n + d.events_ub + 8;
@@ -222,7 +235,8 @@ int ensure_stage_b(c3r_ctx* ctx, Slot& s) {
     return 0;
 }
 
-int nn_forward(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches);
+int nn_forward(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches,
+               const __half* xop_ready = nullptr);
 
 // Stage B: windows, padding, alt_info, network.  Needs n_cand on the host.
 int run_stage_b(c3r_ctx* ctx, Slot& s) {
@@ -232,7 +246,10 @@ int run_stage_b(c3r_ctx* ctx, Slot& s) {
     const int64_t n = s.n_cand;
     if (n > 0) {
         const unsigned grid = (unsigned)(n < ctx->sm_count * 16 ? n : ctx->sm_count * 16);
-        k_window<<<grid, 128, 0, st>>>(d, d.padding ? 0 : 1);
+        if (s.fused_window) {
+            if (d.C == 18) k_window_xop<18, 48><<<grid, 128, 0, st>>>(d, P<__half>(s.xop));
+            else k_window_xop<30, 64><<<grid, 128, 0, st>>>(d, P<__half>(s.xop));
+        } else k_window<<<grid, 128, 0, st>>>(d, d.padding ? 0 : 1);
         ++L;
         if (d.padding) {
             k_padding<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d); ++L;
@@ -245,7 +262,7 @@ int run_stage_b(c3r_ctx* ctx, Slot& s) {
     CK(cudaEventRecord(s.ev_alt, st));
     if (n > 0) {
         int nl = 0;
-        int rc = nn_forward(ctx, d.tensor, n, P<float>(s.probs), st, &nl);
+        int rc = nn_forward(ctx, d.tensor, n, P<float>(s.probs), st, &nl, s.fused_window ? P<__half>(s.xop) : nullptr);
         if (rc) return rc;
         L += nl;
     }
@@ -372,7 +389,7 @@ void c3r_destroy(c3r_ctx* ctx) {
                      &s.word_base, &s.row_pos, &s.counts, &s.row_depth, &s.row_flag, &s.head_cnt, &s.tail_cnt,
                      &s.skipdiff, &s.max_skip, &s.row_ins, &s.row_del, &s.binc, &s.bin_cur, &s.events, &s.raw, &s.cov, &s.cov_tile, &s.refnib,
                      &s.cand_row, &s.cand_pos, &s.cand_depth, &s.tensor, &s.alt_off, &s.alt_n, &s.alt, &s.cur_ref,
-                     &s.deleted, &s.probs, &s.scalars, &s.scan_scratch, &s.pbed, &s.cbed, &s.known, &s.covP};
+                     &s.deleted, &s.probs, &s.scalars, &s.scan_scratch, &s.pbed, &s.cbed, &s.known, &s.covP, &s.xop};
         for (Buf* b : bs) release(*b);
         Pin* ps[] = {&s.h_scalars, &s.h_pos, &s.h_depth, &s.h_probs, &s.h_alt_off, &s.h_alt_n, &s.h_alt, &s.h_tensor,
                      &s.h_row_pos, &s.h_counts, &s.h_row_depth};
@@ -614,10 +631,12 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
         k_refnib<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>((const uint8_t*)s.ref.p, ref_len, (uint32_t*)s.refnib.p, nw);
         ++s.launches;
     }
-    // The copies above overlap the network pass of the ticket before this one; the position / row stages do not
-    // start under it: their ~25 short kernels would only get SMs at the boundaries of the persistent network
-    // kernels, delaying both (measured: 2.62 ms per pass interleaved, against 2.35 ms of device work).
-    if (ctx->prm.nn_impl == 1 && getenv("C3R_INTERLEAVE") == nullptr)
+    // The copies above overlap the network pass of the ticket before this one, and so do the position / row stages:
+    // the network's partly filled rounds and its tail leave SMs idle that these ~20 short kernels take (measured with
+    // the fused LSTM2: 9.66 M sites/s end to end against 8.73 M when they wait for the pass to end).  With the
+    // hoisted LSTM2 (C3R_LSTM2=hoisted) every SM is busy and interleaving delays both (2.62 against 2.35 ms per
+    // pass): there, and with C3R_NO_INTERLEAVE, the stages wait.
+    if (ctx->prm.nn_impl == 1 && (!lstm2_fused() || getenv("C3R_NO_INTERLEAVE") != nullptr))
         if (cudaEvent_t done = tc_pass_done(ctx->tc)) CK(cudaStreamWaitEvent(st, done, 0));
     s.in_use = true;                                 // from here on every error path releases the slot (below)
     int rc = run_stage_a(ctx, s);
@@ -840,24 +859,27 @@ int build_net(c3r_ctx* ctx, const std::map<std::string, std::pair<const float*, 
     return C3R_OK;
 }
 
-static int nn_forward_impl(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches);
+static int nn_forward_impl(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches,
+                           const __half* xop_ready);
 
 // Tickets run on their own streams but share the network's scratch buffers: passes are ordered by events.
-int nn_forward(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches) {
+int nn_forward(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches,
+               const __half* xop_ready) {
     if (ctx->prm.nn_impl == 1)                       // the tensor-core pass orders itself buffer by buffer (TcPipe)
-        return nn_forward_impl(ctx, tensor_dev, n, probs_dev, st, launches);
+        return nn_forward_impl(ctx, tensor_dev, n, probs_dev, st, launches, xop_ready);
     if (!ctx->nn_done) CK(cudaEventCreateWithFlags(&ctx->nn_done, cudaEventDisableTiming));
     else CK(cudaStreamWaitEvent(st, ctx->nn_done, 0));
-    const int rc = nn_forward_impl(ctx, tensor_dev, n, probs_dev, st, launches);
+    const int rc = nn_forward_impl(ctx, tensor_dev, n, probs_dev, st, launches, nullptr);
     CK(cudaEventRecord(ctx->nn_done, st));
     return rc;
 }
 
-static int nn_forward_impl(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches) {
+static int nn_forward_impl(c3r_ctx* ctx, const int32_t* tensor_dev, int64_t n, float* probs_dev, cudaStream_t st, int* launches,
+                           const __half* xop_ready) {
     *launches = 0;
     if (ctx->prm.nn_impl == 1) {
         std::string terr;
-        int nl = tc_forward(ctx->tc, ctx->net, tensor_dev, n, probs_dev, st, &terr);
+        int nl = tc_forward(ctx->tc, ctx->net, tensor_dev, n, probs_dev, st, &terr, xop_ready);
         if (nl < 0) return fail(ctx, C3R_ERR_CUDA, "tensor-core forward failed: " + terr);
         *launches = nl;
         ctx->tc_dirty = true;

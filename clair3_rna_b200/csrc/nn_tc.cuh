@@ -1411,8 +1411,9 @@ inline cudaError_t tc_l4_heads(TcNet& t, const NetF32& net, const TcSub& b, floa
     return cudaGetLastError();
 }
 
+// `xop_ready`: LSTM1's operand images of all n sites, already built by k_window_xop (then `tensor` is not read)
 inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_t n, float* probs, cudaStream_t st,
-                      std::string* err) {
+                      std::string* err, const __half* xop_ready = nullptr) {
     if (!t.ready) { *err = "weights not packed"; return -1; }
     if (!t.pipe) t.pipe = new TcPipe();
     if (tc_pipe_init(*t.pipe, err)) return -1;
@@ -1429,9 +1430,14 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         tiles += tiles & 1;                  // CTA pairs
         if (tc_ensure(t, tiles, err)) return -1;
         TCK(cudaStreamWaitEvent(st, P.h1_free, 0), "wait");         // the previous pass no longer reads xop / h1
-        if (t.C == 18) k_xop<18, 48><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
-        else k_xop<30, 64><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
-        ++launches;
+        const int kx_ = t.C == 18 ? 48 : 64;
+        const __half* xop_in = t.xop;
+        if (xop_ready) xop_in = xop_ready + (size_t)(o / TC_TILE) * NT * (size_t)(kx_ * TC_TILE);
+        else {
+            if (t.C == 18) k_xop<18, 48><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
+            else k_xop<30, 64><<<tiles * NT, TC_TILE, 0, st>>>(tensor + o * NT * t.C, t.xop, m);
+            ++launches;
+        }
         // A = the tile pairs that fill whole rounds of the recurrent kernels, B = the rest
         // tile pairs one round of the LSTM2 kernel takes (fused: clusters of 2*NP CTAs, half of them per direction)
         const int pairs = tiles / 2;
@@ -1444,7 +1450,7 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         auto lstm1 = [&](const TcSub& b, cudaStream_t s) -> cudaError_t {
             LstmArgs a1;
             const int kx = t.C == 18 ? 48 : 64;
-            a1.Wimg = t.img1; a1.xop = t.xop + (size_t)b.t0 * NT * kx * TC_TILE; a1.C = t.C; a1.zx = nullptr;
+            a1.Wimg = t.img1; a1.xop = xop_in + (size_t)b.t0 * NT * kx * TC_TILE; a1.C = t.C; a1.zx = nullptr;
             a1.hout = t.h1 + (size_t)b.t0 * NT * 4 * TC_IMG;
             a1.hout_lo = (zx_terms() & 2) ? t.h1_lo + (size_t)b.t0 * NT * 4 * TC_IMG : nullptr; a1.kb_out = 4;
             a1.n_sites = b.ns; a1.n_tiles = b.nt; a1.err = t.err; a1.trace = b.t0 == 0 ? t.trace : nullptr;

@@ -21,6 +21,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include "scan.cuh"
 
 namespace c3r {
@@ -382,15 +383,41 @@ __device__ __forceinline__ void cmp_one(const Dev& d, EventStage& st, const CmpO
     if (x) cmp_emit(d, st, c, w, rw, x);
 }
 
+// staged events -> raw list (one global atomic per flush), per-row counters
+__device__ __forceinline__ void cmp_flush(const Dev& d, EventStage& st) {
+    __syncthreads();
+    const int n = st.n < CMP_STAGE ? st.n : CMP_STAGE;
+    if (threadIdx.x == 0 && n > 0) st.base = (int)atomicAdd((unsigned long long*)d.n_raw, (unsigned long long)n);
+    __syncthreads();
+    if (n > 0) {
+        const long long base = st.base;
+        if (base + n > d.events_ub) { if (threadIdx.x == 0) atomicExch(d.err, 3); }
+        else {
+            for (int i = threadIdx.x; i < n; i += CMP_THREADS) {
+                const RowEvent e = st.buf[i];
+                d.raw[base + i] = e;
+                atomicAdd(&d.binc[e.row], 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st.n = 0;
+    __syncthreads();
+}
+
+// Persistent blocks: a block walks chunks of CMP_THREADS ops and appends its staged events to the raw list when
+// the stage is half full - a few hundred atomics on the list's end counter per pass instead of one per 256 ops
+// (same-address atomics are served one per ~27 cycles: 4 135 of them were most of this kernel's 63 us).
 __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
     __shared__ EventStage st;
     __shared__ CmpOp wops[CMP_THREADS / 32][32];         // the warp's ops, so that any lane can take any word
     __shared__ int32_t wpre[CMP_THREADS / 32][32];       // exclusive prefix of their word counts
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int NC = d.C == 30 ? 6 : 4;
     if (threadIdx.x == 0) st.n = 0;
     __syncthreads();
+    for (int64_t k0 = (int64_t)blockIdx.x * blockDim.x; k0 < d.n_ops; k0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = k0 + threadIdx.x;
     CmpOp cmp;
     cmp.w0 = 0; cmp.w1 = -1; cmp.kw = 0; cmp.sh = 0; cmp.rbase = 0; cmp.info = 0; cmp.m0 = 0; cmp.m1 = 0;
     do {
@@ -510,20 +537,12 @@ __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
             cmp_one(d, st, c, c.w0 + (g - wpre[warp][i]));
         }
     }
-    // ---- staged events -> raw list (one global atomic per block), per-row counters
     __syncthreads();
-    const int n = st.n < CMP_STAGE ? st.n : CMP_STAGE;
-    if (threadIdx.x == 0 && n > 0) st.base = (int)atomicAdd((unsigned long long*)d.n_raw, (unsigned long long)n);
+    const bool fl = st.n >= CMP_STAGE / 2;               // block-uniform: read between two barriers
     __syncthreads();
-    if (n > 0) {
-        const long long base = st.base;
-        if (base + n > d.events_ub) { if (threadIdx.x == 0) atomicExch(d.err, 3); return; }
-        for (int i = threadIdx.x; i < n; i += CMP_THREADS) {
-            const RowEvent e = st.buf[i];
-            d.raw[base + i] = e;
-            atomicAdd(&d.binc[e.row], 1);
-        }
+    if (fl) cmp_flush(d, st);
     }
+    cmp_flush(d, st);
 }
 
 // exclusive scan of the per-row event counters in place
@@ -1189,6 +1208,56 @@ __global__ void k_window(Dev d, int apply_scale) {
             int32_t v = (j >= j0 && j < j1) ? src[j] : 0;
             if (sc) v = rescale(v, depth, d.max_depth);
             dst[j] = v;
+        }
+    }
+}
+// K4 fused with the network's input stage: the window goes straight into LSTM1's fp16 operand images
+//   xop[tile][33][KX/8][128 rows][8 halfs]   (k < C: x, C <= k < 2C: x again - it meets W_lo -, k = 2C, 2C+1: 1 - they
+//   meet the bias rows -, rest 0; nn_tc.cuh)
+// instead of int32 tensor[n][33][C] that k_xop would read back: no 2.4 KB per site round trip through HBM.  Used
+// when nobody asks for the tensor itself (keep_tensor) and no padding pass has to patch it.  Block = one site of
+// the last tile's 128 (sites beyond n are zero rows), thread = one 16-byte cell (t, k8).
+template <int C, int KX>
+__global__ void __launch_bounds__(128) k_window_xop(Dev d, __half* __restrict__ xop) {
+    const int64_t n = *d.n_cand < d.cand_cap ? *d.n_cand : d.cand_cap;
+    const int64_t n_pad = ((n + 255) / 256) * 256;             // tiles come in pairs
+    constexpr int CELLS = WIN * (KX / 8);
+    for (int64_t i = blockIdx.x; i < n_pad; i += gridDim.x) {
+        const int64_t tile = i >> 7;
+        const int r = (int)(i & 127);
+        __half* base = xop + (size_t)tile * WIN * (size_t)(KX * 128) + r * 8;
+        const bool live = i < n;
+        int32_t depth = 0;
+        const int32_t* src = d.counts;
+        int j0 = 0, j1 = WIN;                                  // window rows that are columns of the candidate's run
+        if (live) {
+            depth = d.cand_depth[i];
+            src = d.counts + ((int64_t)d.cand_row[i] - FLANK) * C;
+            if (d.head_tail) {
+                int nb, na;
+                printed_run(d, (int64_t)d.cand_pos[i] - 1 - d.R0, &nb, &na);
+                j0 = FLANK - nb; j1 = FLANK + na + 1;
+            }
+        }
+        const bool sc = live && depth > 0 && (double)depth > (double)d.max_depth * 1.5;
+        for (int cell = threadIdx.x; cell < CELLS; cell += blockDim.x) {
+            const int t = cell / (KX / 8), k8 = cell % (KX / 8);
+            __align__(16) __half hv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k8 * 8 + j;
+                float v = 0.0f;
+                if (k < 2 * C) {
+                    const int c = k < C ? k : k - C;
+                    if (live && t >= j0 && t < j1) {
+                        int32_t x = src[t * C + c];
+                        if (sc) x = rescale(x, depth, d.max_depth);
+                        v = (float)x;
+                    }
+                } else if (k < 2 * C + 2) v = 1.0f;
+                hv[j] = __float2half(v);
+            }
+            *(uint4*)(base + (size_t)t * (KX * 128) + (size_t)k8 * (128 * 8)) = *(const uint4*)hv;
         }
     }
 }

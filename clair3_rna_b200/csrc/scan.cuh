@@ -1,4 +1,4 @@
-// Device-wide inclusive scan in ONE pass: decoupled look-back over tiles handed out by an atomic ticket.
+// Device-wide inclusive scan in ONE pass: co-resident blocks walk the tiles round robin, tile prefixes by direct summation.
 //
 // The pileup path needs a handful of small scans (CIGAR ops, bitmap words, rows,
 // bins, candidates); each is expressed as an `Op` functor so the load (e.g. decode
@@ -16,13 +16,21 @@
 //
 // One kernel per scan, every element loaded once (the three-pass form this replaces launched three kernels and
 // called load() twice per element):
-//   * a block takes its tile from an atomic ticket, so the tiles before it are held by blocks that are running or
-//     done - look-back never waits for a block that is not resident, whatever the grid and the device-side size;
-//   * the tile's aggregate, then its inclusive prefix, are published as (value, status word) with a release store;
-//     the status carries the scan's epoch, so the descriptors are never cleared between scans of a slot;
-//   * one warp looks back 32 tiles at a time; the block scan is two levels of warp shuffles (2 __syncthreads);
-//   * the last block to leave resets the ticket; the spins are bounded (a protocol bug sets the error flag instead
-//     of hanging the GPU).
+//   * the grid is no larger than what the device holds at once (occupancy query) and block b takes tiles b,
+//     b + grid, ... in increasing order, so the tiles before any tile are held by blocks that are resident or done
+//     (should another stream's kernel delay part of the grid, the waiting blocks spin - bounded - until it arrives).
+//     An atomic ticket per tile, the usual way to get that guarantee, costs more than the scan itself here: ~27
+//     cycles per atomic on ONE address, serialised, is 16 us for a grid of 1184 blocks;
+//   * the tile's aggregate is published as (value, status word) with a release store; the status carries the
+//     scan's epoch, so the descriptors are never cleared between scans of a slot;
+//   * a tile's exclusive prefix is the ordered sum of the aggregates of the tiles before it, taken by the whole
+//     block at once (thread i polls and adds a contiguous run of predecessors, then an ordered block reduction) -
+//     no chain of look-back hops: these scans are a few hundred to a few thousand tiles that all start together,
+//     where a look-back walks back window after window while the inclusive prefixes trickle forward (measured:
+//     27-61 us per scan, as slow as the three kernels it replaced).  Every SCAN_CP-th tile also publishes its
+//     exclusive prefix as a checkpoint, so a tile sums at most SCAN_CP aggregates;
+//   * the block scan is two levels of warp shuffles (2 __syncthreads);
+//   * the spins are bounded (a protocol bug sets the error flag instead of hanging the GPU).
 // The host only knows an upper bound of most sizes (row and candidate counts live on the device): the grid is sized
 // from the bound, blocks whose ticket lies beyond size() leave at once.
 #pragma once
@@ -36,13 +44,14 @@ constexpr int SCAN_IPT = 8;       // items per thread
 constexpr int SCAN_TILE = SCAN_BT * SCAN_IPT;
 constexpr int SCAN_MAX_GRID = 148 * 8;
 constexpr uint32_t SCAN_SPINS = 1u << 22;
+constexpr int SCAN_CP = 1024;     // tiles between checkpoints (exclusive prefixes published for the tiles after them)
 
-// per-slot scan state: ticket / exit counters and the tile descriptors (sized for the largest scan of the slot)
+// per-slot scan state: the tile descriptors (sized for the largest scan of the slot)
 struct ScanState {
-    unsigned int* ctrl;           // [0] ticket, [1] blocks that have left
-    uint32_t* status;             // [tiles]: epoch << 2 | {1: aggregate published, 2: inclusive prefix published}
+    unsigned int* ctrl;           // (unused: kept for layout stability of the scratch buffer)
+    uint32_t* status;             // [tiles]: epoch << 2 | {1: aggregate published, 3: and (checkpoint tiles) its prefix}
     void* aggr;                   // [tiles] T
-    void* incl;                   // [tiles] T
+    void* incl;                   // [tiles / SCAN_CP + 1] T: exclusive prefix of checkpoint tile k * SCAN_CP
     int* err;                     // set to 900 when a look-back spin runs out
 };
 
@@ -87,24 +96,28 @@ __device__ __forceinline__ typename Op::T warp_scan_inclusive(const Op& op, type
     return v;
 }
 
+// wait until tile t of this scan has published (state bits & want) == want; returns false when the spin ran out
+__device__ __forceinline__ bool scan_wait(const ScanState& st, int64_t t, uint32_t epoch, uint32_t want) {
+    for (uint32_t spins = 0; spins < SCAN_SPINS; ++spins) {
+        const uint32_t s = ld_acquire_u32(&st.status[t]);
+        if ((s >> 2) == epoch && (s & want) == want) return true;
+    }
+    if (st.err) atomicExch(st.err, 900);
+    return false;
+}
+
 template <class Op>
 __global__ void __launch_bounds__(SCAN_BT) scan_lookback_kernel(Op op, ScanState st, uint32_t epoch, typename Op::T* total_out) {
     typedef typename Op::T T;
     __shared__ T warp_tot[SCAN_BT / 32];
     __shared__ T tile_prefix;
-    __shared__ unsigned int tile_s;
     const int64_t n = op.size();
     const int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* aggr = (T*)st.aggr;
-    T* incl = (T*)st.incl;
-    const uint32_t s_aggr = (epoch << 2) | 1u, s_incl = (epoch << 2) | 2u;
-    for (;;) {
-        __syncthreads();                                     // tile_s / tile_prefix of the previous round are consumed
-        if (threadIdx.x == 0) tile_s = atomicAdd(&st.ctrl[0], 1u);
-        __syncthreads();
-        const int64_t tile = tile_s;
-        if (tile >= n_tiles) break;
+    T* cpx = (T*)st.incl;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();                                     // tile_prefix / warp_tot of the previous round are consumed
         const int64_t i0 = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_IPT;
         T own[SCAN_IPT];
         T acc = op.identity();
@@ -126,64 +139,44 @@ __global__ void __launch_bounds__(SCAN_BT) scan_lookback_kernel(Op op, ScanState
         T texcl = shfl_up_pod(winc, 1);                      // exclusive within the warp
         if (lane == 0) texcl = op.identity();
         const T excl_in_tile = op.combine(wbase, texcl);
-        if (warp == SCAN_BT / 32 - 1) {
-            // the last warp owns the tile aggregate (its lane 31's inclusive value) and does the look-back
-            const T tile_aggr = shfl_idx_pod(op.combine(wbase, winc), 31);
-            if (tile == 0) {
-                if (lane == 0) {
-                    incl[0] = tile_aggr;
-                    __threadfence();
-                    st_release_u32(&st.status[0], s_incl);
-                    tile_prefix = op.identity();
-                }
-            } else {
-                if (lane == 0) {
-                    aggr[tile] = tile_aggr;
-                    __threadfence();
-                    st_release_u32(&st.status[tile], s_aggr);
-                }
-                // windows of 32 predecessors, nearest first: lane l looks at tile - 1 - l (- 32 per window)
-                T prefix = op.identity();                    // combined aggregates of the tiles looked at so far
-                int64_t base = tile - 1;
-                bool done = false;
-                uint32_t spins = 0;
-                while (!done) {
-                    const int64_t t = base - lane;
-                    uint32_t s = 0;
-                    if (t >= 0) {
-                        s = ld_acquire_u32(&st.status[t]);
-                        while ((s >> 2) != epoch || (s & 3u) == 0u) {          // not yet published in this scan
-                            if (++spins > SCAN_SPINS) { if (st.err) atomicExch(st.err, 900); s = s_incl; break; }
-                            s = ld_acquire_u32(&st.status[t]);
-                        }
-                    }
-                    const bool has_incl = t >= 0 && (s & 3u) == 2u;
-                    const uint32_t incl_mask = __ballot_sync(0xffffffffu, has_incl || t < 0);
-                    // lanes up to (and including) the first one holding an inclusive prefix (or beyond tile 0) contribute
-                    const int stop = __ffs(incl_mask) - 1;                      // -1: none in this window
-                    const int last = stop < 0 ? 31 : stop;
-                    T v = op.identity();
-                    if (t >= 0 && lane <= last) v = has_incl ? incl[t] : aggr[t];
-                    // combine in tile order: the farthest tile first
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const T u = shfl_idx_pod(v, (lane + d) & 31);
-                        if (lane + d < 32) v = op.combine(u, v);
-                    }
-                    // lane 0 now holds tiles [base - last .. base] combined (lanes beyond `last` held the identity)
-                    const T wsum = shfl_idx_pod(v, 0);
-                    prefix = op.combine(wsum, prefix);
-                    if (stop >= 0) done = true;
-                    base -= 32;
-                }
-                if (lane == 0) {
-                    incl[tile] = op.combine(prefix, tile_aggr);
-                    __threadfence();
-                    st_release_u32(&st.status[tile], s_incl);
-                    tile_prefix = prefix;
-                }
+        T tile_aggr = op.identity();
+        if (threadIdx.x == SCAN_BT - 1) {                    // the last thread's inclusive value is the tile aggregate
+            tile_aggr = op.combine(wbase, winc);
+            aggr[tile] = tile_aggr;
+            __threadfence();
+            st_release_u32(&st.status[tile], (epoch << 2) | 1u);
+        }
+        // ---- exclusive prefix of the tile: checkpoint prefix + the aggregates of the tiles since, in order
+        const int64_t cp = tile == 0 ? 0 : ((tile - 1) / SCAN_CP) * SCAN_CP;     // nearest checkpoint tile below `tile`
+        const int64_t cnt = tile - cp;                       // predecessors to add: tiles cp .. tile-1
+        const int64_t per = (cnt + SCAN_BT - 1) / SCAN_BT;
+        T part = op.identity();
+        {
+            const int64_t a = cp + (int64_t)threadIdx.x * per, b = a + per < tile ? a + per : tile;
+            for (int64_t t = a; t < b; ++t) {
+                if (!scan_wait(st, t, epoch, 1u)) break;
+                part = op.combine(part, aggr[t]);
             }
-            if (lane == 0 && tile == n_tiles - 1 && total_out) *total_out = op.combine(tile_prefix, tile_aggr);
+        }
+        __syncthreads();                                     // warp_tot is free again
+        const T pinc = warp_scan_inclusive(op, part);
+        if (lane == 31) warp_tot[warp] = pinc;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BT - 1) {
+            T prefix = op.identity();
+            if (cp > 0) {                                    // the checkpoint tile's own exclusive prefix
+                scan_wait(st, cp, epoch, 3u);
+                prefix = cpx[cp / SCAN_CP];
+            }
+#pragma unroll
+            for (int w = 0; w < SCAN_BT / 32; ++w) prefix = op.combine(prefix, warp_tot[w]);
+            tile_prefix = prefix;
+            if (tile > 0 && tile % SCAN_CP == 0) {           // this tile is a checkpoint for the tiles after it
+                cpx[tile / SCAN_CP] = prefix;
+                __threadfence();
+                st_release_u32(&st.status[tile], (epoch << 2) | 3u);
+            }
+            if (tile == n_tiles - 1 && total_out) *total_out = op.combine(prefix, tile_aggr);
         }
         __syncthreads();
         T run = op.combine(tile_prefix, excl_in_tile);
@@ -196,15 +189,6 @@ __global__ void __launch_bounds__(SCAN_BT) scan_lookback_kernel(Op op, ScanState
         }
     }
     if (n_tiles == 0 && total_out && blockIdx.x == 0 && threadIdx.x == 0) *total_out = op.identity();
-    // the last block to leave hands the ticket back
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&st.ctrl[1], 1u) == gridDim.x - 1) {
-            st.ctrl[0] = 0u;
-            st.ctrl[1] = 0u;
-            __threadfence();
-        }
-    }
 }
 
 // Host helper.  `n_upper` bounds op.size(); the state's descriptors must hold ceil(n_upper/SCAN_TILE) entries of T.
@@ -215,7 +199,17 @@ inline int device_scan(const Op& op, int64_t n_upper, const ScanState& st, uint3
                        cudaStream_t stream) {
     if (n_upper <= 0) n_upper = 1;
     int64_t nb64 = (n_upper + SCAN_TILE - 1) / SCAN_TILE;
-    const unsigned nb = (unsigned)(nb64 < SCAN_MAX_GRID ? nb64 : SCAN_MAX_GRID);
+    // co-resident grid: blocks per SM of this instantiation x SMs (queried once)
+    static int resident = 0;
+    if (!resident) {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_lookback_kernel<Op>, SCAN_BT, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        resident = per_sm * (sms > 0 ? sms : 1);
+        if (resident > SCAN_MAX_GRID) resident = SCAN_MAX_GRID;
+    }
+    const unsigned nb = (unsigned)(nb64 < resident ? nb64 : resident);
     epoch = (epoch + 1u) & 0x3fffffffu;
     if (epoch == 0u) epoch = 1u;                         // 0 is the state of a cleared descriptor
     scan_lookback_kernel<Op><<<nb, SCAN_BT, 0, stream>>>(op, st, epoch, total_out);
