@@ -42,16 +42,14 @@ def peaks():
 
 
 def measured_traffic(workload_name):
-    """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/), when it is of this workload"""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
-        return None, None
-    z = json.load(open(p))
-    if z.get("workload") != workload_name:
-        return None, None
-    d = z["dram_bytes_per_launch"]
-    k5 = sum(v for k, v in d.items() if k.startswith("k_lstm_tc") or k.startswith("k_xop") or k in ("k_gemm_zx", "k_heads", "k_gemm_tc"))
-    return k5, d.get("count_path")
+    """DRAM bytes per pass and stage from the newest committed `ncu --set full` capture (profiles/rN*_traffic.json,
+    written by tools/make_profile_md.py), when it is of this workload: ({stage: bytes}, file name) or ({}, None)"""
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        z = json.load(open(p))
+        if z.get("workload") == workload_name and "dram_bytes_per_stage" in z:
+            return z["dram_bytes_per_stage"], os.path.relpath(p, ROOT)
+    return {}, None
 
 
 def dataset(cfg_idx, scale, contig_slot, cache_dir="/tmp/c3r_bench_cache"):
@@ -513,12 +511,23 @@ def main():
         pk = peaks()
         st = stage_acc / args.steps                              # ms per step per stage
         k5_ms, k2_ms = float(st[6]), float(st[2]) + float(st[3])    # K2 = compare/event pass + row pass
-        tr_k5, tr_k2 = measured_traffic(cfg.name) if args.scale == 1.0 else (None, None)
+        tr, tr_src = measured_traffic(cfg.name) if args.scale == 1.0 else ({}, None)
         flops = FLOP_PER_SITE[C] * n_cand
         ach_tf = flops / (k5_ms * 1e-3) / 1e12 if k5_ms > 0 else 0.0
-        # count path algorithmic bytes: 0.5 B/aligned base + 16 B/op + 4*C+8 B/row
-        k2_bytes = 0.5 * batch.n_aligned_bases() + 16.0 * batch.n_ops + (4 * C + 8) * n_rows
-        ach_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+        # algorithmic bytes per unit (DESIGN.md section 4 / SURVEY.md 8d)
+        NW = (clen + P.NO_OF_POSITIONS + 31) // 32
+        KX = 48 if C == 18 else 64
+        alg = {
+            "k1": 16.0 * batch.n_ops + 16.0 * batch.n_reads + 20.0 * NW + 4.0 * n_rows,      # op geometry, bitmaps, row ranks
+            "k2": 0.5 * batch.n_aligned_bases() + 16.0 * batch.n_ops + (4 * C + 8) * n_rows,  # bases, ops, count rows
+            "k3": 9.0 * n_rows + 12.0 * n_cand,                                              # flag + bitmap per row, list entry
+            "k4": (33 * 4 * C + 33 * KX * 2) * float(n_cand),                                # window read, operand image written
+        }
+
+        def hbm_roofline(kernel, key, ms):
+            gbs = alg[key] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                    "traffic": tr.get(key), "algorithmic_bytes": alg[key], "ms": ms, "peak_source": pk["src"], "traffic_source": tr_src}
         line = {
             "metric": "candidate sites/sec (tensor+inference)", "value": value, "unit": "sites/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -531,18 +540,19 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "stage_ms": {"memset": float(st[0]), "k1_scan_rows": float(st[1]), "k2_compare_events": float(st[2]), "k2_rows": float(st[3]),
-                         "k3_filter": float(st[4]), "k4_window_alt(+host sync)": float(st[5]), "k5_network": k5_ms},
-            "roofline": {"kernel": "K5 network (k_xop, k_lstm_tc<4>, k_gemm_zx, k_lstm_tc<5>, k_gemm_tc, k_heads)", "bound": "tensor",
+                         "k3_filter": float(st[4]), "k4_window_alt": float(st[5]), "k5_network": k5_ms},
+            "roofline": {"kernel": "K5 network (k_lstm_tc<4>, k_lstm2_fused, k_gemm_tc L4 + L5, k_l4_finish, k_heads_out)", "bound": "tensor",
                          "achieved": ach_tf, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sus"],
-                         "traffic": tr_k5, "traffic_source": "profiles/r1_traffic.json (ncu dram bytes, sum over the K5 kernels)" if tr_k5 else None,
+                         "traffic": tr.get("k5"), "traffic_source": tr_src,
                          "peak_source": pk["src"] + " bf16 sustained",
-                         "hbm_gbs_of_traffic": (tr_k5 / (k5_ms * 1e-3) / 1e9) if (tr_k5 and k5_ms > 0) else None,
-                         "note": "useful flops (47.786 MFLOP/site) over the CUDA-event time of the six network kernels; the "
-                                 "two largest (k_gemm_zx, k_lstm_tc<5>) are limited by moving the hoisted LSTM2 projection "
-                                 "through HBM, see profiles/r1_summary.md"},
-            "roofline_count": {"kernel": "K2 count path (k_cmp, event scan, k_scatter, k_cov_aggr, k_rows)", "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                               "frac": ach_gbs / pk["hbm"], "traffic": tr_k2, "algorithmic_bytes": k2_bytes,
-                               "peak_source": pk["src"]},
+                         "hbm_gbs_of_traffic": (tr["k5"] / (k5_ms * 1e-3) / 1e9) if (tr.get("k5") and k5_ms > 0) else None,
+                         "note": "useful flops (47.786 MFLOP/site) over the CUDA-event time of the network kernels of a pass; "
+                                 "traffic = h1 and h2 (hi + lo) written once and read once, nothing else of size leaves the SMs "
+                                 "(profiles/, newest rN summary)"},
+            "roofline_count": hbm_roofline("K2 count path (k_cmp, event scan, k_scatter, k_rows)", "k2", k2_ms),
+            "roofline_k1": hbm_roofline("K1 CIGAR scan, coverage bitmaps, row ranks", "k1", float(st[1])),
+            "roofline_k3": hbm_roofline("K3 candidate list (OpCand scan)", "k3", float(st[4])),
+            "roofline_k4": hbm_roofline("K4 window assembly into LSTM1's operand images + alt table", "k4", float(st[5])),
         }
         if not args.no_cpu_baseline:
             n, dt, prod, cons = run_cpu(cfg, batch, ref, w, C, 1, 12)
