@@ -44,9 +44,9 @@ struct Slot {
     // inputs
     Buf pos, flag, mapq, hp, cigar_off, cigar, seq_off, seq, ref;
     // per read/op
-    Buf admit, read_end, op_head, op_x, op_y, op_rid, blockmax;
+    Buf admit, read_end, op_head, op_x, op_y, op_info, blockmax;
     // position space
-    Buf covA, covE, rowR, wdiff, word_base;
+    Buf covA, covE, rowR, cov_up, ptile, ctile, word_base;
     // row space
     Buf row_pos, counts, row_depth, row_flag, head_cnt, tail_cnt, skipdiff, max_skip, row_ins, row_del;
     Buf binc, bin_cur, events, raw, cov, cov_tile, refnib;
@@ -58,6 +58,7 @@ struct Slot {
     Buf scan_scratch;     // look-back scan state: ticket counters, tile status words, tile aggregates / prefixes
     ScanState scan = {};
     uint32_t scan_epoch = 0;
+    size_t cov_up_bytes = 0;
     // pinned results
     Pin h_scalars, h_pos, h_depth, h_probs, h_alt_off, h_alt_n, h_alt, h_tensor, h_row_pos, h_counts, h_row_depth;
     Dev d;
@@ -148,7 +149,7 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     CK(cudaMemsetAsync(s.op_head.p, 0xff, (size_t)(d.n_ops + 1) * 4, st));
     CK(cudaMemsetAsync(s.covA.p, 0, (size_t)(d.NW + 4) * 4, st));
     CK(cudaMemsetAsync(s.covE.p, 0, (size_t)(d.NW + 4) * 4, st));
-    CK(cudaMemsetAsync(s.wdiff.p, 0, (size_t)(d.NW + 4) * 8, st));
+    CK(cudaMemsetAsync(s.cov_up.p, 0, s.cov_up_bytes, st));
     CK(cudaMemsetAsync(s.scalars.p, 0, 64, st));
     CK(cudaMemsetAsync(s.blockmax.p, 0, (size_t)(d.n_reads / 256 + 2) * 4, st));
     CK(cudaEventRecord(s.ev[1], st));
@@ -157,16 +158,16 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
         ++L;
     }
     { OpCigar op; op.d = d; if (d.n_ops > 0) L += device_scan(op, d.n_ops, s.scan, s.scan_epoch, (ScanElem*)nullptr, st); }
-    { OpWords op; op.d = d; L += device_scan(op, d.NW, s.scan, s.scan_epoch, (Int2*)nullptr, st); }
     if (d.n_known > 0) { k_mark_known<<<(unsigned)((d.n_known + 255) / 256), 256, 0, st>>>(d); ++L; }
+    const unsigned ptiles = (unsigned)((d.NW + PT_WORDS - 1) / PT_WORDS);
+    k_row_bits<<<ptiles, 256, 0, st>>>(d); ++L;
     if (d.n_pbed >= 0) { k_bed_mask<<<(unsigned)((d.NW + 4 + 255) / 256), 256, 0, st>>>(d, (uint32_t*)s.covP.p); ++L; }
     if (d.head_tail) {
         k_last_col<<<(unsigned)((d.NW + 255) / 256), 256, 0, st>>>(d);
         k_last_gap<<<(unsigned)((d.NW + 255) / 256), 256, 0, st>>>(d);
         L += 2;
     }
-    { OpRows op; op.d = d; L += device_scan(op, d.NW, s.scan, s.scan_epoch, (int32_t*)nullptr, st); }
-    k_clear_rows<<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(d); ++L;
+    k_row_rank<<<ptiles, 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[2], st));
     if (d.n_ops > 0) {
         const int64_t chunks = (d.n_ops + CMP_THREADS - 1) / CMP_THREADS;
@@ -176,17 +177,19 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     }
     if (d.padding) { OpSkip op; op.d = d; L += device_scan(op, d.L_ub, s.scan, s.scan_epoch, (Int2*)nullptr, st); }
     { OpEvents op; op.d = d; L += device_scan(op, d.L_ub + 1, s.scan, s.scan_epoch, (int32_t*)nullptr, st); }
-    k_scatter<<<(unsigned)(ctx->sm_count * 32), 256, 0, st>>>(d); ++L;
+    if (d.C == 18) k_scatter_aggr<4><<<(unsigned)(ctx->sm_count * 8 + 1), 1024, 0, st>>>(d);
+    else k_scatter_aggr<6><<<(unsigned)(ctx->sm_count * 8 + 1), 1024, 0, st>>>(d);
+    ++L;
     CK(cudaEventRecord(s.ev[3], st));
+    int64_t nb = (d.L_ub + COV_TILE - 1) / COV_TILE;
     {
-        int64_t nb = (d.L_ub + COV_TILE - 1) / COV_TILE;
         const unsigned grid = (unsigned)(nb < ctx->sm_count * 16 ? nb : ctx->sm_count * 16);
-        if (d.C == 18) { k_cov_aggr<4><<<1, 1024, 0, st>>>(d); k_rows<18><<<grid, ROWS_WARPS * 32, 0, st>>>(d); }
-        else { k_cov_aggr<6><<<1, 1024, 0, st>>>(d); k_rows<30><<<grid, ROWS_WARPS * 32, 0, st>>>(d); }
-        L += 2;
+        if (d.C == 18) k_rows<18><<<grid, ROWS_WARPS * 32, 0, st>>>(d);
+        else k_rows<30><<<grid, ROWS_WARPS * 32, 0, st>>>(d);
+        ++L;
     }
     CK(cudaEventRecord(s.ev[4], st));
-    { OpCand op; op.d = d; L += device_scan(op, d.L_ub, s.scan, s.scan_epoch, (int32_t*)nullptr, st); }
+    k_cand_emit<<<(unsigned)(nb < ctx->sm_count * 16 ? nb : ctx->sm_count * 16), 256, 0, st>>>(d); ++L;
     CK(cudaEventRecord(s.ev[5], st));
     CK(cudaGetLastError());
     return 0;
@@ -247,8 +250,10 @@ int run_stage_b(c3r_ctx* ctx, Slot& s) {
     if (n > 0) {
         const unsigned grid = (unsigned)(n < ctx->sm_count * 16 ? n : ctx->sm_count * 16);
         if (s.fused_window) {
-            if (d.C == 18) k_window_xop<18, 48><<<grid, 128, 0, st>>>(d, P<__half>(s.xop));
-            else k_window_xop<30, 64><<<grid, 128, 0, st>>>(d, P<__half>(s.xop));
+            const int64_t wb = ((n + 255) / 256) * 2 * WIN;                // (tile, window row) blocks
+            const unsigned gx = (unsigned)(wb < (int64_t)ctx->sm_count * 32 ? wb : (int64_t)ctx->sm_count * 32);
+            if (d.C == 18) k_window_xop<18, 48><<<gx, 128, 0, st>>>(d, P<__half>(s.xop));
+            else k_window_xop<30, 64><<<gx, 128, 0, st>>>(d, P<__half>(s.xop));
         } else k_window<<<grid, 128, 0, st>>>(d, d.padding ? 0 : 1);
         ++L;
         if (d.padding) {
@@ -385,7 +390,7 @@ void c3r_destroy(c3r_ctx* ctx) {
     for (int i = 0; i < N_SLOTS; ++i) {
         Slot& s = ctx->slots[i];
         Buf* bs[] = {&s.pos, &s.flag, &s.mapq, &s.hp, &s.cigar_off, &s.cigar, &s.seq_off, &s.seq, &s.ref, &s.admit,
-                     &s.read_end, &s.op_head, &s.op_x, &s.op_y, &s.op_rid, &s.blockmax, &s.covA, &s.covE, &s.rowR, &s.wdiff,
+                     &s.read_end, &s.op_head, &s.op_x, &s.op_y, &s.op_info, &s.blockmax, &s.covA, &s.covE, &s.rowR, &s.cov_up, &s.ptile, &s.ctile,
                      &s.word_base, &s.row_pos, &s.counts, &s.row_depth, &s.row_flag, &s.head_cnt, &s.tail_cnt,
                      &s.skipdiff, &s.max_skip, &s.row_ins, &s.row_del, &s.binc, &s.bin_cur, &s.events, &s.raw, &s.cov, &s.cov_tile, &s.refnib,
                      &s.cand_row, &s.cand_pos, &s.cand_depth, &s.tensor, &s.alt_off, &s.alt_n, &s.alt, &s.cur_ref,
@@ -547,9 +552,16 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
 #define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
     EN(pos, R * 4); EN(flag, R * 2); EN(mapq, R); EN(hp, R); EN(cigar_off, (R + 1) * 4); EN(cigar, O * 4);
     EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 64); if (ref) { EN(ref, ref_len + 16); }
-    EN(admit, R); EN(read_end, R * 4); EN(blockmax, (R / 256 + 2) * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_rid, O * 4);
-    EN(covA, (d.NW + 4) * 4); EN(covE, (d.NW + 4) * 4); EN(rowR, (d.NW + 4) * 4); EN(wdiff, (d.NW + 4) * 8);
-    EN(word_base, (d.NW + 4) * 4);
+    EN(admit, R); EN(read_end, R * 4); EN(blockmax, (R / 256 + 2) * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_info, O * 4);
+    // position space: buffers padded to whole tiles of PT_WORDS words (k_row_bits / k_row_rank store 16 bytes per thread);
+    // the summary levels of covA and covE (mark_range) share one buffer: level l has NW / 32^l + 2 words
+    const int64_t NWp = ((d.NW + PT_WORDS - 1) / PT_WORDS) * PT_WORDS + 8;
+    EN(covA, NWp * 4); EN(covE, NWp * 4); EN(rowR, NWp * 4); EN(word_base, NWp * 4);
+    EN(ptile, (NWp / PT_WORDS + 4) * 4); EN(ctile, (L_ub / COV_TILE + 4) * 4);
+    int64_t up_words[COV_UP], up_total = 0;
+    { int64_t n = d.NW; for (int l = 0; l < COV_UP; ++l) { n = (n >> 5) + 2; up_words[l] = n; up_total += n; } }
+    EN(cov_up, 2 * up_total * 4);
+    s.cov_up_bytes = (size_t)(2 * up_total * 4);
     EN(row_pos, (L_ub + 2) * 4); EN(counts, ((L_ub + 32) * d.C) * 4); EN(row_depth, (L_ub + 2) * 4); EN(row_flag, L_ub + 2);
     EN(head_cnt, (L_ub + 2) * 4); EN(tail_cnt, (L_ub + 2) * 4); EN(skipdiff, (L_ub + 2) * 8); EN(max_skip, (L_ub + 2) * 4);
     EN(row_ins, (L_ub + 2) * 4); EN(row_del, (L_ub + 2) * 4);
@@ -589,9 +601,15 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.cigar_off = P<int32_t>(s.cigar_off); d.cigar = P<uint32_t>(s.cigar); d.seq_off = P<int64_t>(s.seq_off);
     d.seq = P<uint8_t>(s.seq); d.ref = ref ? P<uint8_t>(s.ref) : P<uint8_t>(ctx->ref_res);
     d.admit = P<uint8_t>(s.admit); d.read_end = P<int32_t>(s.read_end); d.op_head = P<int32_t>(s.op_head);
-    d.op_x = P<int32_t>(s.op_x); d.op_y = P<uint32_t>(s.op_y); d.op_rid = P<int32_t>(s.op_rid);
-    d.covA = P<uint32_t>(s.covA); d.covE = P<uint32_t>(s.covE); d.rowR = P<uint32_t>(s.rowR); d.wdiff = P<Int2>(s.wdiff);
+    d.op_x = P<int32_t>(s.op_x); d.op_y = P<uint32_t>(s.op_y); d.op_info = P<uint32_t>(s.op_info);
+    d.covA = P<uint32_t>(s.covA); d.covE = P<uint32_t>(s.covE); d.rowR = P<uint32_t>(s.rowR);
     d.word_base = P<int32_t>(s.word_base);
+    {
+        uint32_t* u = P<uint32_t>(s.cov_up);
+        for (int l = 0; l < COV_UP; ++l) { d.upA[l] = u; u += up_words[l]; }
+        for (int l = 0; l < COV_UP; ++l) { d.upE[l] = u; u += up_words[l]; }
+    }
+    d.ptile = P<int32_t>(s.ptile); d.ctile = P<int32_t>(s.ctile); d.kctr = P<int32_t>(s.scalars) + 12;
     d.n_rows = P<int64_t>(s.scalars); d.n_cand = P<int64_t>(s.scalars) + 1; d.err = P<int32_t>(s.scalars) + 6;
     d.row_pos = P<int32_t>(s.row_pos); d.counts = P<int32_t>(s.counts); d.row_depth = P<int32_t>(s.row_depth);
     d.row_flag = P<uint8_t>(s.row_flag); d.head_cnt = P<int32_t>(s.head_cnt); d.tail_cnt = P<int32_t>(s.tail_cnt);

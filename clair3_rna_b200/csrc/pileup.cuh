@@ -30,6 +30,10 @@ constexpr int MPILEUP_MAX_DEPTH = 8000;      // htslib bam_plp maxcnt as samtool
 constexpr int WIN = 33;
 constexpr int FLANK = 16;
 constexpr int TILE_ROWS = 32;
+constexpr int COV_UP = 5;                    // summary levels above a coverage bitmap: 32^6 positions > int32
+constexpr int PT_WORDS = 1024;               // bitmap words per position tile (k_row_bits / k_row_rank: 256 threads x 4 words)
+constexpr uint32_t OP_SKIP = 0xffffffffu;
+constexpr int COV_TILE = 256;                // rows per k_rows block / coverage aggregate
 
 struct RowEvent {              // something other than "a base equal to the reference" at a row
     uint32_t info;             // rid << 4 | hp << 2 | is_del << 1 | reverse
@@ -77,9 +81,13 @@ struct Dev {
     int32_t* tail;              // [0] offset of the last printed column + 1, [1] offset of the last gap below it + 1
     // ---- per read / per op
     uint8_t* admit; int32_t* read_end; int32_t* op_head;
-    int32_t* op_x; uint32_t* op_y; int32_t* op_rid;
+    int32_t* op_x; uint32_t* op_y;
+    uint32_t* op_info;          // rid << 4 | hp << 2 | last op of its read << 1 | reverse;  OP_SKIP: read not admitted
     // ---- position space
-    uint32_t* covA; uint32_t* covE; uint32_t* rowR; Int2* wdiff; int32_t* word_base;
+    uint32_t* covA; uint32_t* covE; uint32_t* rowR; int32_t* word_base;
+    uint32_t* upA[COV_UP]; uint32_t* upE[COV_UP];   // "whole word set" summaries of covA / covE, level l+1 over level l (mark_range)
+    int32_t* ptile;             // [NW / PT_WORDS + 2]: rows per tile of PT_WORDS bitmap words, then their exclusive prefix
+    int32_t* kctr;              // [4] block tickets of the kernels whose last block finishes a job (zeroed with the scalars)
     // ---- row space
     int64_t L_ub;
     int64_t* n_rows;            // device scalar L
@@ -94,6 +102,7 @@ struct Dev {
     int32_t* cov_tile;             // [L_ub/256+2][4 or 6]: sums of cov over tiles of 256 rows, then their exclusive prefix
     const uint32_t* refnib; int64_t n_ref_words;     // one-hot reference nibbles of the loaded window (k_refnib)
     int32_t* blockmax;             // [n_reads/256+1]: largest end of the admitted reads of each block of 256 reads
+    int32_t* ctile;                // [L_ub/256+2]: candidates per tile of 256 rows (k_rows), then their exclusive prefix
     // ---- candidates
     int64_t* n_cand; int32_t* cand_row; int64_t cand_cap;
     int32_t* cand_pos; int32_t* cand_depth;
@@ -134,21 +143,41 @@ __device__ __forceinline__ int ref_index(const Dev& d, int32_t p, bool* is_acgt)
     return idx < 0 ? 0 : idx;
 }
 
-// set bits [a, b) (region offsets, already clipped) in bitmap bm; interior whole words go
-// through the word-level difference array (one +1/-1 pair instead of a store per word)
-__device__ __forceinline__ void mark_range(uint32_t* bm, int32_t* wdiff_field, int stride, int64_t a, int64_t b) {
+// set bits [a, b) (region offsets, already clipped) of bitmap bm.  The two end words take an atomicOr each; the whole
+// words between them are not written: they become a bit range of the next level ("this whole word is set"), marked
+// the same way - at most two atomics per level, whatever the length (a read spanning introns of 100 kb is 3 000
+// words).  k_row_bits folds the levels back into level 0.
+__device__ __forceinline__ void mark_range(uint32_t* bm, uint32_t* const* up, int64_t a, int64_t b) {
     if (b <= a) return;
-    const int64_t wa = a >> 5, wb = (b - 1) >> 5;
-    const uint32_t ma = 0xffffffffu << (a & 31);
-    const uint32_t mb = 0xffffffffu >> (31 - ((b - 1) & 31));
-    if (wa == wb) { atomicOr(&bm[wa], ma & mb); return; }
-    atomicOr(&bm[wa], ma);
-    atomicOr(&bm[wb], mb);
-    if (wb > wa + 1) {
-        atomicAdd(&wdiff_field[(wa + 1) * stride], 1);
-        atomicAdd(&wdiff_field[wb * stride], -1);
+    int64_t lo = a, hi = b;
+#pragma unroll 1
+    for (int l = 0;; ++l) {
+        const int64_t wa = lo >> 5, wb = (hi - 1) >> 5;
+        const uint32_t ma = 0xffffffffu << (lo & 31);
+        const uint32_t mb = 0xffffffffu >> (31 - ((hi - 1) & 31));
+        if (wa == wb) { atomicOr(&bm[wa], ma & mb); return; }
+        atomicOr(&bm[wa], ma);
+        atomicOr(&bm[wb], mb);
+        if (wb <= wa + 1) return;
+        if (l == COV_UP) {                               // beyond the top level (not reachable with int32 positions)
+            for (int64_t w = wa + 1; w < wb; ++w) atomicOr(&bm[w], 0xffffffffu);
+            return;
+        }
+        lo = wa + 1; hi = wb; bm = up[l];
     }
 }
+// is level-0 word w inside a range marked at a higher level?  (4 consecutive words, w4 % 4 == 0: bit j = word w4 + j)
+__device__ __forceinline__ uint32_t up_full4(uint32_t* const* up, int64_t w4) {
+    uint32_t m = (up[0][w4 >> 5] >> (w4 & 31)) & 0xfu;
+    int64_t idx = w4 >> 5;
+#pragma unroll
+    for (int l = 1; l < COV_UP; ++l) {
+        if ((up[l][idx >> 5] >> (idx & 31)) & 1u) m = 0xfu;
+        idx >>= 5;
+    }
+    return m;
+}
+__device__ __forceinline__ bool up_full(uint32_t* const* up, int64_t w) { return (up_full4(up, w & ~3ll) >> (w & 3)) & 1u; }
 
 // ---------------------------------------------------------------- K0: reads
 // admit flag per read (samtools mpileup filters) and segment heads
@@ -171,7 +200,11 @@ __global__ void k_read_prepare(Dev d) {
 // op's own lengths gives its start offsets.  The store marks coverage bitmaps.
 struct OpCigar {
     typedef ScanElem T;
+    // per-read values of the read a thread's consecutive ops belong to (a thread stores 8 ops in a row and a read has
+    // dozens: the dependent loads pos[r], seq_off[r], ... are paid once per read change, not once per op)
+    struct Ctx { int32_t r, pos, kend; uint32_t seq_off, info; bool admit; };
     Dev d;
+    __device__ void ctx_init(Ctx& c) const { c.r = -1; c.pos = 0; c.kend = 0; c.seq_off = 0; c.info = 0; c.admit = false; }
     __device__ T identity() const { T t; t.v = 0; t.rid = -1; t.flag = 0; return t; }
     __device__ T combine(const T& a, const T& b) const {
         if (b.flag) return b;
@@ -187,45 +220,42 @@ struct OpCigar {
         t.rid = h; t.flag = h >= 0 ? 1 : 0;
         return t;
     }
-    __device__ void store(int64_t k, const T& incl, const T& own) const {
+    __device__ void store(int64_t k, const T& incl, const T& own, Ctx& c) const {
         const int32_t r = incl.rid;
+        if (r != c.r) {
+            c.r = r;
+            c.pos = d.pos[r];
+            c.seq_off = (uint32_t)d.seq_off[r];
+            c.kend = d.cigar_off[r + 1];
+            c.admit = d.admit[r] != 0;
+            uint32_t hp = d.hp[r];
+            hp = hp == 1 ? 1u : hp == 2 ? 2u : 0u;
+            c.info = ((uint32_t)r << 4) | (hp << 2) | ((d.flag[r] >> 4) & 1u);
+        }
         const uint32_t rl = (uint32_t)(own.v >> 32), ql = (uint32_t)own.v;
         const uint32_t rx = (uint32_t)(incl.v >> 32) - rl, qy = (uint32_t)incl.v - ql;
-        const int32_t x = d.pos[r] + (int32_t)rx;
+        const int32_t x = c.pos + (int32_t)rx;
+        const bool last = k + 1 == c.kend;
         d.op_x[k] = x;
-        d.op_y[k] = (uint32_t)d.seq_off[r] + qy;
-        d.op_rid[k] = r;
-        if (!d.admit[r]) return;
+        d.op_y[k] = c.seq_off + qy;
+        d.op_info[k] = c.admit ? (c.info | (last ? 2u : 0u)) : OP_SKIP;
+        if (!c.admit) return;
         const uint32_t op = d.cigar[k] & 15u;
         if (rl && (op_is_match(op) || op == 2)) {
             int64_t a = (int64_t)x - d.R0, b = a + rl;
             if (a < 0) a = 0;
             if (b > d.W) b = d.W;
-            mark_range(d.covE, &d.wdiff[0].b, 2, a, b);
+            mark_range(d.covE, d.upE, a, b);
         }
-        if (k + 1 == d.cigar_off[r + 1]) {          // last op: the read's whole span
-            const int32_t end = d.pos[r] + (int32_t)(incl.v >> 32);
+        if (last) {                                      // last op: the read's whole span
+            const int32_t end = c.pos + (int32_t)(incl.v >> 32);
             d.read_end[r] = end;
             atomicMax(&d.blockmax[r >> 8], end);
-            int64_t a = (int64_t)d.pos[r] - d.R0, b = (int64_t)end - d.R0;
+            int64_t a = (int64_t)c.pos - d.R0, b = (int64_t)end - d.R0;
             if (a < 0) a = 0;
             if (b > d.W) b = d.W;
-            mark_range(d.covA, &d.wdiff[0].a, 2, a, b);
+            mark_range(d.covA, d.upA, a, b);
         }
-    }
-};
-
-// ------------------------------------- S2: whole-word coverage from the diff
-struct OpWords {
-    typedef Int2 T;
-    Dev d;
-    __device__ T identity() const { T t; t.a = 0; t.b = 0; return t; }
-    __device__ T combine(const T& x, const T& y) const { T t; t.a = x.a + y.a; t.b = x.b + y.b; return t; }
-    __device__ int64_t size() const { return d.NW; }
-    __device__ T load(int64_t w) const { return d.wdiff[w]; }
-    __device__ void store(int64_t w, const T& incl, const T&) const {
-        if (incl.a > 0) d.covA[w] = 0xffffffffu;
-        if (incl.b > 0) d.covE[w] = 0xffffffffu;
     }
 };
 
@@ -239,12 +269,10 @@ __global__ void k_mark_known(Dev d) {
 }
 
 // -------------------------------------------- S3: rows = dilate16(E) & A, rank
-__device__ __forceinline__ uint32_t row_word(const Dev& d, int64_t w) {
-    uint32_t a = d.covA[w];
-    if (a == 0u) return 0u;                          // most of a contig: no read, no row (and no covE loads)
-    const uint32_t e0 = w > 0 ? d.covE[w - 1] : 0u, e1 = d.covE[w], e2 = (w + 1 < d.NW) ? d.covE[w + 1] : 0u;
+// rowR word from covA word `a` and the covE words below / at / above it
+__device__ __forceinline__ uint32_t row_word(const Dev& d, int64_t w, uint32_t a, uint32_t e0, uint32_t e1, uint32_t e2) {
+    if (a == 0u) return 0u;                          // most of a contig: no read, no row
     // 96-bit smear by 16 to the left and to the right; only the middle word is needed
-    // left smear (towards higher positions): bit i set if any of bits i-16..i set
     unsigned long long lo = ((unsigned long long)e1 << 32) | e0;      // positions of (w-1, w)
     unsigned long long hi = ((unsigned long long)e2 << 32) | e1;      // positions of (w, w+1)
     unsigned long long up = lo;                                       // smear towards higher bits
@@ -252,46 +280,166 @@ __device__ __forceinline__ uint32_t row_word(const Dev& d, int64_t w) {
     unsigned long long dn = hi;                                       // smear towards lower bits
     dn |= dn >> 1; dn |= dn >> 2; dn |= dn >> 4; dn |= dn >> 8; dn |= dn >> 1;
     const uint32_t dil = (uint32_t)(up >> 32) | (uint32_t)dn;
-    // clear bits beyond the region end
-    const int64_t last = d.W - (w << 5);
+    const int64_t last = d.W - (w << 5);             // clear bits beyond the region end
     if (last < 32) a &= last <= 0 ? 0u : (0xffffffffu >> (32 - last));
     return dil & a;
 }
-struct OpRows {
-    typedef int32_t T;
-    Dev d;
-    __device__ T identity() const { return 0; }
-    __device__ T combine(const T& x, const T& y) const { return x + y; }
-    __device__ int64_t size() const { return d.NW; }
-    __device__ T load(int64_t w) const { return __popc(row_word(d, w)); }
-    __device__ void store(int64_t w, const T& incl, const T& own) const {
-        const uint32_t bits = own ? row_word(d, w) : 0u;
-        const int32_t base = incl - own;
-        d.rowR[w] = bits;
-        d.word_base[w] = base;
-        // row_pos of the word's rows: the lanes that are here together write one word's rows at a time
-        // (the k-th lane takes the k-th set bit), instead of every lane walking its own bits
-        const uint32_t act = __activemask();
-        const int lane = threadIdx.x & 31;
-        const int n_act = __popc(act), my = __popc(act & ((1u << lane) - 1u));
-        uint32_t pend = __ballot_sync(act, bits != 0u);
-        while (pend) {
-            const int src = __ffs(pend) - 1;
-            pend &= pend - 1;
-            const uint32_t b = __shfl_sync(act, bits, src);
-            const int32_t bs = __shfl_sync(act, base, src);
-            const int32_t p0 = d.R0 + (int32_t)(__shfl_sync(act, (int32_t)w, src) << 5);
-            const int c = __popc(b);
-            const bool full = b == 0xffffffffu;          // the usual case inside an exon: bit j is position j
-            for (int j = my; j < c; j += n_act)
-                if (bs + j < d.L_ub) d.row_pos[bs + j] = p0 + (full ? j : (int32_t)__fns(b, 0, j + 1));
+
+// exclusive prefix of a[0 .. n) in place by ONE block of 256 threads (8 values per thread and round); the values were
+// written by other blocks of the same kernel (read through L2).  Returns the total to thread 255 only.
+__device__ int32_t block_scan_inplace_256(int32_t* a, int n, int32_t* wsum8, int32_t* carry_s) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) *carry_s = 0;
+    int32_t total = 0;
+    for (int b0 = 0; b0 < n; b0 += 2048) {
+        const int i0 = b0 + 8 * t;
+        int32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = i0 + k < n ? __ldcg(a + i0 + k) : 0;
+        int32_t own = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) own += v[k];
+        int32_t x = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        __syncthreads();                             // wsum8 / carry_s of the previous round are consumed
+        if (lane == 31) wsum8[warp] = x;
+        __syncthreads();
+        int32_t run = *carry_s + x - own;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) if (w < warp) run += wsum8[w];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { if (i0 + k < n) a[i0 + k] = run; run += v[k]; }
+        total = run;
+        __syncthreads();
+        if (t == 255) *carry_s = run;
+    }
+    __syncthreads();
+    return total;
+}
+
+// Position space in two elementwise kernels over tiles of PT_WORDS bitmap words (thread = 4 consecutive words, 16-byte
+// accesses) instead of two device-wide scans over all words - 98 % of the words of a contig carry no row:
+//   k_row_bits  folds the summary levels into covA / covE (covA is written back: the printed-column tests read it),
+//               builds rowR and counts the rows of the tile; the last block to finish turns the tile counts into
+//               their exclusive prefix (a few thousand values) and publishes the row count
+//   k_row_rank  word_base, row_pos, and zeroes the row-space accumulators of the tile's rows (what k_clear_rows did)
+__global__ void __launch_bounds__(256) k_row_bits(Dev d) {
+    __shared__ uint32_t sE[PT_WORDS + 2];            // folded covE of the tile, one halo word on each side
+    __shared__ int32_t wsum[8];
+    __shared__ int32_t carry_s;
+    __shared__ bool is_last;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t w0 = (int64_t)blockIdx.x * PT_WORDS;
+    const int64_t w4 = w0 + 4 * t;
+    uint32_t a[4] = {0u, 0u, 0u, 0u}, e[4] = {0u, 0u, 0u, 0u};
+    if (w4 < d.NW) {                                 // the bitmaps hold NW + 4 zeroed words
+        const uint4 A = *(const uint4*)(d.covA + w4), E = *(const uint4*)(d.covE + w4);
+        const uint32_t mA = up_full4(d.upA, w4), mE = up_full4(d.upE, w4);
+        a[0] = A.x; a[1] = A.y; a[2] = A.z; a[3] = A.w;
+        e[0] = E.x; e[1] = E.y; e[2] = E.z; e[3] = E.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (w4 + j >= d.NW) { a[j] = 0u; e[j] = 0u; continue; }
+            if ((mA >> j) & 1u) a[j] = 0xffffffffu;
+            if ((mE >> j) & 1u) e[j] = 0xffffffffu;
         }
-        if (w == d.NW - 1) {
-            *d.n_rows = incl;
-            if (incl > d.L_ub) atomicExch(d.err, 1);
+        if (mA) *(uint4*)(d.covA + w4) = make_uint4(a[0], a[1], a[2], a[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sE[1 + 4 * t + j] = e[j];
+    if (t == 0) sE[0] = w0 > 0 ? (up_full(d.upE, w0 - 1) ? 0xffffffffu : d.covE[w0 - 1]) : 0u;
+    if (t == 32) {
+        const int64_t w = w0 + PT_WORDS;
+        sE[PT_WORDS + 1] = w < d.NW ? (up_full(d.upE, w) ? 0xffffffffu : d.covE[w]) : 0u;
+    }
+    __syncthreads();
+    uint32_t rr[4];
+    int32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        rr[j] = row_word(d, w4 + j, a[j], sE[4 * t + j], sE[4 * t + j + 1], sE[4 * t + j + 2]);
+        cnt += __popc(rr[j]);
+    }
+    *(uint4*)(d.rowR + w4) = make_uint4(rr[0], rr[1], rr[2], rr[3]);      // buffers are padded to whole tiles
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) wsum[warp] = cnt;
+    __syncthreads();
+    if (t == 0) {
+        int32_t tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += wsum[i];
+        d.ptile[blockIdx.x] = tot;
+        __threadfence();
+        is_last = atomicAdd(&d.kctr[0], 1) == (int)gridDim.x - 1;
+        carry_s = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    // ---- the last block: exclusive prefix of the tile counts in place
+    __threadfence();
+    const int n = (int)gridDim.x;
+    const int32_t total = block_scan_inplace_256(d.ptile, n, wsum, &carry_s);
+    if (t == 255) {
+        d.ptile[n] = total;
+        *d.n_rows = total;
+        if (total > d.L_ub) atomicExch(d.err, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_row_rank(Dev d) {
+    __shared__ int32_t wsum[8];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int NC = d.C == 30 ? 6 : 4;
+    const int64_t w4 = (int64_t)blockIdx.x * PT_WORDS + 4 * t;
+    const int32_t tile_base = d.ptile[blockIdx.x], tile_end = d.ptile[blockIdx.x + 1];
+    const uint4 R = *(const uint4*)(d.rowR + w4);
+    const uint32_t r[4] = {R.x, R.y, R.z, R.w};
+    const int32_t c0 = __popc(r[0]), c1 = __popc(r[1]), c2 = __popc(r[2]), c3 = __popc(r[3]);
+    int32_t x = c0 + c1 + c2 + c3;
+    const int32_t own = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    int32_t b = tile_base + x - own;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < warp) b += wsum[i];
+    *(int4*)(d.word_base + w4) = make_int4(b, b + c0, b + c0 + c1, b + c0 + c1 + c2);
+    if (own) {
+        int32_t idx = b;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int32_t p0 = d.R0 + (int32_t)((w4 + j) << 5);
+            if (r[j] == 0xffffffffu) {                   // the usual case inside an exon
+                for (int q = 0; q < 32; ++q) if (idx + q < d.L_ub) d.row_pos[idx + q] = p0 + q;
+                idx += 32;
+            } else {
+                for (uint32_t m = r[j]; m; m &= m - 1) { if (idx < d.L_ub) d.row_pos[idx] = p0 + __ffs(m) - 1; ++idx; }
+            }
         }
     }
-};
+    // ---- zero the row-space accumulators of the tile's rows; the last tile also takes the two slack rows
+    int64_t z0 = tile_base, z1 = tile_end;
+    if (blockIdx.x == gridDim.x - 1) z1 += 2;
+    if (z1 > d.L_ub + 2) z1 = d.L_ub + 2;
+    for (int64_t i = z0 + t; i < z1; i += 256) {
+        d.binc[i] = 0;
+        d.bin_cur[i] = 0;
+        for (int c = 0; c < NC; ++c) d.cov[i * NC + c] = 0;
+        if (d.padding) {
+            d.head_cnt[i] = 0; d.tail_cnt[i] = 0;
+            Int2 z; z.a = 0; z.b = 0;
+            d.skipdiff[i] = z;
+            d.deleted[i] = 0;
+        }
+    }
+    if (z1 > z0) {                                       // coverage tiles these rows fall into (neighbours overlap: all zero)
+        const int64_t ct0 = z0 / COV_TILE, ct1 = (z1 - 1) / COV_TILE + 1;
+        for (int64_t i = ct0 * NC + t; i < (ct1 + 1) * NC; i += 256) d.cov_tile[i] = 0;
+    }
+}
 
 __device__ __forceinline__ uint32_t nibmask(int n) {         // low n nibbles set, n clamped to 0..8
     uint32_t m;                                              // shl.b32 clamps the shift amount: 1 << 32 == 0
@@ -331,7 +479,6 @@ __global__ void k_refnib(const uint8_t* __restrict__ ref, int64_t ref_len, uint3
 constexpr int NCOV_MAX = 6;                  // Mf Mr Df Dr [M_hp1 M_hp2]
 constexpr int CMP_THREADS = 256;
 constexpr int CMP_STAGE = 1536;              // events staged per block (24 KB)
-constexpr int COV_TILE = 256;                // rows per k_rows block / coverage aggregate
 
 struct __align__(16) CmpOp {                 // an M/=/X op clipped to the region (32 bytes: two 16-byte shared loads)
     int32_t w0, w1;                          // sequence words [w0, w1] holding its bases
@@ -414,6 +561,7 @@ __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
     __shared__ int32_t wpre[CMP_THREADS / 32][32];       // exclusive prefix of their word counts
     const int lane = threadIdx.x & 31;
     const int NC = d.C == 30 ? 6 : 4;
+    if (*d.err == 1) return;                             // more rows than the buffers hold: the host retries with exact bounds
     if (threadIdx.x == 0) st.n = 0;
     __syncthreads();
     for (int64_t k0 = (int64_t)blockIdx.x * blockDim.x; k0 < d.n_ops; k0 += (int64_t)gridDim.x * blockDim.x) {
@@ -422,16 +570,16 @@ __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
     cmp.w0 = 0; cmp.w1 = -1; cmp.kw = 0; cmp.sh = 0; cmp.rbase = 0; cmp.info = 0; cmp.m0 = 0; cmp.m1 = 0;
     do {
         if (k >= d.n_ops) break;
-        const int32_t r = d.op_rid[k];
-        if (r < 0 || !d.admit[r]) break;
+        const uint32_t oi = d.op_info[k];                // OpCigar's store: read ordinal, haplotype, strand, last-op flag
+        if (oi == OP_SKIP) break;                        // read not admitted
+        const int32_t r = (int32_t)(oi >> 4);
         const uint32_t c = d.cigar[k];
         const uint32_t op = c & 15u;
         const int32_t len = (int32_t)(c >> 4);
         if (!op_consumes_ref(op) || len == 0) break;
         const int32_t x = d.op_x[k];
-        const uint32_t rev = (d.flag[r] >> 4) & 1u;
-        uint32_t hp = d.hp[r];
-        hp = hp == 1 ? 1u : hp == 2 ? 2u : 0u;
+        const uint32_t rev = oi & 1u;
+        const uint32_t hp = (oi >> 2) & 3u;
         const int32_t a = x < d.R0 ? d.R0 : x;
         const int32_t b = x + len > d.R1 ? d.R1 : x + len;
 
@@ -470,7 +618,7 @@ __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
                 cmp.kw = (int32_t)(K >> 3);
                 cmp.sh = ((uint32_t)K & 7u) * 4u;
                 cmp.rbase = (int32_t)((int64_t)ra - qa);
-                cmp.info = ((uint32_t)r << 4) | (hp << 2) | rev;
+                cmp.info = oi & ~2u;
             }
         }
         // head / tail marks (only consumed by the padding rule)
@@ -488,22 +636,28 @@ __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
         // indel tokens attach to the last column of an M/=/X/D op (htslib resolve_cigar2)
         const int32_t last = x + len - 1;
         if (last < d.R0 || last >= d.R1) break;
-        const int32_t kend = d.cigar_off[r + 1];
+        if (oi & 2u) break;                              // last op of its read: nothing follows
         int64_t j = k + 1;
-        if (j >= kend) break;
+        bool more = true;                                // op j belongs to this read
         int32_t ins_len = 0, del_len = 0;
         const uint32_t op2 = d.cigar[j] & 15u;
+        if (op2 != 1 && !(op2 == 2 && op != 2)) break;
         if (op2 == 1) {
-            for (; j < kend; ++j) {
-                const uint32_t o = d.cigar[j] & 15u;
-                if (o == 1) ins_len += (int32_t)(d.cigar[j] >> 4);
+            while (more) {
+                const uint32_t cj = d.cigar[j], o = cj & 15u;
+                if (o == 1) ins_len += (int32_t)(cj >> 4);
                 else if (o != 6) break;
+                more = !(d.op_info[j] & 2u);
+                ++j;
             }
         }
-        if (j < kend && (d.cigar[j] & 15u) == 2 && op != 2) {
-            for (; j < kend; ++j) {
-                if ((d.cigar[j] & 15u) == 2) del_len += (int32_t)(d.cigar[j] >> 4);
-                else break;
+        if (more && (d.cigar[j] & 15u) == 2 && op != 2) {
+            while (more) {
+                const uint32_t cj = d.cigar[j];
+                if ((cj & 15u) != 2) break;
+                del_len += (int32_t)(cj >> 4);
+                more = !(d.op_info[j] & 2u);
+                ++j;
             }
         }
         if (!ins_len && !del_len) break;
@@ -548,50 +702,25 @@ __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
 // exclusive scan of the per-row event counters in place
 struct OpEvents {
     typedef int32_t T;
+    struct Ctx {};
     Dev d;
+    __device__ void ctx_init(Ctx&) const {}
     __device__ T identity() const { return 0; }
     __device__ T combine(const T& x, const T& y) const { return x + y; }
     __device__ int64_t size() const { return *d.n_rows + 1; }
     __device__ T load(int64_t i) const { return d.binc[i]; }
-    __device__ void store(int64_t i, const T& incl, const T& own) const { d.binc[i] = incl - own; }
+    __device__ void store(int64_t i, const T& incl, const T& own, Ctx&) const { d.binc[i] = incl - own; }
 };
-// raw events -> CSR by row
-__global__ void k_scatter(Dev d) {
-    const int64_t n = *d.n_raw < d.events_ub ? *d.n_raw : d.events_ub;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const RowEvent e = d.raw[i];
-        const int64_t slot = (int64_t)d.binc[e.row] - d.binc[0] + atomicAdd(&d.bin_cur[e.row], 1);
-        d.events[slot] = e;
-    }
-}
-// zero the live part of the row-space accumulators once the row count is known
-__global__ void k_clear_rows(Dev d) {
-    const int64_t L = *d.n_rows;
-    const int NC = d.C == 30 ? 6 : 4;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= L + 1; i += stride) {
-        d.binc[i] = 0;
-        d.bin_cur[i] = 0;
-        for (int c = 0; c < NC; ++c) d.cov[i * NC + c] = 0;
-        if (i <= L / COV_TILE + 1) for (int c = 0; c < NC; ++c) d.cov_tile[i * NC + c] = 0;
-        if (d.padding) {
-            d.head_cnt[i] = 0; d.tail_cnt[i] = 0;
-            Int2 z; z.a = 0; z.b = 0;
-            d.skipdiff[i] = z;
-            d.deleted[i] = 0;
-        }
-    }
-}
-
 struct OpSkip {
     typedef Int2 T;
+    struct Ctx {};
     Dev d;
+    __device__ void ctx_init(Ctx&) const {}
     __device__ T identity() const { T t; t.a = 0; t.b = 0; return t; }
     __device__ T combine(const T& x, const T& y) const { T t; t.a = x.a + y.a; t.b = x.b + y.b; return t; }
     __device__ int64_t size() const { return *d.n_rows; }
     __device__ T load(int64_t i) const { return d.skipdiff[i]; }
-    __device__ void store(int64_t i, const T& incl, const T&) const {
+    __device__ void store(int64_t i, const T& incl, const T&, Ctx&) const {
         // '>' forward skips, '<' reverse skips, '^' heads, '$' tails (create_tensor_pileup.py:178)
         int32_t m = incl.a > incl.b ? incl.a : incl.b;
         const int32_t h = d.head_cnt[i], t = d.tail_cnt[i];
@@ -744,11 +873,23 @@ __global__ void k_thr_table(uint16_t* thr_snp, uint16_t* thr_indel, double snp_a
     }
 }
 
-// exclusive prefix of the coverage tile sums, in place (single block; there is one tile per 256 rows)
+// raw events -> CSR by row (counting sort: the scan above made binc the bin offsets); block 0 meanwhile turns the
+// coverage tile sums into their exclusive prefix, in place (one tile per 256 rows: a few thousand values, a job for
+// one block that used to be a 12 us kernel of its own between the scatter and k_rows)
 template <int NC>
-struct CovVec { int32_t v[NC]; };
-template <int NC>
-__global__ void __launch_bounds__(1024) k_cov_aggr(Dev d) {
+__global__ void __launch_bounds__(1024) k_scatter_aggr(Dev d) {
+    if (*d.err == 1) return;
+    if (blockIdx.x != 0) {
+        const int64_t n = *d.n_raw < d.events_ub ? *d.n_raw : d.events_ub;
+        const int64_t stride = (int64_t)(gridDim.x - 1) * blockDim.x;
+        const int32_t b0 = d.binc[0];
+        for (int64_t i = (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x; i < n; i += stride) {
+            const RowEvent e = d.raw[i];
+            const int64_t slot = (int64_t)d.binc[e.row] - b0 + atomicAdd(&d.bin_cur[e.row], 1);
+            d.events[slot] = e;
+        }
+        return;
+    }
     __shared__ int32_t wtot[32][NC];
     __shared__ int32_t carry[NC];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -879,16 +1020,43 @@ __device__ void row_indels(const Dev& d, const RowEvent* evs, int32_t n, int32_t
 // rows.  Coverage = tile prefix + in-block prefix of the difference rows; the row's events give everything else:
 // mismatching bases, I/I1/D/D1, phased channels; then the candidate predicate (integer AF threshold
 // tables, first-occurrence tie-break) and the row leaves through shared memory as 16-byte coalesced stores.
+// K3's test: the 33 columns c-16 .. c+16 are all printed (one gap-free run of covP): restates "pop when pos - c == 16
+// and the ring has no empty slot" (create_tensor_pileup.py:565-568).  Head/tail mode: zero rows stand in for the
+// columns before the run; the columns after it are only supplied when the stream ends, i.e. for the final run
+// (create_tensor_pileup.py:508-511, 613-637).
+__device__ __forceinline__ bool window_printed(const Dev& d, int32_t p) {
+    const int64_t o = (int64_t)p - d.R0;
+    if (d.head_tail) {
+        if (!bit_at(d.covP, o)) return false;
+        int nb, na;
+        printed_run(d, o, &nb, &na);
+        return na == FLANK || o >= d.tail[1];
+    }
+    if (o - FLANK < 0 || o + FLANK >= d.W) return false;
+    // 33 consecutive printed columns starting at o-16 (covP = covA inside the pileup BED: mpileup -l never prints
+    // the others, so the ring buffer restarts there)
+    const int64_t s = o - FLANK;
+    const int64_t w = s >> 5;
+    const int sh = (int)(s & 31);
+    const unsigned long long lo = d.covP[w] | ((unsigned long long)d.covP[w + 1] << 32);
+    const unsigned long long bits = lo >> sh;              // 64 - sh >= 33 bits are valid
+    const unsigned long long need = (1ull << 33) - 1ull;
+    return (bits & need) == need;
+}
+
 constexpr int ROWS_WARPS = 8;
 constexpr int ROWS_HEAVY = 32;               // rows with more events than this are walked by the whole warp
 template <int C>
-__global__ void __launch_bounds__(ROWS_WARPS * 32, 5) k_rows(Dev d) {
+__global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d) {
     constexpr int NC = C == 30 ? 6 : 4;
     static_assert(ROWS_WARPS * 32 == COV_TILE, "one block per coverage tile");
     __shared__ __align__(16) int32_t stage[ROWS_WARPS][TILE_ROWS * C];
     __shared__ int32_t wtot[ROWS_WARPS][NC];
     __shared__ uint32_t done_s[ROWS_WARPS][IND_WORDS];
+    __shared__ int32_t carry_s;
+    __shared__ bool is_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (*d.err == 1) return;                             // more rows than the buffers hold: the host retries with exact bounds
     const int64_t L = *d.n_rows;
     const int32_t ev_base = d.binc[0];
     for (int64_t tile = blockIdx.x; tile * COV_TILE < L; tile += gridDim.x) {
@@ -944,6 +1112,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, 5) k_rows(Dev d) {
         int32_t mm_f = 0, mm_r = 0, mm_p = 0, mm_m = 0;              // all mismatch events incl. N / ambiguity codes
         int32_t ins_cnt = 0, del_cnt = 0;
         const bool heavy_me = live && (e1 - e0) > ROWS_HEAVY;
+        bool is_cand = false;
         // rows with many events (a het variant under deep coverage is hundreds of them): the whole warp walks one such
         // row at a time - mismatch counters by warp reduction, its indel tokens compacted into shared memory
         for (uint32_t heavy = __ballot_sync(0xffffffffu, heavy_me); heavy; heavy &= heavy - 1) {
@@ -1103,7 +1272,8 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, 5) k_rows(Dev d) {
                 }
                 cand = iv_overlaps(d.cbed, d.n_cbed, p, p + max_del + 2);
             }
-            const uint8_t flag = cand ? 1 : 0;
+            is_cand = cand && window_printed(d, p);            // K3: eligible and 33 printed columns around it
+            const uint8_t flag = is_cand ? 1 : 0;
             v[ri] = -fsum;
             v[9 + ri] = -rsum;
             d.row_depth[row] = depth;
@@ -1129,52 +1299,55 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, 5) k_rows(Dev d) {
             }
         }
         __syncwarp();
+        // candidates of the tile (K3's list is built from these counts: k_cand_emit)
+        const int nc = __syncthreads_count(is_cand);
+        if (threadIdx.x == 0) d.ctile[tile] = nc;
+    }
+    // ---- the last block to finish turns the per-tile candidate counts into their exclusive prefix
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(&d.kctr[1], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int n_ct = (int)((L + COV_TILE - 1) / COV_TILE);
+    const int32_t total = block_scan_inplace_256(d.ctile, n_ct, &wtot[0][0], &carry_s);
+    if (threadIdx.x == 255) {
+        d.ctile[n_ct] = total;
+        *d.n_cand = total;
     }
 }
 
 // ------------------------------------------------------- K3: candidate list
-// emitted iff eligible and the 33 positions c-16..c+16 are all covered (one gap-free run):
-// restates "pop when pos - c == 16 and the ring has no empty slot" (create_tensor_pileup.py:565-568)
-struct OpCand {
-    typedef int32_t T;
-    Dev d;
-    __device__ T identity() const { return 0; }
-    __device__ T combine(const T& x, const T& y) const { return x + y; }
-    __device__ int64_t size() const { return *d.n_rows; }
-    __device__ T load(int64_t row) const {
-        if (!d.row_flag[row]) return 0;
-        const int64_t o = (int64_t)d.row_pos[row] - d.R0;
-        if (d.head_tail) {
-            // zero rows stand in for the columns before the run; the columns after it are only supplied when the
-            // stream ends, i.e. for the final run (create_tensor_pileup.py:508-511, 613-637)
-            if (!bit_at(d.covP, o)) return 0;
-            int nb, na;
-            printed_run(d, o, &nb, &na);
-            return (na == FLANK || o >= d.tail[1]) ? 1 : 0;
-        }
-        if (o - FLANK < 0 || o + FLANK >= d.W) return 0;
-        // 33 consecutive printed columns starting at o-16 (covP = covA inside the pileup BED: mpileup -l never prints
-        // the others, so the ring buffer restarts there)
-        const int64_t s = o - FLANK;
-        const int64_t w = s >> 5;
-        const int sh = (int)(s & 31);
-        unsigned long long lo = d.covP[w] | ((unsigned long long)d.covP[w + 1] << 32);
-        const unsigned long long bits = lo >> sh;          // 64 - sh >= 33 bits are valid
-        const unsigned long long need = (1ull << 33) - 1ull;
-        return (bits & need) == need ? 1 : 0;
-    }
-    __device__ void store(int64_t row, const T& incl, const T& own) const {
-        if (own) {
-            const int64_t i = incl - 1;
+// k_rows flagged the candidates (eligible and 33 printed columns) and left the per-tile counts' exclusive prefix:
+// block = tile of 256 rows, a candidate's slot = tile prefix + its rank in the tile (position order is kept)
+__global__ void __launch_bounds__(256) k_cand_emit(Dev d) {
+    __shared__ int32_t wcnt[8];
+    const int64_t L = *d.n_rows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t tile = blockIdx.x; tile * COV_TILE < L; tile += gridDim.x) {
+        const int32_t base = d.ctile[tile];
+        if (d.ctile[tile + 1] == base) continue;         // block-uniform
+        const int64_t row = tile * COV_TILE + threadIdx.x;
+        const bool c = row < L && d.row_flag[row];
+        const uint32_t m = __ballot_sync(0xffffffffu, c);
+        __syncthreads();
+        if (lane == 0) wcnt[warp] = __popc(m);
+        __syncthreads();
+        if (c) {
+            int64_t i = base + __popc(m & ((1u << lane) - 1u));
+#pragma unroll
+            for (int w = 0; w < 8; ++w) if (w < warp) i += wcnt[w];
             if (i < d.cand_cap) {
                 d.cand_row[i] = (int32_t)row;
                 d.cand_pos[i] = d.row_pos[row] + 1;
                 d.cand_depth[i] = d.row_depth[row];
             }
         }
-        if (row == *d.n_rows - 1) *d.n_cand = incl;
     }
-};
+}
 
 // ------------------------------------------------------- K4: window assembly
 // tensor[i][k][c] = counts[row_i - 16 + k][c]  (rows of consecutive positions are consecutive);
@@ -1215,49 +1388,59 @@ __global__ void k_window(Dev d, int apply_scale) {
 //   xop[tile][33][KX/8][128 rows][8 halfs]   (k < C: x, C <= k < 2C: x again - it meets W_lo -, k = 2C, 2C+1: 1 - they
 //   meet the bias rows -, rest 0; nn_tc.cuh)
 // instead of int32 tensor[n][33][C] that k_xop would read back: no 2.4 KB per site round trip through HBM.  Used
-// when nobody asks for the tensor itself (keep_tensor) and no padding pass has to patch it.  Block = one site of
-// the last tile's 128 (sites beyond n are zero rows), thread = one 16-byte cell (t, k8).
+// when nobody asks for the tensor itself (keep_tensor) and no padding pass has to patch it.
+// Block = (tile of 128 sites, window row t), thread = site: a thread reads the C counts of ITS row (72 / 120 contiguous
+// bytes, 8-byte loads) and writes the KX/8 16-byte cells of the image; the lanes of a warp are consecutive sites, so
+// every store instruction of a warp is 512 contiguous bytes.  Sites beyond n (the tile pair's padding) are zero rows.
 template <int C, int KX>
 __global__ void __launch_bounds__(128) k_window_xop(Dev d, __half* __restrict__ xop) {
     const int64_t n = *d.n_cand < d.cand_cap ? *d.n_cand : d.cand_cap;
-    const int64_t n_pad = ((n + 255) / 256) * 256;             // tiles come in pairs
-    constexpr int CELLS = WIN * (KX / 8);
-    for (int64_t i = blockIdx.x; i < n_pad; i += gridDim.x) {
-        const int64_t tile = i >> 7;
-        const int r = (int)(i & 127);
-        __half* base = xop + (size_t)tile * WIN * (size_t)(KX * 128) + r * 8;
-        const bool live = i < n;
-        int32_t depth = 0;
-        const int32_t* src = d.counts;
-        int j0 = 0, j1 = WIN;                                  // window rows that are columns of the candidate's run
+    const int64_t n_tiles = ((n + 255) / 256) * 2;             // tiles come in pairs
+    const int r = threadIdx.x;
+    for (int64_t b = blockIdx.x; b < n_tiles * WIN; b += gridDim.x) {
+        const int64_t tile = b / WIN;
+        const int t = (int)(b - tile * WIN);
+        const int64_t i = tile * 128 + r;
+        float x[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) x[c] = 0.0f;
+        bool live = i < n;
         if (live) {
-            depth = d.cand_depth[i];
-            src = d.counts + ((int64_t)d.cand_row[i] - FLANK) * C;
-            if (d.head_tail) {
+            const int32_t depth = d.cand_depth[i];
+            const int32_t row = d.cand_row[i];
+            if (d.head_tail) {                                 // window rows that are columns of the candidate's own run
                 int nb, na;
                 printed_run(d, (int64_t)d.cand_pos[i] - 1 - d.R0, &nb, &na);
-                j0 = FLANK - nb; j1 = FLANK + na + 1;
+                live = t >= FLANK - nb && t < FLANK + na + 1;
+            }
+            if (live) {
+                const int2* src = (const int2*)(d.counts + ((int64_t)row - FLANK + t) * C);     // C is even: 8-byte aligned
+                int32_t v[C];
+#pragma unroll
+                for (int c = 0; c < C / 2; ++c) { const int2 q = src[c]; v[2 * c] = q.x; v[2 * c + 1] = q.y; }
+                if (depth > 0 && (double)depth > (double)d.max_depth * 1.5) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) v[c] = rescale(v[c], depth, d.max_depth);
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) x[c] = (float)v[c];
             }
         }
-        const bool sc = live && depth > 0 && (double)depth > (double)d.max_depth * 1.5;
-        for (int cell = threadIdx.x; cell < CELLS; cell += blockDim.x) {
-            const int t = cell / (KX / 8), k8 = cell % (KX / 8);
-            __align__(16) __half hv[8];
+        __half* base = xop + ((size_t)tile * WIN + t) * (size_t)(KX * 128) + r * 8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = k8 * 8 + j;
-                float v = 0.0f;
-                if (k < 2 * C) {
-                    const int c = k < C ? k : k - C;
-                    if (live && t >= j0 && t < j1) {
-                        int32_t x = src[t * C + c];
-                        if (sc) x = rescale(x, depth, d.max_depth);
-                        v = (float)x;
-                    }
-                } else if (k < 2 * C + 2) v = 1.0f;
-                hv[j] = __float2half(v);
+        for (int k8 = 0; k8 < KX / 8; ++k8) {
+            __align__(16) __half2 hv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float f[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = k8 * 8 + 2 * j + e;          // compile-time after unrolling
+                    f[e] = k < C ? x[k < C ? k : 0] : k < 2 * C ? x[k < 2 * C && k >= C ? k - C : 0] : k < 2 * C + 2 ? 1.0f : 0.0f;
+                }
+                hv[j] = __floats2half2_rn(f[0], f[1]);
             }
-            *(uint4*)(base + (size_t)t * (KX * 128) + (size_t)k8 * (128 * 8)) = *(const uint4*)hv;
+            *(uint4*)(base + (size_t)k8 * (128 * 8)) = *(const uint4*)hv;
         }
     }
 }
@@ -1369,7 +1552,9 @@ __global__ void k_padding(Dev d) {
 // upper bound of alleles per candidate: 3 alt bases + its indel events + reference
 struct OpAltOff {
     typedef long long T;
+    struct Ctx {};
     Dev d;
+    __device__ void ctx_init(Ctx&) const {}
     __device__ T identity() const { return 0; }
     __device__ T combine(const T& x, const T& y) const { return x + y; }
     __device__ int64_t size() const { return *d.n_cand < d.cand_cap ? *d.n_cand : d.cand_cap; }
@@ -1377,7 +1562,7 @@ struct OpAltOff {
         const int32_t row = d.cand_row[i];
         return 4 + (d.binc[row + 1] - d.binc[row]);
     }
-    __device__ void store(int64_t i, const T& incl, const T& own) const { d.alt_off[i] = incl - own; }
+    __device__ void store(int64_t i, const T& incl, const T& own, Ctx&) const { d.alt_off[i] = incl - own; }
 };
 
 // alleles in alt_dict insertion order (create_tensor_pileup.py:223,235,251,259-261): keys are

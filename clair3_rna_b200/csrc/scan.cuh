@@ -10,7 +10,8 @@
 //       __device__ T identity() const;
 //       __device__ T combine(const T& a, const T& b) const;   // associative, a before b
 //       __device__ T load(int64_t i) const;
-//       __device__ void store(int64_t i, const T& inclusive, const T& own) const;
+//       struct Ctx { ... };  __device__ void ctx_init(Ctx&) const;   // thread-local state carried over a thread's
+//       __device__ void store(int64_t i, const T& inclusive, const T& own, Ctx&) const;   // consecutive stores
 //       __device__ int64_t size() const;                 // element count (may read device memory)
 //   };
 //
@@ -180,11 +181,13 @@ __global__ void __launch_bounds__(SCAN_BT) scan_lookback_kernel(Op op, ScanState
         }
         __syncthreads();
         T run = op.combine(tile_prefix, excl_in_tile);
+        typename Op::Ctx ctx;
+        op.ctx_init(ctx);
 #pragma unroll
         for (int k = 0; k < SCAN_IPT; ++k) {
             if (i0 + k < n) {
                 run = op.combine(run, own[k]);
-                op.store(i0 + k, run, own[k]);
+                op.store(i0 + k, run, own[k], ctx);
             }
         }
     }
