@@ -11,6 +11,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 #include <map>
 #include <cuda_runtime.h>
 
@@ -59,6 +60,15 @@ struct Slot {
     ScanState scan = {};
     uint32_t scan_epoch = 0;
     size_t cov_up_bytes = 0;
+    // submit returns once stage A is queued; stage B (windows, alt table, network, result copies) is queued by a later
+    // call into the library, when the candidate count has arrived on the host (advance())
+    bool pending_b = false;
+    cudaEvent_t ev_cnt = nullptr;     // the scalars of stage A are on the host
+    uint64_t order = 0;               // submit order
+    int64_t n_seq_bytes = 0, n_known_sites = 0;
+    bool exact_bounds = false;        // capacity bounds from an exact pass over the CIGARs (retry after a device capacity error)
+    int deferred_rc = 0;              // error of the deferred part, reported by c3r_wait
+    std::string deferred_err;
     // pinned results
     Pin h_scalars, h_pos, h_depth, h_probs, h_alt_off, h_alt_n, h_alt, h_tensor, h_row_pos, h_counts, h_row_depth;
     Dev d;
@@ -82,7 +92,7 @@ struct c3r_ctx {
     Buf nn_scratch;
     NetF32Scratch nscr;
     TcNet tc;                 // tensor-core path state (nn_tc.cuh)
-    bool exact_bounds = false; // capacity bounds from an exact host pass over the CIGARs (retry path)
+    uint64_t submit_seq = 0;
     const c3r_site_filter* filter = nullptr;   // of the submit in progress
     bool tc_dirty = false;    // a tensor-core forward ran since the last device error check
     cudaEvent_t nn_done = nullptr;   // end of the last network pass: the scratch (h1, zx2, h2 ...) is shared by all tickets
@@ -90,6 +100,8 @@ struct c3r_ctx {
     Buf ref_res;              // resident reference window (c3r_set_reference)
     Buf refnib_res;           // its one-hot nibble form (k_refnib)
     int64_t ref_res_start0 = 0, ref_res_len = 0;
+    double t_phase[8] = {};   // C3R_TIMING: host seconds of submit's phases (printed by c3r_destroy)
+    int64_t n_submit = 0;
     Buf fwd_in, fwd_out;      // c3r_forward staging
     cudaStream_t fwd_stream = nullptr;
 };
@@ -195,9 +207,8 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     return 0;
 }
 
-int read_scalars(c3r_ctx* ctx, Slot& s) {
-    CK(cudaMemcpyAsync(s.h_scalars.p, s.scalars.p, 64, cudaMemcpyDeviceToHost, s.st));
-    CK(cudaStreamSynchronize(s.st));
+// the scalars of stage A are on the host: check them
+int parse_scalars(c3r_ctx* ctx, Slot& s) {
     const int64_t* hs = (const int64_t*)s.h_scalars.p;
     s.n_rows = hs[0];
     s.n_cand = hs[1];
@@ -213,6 +224,12 @@ int read_scalars(c3r_ctx* ctx, Slot& s) {
     }
     if (s.n_cand > s.d.cand_cap) return fail(ctx, C3R_ERR_CAPACITY, "candidate capacity exceeded");
     return 0;
+}
+
+int read_scalars(c3r_ctx* ctx, Slot& s) {
+    CK(cudaMemcpyAsync(s.h_scalars.p, s.scalars.p, 64, cudaMemcpyDeviceToHost, s.st));
+    CK(cudaStreamSynchronize(s.st));
+    return parse_scalars(ctx, s);
 }
 
 int ensure_stage_b(c3r_ctx* ctx, Slot& s) {
@@ -371,6 +388,9 @@ int c3r_create(c3r_ctx** out, int device_ordinal, const c3r_params* params) {
         CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
         for (int k = 0; k < N_EV; ++k) CK(cudaEventCreate(&s.ev[k]));
         CK(cudaEventCreateWithFlags(&s.ev_alt, cudaEventDisableTiming));
+        // spin-wait by default: a blocking-sync event wakes the waiting thread ~0.3 ms late (measured), which delays
+        // stage B by as much; C3R_BLOCKING_COUNTS trades that for an idle core while waiting
+        CK(cudaEventCreateWithFlags(&s.ev_cnt, cudaEventDisableTiming | (getenv("C3R_BLOCKING_COUNTS") ? cudaEventBlockingSync : 0)));
         if (ensure(ctx, s.scalars, 256)) return C3R_ERR_CUDA;
         if (ensure_pin(ctx, s.h_scalars, 256)) return C3R_ERR_CUDA;
     }
@@ -384,6 +404,11 @@ int c3r_create(c3r_ctx** out, int device_ordinal, const c3r_params* params) {
 
 void c3r_destroy(c3r_ctx* ctx) {
     if (!ctx) return;
+    if (getenv("C3R_TIMING") && ctx->n_submit)
+        fprintf(stderr, "[c3r] %lld submits, host ms each: buffers %.3f, h2d calls %.3f, stage A launches %.3f, earlier "
+                        "tickets advanced at submit %.3f, deferred part (wait for the counts + stage B + d2h calls) %.3f, - %.3f\n", (long long)ctx->n_submit,
+                1e3 * ctx->t_phase[0] / ctx->n_submit, 1e3 * ctx->t_phase[1] / ctx->n_submit, 1e3 * ctx->t_phase[2] / ctx->n_submit,
+                1e3 * ctx->t_phase[3] / ctx->n_submit, 1e3 * ctx->t_phase[4] / ctx->n_submit, 1e3 * ctx->t_phase[5] / ctx->n_submit);
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->nn_done) cudaEventDestroy(ctx->nn_done);
@@ -401,6 +426,7 @@ void c3r_destroy(c3r_ctx* ctx) {
         for (Pin* b : ps) release(*b);
         for (int k = 0; k < N_EV; ++k) if (s.ev[k]) cudaEventDestroy(s.ev[k]);
         if (s.ev_alt) cudaEventDestroy(s.ev_alt);
+        if (s.ev_cnt) cudaEventDestroy(s.ev_cnt);
         if (s.st) cudaStreamDestroy(s.st);
     }
     release(ctx->wbuf);
@@ -414,6 +440,13 @@ void c3r_destroy(c3r_ctx* ctx) {
     if (ctx->fwd_stream) cudaStreamDestroy(ctx->fwd_stream);
     delete ctx;
 }
+
+int c3r_host_alloc(void** out, int64_t n_bytes) {
+    if (!out || n_bytes <= 0) return C3R_ERR_ARG;
+    *out = nullptr;
+    return cudaHostAlloc(out, (size_t)n_bytes, cudaHostAllocPortable) == cudaSuccess ? C3R_OK : C3R_ERR_CUDA;
+}
+void c3r_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 const char* c3r_last_error(c3r_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
@@ -441,6 +474,7 @@ int c3r_set_reference(c3r_ctx* ctx, const uint8_t* ref, int64_t ref_start1, int6
     return C3R_OK;
 }
 
+static void advance_all(c3r_ctx* ctx, bool block);
 static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
                        int64_t region_start1, int64_t region_end1, c3r_ticket* ticket);
 
@@ -478,104 +512,48 @@ int c3r_submit_chunk_filtered(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* 
     if (!ctx || !rd || !ticket) return C3R_ERR_ARG;
     if (int rc = check_filter(ctx, filter)) return rc;
     ctx->filter = filter;
-    ctx->exact_bounds = false;
     int rc = submit_once(ctx, rd, ref, ref_start1, ref_len, region_start1, region_end1, ticket);
-    if (rc == C3R_ERR_CAPACITY && ctx->err.find("device capacity") != std::string::npos) {
-        ctx->exact_bounds = true;                   // unusual CIGARs: redo with exact bounds
-        rc = submit_once(ctx, rd, ref, ref_start1, ref_len, region_start1, region_end1, ticket);
-        ctx->exact_bounds = false;
-    }
     ctx->filter = nullptr;
     return rc;
 }
 
-static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
-                       int64_t region_start1, int64_t region_end1, c3r_ticket* ticket) {
-    if (!ref) {
-        if (!ctx->ref_res_len) return fail(ctx, C3R_ERR_STATE, "ref == NULL but c3r_set_reference was never called");
-        ref_start1 = ctx->ref_res_start0 + 1;
-        ref_len = ctx->ref_res_len;
-    }
-    if (!ctx->have_weights) return fail(ctx, C3R_ERR_STATE, "c3r_set_weights must be called before c3r_submit_chunk");
-    if (region_end1 < region_start1 || region_start1 < 1) return fail(ctx, C3R_ERR_ARG, "bad region");
-    if (region_end1 > 0x7fff0000LL) return fail(ctx, C3R_ERR_CAPACITY, "positions must fit int32");
-    if (rd->n_seq_bytes * 2 >= 0xffffffffLL) return fail(ctx, C3R_ERR_CAPACITY, "more than 4G bases in one chunk");
-    if (rd->n_reads >= (1LL << 28)) return fail(ctx, C3R_ERR_CAPACITY, "more than 2^28 reads in one chunk");
-    CK(cudaSetDevice(ctx->device));
-    int si = -1;
-    for (int i = 0; i < N_SLOTS; ++i) if (!ctx->slots[i].in_use) { si = i; break; }
-    if (si < 0) return fail(ctx, C3R_ERR_STATE, "all tickets in flight; c3r_release one first");
-    Slot& s = ctx->slots[si];
-    s.launches = 0;
-    s.has_result = false;
+// Row-space capacity of a slot and everything sized by it.  Rows = positions under an M/=/X/D op, dilated by 16 on
+// each side of every N-separated block: a read contributes at most (its M/D length + 32 per block).  Without
+// `cigar_host` the bounds are cheap ones that need no host pass over the CIGARs (M bases <= SEQ bases; deletions are
+// assumed not to outnumber the sequenced bases; row events - indel tokens + read bases that differ from the
+// reference - sized for one base in four); if a chunk breaks that, the device-side capacity checks fire and
+// advance() comes back here with the CIGARs for exact bounds (events then sized for every base).
+static int size_rows(c3r_ctx* ctx, Slot& s, const uint32_t* cigar_host) {
     Dev& d = s.d;
-    memset(&d, 0, sizeof d);
-    const c3r_params& pr = ctx->prm;
-    d.n_reads = rd->n_reads; d.n_ops = rd->n_ops;
-    d.R0 = (int32_t)(region_start1 - 1); d.R1 = (int32_t)region_end1;
-    d.W = (int64_t)d.R1 - d.R0; d.NW = (d.W + 31) / 32;
-    d.C = pr.channels; d.min_cov = pr.min_coverage; d.min_mq = pr.min_mq; d.excl = pr.excl_flags;
-    d.snp_af = pr.snp_min_af; d.indel_af = pr.indel_min_af; d.padding = pr.enable_padding;
-    d.max_depth = pr.max_depth; d.skip_prop = pr.skip_proportion;
-    d.ref_start0 = ref_start1 - 1; d.ref_len = ref_len;
-    d.thr_snp = (const uint16_t*)ctx->thr.p; d.thr_indel = (const uint16_t*)ctx->thr.p + THR_N;
-    // host-side upper bounds from the CIGARs
-    // Capacity bounds.  Rows = positions under an M/=/X/D op, dilated by 16 on each side of every
-    // N-separated block: a read contributes at most (its M/D length + 32 per block).  The cheap
-    // bounds below avoid a host pass over the CIGARs (M bases <= SEQ bases; deletions are assumed
-    // not to outnumber the sequenced bases); if a chunk breaks that assumption the device-side
-    // capacity checks fire and the caller-visible retry in this function uses the exact pass.
-    // Row events = indel tokens (<= ops) + read bases that differ from the reference: sized for one base in
-    // four on the first attempt, for every base on the retry.
     int64_t md_len = 0, n_skip = 0, ev_ub = 0;
-    if (ctx->exact_bounds) {
-        for (int64_t k = 0; k < rd->n_ops; ++k) {
-            const uint32_t c = rd->cigar[k], op = c & 15u;
+    if (cigar_host) {
+        for (int64_t k = 0; k < d.n_ops; ++k) {
+            const uint32_t c = cigar_host[k], op = c & 15u;
             const int64_t len = c >> 4;
             if (op == 0 || op == 2 || op == 7 || op == 8) md_len += len;
             if (op == 3) ++n_skip;
         }
-        ev_ub = rd->n_ops + 2 * rd->n_seq_bytes;
+        ev_ub = d.n_ops + 2 * s.n_seq_bytes;
     } else {
-        md_len = 4 * rd->n_seq_bytes;
-        n_skip = rd->n_ops;
-        ev_ub = rd->n_ops + rd->n_seq_bytes / 2;
+        md_len = 4 * s.n_seq_bytes;
+        n_skip = d.n_ops;
+        ev_ub = d.n_ops + s.n_seq_bytes / 2;
     }
-    int64_t L_ub = md_len + 32 * (n_skip + rd->n_reads) + 64;
-    if (ctx->filter && ctx->filter->n_known_sites > 0) L_ub += 33 * ctx->filter->n_known_sites;   // rows around known sites
+    int64_t L_ub = md_len + 32 * (n_skip + d.n_reads) + 64;
+    L_ub += 33 * s.n_known_sites;                    // rows around known sites
     if (L_ub > d.W) L_ub = d.W;
     if (L_ub < 64) L_ub = 64;
     d.L_ub = L_ub;
     d.events_ub = ev_ub + 8;
     d.cand_cap = L_ub;
-    const int64_t R = rd->n_reads > 0 ? rd->n_reads : 1, O = rd->n_ops > 0 ? rd->n_ops : 1;
 #define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
-    EN(pos, R * 4); EN(flag, R * 2); EN(mapq, R); EN(hp, R); EN(cigar_off, (R + 1) * 4); EN(cigar, O * 4);
-    EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 64); if (ref) { EN(ref, ref_len + 16); }
-    EN(admit, R); EN(read_end, R * 4); EN(blockmax, (R / 256 + 2) * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_info, O * 4);
-    // position space: buffers padded to whole tiles of PT_WORDS words (k_row_bits / k_row_rank store 16 bytes per thread);
-    // the summary levels of covA and covE (mark_range) share one buffer: level l has NW / 32^l + 2 words
-    const int64_t NWp = ((d.NW + PT_WORDS - 1) / PT_WORDS) * PT_WORDS + 8;
-    EN(covA, NWp * 4); EN(covE, NWp * 4); EN(rowR, NWp * 4); EN(word_base, NWp * 4);
-    EN(ptile, (NWp / PT_WORDS + 4) * 4); EN(ctile, (L_ub / COV_TILE + 4) * 4);
-    int64_t up_words[COV_UP], up_total = 0;
-    { int64_t n = d.NW; for (int l = 0; l < COV_UP; ++l) { n = (n >> 5) + 2; up_words[l] = n; up_total += n; } }
-    EN(cov_up, 2 * up_total * 4);
-    s.cov_up_bytes = (size_t)(2 * up_total * 4);
     EN(row_pos, (L_ub + 2) * 4); EN(counts, ((L_ub + 32) * d.C) * 4); EN(row_depth, (L_ub + 2) * 4); EN(row_flag, L_ub + 2);
     EN(head_cnt, (L_ub + 2) * 4); EN(tail_cnt, (L_ub + 2) * 4); EN(skipdiff, (L_ub + 2) * 8); EN(max_skip, (L_ub + 2) * 4);
     EN(row_ins, (L_ub + 2) * 4); EN(row_del, (L_ub + 2) * 4);
     EN(binc, (L_ub + 4) * 4); EN(bin_cur, (L_ub + 4) * 4);
     EN(events, d.events_ub * sizeof(RowEvent)); EN(raw, d.events_ub * sizeof(RowEvent));
     EN(cov, (L_ub + 4) * NCOV_MAX * 4); EN(cov_tile, (L_ub / COV_TILE + 4) * NCOV_MAX * 4);
-    if (ref) { EN(refnib, ((ref_len + 7) / 8 + 1) * 4); }
-    const c3r_site_filter* flt = ctx->filter;
-    d.n_pbed = d.n_cbed = d.n_known = -1;
-    if (flt) {
-        if (flt->n_pileup_bed >= 0) { EN(pbed, (flt->n_pileup_bed + 1) * 8); EN(covP, (d.NW + 4) * 4); d.n_pbed = (int32_t)flt->n_pileup_bed; }
-        if (flt->n_confident_bed >= 0) { EN(cbed, (flt->n_confident_bed + 1) * 8); d.n_cbed = (int32_t)flt->n_confident_bed; }
-        if (flt->n_known_sites >= 0) { EN(known, (flt->n_known_sites + 1) * 4); d.n_known = (int32_t)flt->n_known_sites; }
-    }
+    EN(ctile, (L_ub / COV_TILE + 4) * 4);
     EN(cand_row, (L_ub + 2) * 4); EN(cand_pos, (L_ub + 2) * 4); EN(cand_depth, (L_ub + 2) * 4);
     EN(cur_ref, (L_ub + 2) * 8); EN(deleted, L_ub + 2);
     {
@@ -597,6 +575,79 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
         s.scan.err = P<int32_t>(s.scalars) + 6;
     }
 #undef EN
+    d.row_pos = P<int32_t>(s.row_pos); d.counts = P<int32_t>(s.counts); d.row_depth = P<int32_t>(s.row_depth);
+    d.row_flag = P<uint8_t>(s.row_flag); d.head_cnt = P<int32_t>(s.head_cnt); d.tail_cnt = P<int32_t>(s.tail_cnt);
+    d.skipdiff = P<Int2>(s.skipdiff); d.max_skip = P<int32_t>(s.max_skip);
+    d.row_inscnt = P<int32_t>(s.row_ins); d.row_delcnt = P<int32_t>(s.row_del);
+    d.binc = P<int32_t>(s.binc); d.bin_cur = P<int32_t>(s.bin_cur);
+    d.events = P<RowEvent>(s.events); d.raw = P<RowEvent>(s.raw); d.cov = P<int32_t>(s.cov); d.cov_tile = P<int32_t>(s.cov_tile);
+    d.ctile = P<int32_t>(s.ctile);
+    d.cand_row = P<int32_t>(s.cand_row); d.cand_pos = P<int32_t>(s.cand_pos); d.cand_depth = P<int32_t>(s.cand_depth);
+    d.cur_ref = P<Int2>(s.cur_ref); d.deleted = P<uint8_t>(s.deleted);
+    return 0;
+}
+
+static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
+                       int64_t region_start1, int64_t region_end1, c3r_ticket* ticket) {
+    if (!ref) {
+        if (!ctx->ref_res_len) return fail(ctx, C3R_ERR_STATE, "ref == NULL but c3r_set_reference was never called");
+        ref_start1 = ctx->ref_res_start0 + 1;
+        ref_len = ctx->ref_res_len;
+    }
+    if (!ctx->have_weights) return fail(ctx, C3R_ERR_STATE, "c3r_set_weights must be called before c3r_submit_chunk");
+    if (region_end1 < region_start1 || region_start1 < 1) return fail(ctx, C3R_ERR_ARG, "bad region");
+    if (region_end1 > 0x7fff0000LL) return fail(ctx, C3R_ERR_CAPACITY, "positions must fit int32");
+    if (rd->n_seq_bytes * 2 >= 0xffffffffLL) return fail(ctx, C3R_ERR_CAPACITY, "more than 4G bases in one chunk");
+    if (rd->n_reads >= (1LL << 28)) return fail(ctx, C3R_ERR_CAPACITY, "more than 2^28 reads in one chunk");
+    CK(cudaSetDevice(ctx->device));
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tp = now();
+    auto lap = [&](int k) { const double t = now(); ctx->t_phase[k] += t - tp; tp = t; };
+    ++ctx->n_submit;
+    int si = -1;
+    for (int i = 0; i < N_SLOTS; ++i) if (!ctx->slots[i].in_use) { si = i; break; }
+    if (si < 0) return fail(ctx, C3R_ERR_STATE, "all tickets in flight; c3r_release one first");
+    Slot& s = ctx->slots[si];
+    s.launches = 0;
+    s.has_result = false;
+    Dev& d = s.d;
+    memset(&d, 0, sizeof d);
+    const c3r_params& pr = ctx->prm;
+    d.n_reads = rd->n_reads; d.n_ops = rd->n_ops;
+    d.R0 = (int32_t)(region_start1 - 1); d.R1 = (int32_t)region_end1;
+    d.W = (int64_t)d.R1 - d.R0; d.NW = (d.W + 31) / 32;
+    d.C = pr.channels; d.min_cov = pr.min_coverage; d.min_mq = pr.min_mq; d.excl = pr.excl_flags;
+    d.snp_af = pr.snp_min_af; d.indel_af = pr.indel_min_af; d.padding = pr.enable_padding;
+    d.max_depth = pr.max_depth; d.skip_prop = pr.skip_proportion;
+    d.ref_start0 = ref_start1 - 1; d.ref_len = ref_len;
+    d.thr_snp = (const uint16_t*)ctx->thr.p; d.thr_indel = (const uint16_t*)ctx->thr.p + THR_N;
+    s.n_seq_bytes = rd->n_seq_bytes;
+    s.n_known_sites = (ctx->filter && ctx->filter->n_known_sites > 0) ? ctx->filter->n_known_sites : 0;
+    s.exact_bounds = false;
+    s.deferred_rc = 0;
+    const int64_t R = rd->n_reads > 0 ? rd->n_reads : 1, O = rd->n_ops > 0 ? rd->n_ops : 1;
+#define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
+    EN(pos, R * 4); EN(flag, R * 2); EN(mapq, R); EN(hp, R); EN(cigar_off, (R + 1) * 4); EN(cigar, O * 4);
+    EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 64); if (ref) { EN(ref, ref_len + 16); }
+    EN(admit, R); EN(read_end, R * 4); EN(blockmax, (R / 256 + 2) * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_info, O * 4);
+    // position space: buffers padded to whole tiles of PT_WORDS words (k_row_bits / k_row_rank store 16 bytes per thread);
+    // the summary levels of covA and covE (mark_range) share one buffer: level l has NW / 32^l + 2 words
+    const int64_t NWp = ((d.NW + PT_WORDS - 1) / PT_WORDS) * PT_WORDS + 8;
+    EN(covA, NWp * 4); EN(covE, NWp * 4); EN(rowR, NWp * 4); EN(word_base, NWp * 4);
+    EN(ptile, (NWp / PT_WORDS + 4) * 4);
+    int64_t up_words[COV_UP], up_total = 0;
+    { int64_t n = d.NW; for (int l = 0; l < COV_UP; ++l) { n = (n >> 5) + 2; up_words[l] = n; up_total += n; } }
+    EN(cov_up, 2 * up_total * 4);
+    s.cov_up_bytes = (size_t)(2 * up_total * 4);
+    if (ref) { EN(refnib, ((ref_len + 7) / 8 + 1) * 4); }
+    const c3r_site_filter* flt = ctx->filter;
+    d.n_pbed = d.n_cbed = d.n_known = -1;
+    if (flt) {
+        if (flt->n_pileup_bed >= 0) { EN(pbed, (flt->n_pileup_bed + 1) * 8); EN(covP, (d.NW + 4) * 4); d.n_pbed = (int32_t)flt->n_pileup_bed; }
+        if (flt->n_confident_bed >= 0) { EN(cbed, (flt->n_confident_bed + 1) * 8); d.n_cbed = (int32_t)flt->n_confident_bed; }
+        if (flt->n_known_sites >= 0) { EN(known, (flt->n_known_sites + 1) * 4); d.n_known = (int32_t)flt->n_known_sites; }
+    }
+#undef EN
     d.pos = P<int32_t>(s.pos); d.flag = P<uint16_t>(s.flag); d.mapq = P<uint8_t>(s.mapq); d.hp = P<uint8_t>(s.hp);
     d.cigar_off = P<int32_t>(s.cigar_off); d.cigar = P<uint32_t>(s.cigar); d.seq_off = P<int64_t>(s.seq_off);
     d.seq = P<uint8_t>(s.seq); d.ref = ref ? P<uint8_t>(s.ref) : P<uint8_t>(ctx->ref_res);
@@ -609,15 +660,10 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
         for (int l = 0; l < COV_UP; ++l) { d.upA[l] = u; u += up_words[l]; }
         for (int l = 0; l < COV_UP; ++l) { d.upE[l] = u; u += up_words[l]; }
     }
-    d.ptile = P<int32_t>(s.ptile); d.ctile = P<int32_t>(s.ctile); d.kctr = P<int32_t>(s.scalars) + 12;
+    d.ptile = P<int32_t>(s.ptile); d.kctr = P<int32_t>(s.scalars) + 12;
     d.n_rows = P<int64_t>(s.scalars); d.n_cand = P<int64_t>(s.scalars) + 1; d.err = P<int32_t>(s.scalars) + 6;
-    d.row_pos = P<int32_t>(s.row_pos); d.counts = P<int32_t>(s.counts); d.row_depth = P<int32_t>(s.row_depth);
-    d.row_flag = P<uint8_t>(s.row_flag); d.head_cnt = P<int32_t>(s.head_cnt); d.tail_cnt = P<int32_t>(s.tail_cnt);
-    d.skipdiff = P<Int2>(s.skipdiff); d.max_skip = P<int32_t>(s.max_skip);
-    d.row_inscnt = P<int32_t>(s.row_ins); d.row_delcnt = P<int32_t>(s.row_del);
-    d.binc = P<int32_t>(s.binc); d.bin_cur = P<int32_t>(s.bin_cur);
-    d.events = P<RowEvent>(s.events); d.raw = P<RowEvent>(s.raw); d.cov = P<int32_t>(s.cov); d.cov_tile = P<int32_t>(s.cov_tile);
     d.n_raw = P<int64_t>(s.scalars) + 5;
+    if (int rc0 = size_rows(ctx, s, nullptr)) return rc0;     // row space: cheap capacity bounds first
     d.refnib = ref ? P<uint32_t>(s.refnib) : P<uint32_t>(ctx->refnib_res);
     d.n_ref_words = (ref_len + 7) / 8;
     d.blockmax = P<int32_t>(s.blockmax);
@@ -625,10 +671,9 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.covP = d.n_pbed >= 0 ? P<uint32_t>(s.covP) : d.covA;
     d.head_tail = pr.enable_head_tail;
     d.tail = P<int32_t>(s.scalars) + 8;
-    d.cand_row = P<int32_t>(s.cand_row); d.cand_pos = P<int32_t>(s.cand_pos); d.cand_depth = P<int32_t>(s.cand_depth);
-    d.cur_ref = P<Int2>(s.cur_ref); d.deleted = P<uint8_t>(s.deleted);
 
     cudaStream_t st = s.st;
+    lap(0);
     CK(cudaEventRecord(s.ev[0], st));
     if (rd->n_reads > 0) {
         CK(cudaMemcpyAsync(s.pos.p, rd->pos, rd->n_reads * 4, cudaMemcpyHostToDevice, st));
@@ -657,15 +702,68 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     if (ctx->prm.nn_impl == 1 && (!lstm2_fused() || getenv("C3R_NO_INTERLEAVE") != nullptr))
         if (cudaEvent_t done = tc_pass_done(ctx->tc)) CK(cudaStreamWaitEvent(st, done, 0));
     s.in_use = true;                                 // from here on every error path releases the slot (below)
+    lap(1);
     int rc = run_stage_a(ctx, s);
-    if (!rc) rc = read_scalars(ctx, s);
+    lap(2);
+    // the counts of stage A travel to the host behind it; stage B is queued when they have arrived (advance)
+    if (!rc) { cudaError_t e = cudaMemcpyAsync(s.h_scalars.p, s.scalars.p, 64, cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) rc = fail(ctx, C3R_ERR_CUDA, cudaGetErrorString(e)); }
+    if (!rc) { cudaError_t e = cudaEventRecord(s.ev_cnt, st); if (e != cudaSuccess) rc = fail(ctx, C3R_ERR_CUDA, cudaGetErrorString(e)); }
+    if (rc) { cudaStreamSynchronize(st); s.in_use = false; return rc; }
+    s.pending_b = true;
+    s.order = ++ctx->submit_seq;
+    *ticket = si;
+    // tickets submitted earlier whose counts are in by now get their stage B queued here (never blocks)
+    advance_all(ctx, getenv("C3R_SYNC_SUBMIT") != nullptr);
+    lap(3);
+    return C3R_OK;
+}
+
+// Queue stage B of a ticket whose stage A counts have arrived (block: wait for them).  Errors of this deferred part
+// are kept in the slot and reported by c3r_wait(ticket).
+static int advance(c3r_ctx* ctx, Slot& s, bool block) {
+    if (!s.in_use || !s.pending_b) return 0;
+    if (!block) {
+        const cudaError_t q = cudaEventQuery(s.ev_cnt);
+        if (q == cudaErrorNotReady) return 0;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = 0;
+    { cudaError_t e = cudaEventSynchronize(s.ev_cnt); if (e != cudaSuccess) rc = fail(ctx, C3R_ERR_CUDA, cudaGetErrorString(e)); }
+    s.pending_b = false;
+    if (!rc) rc = parse_scalars(ctx, s);
+    if (rc == C3R_ERR_CAPACITY && !s.exact_bounds && ctx->err.find("device capacity") != std::string::npos) {
+        // unusual CIGARs (more deleted than sequenced bases, ...): exact bounds from the CIGARs, which are still on
+        // the device, and stage A again
+        s.exact_bounds = true;
+        std::vector<uint32_t> cig((size_t)(s.d.n_ops > 0 ? s.d.n_ops : 1));
+        rc = 0;
+        if (s.d.n_ops > 0 && cudaMemcpy(cig.data(), s.cigar.p, (size_t)s.d.n_ops * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = fail(ctx, C3R_ERR_CUDA, "could not read the CIGARs back for exact capacity bounds");
+        if (!rc) rc = size_rows(ctx, s, cig.data());
+        if (!rc) rc = run_stage_a(ctx, s);
+        if (!rc) rc = read_scalars(ctx, s);
+    }
     if (!rc) rc = ensure_stage_b(ctx, s);
     if (!rc) rc = run_stage_b(ctx, s);
     if (!rc) rc = queue_d2h(ctx, s);
-    if (!rc) { cudaError_t e = cudaEventRecord(s.ev[8], st); if (e != cudaSuccess) rc = fail(ctx, C3R_ERR_CUDA, cudaGetErrorString(e)); }
-    if (rc) { cudaStreamSynchronize(st); s.in_use = false; return rc; }
-    *ticket = si;
-    return C3R_OK;
+    if (!rc) { cudaError_t e = cudaEventRecord(s.ev[8], s.st); if (e != cudaSuccess) rc = fail(ctx, C3R_ERR_CUDA, cudaGetErrorString(e)); }
+    if (rc) { cudaStreamSynchronize(s.st); s.deferred_rc = rc; s.deferred_err = ctx->err; }
+    ctx->t_phase[4] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+// every pending ticket, in submit order
+static void advance_all(c3r_ctx* ctx, bool block) {
+    for (;;) {
+        Slot* next = nullptr;
+        for (int i = 0; i < N_SLOTS; ++i) {
+            Slot& s = ctx->slots[i];
+            if (s.in_use && s.pending_b && (!next || s.order < next->order)) next = &s;
+        }
+        if (!next) return;
+        advance(ctx, *next, block);
+        if (next->pending_b) return;                 // not ready yet (non-blocking): the later ones wait their turn
+    }
 }
 
 int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* res) {
@@ -673,6 +771,16 @@ int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* res) {
     Slot& s = ctx->slots[ticket];
     if (!s.in_use) return fail(ctx, C3R_ERR_STATE, "ticket not in flight");
     CK(cudaSetDevice(ctx->device));
+    // Stage B of every ticket submitted so far is queued first (their counts arrive while the pass of the ticket
+    // waited for still runs), so that the device goes from one pass to the next without waiting for the host.
+    advance_all(ctx, true);
+    if (s.deferred_rc) {                             // the deferred part failed: report it and give the ticket back
+        const int rc = s.deferred_rc;
+        ctx->err = s.deferred_err;
+        s.deferred_rc = 0;
+        s.in_use = false;
+        return rc;
+    }
     CK(cudaStreamSynchronize(s.st));
     Dev& d = s.d;
     const int32_t err = ((const int32_t*)s.h_scalars.p)[6];
@@ -720,6 +828,8 @@ int c3r_release(c3r_ctx* ctx, c3r_ticket ticket) {
     Slot& s = ctx->slots[ticket];
     if (s.in_use) { cudaSetDevice(ctx->device); cudaStreamSynchronize(s.st); }
     s.in_use = false;
+    s.pending_b = false;                             // released before its stage B was queued: nothing more to run
+    s.deferred_rc = 0;
     s.has_result = false;
     return C3R_OK;
 }
@@ -729,6 +839,8 @@ int c3r_rerun_resident(c3r_ctx* ctx, c3r_ticket ticket, float* total_ms, float* 
     Slot& s = ctx->slots[ticket];
     if (!s.in_use) return fail(ctx, C3R_ERR_STATE, "ticket not in flight");
     CK(cudaSetDevice(ctx->device));
+    advance_all(ctx, true);
+    if (s.deferred_rc) { ctx->err = s.deferred_err; return s.deferred_rc; }
     CK(cudaStreamSynchronize(s.st));
     s.launches = 0;
     CK(cudaEventRecord(s.ev[0], s.st));

@@ -141,6 +141,7 @@ class Engine:
         if site_filter is None:
             self._check(self.lib.c3r_submit_chunk(self.ctx, C.byref(rd), rp, ref_start1, rn,
                                                   region_start1, region_end1, C.byref(t)), "c3r_submit_chunk")
+            self._keep[int(t.value)] = (arrs, ref)       # the call only queues the copies: inputs live until wait()
             return int(t.value)
         f = L.SiteFilter()
         keep = []
@@ -155,6 +156,7 @@ class Engine:
             setattr(f, "n_" + field, a.shape[0])
         self._check(self.lib.c3r_submit_chunk_filtered(self.ctx, C.byref(rd), rp, ref_start1, rn, region_start1,
                                                        region_end1, C.byref(f), C.byref(t)), "c3r_submit_chunk_filtered")
+        self._keep[int(t.value)] = (arrs, ref, keep)
         return int(t.value)
 
     def wait(self, ticket: int, release: bool = True, copy: bool = True) -> ChunkResult:
@@ -163,7 +165,10 @@ class Engine:
         faults (copying 3-4 MB into fresh memory costs ~1.5 ms per chunk, more than half a device pass) - which
         stay valid until release(ticket); the ticket is then NOT released here."""
         r = L.Result()
-        self._check(self.lib.c3r_wait(self.ctx, ticket, C.byref(r)), "c3r_wait")
+        try:
+            self._check(self.lib.c3r_wait(self.ctx, ticket, C.byref(r)), "c3r_wait")
+        finally:
+            self._keep.pop(ticket, None)
         n, Ct = int(r.n_cand), self.channels
         v = lambda ptr, cnt, dt: _view(ptr, cnt, dt, copy)
         alt_off = v(r.alt_off, n, np.int64)
@@ -183,6 +188,7 @@ class Engine:
         return out
 
     def release(self, ticket: int):
+        self._keep.pop(ticket, None)
         self.lib.c3r_release(self.ctx, ticket)
 
     def call_chunk(self, batch, ref, ref_start1, region_start1, region_end1, site_filter=None) -> ChunkResult:
@@ -231,6 +237,44 @@ class Engine:
             a = a.transpose(0, 6, 1, 2, 4, 3, 5, 7).reshape(tiles * 128, 33, 2, 4 * 160)   # gate, chunk*32 + ug*4 + i
             return a[:n_sites]
         return buf.view(np.float32).reshape(tiles * 128, 128)[:n_sites]
+
+
+class PinnedPool:
+    """A fixed set of page-locked uint8 host buffers (c3r_host_alloc) handed out and taken back: the reference window
+    of a chunk is read from the FASTA straight into one (fasta.fetch_into), given to Engine.submit - which then only
+    queues a DMA instead of having the driver stage pageable memory inside the call - and returned once the chunk's
+    rows are decoded.  get() returns None when the pool is empty or the request is larger than a buffer (the caller
+    falls back to ordinary memory)."""
+
+    def __init__(self, n_buffers: int, n_bytes: int):
+        import queue
+        self.lib = L.load()
+        self.n_bytes = int(n_bytes)
+        self.ptrs = []
+        self.free = queue.SimpleQueue()
+        for _ in range(n_buffers):
+            p = C.c_void_p()
+            if self.lib.c3r_host_alloc(C.byref(p), self.n_bytes) != 0:
+                break
+            self.ptrs.append(p)
+            self.free.put(np.frombuffer((C.c_char * self.n_bytes).from_address(p.value), dtype=np.uint8))
+
+    def get(self, n_bytes: int):
+        if n_bytes > self.n_bytes:
+            return None
+        try:
+            return self.free.get_nowait()
+        except Exception:
+            return None
+
+    def put(self, buf):
+        if buf is not None:
+            self.free.put(buf)
+
+    def close(self):
+        for p in self.ptrs:
+            self.lib.c3r_host_free(p)
+        self.ptrs = []
 
 
 # ---------------------------------------------------------------------- native decode

@@ -11,8 +11,22 @@ def read_fai(path: str) -> dict:
     return fai
 
 
+def fetch_into(path: str, fai: dict, contig: str, start1: int, end1: int, out: np.ndarray) -> np.ndarray:
+    """upper-cased bases of the 1-based inclusive region, clipped to the contig, written into the uint8 buffer `out`
+    (e.g. pinned host memory, engine.PinnedPool) by the native reader (csrc/fasta_io.cpp); returns the filled part."""
+    import ctypes as C
+    from . import lib as L
+    length, offset, linebases, linewidth = fai[contig]
+    n = C.c_int64(0)
+    rc = L.load().c3r_fasta_fetch(path.encode(), length, offset, linebases, linewidth, int(start1), int(end1),
+                                  out.ctypes.data, int(out.size), C.byref(n))
+    if rc != 0:
+        raise RuntimeError("c3r_fasta_fetch(%s, %s:%d-%d) failed with %d" % (path, contig, start1, end1, rc))
+    return out[:n.value]
+
+
 def fetch(path: str, fai: dict, contig: str, start1: int, end1: int) -> np.ndarray:
-    """upper-cased bases of the 1-based inclusive region, clipped to the contig."""
+    """upper-cased bases of the 1-based inclusive region, clipped to the contig (numpy form, no library needed)."""
     length, offset, linebases, linewidth = fai[contig]
     start1, end1 = max(1, start1), min(length, end1)
     if end1 < start1:

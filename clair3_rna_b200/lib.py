@@ -53,7 +53,8 @@ EXPORTS = ["c3r_abi_version", "c3r_default_params", "c3r_create", "c3r_destroy",
            "c3r_set_weights", "c3r_set_reference", "c3r_submit_chunk", "c3r_submit_chunk_filtered", "c3r_wait", "c3r_release", "c3r_rerun_resident", "c3r_forward", "c3r_debug_fetch",
            "c3r_bam_open", "c3r_bam_close", "c3r_bam_error", "c3r_bam_n_ref", "c3r_bam_ref_name", "c3r_bam_ref_len",
            "c3r_bam_header_text", "c3r_bam_idxstats", "c3r_bam_fetch", "c3r_bam_write",
-           "c3r_decode_vcf", "c3r_free_text", "c3r_debug_format_fixed", "c3r_vcf_write_bgzf"]
+           "c3r_decode_vcf", "c3r_free_text", "c3r_debug_format_fixed", "c3r_vcf_write_bgzf",
+           "c3r_host_alloc", "c3r_host_free", "c3r_fasta_fetch"]
 
 _lib = None
 
@@ -107,6 +108,11 @@ def load():
     lib.c3r_decode_vcf.argtypes = [C.POINTER(Result), C.POINTER(Reads), C.c_void_p, C.c_int64, C.c_int64, C.c_char_p,
                                    C.c_double, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64)]
+    lib.c3r_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
+    lib.c3r_host_free.argtypes = [C.c_void_p]
+    lib.c3r_host_free.restype = None
+    lib.c3r_fasta_fetch.argtypes = [C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.c3r_free_text.argtypes = [C.c_void_p]
     lib.c3r_free_text.restype = None
     _lib = lib

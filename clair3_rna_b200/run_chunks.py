@@ -43,6 +43,11 @@ def build_shards(contigs, mapped, chunk_size=P.CHUNK_SIZE):
     return shards, costs
 
 
+def chunk_size_bytes():
+    """bytes of the largest reference window of a chunk: the chunk, its reference flanks and the 33-column window"""
+    return P.CHUNK_SIZE + 2 * P.EXPAND_REFERENCE_REGION + 4 * P.NO_OF_POSITIONS + 64
+
+
 def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, world=1, phased=False, padding=False,
         snp_min_af=P.SNP_MIN_AF, indel_min_af=P.INDEL_MIN_AF, min_coverage=P.MIN_COVERAGE, min_mq=P.MIN_MQ,
         qual=P.QUAL_CUT_OFF, sample_name="SAMPLE", gather=None, stats=None, bed_fn=None, vcf_fn=None, head_tail=False,
@@ -54,7 +59,7 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
     native_threads: threads of each BGZF inflate and of the row decoder (0 = all cores - give every rank its share
     when several ranks run on one host)."""
     from .bam import BamFile
-    from .engine import Engine, decode_vcf_rows
+    from .engine import Engine, PinnedPool, decode_vcf_rows
     fai = fasta.read_fai(ref_fn)
     bf = BamFile(bam_fn)
     idx = {n: m for n, _, m, _ in bf.idxstats()}
@@ -80,6 +85,8 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
     import threading
     tls = threading.local()
     readers = []
+    # reference windows in page-locked buffers: tickets in flight (2) + being decoded (2) + loaded ahead
+    pool = PinnedPool(6 + 2 * max(1, loader_threads), chunk_size_bytes())
 
     def reader():
         # one BAM handle per loader thread (a handle serves one fetch at a time)
@@ -103,9 +110,13 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
         batch = reader().fetch(name, plan.start1, plan.end1)
         tm["fetch"] += time.time() - t
         t = time.time()
-        ref = fasta.fetch(ref_fn, fai, name, plan.ref_start1, plan.ref_end1)
+        pbuf = pool.get(plan.ref_end1 - plan.ref_start1 + 1)
+        if pbuf is not None:
+            ref = fasta.fetch_into(ref_fn, fai, name, plan.ref_start1, plan.ref_end1, pbuf)
+        else:
+            ref = fasta.fetch(ref_fn, fai, name, plan.ref_start1, plan.ref_end1)
         tm["ref"] += time.time() - t
-        return name, batch, ref, plan
+        return name, batch, ref, plan, pbuf
 
     # Three host stages run side by side (the native calls release the GIL): a loader thread fetches + inflates the
     # BAM blocks and reads the reference of the shards ahead, this thread submits shard i+1 and waits for shard i,
@@ -123,10 +134,11 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
         if i is not None:
             loads.append((i, loader.submit(load, i)))
 
-    def decode(res, pbatch, pref, prs1, pname):
+    def decode(res, pbatch, pref, prs1, pname, pbuf):
         t = time.time()
         rows = decode_vcf_rows(res, pbatch, pref, prs1, pname, qual=qual, threads=native_threads)
         tm["decode"] += time.time() - t
+        pool.put(pbuf)                               # the reference window is free again
         return rows
 
     def retire(block):
@@ -152,26 +164,27 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
             if got is None:                          # genotyping chunk without sites
                 rows_of[i] = []
             else:
-                name, batch, ref, plan = got
+                name, batch, ref, plan, pbuf = got
                 retire(len(decoding) >= 2)           # keep a ticket free for this submit
                 t = time.time()
                 nxt = (i, eng.submit(batch, ref, plan.ref_start1, plan.start1, plan.end1, plan.site_filter()),
-                       name, batch, ref, plan.ref_start1)
+                       name, batch, ref, plan.ref_start1, pbuf)
                 tm["submit"] += time.time() - t
                 submit_ms.append(1e3 * (time.time() - t))
         if pending is not None:
-            j, ticket, pname, pbatch, pref, prs1 = pending
+            j, ticket, pname, pbatch, pref, prs1, ppbuf = pending
             t = time.time()
             res = eng.wait(ticket, copy=False)       # arrays over the library's pinned buffers, no copies
             tm["wait"] += time.time() - t
             n_cand += res.n_cand
-            decoding.append((j, ticket, dec.submit(decode, res, pbatch, pref, prs1, pname)))
+            decoding.append((j, ticket, dec.submit(decode, res, pbatch, pref, prs1, pname, ppbuf)))
         retire(False)
         pending = nxt
     while decoding:
         retire(True)
     loader.shutdown()
     dec.shutdown()
+    pool.close()
     if engine is None:
         eng.close()
     bf.close()

@@ -138,7 +138,13 @@ int c3r_set_reference(c3r_ctx* ctx, const uint8_t* ref, int64_t ref_start1, int6
  *   ref / ref_start1 / ref_len: upper-case reference bytes of [ref_start1, ref_start1+ref_len)
  *                               (create_tensor_pileup.py:416-428, expandReferenceRegion)
  *                               ref == NULL: use the window given to c3r_set_reference
- *   region_start1..region_end1: the 1-based inclusive mpileup region (:412-415)          */
+ *   region_start1..region_end1: the 1-based inclusive mpileup region (:412-415)
+ * The call queues the host-to-device copies and the position / row stages and returns; it does not wait for the
+ * device.  `reads` and `ref` must stay valid and unchanged until c3r_wait(ticket) has returned (pinned host memory is
+ * read by DMA after the call).  The stages that need the candidate count (windows, allele table, network, result
+ * copies) are queued by a later call into the library once the count has reached the host - by the next
+ * c3r_submit_chunk if it is in by then, else by c3r_wait - so errors found on the device (capacity, the 8000-read
+ * depth cap of mpileup) are returned by c3r_wait, which then also gives the ticket back.          */
 int c3r_submit_chunk(c3r_ctx* ctx, const c3r_reads* reads, const uint8_t* ref, int64_t ref_start1,
                      int64_t ref_len, int64_t region_start1, int64_t region_end1, c3r_ticket* ticket);
 
@@ -164,6 +170,9 @@ typedef struct {
 int c3r_submit_chunk_filtered(c3r_ctx* ctx, const c3r_reads* reads, const uint8_t* ref, int64_t ref_start1,
                               int64_t ref_len, int64_t region_start1, int64_t region_end1,
                               const c3r_site_filter* filter, c3r_ticket* ticket);
+/* Blocks until the ticket's results are in the library's pinned host buffers (valid until c3r_release).  Before it
+ * blocks it queues the candidate-count dependent stages of EVERY ticket submitted so far, so with two tickets in
+ * flight the device goes from one chunk's network pass to the next without waiting for the host. */
 int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* result);
 int c3r_release(c3r_ctx* ctx, c3r_ticket ticket);
 
@@ -180,6 +189,18 @@ int c3r_forward(c3r_ctx* ctx, const int32_t* tensor, int64_t n, float* probs, fl
  * host (which: 0 = LSTM1 output, packed fp16; 1 = LSTM2 input projection, fp32 ZX layout;
  * 2 = LSTM2 output, packed fp16; 3 = L4 output, fp32 [sites,128]).  Layouts in csrc/nn_tc.cuh. */
 int c3r_debug_fetch(c3r_ctx* ctx, int which, void* dst, int64_t max_bytes, int64_t* n_bytes);
+
+/* Page-locked host memory for the arrays handed to c3r_submit_chunk (read by DMA while the call has long returned;
+ * pageable memory is staged by the driver inside the call instead: 0.5 ms per 5 MB reference window).  Needs a
+ * CUDA device.  Release with c3r_host_free. */
+int c3r_host_alloc(void** out, int64_t n_bytes);
+void c3r_host_free(void* p);
+
+/* Upper-cased bases of the 1-based inclusive region [start1, end1] (clipped to the contig) of an indexed FASTA into
+ * `out` (out_cap bytes; *n_out receives the count).  contig_len / offset / linebases / linewidth are the contig's
+ * .fai columns.  Replaces the per-chunk `samtools faidx` of shared/utils.py:168-194 (reference_sequence_from). */
+int c3r_fasta_fetch(const char* path, int64_t contig_len, int64_t offset, int64_t linebases, int64_t linewidth,
+                    int64_t start1, int64_t end1, uint8_t* out, int64_t out_cap, int64_t* n_out);
 
 /* ------------------------------------------------------------------------------------------
  * Probabilities + allele table -> VCF data lines (host, multi-threaded; csrc/decode.cpp).  Replaces the
