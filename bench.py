@@ -292,15 +292,16 @@ def shard_cfg5_leg(scale, rank, world, local_rank, cores, barrier, gloo, eng):
 
     cold = {}
     barrier()
+    n_loaders, n_native = max(1, min(4, cores // (2 * world))), max(1, cores // (2 * world))
     # first pass: cold (BAM handles and their indexes opened, file cache and buffers touched for the first time)
     run_chunks.run(bam, fa, wnpz, None, device=local_rank, rank=rank, world=world, merge=False, stats=cold,
-                   engine=eng, loader_threads=max(1, min(4, cores // (2 * world))), native_threads=max(1, cores // (2 * world)))
+                   engine=eng, loader_threads=n_loaders, native_threads=n_native)
     stats = {}
     barrier()
     t0 = time.time()
     merged = run_chunks.run(bam, fa, wnpz, os.path.join(tmp, "merged.vcf") if rank == 0 else None, device=local_rank,
                             rank=rank, world=world, gather=gather if world > 1 else None, stats=stats, engine=eng,
-                            loader_threads=max(1, min(4, cores // (2 * world))), native_threads=max(1, cores // (2 * world)))
+                            loader_threads=n_loaders, native_threads=n_native)
     t_all = time.time() - t0
     mine = dict(rank=rank, shards=stats["shards"], candidates=stats["candidates"], loop_s=stats["seconds"], cold_loop_s=cold["seconds"],
                 host_s=stats["host_seconds"], cost=stats["cost"], total_s=t_all)
@@ -334,6 +335,16 @@ def shard_cfg5_leg(scale, rank, world, local_rank, cores, barrier, gloo, eng):
                       "host_s": {k: round(v, 3) for k, v in a["host_s"].items()}} for a in allst],
         "host_feed": "host seconds of the slowest rank: " + ", ".join(
             "%s %.2f" % (k, v) for k, v in max(allst, key=lambda a: a["loop_s"])["host_s"].items()),
+        "host": (lambda a: {
+            "cores": cores, "ranks": world, "loader_threads_per_rank": n_loaders, "native_threads_per_call": n_native,
+            # share of the slowest rank's loop each host thread group is busy: the largest one is what bounds the loop
+            "busy": {"decoder thread (c3r_decode_vcf + row strings)": round(a["host_s"]["decode"] / a["loop_s"], 3),
+                     "loader threads (BAM fetch + inflate, FASTA window), each": round((a["host_s"]["fetch"] + a["host_s"]["ref"]) / n_loaders / a["loop_s"], 3),
+                     "submitting thread: submit + wait for the device": round((a["host_s"]["submit"] + a["host_s"]["wait"]) / a["loop_s"], 3),
+                     "submitting thread: waiting for the decoder": round(a["host_s"]["decode_wait"] / a["loop_s"], 3),
+                     "submitting thread: waiting for a loader": round(a["host_s"]["load_wait"] / a["loop_s"], 3)},
+            "cpu_seconds_per_genome": round(sum(x["host_s"][k] for x in allst for k in ("fetch", "ref", "submit", "decode")), 2),
+        })(max(allst, key=lambda a: a["loop_s"])),
         "dataset_prep_s": prep_s,
     }
 

@@ -45,9 +45,9 @@ struct Slot {
     // inputs
     Buf pos, flag, mapq, hp, cigar_off, cigar, seq_off, seq, ref;
     // per read/op
-    Buf admit, read_end, op_head, op_x, op_y, op_info, blockmax;
+    Buf admit, read_end, op_x, op_y, op_info, blockmax;
     // position space
-    Buf covA, covE, rowR, cov_up, ptile, ctile, word_base;
+    Buf covA, covE, rowR, cov_up, ptile, ctile, csuper, word_base;
     // row space
     Buf row_pos, counts, row_depth, row_flag, head_cnt, tail_cnt, skipdiff, max_skip, row_ins, row_del;
     Buf binc, bin_cur, events, raw, cov, cov_tile, refnib;
@@ -158,7 +158,6 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     cudaStream_t st = s.st;
     int& L = s.launches;
     // clear accumulators
-    CK(cudaMemsetAsync(s.op_head.p, 0xff, (size_t)(d.n_ops + 1) * 4, st));
     CK(cudaMemsetAsync(s.covA.p, 0, (size_t)(d.NW + 4) * 4, st));
     CK(cudaMemsetAsync(s.covE.p, 0, (size_t)(d.NW + 4) * 4, st));
     CK(cudaMemsetAsync(s.cov_up.p, 0, s.cov_up_bytes, st));
@@ -166,10 +165,15 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     CK(cudaMemsetAsync(s.blockmax.p, 0, (size_t)(d.n_reads / 256 + 2) * 4, st));
     CK(cudaEventRecord(s.ev[1], st));
     if (d.n_reads > 0) {
-        k_read_prepare<<<(unsigned)((d.n_reads + 255) / 256), 256, 0, st>>>(d);
+        // 8 lanes per read, a whole warp when reads carry hundreds of ops (the group walks a read's ops G at a time)
+        static const int force_g = getenv("C3R_CIGAR_G") ? atoi(getenv("C3R_CIGAR_G")) : 0;
+        const int64_t avg = d.n_ops / d.n_reads;
+        const int G = force_g ? force_g : avg > 96 ? 32 : 8;
+        if (G == 32) k_cigar<32><<<(unsigned)((d.n_reads * 32 + 255) / 256), 256, 0, st>>>(d);
+        else if (G == 16) k_cigar<16><<<(unsigned)((d.n_reads * 16 + 255) / 256), 256, 0, st>>>(d);
+        else k_cigar<8><<<(unsigned)((d.n_reads * 8 + 255) / 256), 256, 0, st>>>(d);
         ++L;
     }
-    { OpCigar op; op.d = d; if (d.n_ops > 0) L += device_scan(op, d.n_ops, s.scan, s.scan_epoch, (ScanElem*)nullptr, st); }
     if (d.n_known > 0) { k_mark_known<<<(unsigned)((d.n_known + 255) / 256), 256, 0, st>>>(d); ++L; }
     const unsigned ptiles = (unsigned)((d.NW + PT_WORDS - 1) / PT_WORDS);
     k_row_bits<<<ptiles, 256, 0, st>>>(d); ++L;
@@ -195,7 +199,8 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     CK(cudaEventRecord(s.ev[3], st));
     int64_t nb = (d.L_ub + COV_TILE - 1) / COV_TILE;
     {
-        const unsigned grid = (unsigned)(nb < ctx->sm_count * 16 ? nb : ctx->sm_count * 16);
+        const int64_t res = (int64_t)ctx->sm_count * (d.C == 30 ? 4 : 5);      // resident blocks: tiles come from a counter
+        const unsigned grid = (unsigned)(nb < res ? nb : res);
         if (d.C == 18) k_rows<18><<<grid, ROWS_WARPS * 32, 0, st>>>(d);
         else k_rows<30><<<grid, ROWS_WARPS * 32, 0, st>>>(d);
         ++L;
@@ -415,7 +420,7 @@ void c3r_destroy(c3r_ctx* ctx) {
     for (int i = 0; i < N_SLOTS; ++i) {
         Slot& s = ctx->slots[i];
         Buf* bs[] = {&s.pos, &s.flag, &s.mapq, &s.hp, &s.cigar_off, &s.cigar, &s.seq_off, &s.seq, &s.ref, &s.admit,
-                     &s.read_end, &s.op_head, &s.op_x, &s.op_y, &s.op_info, &s.blockmax, &s.covA, &s.covE, &s.rowR, &s.cov_up, &s.ptile, &s.ctile,
+                     &s.read_end, &s.op_x, &s.op_y, &s.op_info, &s.blockmax, &s.covA, &s.covE, &s.rowR, &s.cov_up, &s.ptile, &s.ctile, &s.csuper,
                      &s.word_base, &s.row_pos, &s.counts, &s.row_depth, &s.row_flag, &s.head_cnt, &s.tail_cnt,
                      &s.skipdiff, &s.max_skip, &s.row_ins, &s.row_del, &s.binc, &s.bin_cur, &s.events, &s.raw, &s.cov, &s.cov_tile, &s.refnib,
                      &s.cand_row, &s.cand_pos, &s.cand_depth, &s.tensor, &s.alt_off, &s.alt_n, &s.alt, &s.cur_ref,
@@ -553,7 +558,7 @@ static int size_rows(c3r_ctx* ctx, Slot& s, const uint32_t* cigar_host) {
     EN(binc, (L_ub + 4) * 4); EN(bin_cur, (L_ub + 4) * 4);
     EN(events, d.events_ub * sizeof(RowEvent)); EN(raw, d.events_ub * sizeof(RowEvent));
     EN(cov, (L_ub + 4) * NCOV_MAX * 4); EN(cov_tile, (L_ub / COV_TILE + 4) * NCOV_MAX * 4);
-    EN(ctile, (L_ub / COV_TILE + 4) * 4);
+    EN(ctile, (L_ub / COV_TILE + 4) * 4); EN(csuper, (L_ub / (64 * COV_TILE) + 4) * 4);
     EN(cand_row, (L_ub + 2) * 4); EN(cand_pos, (L_ub + 2) * 4); EN(cand_depth, (L_ub + 2) * 4);
     EN(cur_ref, (L_ub + 2) * 8); EN(deleted, L_ub + 2);
     {
@@ -581,7 +586,7 @@ static int size_rows(c3r_ctx* ctx, Slot& s, const uint32_t* cigar_host) {
     d.row_inscnt = P<int32_t>(s.row_ins); d.row_delcnt = P<int32_t>(s.row_del);
     d.binc = P<int32_t>(s.binc); d.bin_cur = P<int32_t>(s.bin_cur);
     d.events = P<RowEvent>(s.events); d.raw = P<RowEvent>(s.raw); d.cov = P<int32_t>(s.cov); d.cov_tile = P<int32_t>(s.cov_tile);
-    d.ctile = P<int32_t>(s.ctile);
+    d.ctile = P<int32_t>(s.ctile); d.csuper = P<int32_t>(s.csuper);
     d.cand_row = P<int32_t>(s.cand_row); d.cand_pos = P<int32_t>(s.cand_pos); d.cand_depth = P<int32_t>(s.cand_depth);
     d.cur_ref = P<Int2>(s.cur_ref); d.deleted = P<uint8_t>(s.deleted);
     return 0;
@@ -619,6 +624,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.C = pr.channels; d.min_cov = pr.min_coverage; d.min_mq = pr.min_mq; d.excl = pr.excl_flags;
     d.snp_af = pr.snp_min_af; d.indel_af = pr.indel_min_af; d.padding = pr.enable_padding;
     d.max_depth = pr.max_depth; d.skip_prop = pr.skip_proportion;
+    d.dbg = getenv("C3R_DBG") ? atoi(getenv("C3R_DBG")) : 0;
     d.ref_start0 = ref_start1 - 1; d.ref_len = ref_len;
     d.thr_snp = (const uint16_t*)ctx->thr.p; d.thr_indel = (const uint16_t*)ctx->thr.p + THR_N;
     s.n_seq_bytes = rd->n_seq_bytes;
@@ -629,7 +635,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
 #define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
     EN(pos, R * 4); EN(flag, R * 2); EN(mapq, R); EN(hp, R); EN(cigar_off, (R + 1) * 4); EN(cigar, O * 4);
     EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 64); if (ref) { EN(ref, ref_len + 16); }
-    EN(admit, R); EN(read_end, R * 4); EN(blockmax, (R / 256 + 2) * 4); EN(op_head, (O + 1) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_info, O * 4);
+    EN(admit, R); EN(read_end, R * 4); EN(blockmax, (R / 256 + 2) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_info, O * 4);
     // position space: buffers padded to whole tiles of PT_WORDS words (k_row_bits / k_row_rank store 16 bytes per thread);
     // the summary levels of covA and covE (mark_range) share one buffer: level l has NW / 32^l + 2 words
     const int64_t NWp = ((d.NW + PT_WORDS - 1) / PT_WORDS) * PT_WORDS + 8;
@@ -651,7 +657,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.pos = P<int32_t>(s.pos); d.flag = P<uint16_t>(s.flag); d.mapq = P<uint8_t>(s.mapq); d.hp = P<uint8_t>(s.hp);
     d.cigar_off = P<int32_t>(s.cigar_off); d.cigar = P<uint32_t>(s.cigar); d.seq_off = P<int64_t>(s.seq_off);
     d.seq = P<uint8_t>(s.seq); d.ref = ref ? P<uint8_t>(s.ref) : P<uint8_t>(ctx->ref_res);
-    d.admit = P<uint8_t>(s.admit); d.read_end = P<int32_t>(s.read_end); d.op_head = P<int32_t>(s.op_head);
+    d.admit = P<uint8_t>(s.admit); d.read_end = P<int32_t>(s.read_end);
     d.op_x = P<int32_t>(s.op_x); d.op_y = P<uint32_t>(s.op_y); d.op_info = P<uint32_t>(s.op_info);
     d.covA = P<uint32_t>(s.covA); d.covE = P<uint32_t>(s.covE); d.rowR = P<uint32_t>(s.rowR);
     d.word_base = P<int32_t>(s.word_base);

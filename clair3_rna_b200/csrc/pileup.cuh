@@ -70,6 +70,8 @@ struct Dev {
     // ---- params
     int32_t C; int32_t min_cov; int32_t min_mq; uint32_t excl; double snp_af, indel_af;
     int32_t padding; int32_t max_depth; double skip_prop;
+    int32_t dbg;                // experiments (C3R_DBG): 1 = no tie-break walk, 2 = no heavy-row path
+
     const uint16_t* thr_snp; const uint16_t* thr_indel;     // THR_N entries each (k_thr_table)
     // ---- optional site filters (create_tensor_pileup.py:446-451, 480-481, 551-556); n < 0: not given.
     // Intervals: sorted, disjoint, non-touching (start0, end0) pairs; known: sorted 1-based positions.
@@ -80,7 +82,7 @@ struct Dev {
     const uint32_t* covP; int32_t head_tail;
     int32_t* tail;              // [0] offset of the last printed column + 1, [1] offset of the last gap below it + 1
     // ---- per read / per op
-    uint8_t* admit; int32_t* read_end; int32_t* op_head;
+    uint8_t* admit; int32_t* read_end;
     int32_t* op_x; uint32_t* op_y;
     uint32_t* op_info;          // rid << 4 | hp << 2 | last op of its read << 1 | reverse;  OP_SKIP: read not admitted
     // ---- position space
@@ -102,7 +104,8 @@ struct Dev {
     int32_t* cov_tile;             // [L_ub/256+2][4 or 6]: sums of cov over tiles of 256 rows, then their exclusive prefix
     const uint32_t* refnib; int64_t n_ref_words;     // one-hot reference nibbles of the loaded window (k_refnib)
     int32_t* blockmax;             // [n_reads/256+1]: largest end of the admitted reads of each block of 256 reads
-    int32_t* ctile;                // [L_ub/256+2]: candidates per tile of 256 rows (k_rows), then their exclusive prefix
+    int32_t* ctile;                // [L_ub/256+2]: candidates per tile of 256 rows (k_rows)
+    int32_t* csuper;               // [L_ub/16384+2]: candidates per group of 64 tiles
     // ---- candidates
     int64_t* n_cand; int32_t* cand_row; int64_t cand_cap;
     int32_t* cand_pos; int32_t* cand_depth;
@@ -147,6 +150,9 @@ __device__ __forceinline__ int ref_index(const Dev& d, int32_t p, bool* is_acgt)
 // words between them are not written: they become a bit range of the next level ("this whole word is set"), marked
 // the same way - at most two atomics per level, whatever the length (a read spanning introns of 100 kb is 3 000
 // words).  k_row_bits folds the levels back into level 0.
+// (testing the word first and skipping the atomic when the bits are already there was measured slower: 44 against
+// 33 us for k_cigar at config 2 - the dependent load costs more than the atomics it saves)
+__device__ __forceinline__ void or_bits(uint32_t* w, uint32_t m) { atomicOr(w, m); }
 __device__ __forceinline__ void mark_range(uint32_t* bm, uint32_t* const* up, int64_t a, int64_t b) {
     if (b <= a) return;
     int64_t lo = a, hi = b;
@@ -155,12 +161,12 @@ __device__ __forceinline__ void mark_range(uint32_t* bm, uint32_t* const* up, in
         const int64_t wa = lo >> 5, wb = (hi - 1) >> 5;
         const uint32_t ma = 0xffffffffu << (lo & 31);
         const uint32_t mb = 0xffffffffu >> (31 - ((hi - 1) & 31));
-        if (wa == wb) { atomicOr(&bm[wa], ma & mb); return; }
-        atomicOr(&bm[wa], ma);
-        atomicOr(&bm[wb], mb);
+        if (wa == wb) { or_bits(&bm[wa], ma & mb); return; }
+        or_bits(&bm[wa], ma);
+        or_bits(&bm[wb], mb);
         if (wb <= wa + 1) return;
         if (l == COV_UP) {                               // beyond the top level (not reachable with int32 positions)
-            for (int64_t w = wa + 1; w < wb; ++w) atomicOr(&bm[w], 0xffffffffu);
+            for (int64_t w = wa + 1; w < wb; ++w) or_bits(&bm[w], 0xffffffffu);
             return;
         }
         lo = wa + 1; hi = wb; bm = up[l];
@@ -179,85 +185,69 @@ __device__ __forceinline__ uint32_t up_full4(uint32_t* const* up, int64_t w4) {
 }
 __device__ __forceinline__ bool up_full(uint32_t* const* up, int64_t w) { return (up_full4(up, w & ~3ll) >> (w & 3)) & 1u; }
 
-// ---------------------------------------------------------------- K0: reads
-// admit flag per read (samtools mpileup filters) and segment heads
-__global__ void k_read_prepare(Dev d) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= d.n_reads) return;
+// ------------------------------------------------- K1: CIGAR geometry per read
+// G lanes per read (G = 8, or 32 when reads carry hundreds of ops): the group walks the read's ops G at a time, an
+// inclusive scan inside the group (shuffles) gives every op the reference / query lengths consumed before it, and
+// the running totals carry over to the next G ops.  Per op: reference start op_x, base index op_y, op_info
+// (read ordinal, haplotype, strand, last-op flag; OP_SKIP when the read is not admitted); M/=/X/D ops mark covE,
+// the read's whole span marks covA.  Also the admit flag per read (samtools mpileup filters).
+// No device-wide scan, no segment heads: reads are independent (this replaced a segmented look-back scan over all
+// ops that took 50 us for a million ops, most of it waiting on its own cross-block protocol).
+template <int G>
+__global__ void __launch_bounds__(256) k_cigar(Dev d) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gl = threadIdx.x & (G - 1);
+    if (r >= d.n_reads) return;                          // whole groups leave together (256 % G == 0)
+    const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (threadIdx.x & 31 & ~(G - 1)));
     const uint32_t f = d.flag[r];
+    const int32_t a = d.cigar_off[r], b = d.cigar_off[r + 1];
+    const int32_t pos = d.pos[r];
     bool ok = !(f & (0x4u | 0x100u | 0x200u | 0x400u)) && !(f & d.excl) && (int)d.mapq[r] >= d.min_mq;
     if ((f & 0x1u) && !(f & 0x2u)) ok = false;
-    const int32_t a = d.cigar_off[r], b = d.cigar_off[r + 1];
     if (b <= a) ok = false;
-    d.admit[r] = ok ? 1 : 0;
-    d.read_end[r] = d.pos[r];
-    if (b > a) d.op_head[a] = (int32_t)r;
-}
-
-// ------------------------------------------------- K1: CIGAR segmented scan
-// element k = CIGAR op k.  The inclusive segmented scan yields, per op, the reference
-// and query lengths consumed by the read up to and including the op; subtracting the
-// op's own lengths gives its start offsets.  The store marks coverage bitmaps.
-struct OpCigar {
-    typedef ScanElem T;
-    // per-read values of the read a thread's consecutive ops belong to (a thread stores 8 ops in a row and a read has
-    // dozens: the dependent loads pos[r], seq_off[r], ... are paid once per read change, not once per op)
-    struct Ctx { int32_t r, pos, kend; uint32_t seq_off, info; bool admit; };
-    Dev d;
-    __device__ void ctx_init(Ctx& c) const { c.r = -1; c.pos = 0; c.kend = 0; c.seq_off = 0; c.info = 0; c.admit = false; }
-    __device__ T identity() const { T t; t.v = 0; t.rid = -1; t.flag = 0; return t; }
-    __device__ T combine(const T& a, const T& b) const {
-        if (b.flag) return b;
-        T t; t.v = a.v + b.v; t.rid = a.rid; t.flag = a.flag; return t;
-    }
-    __device__ int64_t size() const { return d.n_ops; }
-    __device__ T load(int64_t k) const {
-        const uint32_t c = d.cigar[k];
+    uint32_t hp = d.hp[r];
+    hp = hp == 1 ? 1u : hp == 2 ? 2u : 0u;
+    const uint32_t info = ((uint32_t)r << 4) | (hp << 2) | ((f >> 4) & 1u);
+    uint32_t x = 0, y = (uint32_t)d.seq_off[r];          // reference bases consumed so far, base index in the sequence pool
+    for (int32_t k0 = a; k0 < b; k0 += G) {
+        const int32_t k = k0 + gl;
+        const uint32_t c = k < b ? d.cigar[k] : 0u;
         const uint32_t op = c & 15u, len = c >> 4;
-        T t;
-        t.v = ((unsigned long long)(op_consumes_ref(op) ? len : 0u) << 32) | (op_consumes_qry(op) ? len : 0u);
-        const int32_t h = d.op_head[k];
-        t.rid = h; t.flag = h >= 0 ? 1 : 0;
-        return t;
+        const uint32_t rl = op_consumes_ref(op) ? len : 0u, ql = op_consumes_qry(op) ? len : 0u;
+        uint32_t ir = rl, iq = ql;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const uint32_t ur = __shfl_up_sync(gmask, ir, o, G), uq = __shfl_up_sync(gmask, iq, o, G);
+            if (gl >= o) { ir += ur; iq += uq; }
+        }
+        if (k < b) {
+            const int32_t ox = pos + (int32_t)(x + ir - rl);
+            d.op_x[k] = ox;
+            d.op_y[k] = y + iq - ql;
+            d.op_info[k] = ok ? (info | (k + 1 == b ? 2u : 0u)) : OP_SKIP;
+            if (ok && rl && (op_is_match(op) || op == 2)) {
+                int64_t lo = (int64_t)ox - d.R0, hi = lo + rl;
+                if (lo < 0) lo = 0;
+                if (hi > d.W) hi = d.W;
+                mark_range(d.covE, d.upE, lo, hi);
+            }
+        }
+        x += __shfl_sync(gmask, ir, G - 1, G);
+        y += __shfl_sync(gmask, iq, G - 1, G);
     }
-    __device__ void store(int64_t k, const T& incl, const T& own, Ctx& c) const {
-        const int32_t r = incl.rid;
-        if (r != c.r) {
-            c.r = r;
-            c.pos = d.pos[r];
-            c.seq_off = (uint32_t)d.seq_off[r];
-            c.kend = d.cigar_off[r + 1];
-            c.admit = d.admit[r] != 0;
-            uint32_t hp = d.hp[r];
-            hp = hp == 1 ? 1u : hp == 2 ? 2u : 0u;
-            c.info = ((uint32_t)r << 4) | (hp << 2) | ((d.flag[r] >> 4) & 1u);
-        }
-        const uint32_t rl = (uint32_t)(own.v >> 32), ql = (uint32_t)own.v;
-        const uint32_t rx = (uint32_t)(incl.v >> 32) - rl, qy = (uint32_t)incl.v - ql;
-        const int32_t x = c.pos + (int32_t)rx;
-        const bool last = k + 1 == c.kend;
-        d.op_x[k] = x;
-        d.op_y[k] = c.seq_off + qy;
-        d.op_info[k] = c.admit ? (c.info | (last ? 2u : 0u)) : OP_SKIP;
-        if (!c.admit) return;
-        const uint32_t op = d.cigar[k] & 15u;
-        if (rl && (op_is_match(op) || op == 2)) {
-            int64_t a = (int64_t)x - d.R0, b = a + rl;
-            if (a < 0) a = 0;
-            if (b > d.W) b = d.W;
-            mark_range(d.covE, d.upE, a, b);
-        }
-        if (last) {                                      // last op: the read's whole span
-            const int32_t end = c.pos + (int32_t)(incl.v >> 32);
-            d.read_end[r] = end;
+    if (gl == 0) {
+        d.admit[r] = ok ? 1 : 0;
+        const int32_t end = pos + (int32_t)x;
+        d.read_end[r] = b > a ? end : pos;
+        if (ok) {                                        // the read's whole span
             atomicMax(&d.blockmax[r >> 8], end);
-            int64_t a = (int64_t)c.pos - d.R0, b = (int64_t)end - d.R0;
-            if (a < 0) a = 0;
-            if (b > d.W) b = d.W;
-            mark_range(d.covA, d.upA, a, b);
+            int64_t lo = (int64_t)pos - d.R0, hi = (int64_t)end - d.R0;
+            if (lo < 0) lo = 0;
+            if (hi > d.W) hi = d.W;
+            mark_range(d.covA, d.upA, lo, hi);
         }
     }
-};
+}
 
 // Genotyping mode: a known site is a candidate even in the middle of an intron, where the columns only carry
 // `>` / `<`; marking the site like an aligned base gives it and its 16 neighbours on each side count rows.
@@ -435,6 +425,8 @@ __global__ void __launch_bounds__(256) k_row_rank(Dev d) {
             d.deleted[i] = 0;
         }
     }
+    if (blockIdx.x == 0)
+        for (int64_t i = t; i < d.L_ub / (64 * COV_TILE) + 2; i += 256) d.csuper[i] = 0;
     if (z1 > z0) {                                       // coverage tiles these rows fall into (neighbours overlap: all zero)
         const int64_t ct0 = z0 / COV_TILE, ct1 = (z1 - 1) / COV_TILE + 1;
         for (int64_t i = ct0 * NC + t; i < (ct1 + 1) * NC; i += 256) d.cov_tile[i] = 0;
@@ -562,15 +554,21 @@ __global__ void __launch_bounds__(CMP_THREADS) k_cmp(Dev d) {
     const int lane = threadIdx.x & 31;
     const int NC = d.C == 30 ? 6 : 4;
     if (*d.err == 1) return;                             // more rows than the buffers hold: the host retries with exact bounds
+    __shared__ int chunk_s;
     if (threadIdx.x == 0) st.n = 0;
+    // chunks of CMP_THREADS ops are handed out by a counter: a chunk's cost goes with the bases under its ops (a HiFi
+    // match of kilobases next to 3-base exon ends), a static split leaves the blocks finishing far apart
+    for (;;) {
+    if (threadIdx.x == 0) chunk_s = atomicAdd(&d.kctr[3], 1);
     __syncthreads();
-    for (int64_t k0 = (int64_t)blockIdx.x * blockDim.x; k0 < d.n_ops; k0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k0 = (int64_t)chunk_s * CMP_THREADS;
+    if (k0 >= d.n_ops) break;
     const int64_t k = k0 + threadIdx.x;
     CmpOp cmp;
     cmp.w0 = 0; cmp.w1 = -1; cmp.kw = 0; cmp.sh = 0; cmp.rbase = 0; cmp.info = 0; cmp.m0 = 0; cmp.m1 = 0;
     do {
         if (k >= d.n_ops) break;
-        const uint32_t oi = d.op_info[k];                // OpCigar's store: read ordinal, haplotype, strand, last-op flag
+        const uint32_t oi = d.op_info[k];                // from k_cigar: read ordinal, haplotype, strand, last-op flag
         if (oi == OP_SKIP) break;                        // read not admitted
         const int32_t r = (int32_t)(oi >> 4);
         const uint32_t c = d.cigar[k];
@@ -1024,21 +1022,21 @@ __device__ void row_indels(const Dev& d, const RowEvent* evs, int32_t n, int32_t
 // and the ring has no empty slot" (create_tensor_pileup.py:565-568).  Head/tail mode: zero rows stand in for the
 // columns before the run; the columns after it are only supplied when the stream ends, i.e. for the final run
 // (create_tensor_pileup.py:508-511, 613-637).
-__device__ __forceinline__ bool window_printed(const Dev& d, int32_t p) {
-    const int64_t o = (int64_t)p - d.R0;
-    if (d.head_tail) {
-        if (!bit_at(d.covP, o)) return false;
-        int nb, na;
-        printed_run(d, o, &nb, &na);
-        return na == FLANK || o >= d.tail[1];
+// (out of line and with its operands by value: it runs for the few eligible rows only and must not cost k_rows registers)
+__device__ __noinline__ bool window_printed(const uint32_t* covP, int64_t o, int64_t W, int head_tail, int32_t tail1) {
+    if (head_tail) {
+        if (!((covP[o >> 5] >> (o & 31)) & 1u)) return false;
+        const unsigned long long up = (covP[o >> 5] | ((unsigned long long)covP[(o >> 5) + 1] << 32)) >> (o & 31);   // bit 0 = o
+        const int na = __ffsll((long long)~(up >> 1)) - 1;                    // printed columns right above o (printed_run)
+        return na >= FLANK || o >= tail1;
     }
-    if (o - FLANK < 0 || o + FLANK >= d.W) return false;
+    if (o - FLANK < 0 || o + FLANK >= W) return false;
     // 33 consecutive printed columns starting at o-16 (covP = covA inside the pileup BED: mpileup -l never prints
     // the others, so the ring buffer restarts there)
     const int64_t s = o - FLANK;
     const int64_t w = s >> 5;
     const int sh = (int)(s & 31);
-    const unsigned long long lo = d.covP[w] | ((unsigned long long)d.covP[w + 1] << 32);
+    const unsigned long long lo = covP[w] | ((unsigned long long)covP[w + 1] << 32);
     const unsigned long long bits = lo >> sh;              // 64 - sh >= 33 bits are valid
     const unsigned long long need = (1ull << 33) - 1ull;
     return (bits & need) == need;
@@ -1053,8 +1051,6 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
     __shared__ __align__(16) int32_t stage[ROWS_WARPS][TILE_ROWS * C];
     __shared__ int32_t wtot[ROWS_WARPS][NC];
     __shared__ uint32_t done_s[ROWS_WARPS][IND_WORDS];
-    __shared__ int32_t carry_s;
-    __shared__ bool is_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (*d.err == 1) return;                             // more rows than the buffers hold: the host retries with exact bounds
     const int64_t L = *d.n_rows;
@@ -1251,7 +1247,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
                         bool tie = false;
 #pragma unroll
                         for (int i = 0; i < 6; ++i) if (i != ri && cls[i] == top) tie = true;
-                        if (tie) {
+                        if (tie && !(d.dbg & 1)) {
                             uint32_t key[6];
                             first_keys(d, (int32_t)row, p, ri, acgt, key);
                             for (int i = 0; i < 6; ++i) if (i != ri && cls[i] == top && key[i] < key[ri]) pass = true;
@@ -1272,7 +1268,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
                 }
                 cand = iv_overlaps(d.cbed, d.n_cbed, p, p + max_del + 2);
             }
-            is_cand = cand && window_printed(d, p);            // K3: eligible and 33 printed columns around it
+            is_cand = cand && window_printed(d.covP, (int64_t)p - d.R0, d.W, d.head_tail, d.head_tail ? d.tail[1] : 0);   // K3
             const uint8_t flag = is_cand ? 1 : 0;
             v[ri] = -fsum;
             v[9 + ri] = -rsum;
@@ -1299,47 +1295,58 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
             }
         }
         __syncwarp();
-        // candidates of the tile (K3's list is built from these counts: k_cand_emit)
+        // candidates of the tile and of its group of 64 tiles (K3's list is built from these counts: k_cand_emit)
         const int nc = __syncthreads_count(is_cand);
-        if (threadIdx.x == 0) d.ctile[tile] = nc;
-    }
-    // ---- the last block to finish turns the per-tile candidate counts into their exclusive prefix
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        is_last = atomicAdd(&d.kctr[1], 1) == (int)gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    const int n_ct = (int)((L + COV_TILE - 1) / COV_TILE);
-    const int32_t total = block_scan_inplace_256(d.ctile, n_ct, &wtot[0][0], &carry_s);
-    if (threadIdx.x == 255) {
-        d.ctile[n_ct] = total;
-        *d.n_cand = total;
+        if (threadIdx.x == 0) {
+            d.ctile[tile] = nc;
+            if (nc) atomicAdd(&d.csuper[tile >> 6], nc);
+        }
     }
 }
 
 // ------------------------------------------------------- K3: candidate list
-// k_rows flagged the candidates (eligible and 33 printed columns) and left the per-tile counts' exclusive prefix:
-// block = tile of 256 rows, a candidate's slot = tile prefix + its rank in the tile (position order is kept)
+// k_rows flagged the candidates (eligible and 33 printed columns) and counted them per tile of 256 rows and per group
+// of 64 tiles.  Block = tile; its first slot = the groups before its group + the tiles before it in its group (a few
+// dozen cached loads, no scan and no serial tail); a candidate's slot = that + its rank in the tile (position order).
 __global__ void __launch_bounds__(256) k_cand_emit(Dev d) {
-    __shared__ int32_t wcnt[8];
+    __shared__ int32_t wsum[8];
+    __shared__ int32_t base_s;
     const int64_t L = *d.n_rows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t tile = blockIdx.x; tile * COV_TILE < L; tile += gridDim.x) {
-        const int32_t base = d.ctile[tile];
-        if (d.ctile[tile + 1] == base) continue;         // block-uniform
+    const int64_t n_ct = (L + COV_TILE - 1) / COV_TILE;
+    auto block_sum = [&](int32_t v) {                    // sum over the block, returned to every thread
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) wsum[warp] = v;
+        __syncthreads();
+        int32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        return t;
+    };
+    if (blockIdx.x == 0) {                               // the candidate count
+        int32_t v = 0;
+        for (int64_t i = threadIdx.x; i < (n_ct + 63) / 64; i += 256) v += d.csuper[i];
+        const int32_t total = block_sum(v);
+        if (threadIdx.x == 0) *d.n_cand = total;
+    }
+    for (int64_t tile = blockIdx.x; tile < n_ct; tile += gridDim.x) {
+        if (d.ctile[tile] == 0) continue;                // block-uniform
+        int32_t v = 0;
+        for (int64_t i = threadIdx.x; i < (tile >> 6); i += 256) v += d.csuper[i];
+        for (int64_t i = (tile & ~63ll) + threadIdx.x; i < tile; i += 256) v += d.ctile[i];
+        const int32_t base = block_sum(v);
         const int64_t row = tile * COV_TILE + threadIdx.x;
         const bool c = row < L && d.row_flag[row];
         const uint32_t m = __ballot_sync(0xffffffffu, c);
         __syncthreads();
-        if (lane == 0) wcnt[warp] = __popc(m);
+        if (lane == 0) wsum[warp] = __popc(m);
         __syncthreads();
         if (c) {
             int64_t i = base + __popc(m & ((1u << lane) - 1u));
 #pragma unroll
-            for (int w = 0; w < 8; ++w) if (w < warp) i += wcnt[w];
+            for (int w = 0; w < 8; ++w) if (w < warp) i += wsum[w];
             if (i < d.cand_cap) {
                 d.cand_row[i] = (int32_t)row;
                 d.cand_pos[i] = d.row_pos[row] + 1;

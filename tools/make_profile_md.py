@@ -25,7 +25,7 @@ def launch_rows(path, which=2):
     h = [i for i, r in enumerate(rows) if r[0] == 'ID'][0]
     H, body = rows[h], rows[h + 1:]
     ik, iv, iu = H.index('Kernel Name'), H.index('Metric Value'), H.index('Metric Unit')
-    starts = [i for i, r in enumerate(body) if 'k_read_prepare' in r[ik]] + [len(body)]
+    starts = [i for i, r in enumerate(body) if 'k_cigar' in r[ik]] + [len(body)]
     seg = body[starts[which]:starts[which + 1]]
     return [(short(r[ik]), float(r[iv].replace(',', '')) * TUNIT.get(r[iu], 1.0)) for r in seg]
 
@@ -70,7 +70,7 @@ def full_rows(rep):
 def stage_of(name):
     if name.startswith("k_lstm") or name.startswith("k_gemm") or name.startswith("k_l4") or name.startswith("k_heads") or name.startswith("k_xop"):
         return "k5"
-    if "OpCand" in name:
+    if "OpCand" in name or name.startswith("k_cand_emit"):
         return "k3"
     if name.startswith("k_window") or name.startswith("k_padding") or name.startswith("k_rescale") or "OpAltOff" in name or name.startswith("k_altinfo"):
         return "k4"

@@ -10,7 +10,7 @@ rows = [r for r in csv.reader(open("gpurun_out/launches_$TAG.csv")) if len(r) > 
 h = [i for i, r in enumerate(rows) if r[0] == 'ID'][0]
 H, body = rows[h], rows[h + 1:]
 ik, iv, iu = H.index('Kernel Name'), H.index('Metric Value'), H.index('Metric Unit')
-starts = [i for i, r in enumerate(body) if 'k_read_prepare' in r[ik]]
+starts = [i for i, r in enumerate(body) if 'k_cigar' in r[ik]]
 seg = body[starts[2]:starts[3]] if len(starts) > 3 else body[starts[-1]:]
 tot = 0
 for r in seg:

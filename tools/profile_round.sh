@@ -12,7 +12,7 @@ rows = [r for r in csv.reader(open("gpurun_out/launches_$TAG.csv")) if len(r) > 
 h = [i for i, r in enumerate(rows) if r[0] == 'ID'][0]
 body = rows[h + 1:]
 ik = rows[h].index('Kernel Name')
-s = [i for i, r in enumerate(body) if 'k_read_prepare' in r[ik]]
+s = [i for i, r in enumerate(body) if 'k_cigar' in r[ik]]
 print(s[2], s[3] - s[2])
 PY
 )

@@ -7,7 +7,7 @@ def launch_table(path, which):
     h = [i for i, r in enumerate(rows) if r[0] == 'ID'][0]
     H, body = rows[h], rows[h + 1:]
     ik, iv, iu = H.index('Kernel Name'), H.index('Metric Value'), H.index('Metric Unit')
-    starts = [i for i, r in enumerate(body) if 'k_read_prepare' in r[ik]] + [len(body)]
+    starts = [i for i, r in enumerate(body) if 'k_cigar' in r[ik]] + [len(body)]
     seg = body[starts[which]:starts[which + 1]]
     agg = collections.OrderedDict()
     for r in seg:
