@@ -338,7 +338,7 @@ def shard_cfg5_leg(scale, rank, world, local_rank, cores, barrier, gloo, eng):
         "host": (lambda a: {
             "cores": cores, "ranks": world, "loader_threads_per_rank": n_loaders, "native_threads_per_call": n_native,
             # share of the slowest rank's loop each host thread group is busy: the largest one is what bounds the loop
-            "busy": {"decoder thread (c3r_decode_vcf + row strings)": round(a["host_s"]["decode"] / a["loop_s"], 3),
+            "busy": {"decoder threads (2; c3r_decode_vcf + row strings), each": round(a["host_s"]["decode"] / 2 / a["loop_s"], 3),
                      "loader threads (BAM fetch + inflate, FASTA window), each": round((a["host_s"]["fetch"] + a["host_s"]["ref"]) / n_loaders / a["loop_s"], 3),
                      "submitting thread: submit + wait for the device": round((a["host_s"]["submit"] + a["host_s"]["wait"]) / a["loop_s"], 3),
                      "submitting thread: waiting for the decoder": round(a["host_s"]["decode_wait"] / a["loop_s"], 3),

@@ -51,11 +51,18 @@ enum Fam { REF = 0, HOMO_SNP, HET_SNP, HOMO_INS, HET_ACGT_INS, HET_INSINS, HOMO_
 
 // find_alt_base: X alleles by descending count (stable); falls back to the best supported base when `want`
 // is absent or trails it by >= 9 reads.  Returns the ranked bases; *chosen = 0 when there is no X allele.
-std::vector<char> snp_alts(const std::vector<Allele>& alt, char want, char* chosen) {
-    std::vector<std::pair<char, int>> ranked;
-    for (const Allele& a : alt) if (a.kind == 'X') ranked.emplace_back(a.key[0], a.count);
-    std::stable_sort(ranked.begin(), ranked.end(), [](const auto& x, const auto& y) { return x.second > y.second; });
-    std::vector<char> out;
+// (scratch vectors are per thread and reused: this runs once or twice per candidate, millions of times per genome)
+const std::vector<char>& snp_alts(const std::vector<Allele>& alt, char want, char* chosen) {
+    static thread_local std::vector<std::pair<char, int>> ranked;
+    static thread_local std::vector<char> out;
+    ranked.clear();
+    out.clear();
+    for (const Allele& a : alt) if (a.kind == 'X') {
+        // stable insertion by descending count (at most a handful of entries)
+        size_t i = ranked.size();
+        ranked.emplace_back(a.key[0], a.count);
+        while (i > 0 && ranked[i - 1].second < a.count) { std::swap(ranked[i - 1], ranked[i]); --i; }
+    }
     *chosen = 0;
     if (ranked.empty()) return out;
     bool have = false;
@@ -172,7 +179,7 @@ Decision decide(char center, const float* probs, const std::vector<Allele>& alt)
             D.ref_base = ctr; D.has_ref = true;
             if (lab[0] != center && lab[1] != center) {
                 char chosen;
-                const std::vector<char> ranked = snp_alts(alt, 0, &chosen);
+                const std::vector<char>& ranked = snp_alts(alt, 0, &chosen);
                 if (ranked.size() < 2) { v.v[i] = 0; continue; }
                 D.alt_base = std::string(1, ranked[0]) + "," + std::string(1, ranked[1]); D.has_alt = true;
             } else {
@@ -195,7 +202,7 @@ Decision decide(char center, const float* probs, const std::vector<Allele>& alt)
             D.ref_base = ctr; D.alt_base = ins; D.has_ref = D.has_alt = true;
             if (ACGT[i] != center) {
                 char chosen;
-                const std::vector<char> ranked = snp_alts(alt, 0, &chosen);
+                const std::vector<char>& ranked = snp_alts(alt, 0, &chosen);
                 if (ranked.empty()) { v.v[i] = 0; continue; }
                 D.alt_base = std::string(1, ranked[0]) + "," + D.alt_base;
             }
@@ -340,7 +347,9 @@ bool vcf_row(const char* contig, int pos, const std::string& ref33, int depth, c
     else if (f[HOMO_SNP] || f[HOMO_INS] || f[HOMO_DEL]) gt = "1/1";
     else if (f[HET_SNP] || f[HET_ACGT_INS] || f[HET_INSINS] || f[HET_ACGT_DEL] || f[HET_DELDEL]) gt = "0/1";
     if (multi) gt = "1/2";
-    std::vector<std::pair<std::string, int>> snp, ins, dele;
+    static thread_local std::vector<std::pair<std::string, int>> snp, ins, dele;
+    static thread_local std::vector<long> counts;
+    snp.clear(); ins.clear(); dele.clear(); counts.clear();
     int ref_count = 0;
     for (const Allele& a : alt) {
         if (a.kind == 'X') dict_set(snp, a.key.substr(0, 1), a.count);
@@ -350,7 +359,6 @@ bool vcf_row(const char* contig, int pos, const std::string& ref33, int depth, c
     }
     if (ref_count < 0) ref_count = 0;
     long support = 0;
-    std::vector<long> counts;
     auto first_len_match = [&](size_t ln) { for (const auto& kv : dele) if (kv.first.size() == ln) return kv.second; return 0; };
     if (is_ref) {
         support = ref_count;

@@ -120,10 +120,12 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
 
     # Three host stages run side by side (the native calls release the GIL): a loader thread fetches + inflates the
     # BAM blocks and reads the reference of the shards ahead, this thread submits shard i+1 and waits for shard i,
-    # a decoder thread turns finished results into VCF rows.  Tickets: one running, one queued, two being decoded.
+    # decoder threads turn finished results into VCF rows.  Tickets: one running, one queued, two being decoded.
     from collections import deque
     from concurrent.futures import ThreadPoolExecutor
-    loader, dec = ThreadPoolExecutor(max(1, loader_threads)), ThreadPoolExecutor(1)
+    # two decoder workers (the two tickets being decoded proceed side by side), each with half of the native threads
+    loader, dec = ThreadPoolExecutor(max(1, loader_threads)), ThreadPoolExecutor(2)
+    dec_threads = max(1, (native_threads if native_threads > 0 else len(os.sched_getaffinity(0))) // 2)
     tm.update(load_wait=0.0, decode_wait=0.0)
     submit_ms = []
     it = iter(mine)
@@ -136,7 +138,7 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
 
     def decode(res, pbatch, pref, prs1, pname, pbuf):
         t = time.time()
-        rows = decode_vcf_rows(res, pbatch, pref, prs1, pname, qual=qual, threads=native_threads)
+        rows = decode_vcf_rows(res, pbatch, pref, prs1, pname, qual=qual, threads=dec_threads)
         tm["decode"] += time.time() - t
         pool.put(pbuf)                               # the reference window is free again
         return rows
