@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(256) k_row_rank(Dev d) {
     }
     if (blockIdx.x == 0)
         for (int64_t i = t; i < d.L_ub / (64 * COV_TILE) + 2; i += 256) d.csuper[i] = 0;
+    for (int64_t i = z0 / COV_TILE + t; i <= (z1 > z0 ? (z1 - 1) / COV_TILE : z0 / COV_TILE); i += 256) d.ctile[i] = 0;
     if (z1 > z0) {                                       // coverage tiles these rows fall into (neighbours overlap: all zero)
         const int64_t ct0 = z0 / COV_TILE, ct1 = (z1 - 1) / COV_TILE + 1;
         for (int64_t i = ct0 * NC + t; i < (ct1 + 1) * NC; i += 256) d.cov_tile[i] = 0;
@@ -1049,7 +1050,6 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
     constexpr int NC = C == 30 ? 6 : 4;
     static_assert(ROWS_WARPS * 32 == COV_TILE, "one block per coverage tile");
     __shared__ __align__(16) int32_t stage[ROWS_WARPS][TILE_ROWS * C];
-    __shared__ int32_t wtot[ROWS_WARPS][NC];
     __shared__ uint32_t done_s[ROWS_WARPS][IND_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (*d.err == 1) return;                             // more rows than the buffers hold: the host retries with exact bounds
@@ -1080,42 +1080,87 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
             const int64_t ro = (int64_t)p - d.ref_start0;
             if (ro >= 0 && ro < d.ref_len) rc = d.ref[ro];
         }
-        // ---- block-wide inclusive prefix of the coverage differences
+        // ---- inclusive prefix of the coverage differences.  A warp works out its own starting coverage - the tile's
+        // carry plus the difference rows of the warps before it in the tile, which it simply reads as well (the same
+        // lines its neighbours load: cache hits) - so the tile loop has NO block barrier: a warp held up by a row with
+        // hundreds of indel tokens used to hold the other seven at the barriers (30 % of this kernel's stall samples).
+        int32_t pre[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) pre[c] = 0;
+        for (int w = 0; w < warp; ++w) {
+            const int64_t rw = base + w * 32 + lane;             // rows before this warp's rows
+            if (rw >= L) continue;                               // (only in a warp that has no live row itself)
+            if (NC == 4) { const int4 t = *(const int4*)(d.cov + rw * 4); pre[0] += t.x; pre[1] += t.y; pre[2] += t.z; pre[3] += t.w; }
+            else {
+                const int2* q = (const int2*)(d.cov + rw * 6);
+                const int2 t0 = q[0], t1 = q[1], t2 = q[2];
+                pre[0] += t0.x; pre[1] += t0.y; pre[2] += t1.x; pre[3] += t1.y; pre[NC - 2] += t2.x; pre[NC - 1] += t2.y;
+            }
+        }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             int32_t x = cv[c];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-            cv[c] = x;
+            int32_t b = pre[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+            cv[c] = x + b + carry[c];
         }
-        __syncthreads();                                 // previous sub-tile's readers of wtot are done
-        if (lane == 31)
-#pragma unroll
-            for (int c = 0; c < NC; ++c) wtot[warp][c] = cv[c];
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            int32_t before = carry[c];
-#pragma unroll
-            for (int w = 0; w < ROWS_WARPS; ++w) if (w < warp) before += wtot[w][c];
-            cv[c] += before;
-        }
-        // ---- events of the row
+        // ---- events of the warp's 32 rows.  They are contiguous in the CSR list, so the warp reads them together
+        // (32 events = 512 contiguous bytes per step) and counts the mismatching bases into per-row counters in
+        // shared memory (the row's slice of the staging tile) - a thread walking its own row's events one dependent
+        // load after the other was what this kernel spent its time on.  Indel tokens only set the row's bit here.
         int32_t* v = &stage[warp][lane * C];
+        constexpr int KA = C == 30 ? 20 : 10;                        // [fwd A C G T N][rev A C G T N] ([hp1 ..][hp2 ..])
+        static_assert(KA <= C, "the counters of a row fit its slice of the staging tile");
 #pragma unroll
-        for (int i = 0; i < C; ++i) v[i] = 0;
+        for (int i = 0; i < KA; ++i) v[i] = 0;
+        const int32_t E1w = __reduce_max_sync(0xffffffffu, live ? e1 : 0);
+        const int32_t E0w = min(__reduce_min_sync(0xffffffffu, live ? e0 : 0x7fffffff), E1w);    // a warp without live rows: empty range
+        const int32_t ev_row0 = (int32_t)(base + warp * 32);
+        uint32_t indel_rows = 0;
+        __syncwarp();
+        for (int32_t s = E0w + lane; s < E1w; s += 32) {
+            const RowEvent e = d.events[s];
+            const int rl = e.row - ev_row0;
+            if (e.len != 0) indel_rows |= 1u << rl;
+            else if (e.yb <= 4u) {
+                int32_t* a = &stage[warp][rl * C];
+                atomicAdd(&a[(e.info & 1u) * 5 + e.yb], 1);
+                if (C == 30) {
+                    const uint32_t hp = (e.info >> 2) & 3u;
+                    if (hp == 1 || hp == 2) atomicAdd(&a[10 + (hp - 1) * 5 + e.yb], 1);
+                }
+            }
+        }
+        indel_rows = __reduce_or_sync(0xffffffffu, indel_rows);
+        __syncwarp();
         unsigned long long wf = 0, wr = 0, wp = 0, wm = 0;           // mismatching A,C,G,T as four 16-bit fields
         int32_t mm_f = 0, mm_r = 0, mm_p = 0, mm_m = 0;              // all mismatch events incl. N / ambiguity codes
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const int32_t cf = v[b], cr = v[5 + b];
+            mm_f += cf; mm_r += cr;
+            if (b < 4) { wf |= (unsigned long long)cf << (16 * b); wr |= (unsigned long long)cr << (16 * b); }
+            if (C == 30) {
+                const int32_t cp = v[10 + b], cm = v[15 + b];
+                mm_p += cp; mm_m += cm;
+                if (b < 4) { wp |= (unsigned long long)cp << (16 * b); wm |= (unsigned long long)cm << (16 * b); }
+            }
+        }
+        __syncwarp();                                                // every lane holds its counters: the tile is free
+#pragma unroll
+        for (int i = 0; i < C; ++i) v[i] = 0;
         int32_t ins_cnt = 0, del_cnt = 0;
-        const bool heavy_me = live && (e1 - e0) > ROWS_HEAVY;
+        const bool has_indel = live && ((indel_rows >> lane) & 1u);
+        const bool heavy_me = has_indel && (e1 - e0) > ROWS_HEAVY;
         bool is_cand = false;
-        // rows with many events (a het variant under deep coverage is hundreds of them): the whole warp walks one such
-        // row at a time - mismatch counters by warp reduction, its indel tokens compacted into shared memory
+        // rows with indel tokens among many events (a het indel under deep coverage is hundreds of them): the whole warp
+        // walks one such row at a time - token totals by ballots, distinct alleles by leader enumeration
         for (uint32_t heavy = __ballot_sync(0xffffffffu, heavy_me); heavy; heavy &= heavy - 1) {
             const int src = __ffs(heavy) - 1;
             const int32_t E0 = __shfl_sync(0xffffffffu, e0, src), E1 = __shfl_sync(0xffffffffu, e1, src);
-            unsigned long long af = 0, ar = 0, ap = 0, am = 0;
-            int32_t cf = 0, cr = 0, cp = 0, cm = 0;
             int32_t t[8] = {0, 0, 0, 0, 0, 0, 0, 0};         // indel tokens: ins f, ins r, del f, del r, IP, DP, IM, DM (warp-uniform)
             for (int32_t s0 = E0; s0 < E1; s0 += 32) {
                 const int32_t s = s0 + lane;
@@ -1123,13 +1168,6 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
                 e.info = 0; e.len = 0; e.yb = 5u; e.row = 0;
                 if (s < E1) e = d.events[s];
                 const uint32_t hp = (e.info >> 2) & 3u;
-                if (e.len == 0 && e.yb <= 4u) {
-                    const unsigned long long inc = e.yb < 4u ? 1ull << (16 * e.yb) : 0ull;
-                    if (e.info & 1u) { ar += inc; ++cr; } else { af += inc; ++cf; }
-                    if (C == 30) {
-                        if (hp == 1) { ap += inc; ++cp; } else if (hp == 2) { am += inc; ++cm; }
-                    }
-                }
                 if (__any_sync(0xffffffffu, e.len != 0)) {
                     const int x = e.len != 0 ? (int)(e.info & 3u) : -1;       // is_del << 1 | rev
 #pragma unroll
@@ -1140,19 +1178,6 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
                             t[4 + y] += __popc(__ballot_sync(0xffffffffu, x >= 0 && (int)hp == 1 + (y >> 1) && (x >> 1) == (y & 1)));
                     }
                 }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                af += __shfl_xor_sync(0xffffffffu, af, o); ar += __shfl_xor_sync(0xffffffffu, ar, o);
-                cf += __shfl_xor_sync(0xffffffffu, cf, o); cr += __shfl_xor_sync(0xffffffffu, cr, o);
-                if (C == 30) {
-                    ap += __shfl_xor_sync(0xffffffffu, ap, o); am += __shfl_xor_sync(0xffffffffu, am, o);
-                    cp += __shfl_xor_sync(0xffffffffu, cp, o); cm += __shfl_xor_sync(0xffffffffu, cm, o);
-                }
-            }
-            if (lane == src) {
-                wf = af; wr = ar; wp = ap; wm = am;
-                mm_f = cf; mm_r = cr; mm_p = cp; mm_m = cm;
             }
             const int32_t n_ind = t[0] + t[1] + t[2] + t[3];
             if (n_ind > 0 && E1 - E0 > IND_MAX) {            // longer than the bitmap: serial walk of the list
@@ -1175,21 +1200,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
             __syncwarp();
         }
         if (live) {
-            if (!heavy_me) {
-                bool any_indel = false;
-                for (int32_t s = e0; s < e1; ++s) {
-                    const RowEvent e = d.events[s];
-                    if (e.len != 0) { any_indel = true; continue; }
-                    const uint32_t rev = e.info & 1u;
-                    const uint32_t hp = (e.info >> 2) & 3u;
-                    const unsigned long long inc = e.yb < 4u ? 1ull << (16 * e.yb) : 0ull;
-                    if (rev) { wr += inc; ++mm_r; } else { wf += inc; ++mm_f; }
-                    if (C == 30) {
-                        if (hp == 1) { wp += inc; ++mm_p; } else if (hp == 2) { wm += inc; ++mm_m; }
-                    }
-                }
-                if (any_indel) row_indels<C>(d, d.events + e0, e1 - e0, v, ins_cnt, del_cnt);
-            }
+            if (has_indel && !heavy_me) row_indels<C>(d, d.events + e0, e1 - e0, v, ins_cnt, del_cnt);
             if (rc >= 'a') rc -= 32;
             const int ri_raw = rc == 'A' ? 0 : rc == 'C' ? 1 : rc == 'G' ? 2 : rc == 'T' ? 3 : -1;
             const bool acgt = ri_raw >= 0;
@@ -1296,10 +1307,10 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d
         }
         __syncwarp();
         // candidates of the tile and of its group of 64 tiles (K3's list is built from these counts: k_cand_emit)
-        const int nc = __syncthreads_count(is_cand);
-        if (threadIdx.x == 0) {
-            d.ctile[tile] = nc;
-            if (nc) atomicAdd(&d.csuper[tile >> 6], nc);
+        const int nc = __popc(__ballot_sync(0xffffffffu, is_cand));
+        if (lane == 0 && nc) {
+            atomicAdd(&d.ctile[tile], nc);
+            atomicAdd(&d.csuper[tile >> 6], nc);
         }
     }
 }
