@@ -529,7 +529,9 @@ def main():
         NW = (clen + P.NO_OF_POSITIONS + 31) // 32
         KX = 48 if C == 18 else 64
         alg = {
-            "k1": 16.0 * batch.n_ops + 16.0 * batch.n_reads + 20.0 * NW + 4.0 * n_rows,      # op geometry, bitmaps, row ranks
+            # K1: 4 B read + 12 B written per op, ~30 B per read; 8 B (covA, covE) + 4 B (rowR) + 4 B read again + 4 B
+            # (word_base) per 32 positions; 4 B (row_pos) + 24 B of zeroed accumulators per row
+            "k1": 16.0 * batch.n_ops + 30.0 * batch.n_reads + 20.0 * NW + 28.0 * n_rows,
             "k2": 0.5 * batch.n_aligned_bases() + 16.0 * batch.n_ops + (4 * C + 8) * n_rows,  # bases, ops, count rows
             "k3": 9.0 * n_rows + 12.0 * n_cand,                                              # flag + bitmap per row, list entry
             "k4": (33 * 4 * C + 33 * KX * 2) * float(n_cand),                                # window read, operand image written
@@ -561,8 +563,8 @@ def main():
                                  "traffic = h1 and h2 (hi + lo) written once and read once, nothing else of size leaves the SMs "
                                  "(profiles/, newest rN summary)"},
             "roofline_count": hbm_roofline("K2 count path (k_cmp, event scan, k_scatter, k_rows)", "k2", k2_ms),
-            "roofline_k1": hbm_roofline("K1 CIGAR scan, coverage bitmaps, row ranks", "k1", float(st[1])),
-            "roofline_k3": hbm_roofline("K3 candidate list (OpCand scan)", "k3", float(st[4])),
+            "roofline_k1": hbm_roofline("K1 CIGAR geometry, coverage bitmaps, row bits and ranks (k_cigar, k_row_bits, k_row_rank)", "k1", float(st[1])),
+            "roofline_k3": hbm_roofline("K3 candidate list (k_cand_emit; the window test runs inside k_rows)", "k3", float(st[4])),
             "roofline_k4": hbm_roofline("K4 window assembly into LSTM1's operand images + alt table", "k4", float(st[5])),
         }
         if not args.no_cpu_baseline:

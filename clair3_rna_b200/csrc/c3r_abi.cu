@@ -2,10 +2,12 @@
 // pileup.cuh (integer half) and nn_fp32.cuh / nn_tc.cuh (network forward).
 //
 // One context = one GPU.  A ticket owns a slot: device input buffers, scratch, pinned
-// result buffers and a stream.  submit() copies the flat records to HBM, runs the
-// position/row-space stages, reads back two scalars (rows, candidates) to size the
-// candidate-space buffers, then queues windows, alt_info, the network and the D2H
-// copies; wait() synchronises the slot's stream.
+// result buffers and a stream.  submit() queues the copies of the flat records to HBM and
+// the position/row-space stages (stage A) and returns; the scalars stage A leaves (rows,
+// candidates, error word) travel to the host behind it, and the next call into the library
+// that finds them there sizes the candidate-space buffers and queues windows, alt_info, the
+// network and the D2H copies (stage B, advance()); wait() does that for every ticket in
+// flight, then synchronises the slot's stream.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -98,7 +98,7 @@ struct Dev {
     int32_t* row_inscnt; int32_t* row_delcnt;
     // ---- row events (CSR by row): binc = event counts, then offsets (L_ub+2); cov = coverage difference rows
     int32_t* binc; int32_t* bin_cur; RowEvent* events;
-    RowEvent* raw; int64_t* n_raw; // events in discovery order (k_cmp) before the counting sort (k_scatter)
+    RowEvent* raw; int64_t* n_raw; // events in discovery order (k_cmp) before the counting sort (k_scatter_aggr)
     int64_t events_ub;
     int32_t* cov;                  // [L_ub+2][4 or 6]: Mf Mr Df Dr [M_hp1 M_hp2]
     int32_t* cov_tile;             // [L_ub/256+2][4 or 6]: sums of cov over tiles of 256 rows, then their exclusive prefix
@@ -468,7 +468,7 @@ __global__ void k_refnib(const uint8_t* __restrict__ ref, int64_t ref_len, uint3
 // k_cmp: one thread per CIGAR op for the bookkeeping; the sequence words of a warp's 32 ops are then dealt
 // out to its lanes one word each.  Read bases are compared 8 at a time (one 32-bit word of nt16 nibbles against the one-hot reference
 // nibbles, funnel-shifted into register).  Events are staged in shared memory and appended to the raw
-// list with one global atomic per block; k_scatter then counting-sorts them by row (CSR).
+// list with one global atomic per flush; k_scatter_aggr then counting-sorts them by row (CSR).
 constexpr int NCOV_MAX = 6;                  // Mf Mr Df Dr [M_hp1 M_hp2]
 constexpr int CMP_THREADS = 256;
 constexpr int CMP_STAGE = 1536;              // events staged per block (24 KB)
