@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 FLOP_PER_SITE = {18: 47.786e6, 30: 48.597e6}       # SURVEY.md §8(d), BASELINE.md §3
 
 
-E2E_DEPTH = 1        # submits queued ahead of the one being waited for in the end-to-end leg (2 measured the same)
+E2E_DEPTH = int(os.environ.get("C3R_E2E_DEPTH", "2"))        # submits queued ahead of the one being waited for in the end-to-end leg (three tickets in flight)
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -479,10 +479,12 @@ def main():
         ts = [eng.submit(pbatch, None, 1, region[0], region[1]) for _ in range(E2E_DEPTH + 1)]
         for t in ts:
             eng.wait(t)
-    # E2E_DEPTH + 1 tickets in flight: the host submits step i+1 (H2D + position/row stages, then a host read of
-    # the candidate count) while the GPU still runs step i's network.  The pipeline is primed with untimed submits (like warm-up steps)
-    # and drained after the timed region: each of the K timed steps is one submit (its H2D inside) + one wait (its
-    # D2H inside).
+    # E2E_DEPTH + 1 = 3 tickets in flight: while the GPU runs step i's network, step i+2's H2D copies and position /
+    # row stages run on the SMs it leaves idle, and step i+1's window / allele / network stages are already queued
+    # (c3r_wait queues them as soon as the candidate count is in) - so LSTM1 of step i+1 runs beside the remainder
+    # round of step i's LSTM2 (tc_forward).  The pipeline is primed with untimed submits (like warm-up steps) and
+    # drained after the timed region: each of the K timed steps is one submit (its H2D inside) + one wait (its D2H
+    # inside).
     sampler.pause()
     barrier()
     from collections import deque
@@ -549,7 +551,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "candidates_per_gpu": n_cand, "rows_per_gpu": n_rows, "channels": C,
                        "l2_flush": "256 MiB write between timed steps", "reference": "resident in HBM (c3r_set_reference), not part of h2d", "nn_impl": args.nn_impl},
-            "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "tickets_in_flight": E2E_DEPTH + 1},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "stage_ms": {"memset": float(st[0]), "k1_scan_rows": float(st[1]), "k2_compare_events": float(st[2]), "k2_rows": float(st[3]),

@@ -411,6 +411,8 @@ int c3r_create(c3r_ctx** out, int device_ordinal, const c3r_params* params) {
 
 void c3r_destroy(c3r_ctx* ctx) {
     if (!ctx) return;
+    if (getenv("C3R_TIMING") && ctx->tc.pipe)
+        fprintf(stderr, "[c3r] %ld network passes, %ld with LSTM1 in pieces beside the previous pass\n", ctx->tc.pipe->n_pass, ctx->tc.pipe->n_overlap);
     if (getenv("C3R_TIMING") && ctx->n_submit)
         fprintf(stderr, "[c3r] %lld submits, host ms each: buffers %.3f, h2d calls %.3f, stage A launches %.3f, earlier "
                         "tickets advanced at submit %.3f, deferred part (wait for the counts + stage B + d2h calls) %.3f, - %.3f\n", (long long)ctx->n_submit,
@@ -481,7 +483,7 @@ int c3r_set_reference(c3r_ctx* ctx, const uint8_t* ref, int64_t ref_start1, int6
     return C3R_OK;
 }
 
-static void advance_all(c3r_ctx* ctx, bool block);
+static void advance_all(c3r_ctx* ctx, bool block, uint64_t block_upto = ~0ull);
 static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, int64_t ref_start1, int64_t ref_len,
                        int64_t region_start1, int64_t region_end1, c3r_ticket* ticket);
 
@@ -760,8 +762,9 @@ static int advance(c3r_ctx* ctx, Slot& s, bool block) {
     return 0;
 }
 
-// every pending ticket, in submit order
-static void advance_all(c3r_ctx* ctx, bool block) {
+// every pending ticket, in submit order; tickets up to submit number `block_upto` are waited for, later ones only
+// taken when their counts are already in
+static void advance_all(c3r_ctx* ctx, bool block, uint64_t block_upto) {
     for (;;) {
         Slot* next = nullptr;
         for (int i = 0; i < N_SLOTS; ++i) {
@@ -769,7 +772,7 @@ static void advance_all(c3r_ctx* ctx, bool block) {
             if (s.in_use && s.pending_b && (!next || s.order < next->order)) next = &s;
         }
         if (!next) return;
-        advance(ctx, *next, block);
+        advance(ctx, *next, block && next->order <= block_upto);
         if (next->pending_b) return;                 // not ready yet (non-blocking): the later ones wait their turn
     }
 }
@@ -779,9 +782,10 @@ int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* res) {
     Slot& s = ctx->slots[ticket];
     if (!s.in_use) return fail(ctx, C3R_ERR_STATE, "ticket not in flight");
     CK(cudaSetDevice(ctx->device));
-    // Stage B of every ticket submitted so far is queued first (their counts arrive while the pass of the ticket
-    // waited for still runs), so that the device goes from one pass to the next without waiting for the host.
-    advance_all(ctx, true);
+    // Stage B of this ticket and of the one submitted after it is queued first (the latter's counts arrive while the
+    // pass of the ticket waited for still runs), so that the device goes from one pass to the next without waiting
+    // for the host; tickets further ahead are taken along when their counts happen to be in.
+    advance_all(ctx, true, s.order + 1);
     if (s.deferred_rc) {                             // the deferred part failed: report it and give the ticket back
         const int rc = s.deferred_rc;
         ctx->err = s.deferred_err;
@@ -907,7 +911,7 @@ int c3r_debug_fetch(c3r_ctx* ctx, int which, void* dst, int64_t max_bytes, int64
     const void* src = nullptr;
     size_t bytes = 0;
     switch (which) {
-        case 0: src = t.h1; bytes = tiles * NT * 4 * TC_IMG * 2; break;
+        case 0: src = t.h1_cur ? t.h1_cur : t.h1; bytes = tiles * NT * 4 * TC_IMG * 2; break;
         case 1:
             if (lstm2_fused()) return fail(ctx, C3R_ERR_STATE, "zx2 does not exist: LSTM2 runs fused (C3R_LSTM2=hoisted keeps it)");
             src = t.zx2; bytes = tiles * NT * 10 * ZX_CHUNK_WORDS * 4; break;

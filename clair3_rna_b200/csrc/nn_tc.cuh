@@ -1061,6 +1061,7 @@ struct TcNet {
     size_t abytes = 0;
     int cap_tiles = 0;
     __half *h1 = nullptr, *h2 = nullptr, *h1_lo = nullptr, *h2_lo = nullptr, *xop = nullptr;
+    __half* h1_cur = nullptr;      // the h1 buffer of the pass queued last (fused LSTM2 alternates between h1 and h1_lo)
     float *zx2 = nullptr, *l4 = nullptr, *l4p = nullptr;   // l4p: L4's partial sums [L4_KSPLIT][tiles*128][128]
     size_t l4_stride = 0;
     __half *l4h = nullptr, *l4h_lo = nullptr;              // l4 as fp16 operand images [tile][2 kb][TC_IMG] (hi, lo)
@@ -1342,6 +1343,13 @@ struct TcPipe {
     // (xop, LSTM1: they write xop and h1) once the previous pass's projection GEMM has read h1; it may write zx2 /
     // h2 / l4 once the previous pass has ended.  (An event that was never recorded does not block.)
     cudaEvent_t h1_free = nullptr, pass_done = nullptr;
+    // Fused LSTM2: h1 is double-buffered (the second buffer is the unused low-order image), so LSTM1 of the NEXT pass
+    // can run on the SMs the last LSTM2 launch of this pass leaves idle (its remainder round: 84 of 148 SMs at config
+    // 2).  h1_free2[b]: LSTM2 has read buffer b;  xop_free: LSTM1 has read the shared operand image;
+    // last_ready / last_done: the last LSTM2 launch of the previous pass may start / has ended;  last_pairs: its tile pairs.
+    cudaEvent_t h1_free2[2] = {}, xop_free = nullptr, last_ready = nullptr, last_done = nullptr;
+    int last_pairs = 0, parity = 0;
+    long n_pass = 0, n_overlap = 0;      // passes queued / passes whose LSTM1 went in pieces beside the previous pass (C3R_TIMING)
     bool ok = false;
 };
 inline int tc_pipe_init(TcPipe& p, std::string* err) {
@@ -1350,6 +1358,8 @@ inline int tc_pipe_init(TcPipe& p, std::string* err) {
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p.ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.h1_free, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.pass_done, cudaEventDisableTiming);
+    for (cudaEvent_t* ev : {&p.h1_free2[0], &p.h1_free2[1], &p.xop_free, &p.last_ready, &p.last_done})
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { *err = std::string("pipeline streams: ") + cudaGetErrorString(e); return -1; }
     p.ok = true;
     return 0;
@@ -1359,6 +1369,7 @@ inline void tc_pipe_release(TcPipe* p) {
     for (cudaEvent_t e : p->ev) if (e) cudaEventDestroy(e);
     if (p->h1_free) cudaEventDestroy(p->h1_free);
     if (p->pass_done) cudaEventDestroy(p->pass_done);
+    for (cudaEvent_t ev : {p->h1_free2[0], p->h1_free2[1], p->xop_free, p->last_ready, p->last_done}) if (ev) cudaEventDestroy(ev);
     delete p;
 }
 
@@ -1368,10 +1379,10 @@ inline cudaEvent_t tc_pass_done(const TcNet& t) { return t.pipe && t.pipe->ok ? 
 // tiles [t0, t0 + nt) of the pass, sites [s0, s0 + ns)
 struct TcSub { int t0, nt; int64_t s0, ns; };
 
-inline cudaError_t tc_lstm2(TcNet& t, const TcSub& b, cudaStream_t st) {
+inline cudaError_t tc_lstm2(TcNet& t, const TcSub& b, cudaStream_t st, const __half* h1buf) {
     if (lstm2_fused()) {
         Lstm2fArgs f;
-        f.wstream = t.wstream2; f.h1 = t.h1 + (size_t)b.t0 * NT * 4 * TC_IMG;
+        f.wstream = t.wstream2; f.h1 = h1buf + (size_t)b.t0 * NT * 4 * TC_IMG;
         f.hout = t.h2 + (size_t)b.t0 * NT * 5 * TC_IMG;
         f.hout_lo = (l4_terms() & 2) ? t.h2_lo + (size_t)b.t0 * NT * 5 * TC_IMG : nullptr;
         f.n_tiles = b.nt; f.err = t.err;
@@ -1429,7 +1440,15 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         int tiles = (int)((m + TC_TILE - 1) / TC_TILE);
         tiles += tiles & 1;                  // CTA pairs
         if (tc_ensure(t, tiles, err)) return -1;
-        TCK(cudaStreamWaitEvent(st, P.h1_free, 0), "wait");         // the previous pass no longer reads xop / h1
+        const bool fused = lstm2_fused();
+        const int hb = fused ? P.parity : 0;                        // h1 buffer of this pass
+        if (fused) P.parity ^= 1;
+        __half* const h1buf = hb ? t.h1_lo : t.h1;
+        t.h1_cur = h1buf;
+        if (fused) {
+            TCK(cudaStreamWaitEvent(st, P.h1_free2[hb], 0), "wait");   // LSTM2 of the pass before the previous one has read this buffer
+            if (!xop_ready) TCK(cudaStreamWaitEvent(st, P.xop_free, 0), "wait");   // LSTM1 of the previous pass has read the shared image
+        } else TCK(cudaStreamWaitEvent(st, P.h1_free, 0), "wait");  // the previous pass no longer reads xop / h1
         const int kx_ = t.C == 18 ? 48 : 64;
         const __half* xop_in = t.xop;
         if (xop_ready) xop_in = xop_ready + (size_t)(o / TC_TILE) * NT * (size_t)(kx_ * TC_TILE);
@@ -1451,8 +1470,8 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
             LstmArgs a1;
             const int kx = t.C == 18 ? 48 : 64;
             a1.Wimg = t.img1; a1.xop = xop_in + (size_t)b.t0 * NT * kx * TC_TILE; a1.C = t.C; a1.zx = nullptr;
-            a1.hout = t.h1 + (size_t)b.t0 * NT * 4 * TC_IMG;
-            a1.hout_lo = (zx_terms() & 2) ? t.h1_lo + (size_t)b.t0 * NT * 4 * TC_IMG : nullptr; a1.kb_out = 4;
+            a1.hout = h1buf + (size_t)b.t0 * NT * 4 * TC_IMG;
+            a1.hout_lo = (!fused && (zx_terms() & 2)) ? t.h1_lo + (size_t)b.t0 * NT * 4 * TC_IMG : nullptr; a1.kb_out = 4;
             a1.n_sites = b.ns; a1.n_tiles = b.nt; a1.err = t.err; a1.trace = b.t0 == 0 ? t.trace : nullptr;
             return t.C == 18 ? launch_lstm<4, 48>(a1, t.sm_count, s) : launch_lstm<4, 64>(a1, t.sm_count, s);
         };
@@ -1473,9 +1492,37 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
         const int idle_pairs = (t.sm_count - busy_b) / 2;
         int m_early = 2 * idle_pairs * zx_overlap_tiles();
         if (m_early > A.nt * NT) m_early = A.nt * NT;
-        if (lstm2_fused()) {                                        // no projection GEMM: LSTM2 reads h1 itself
-            TcSub all; all.t0 = 0; all.nt = tiles; all.s0 = 0; all.ns = m;
-            TCK(lstm1(all, st), "lstm1");
+        if (fused) {                                                // no projection GEMM: LSTM2 reads h1 itself
+            // The last LSTM2 launch of the pass before this one (its remainder round, or its only round) leaves
+            // sm_count - 4 x pairs SMs idle: while it is still ahead of us, LSTM1 of THIS pass goes in pieces that fit
+            // beside it - two pieces (an LSTM1 round takes less than half an LSTM2 round), then the rest once it has
+            // ended.  At config 2 (37 + 21 tile pairs): 16 + 16 pairs of LSTM1 run under the previous pass's
+            // remainder round and the remaining 26 are ONE round instead of two.
+            const int ip = (t.sm_count - 4 * P.last_pairs) / 4;     // tile pairs (both directions) that fit beside it
+            bool overlap = o == 0 && P.last_pairs > 0 && ip >= 8 && pairs > ip && getenv("C3R_NO_LSTM1_OVERLAP") == nullptr;
+            if (overlap) {
+                overlap = cudaEventQuery(P.last_done) == cudaErrorNotReady;
+                (void)cudaGetLastError();
+            }
+            auto piece = [&](int p0, int np) {
+                TcSub b; b.t0 = 2 * p0; b.nt = 2 * np; b.s0 = (int64_t)b.t0 * TC_TILE;
+                const int64_t left = m - b.s0;
+                b.ns = left < 0 ? 0 : left < (int64_t)b.nt * TC_TILE ? left : (int64_t)b.nt * TC_TILE;
+                return b;
+            };
+            ++P.n_pass;
+            if (overlap) {
+                ++P.n_overlap;
+                TCK(cudaStreamWaitEvent(st, P.last_ready, 0), "wait");
+                int done = 0;
+                for (int c = 0; c < 2 && pairs - done > ip; ++c) { TCK(lstm1(piece(done, ip), st), "lstm1"); done += ip; ++launches; }
+                TCK(cudaStreamWaitEvent(st, P.last_done, 0), "wait");
+                TCK(lstm1(piece(done, pairs - done), st), "lstm1");
+            } else {
+                TcSub all; all.t0 = 0; all.nt = tiles; all.s0 = 0; all.ns = m;
+                TCK(lstm1(all, st), "lstm1");
+            }
+            TCK(cudaEventRecord(P.xop_free, st), "event");
             TCK(cudaStreamWaitEvent(st, P.pass_done, 0), "wait");   // the previous pass no longer reads h2 / l4
             ++launches;
         } else if (B.nt == 0 || A.nt == 0 || idle_pairs < 8 || m_early <= 0) {
@@ -1497,20 +1544,30 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
             TCK(zx(m_early, tiles * NT - m_early, 1 << 30, st), "zx2 gemm");
             launches += 4;
         }
-        if (!lstm2_fused()) TCK(cudaEventRecord(P.h1_free, st), "event");
+        if (!fused) { TCK(cudaEventRecord(P.h1_free, st), "event"); P.last_pairs = 0; }
         float* pr = probs + o * 24;
-        TCK(tc_lstm2(t, A, st), "lstm2");
+        if (fused && B.nt == 0) TCK(cudaEventRecord(P.last_ready, st), "event");
+        TCK(tc_lstm2(t, A, st, h1buf), "lstm2");
         ++launches;
         if (B.nt == 0) {
-            if (lstm2_fused()) TCK(cudaEventRecord(P.h1_free, st), "event");
+            if (fused) {
+                TCK(cudaEventRecord(P.last_done, st), "event");
+                TCK(cudaEventRecord(P.h1_free2[hb], st), "event");
+                P.last_pairs = pa;
+            }
             TCK(tc_l4_heads(t, net, A, pr, st), "l4/heads");
             launches += 4;
             TCK(cudaEventRecord(P.pass_done, st), "event");
             continue;
         }
         TCK(cudaEventRecord(P.ev[0], st), "event");
-        TCK(tc_lstm2(t, B, st), "lstm2");
-        if (lstm2_fused()) TCK(cudaEventRecord(P.h1_free, st), "event");
+        if (fused) TCK(cudaEventRecord(P.last_ready, st), "event");
+        TCK(tc_lstm2(t, B, st, h1buf), "lstm2");
+        if (fused) {
+            TCK(cudaEventRecord(P.last_done, st), "event");
+            TCK(cudaEventRecord(P.h1_free2[hb], st), "event");
+            P.last_pairs = B.nt / 2;
+        }
         TCK(cudaStreamWaitEvent(P.s2, P.ev[0], 0), "wait");
         TCK(tc_l4_heads(t, net, A, pr, P.s2), "l4/heads");
         TCK(cudaEventRecord(P.ev[1], P.s2), "event");

@@ -149,3 +149,31 @@ def test_chunked_calls_equal_one_piece():
     for i, p in enumerate(whole.pos.tolist()):
         assert merged[p][0] == whole.tensor[i].tobytes()
         assert np.abs(np.frombuffer(merged[p][1], np.float32) - whole.probs[i]).max() <= 1e-6
+
+
+def test_three_tickets_in_flight_at_full_size():
+    """config 2 at full size (58 tile pairs: a full round + a remainder round of the recurrent kernels) with three
+    tickets in flight: LSTM1 of a pass is then queued in pieces that run beside the previous pass's remainder round
+    on the second h1 buffer (tc_forward), and the candidate-count dependent stages of a ticket are queued by later
+    calls (advance).  Every ticket must give the result of a call made alone, bit for bit."""
+    from clair3_rna_b200 import weights, params as P
+    from clair3_rna_b200.engine import Engine
+    cfg, batch, ref, clen = make(2)
+    eng = Engine(0, 18)
+    eng.set_weights(weights.synthetic(18, sharpen=8.0))
+    eng.set_reference(ref, 1)
+    region = (1, clen + P.NO_OF_POSITIONS)
+    alone = eng.call_chunk(batch, None, 1, *region)
+    assert alone.n_cand > 2 * 37 * 128                      # more than one round of tile pairs
+    from collections import deque
+    q = deque(eng.submit(batch, None, 1, *region) for _ in range(2))
+    for _ in range(6):
+        q.append(eng.submit(batch, None, 1, *region))
+        r = eng.wait(q.popleft())
+        assert np.array_equal(r.pos, alone.pos) and np.array_equal(r.depth, alone.depth)
+        assert np.array_equal(r.probs, alone.probs)
+        assert np.array_equal(r.alt_n, alone.alt_n)
+    while q:
+        r = eng.wait(q.popleft())
+        assert np.array_equal(r.probs, alone.probs)
+    eng.close()
