@@ -1497,9 +1497,10 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
             // sm_count - 4 x pairs SMs idle: while it is still ahead of us, LSTM1 of THIS pass goes in pieces that fit
             // beside it - two pieces (an LSTM1 round takes less than half an LSTM2 round), then the rest once it has
             // ended.  At config 2 (37 + 21 tile pairs): 16 + 16 pairs of LSTM1 run under the previous pass's
-            // remainder round and the remaining 26 are ONE round instead of two.
+            // remainder round and the remaining 26 are ONE round instead of two; a 5 Mb chunk of config 5 (20 pairs,
+            // one partly filled round) puts all of its LSTM1 beside the previous chunk's LSTM2.
             const int ip = (t.sm_count - 4 * P.last_pairs) / 4;     // tile pairs (both directions) that fit beside it
-            bool overlap = o == 0 && P.last_pairs > 0 && ip >= 8 && pairs > ip && getenv("C3R_NO_LSTM1_OVERLAP") == nullptr;
+            bool overlap = o == 0 && P.last_pairs > 0 && ip >= 8 && getenv("C3R_NO_LSTM1_OVERLAP") == nullptr;
             if (overlap) {
                 overlap = cudaEventQuery(P.last_done) == cudaErrorNotReady;
                 (void)cudaGetLastError();
@@ -1515,9 +1516,15 @@ inline int tc_forward(TcNet& t, const NetF32& net, const int32_t* tensor, int64_
                 ++P.n_overlap;
                 TCK(cudaStreamWaitEvent(st, P.last_ready, 0), "wait");
                 int done = 0;
-                for (int c = 0; c < 2 && pairs - done > ip; ++c) { TCK(lstm1(piece(done, ip), st), "lstm1"); done += ip; ++launches; }
-                TCK(cudaStreamWaitEvent(st, P.last_done, 0), "wait");
-                TCK(lstm1(piece(done, pairs - done), st), "lstm1");
+                for (int c = 0; c < 2 && done < pairs; ++c) {
+                    const int np = pairs - done < ip ? pairs - done : ip;
+                    TCK(lstm1(piece(done, np), st), "lstm1");
+                    done += np; ++launches;
+                }
+                if (done < pairs) {
+                    TCK(cudaStreamWaitEvent(st, P.last_done, 0), "wait");
+                    TCK(lstm1(piece(done, pairs - done), st), "lstm1");
+                } else --launches;                                      // (the common count below adds one)
             } else {
                 TcSub all; all.t0 = 0; all.nt = tiles; all.s0 = 0; all.ns = m;
                 TCK(lstm1(all, st), "lstm1");
