@@ -358,9 +358,10 @@ __global__ void __launch_bounds__(L2F_THREADS, 1) k_lstm2_fused(Lstm2fArgs a) {
 // c*32 + (hr*64+j)%32; i, f, o columns carry 0.5 * z like every other packed LSTM weight.
 inline void lstm2f_pack(std::vector<uint8_t>& out, const float* h, size_t o_w2, size_t o_b2, size_t o_u2) {
     out.assign((size_t)4 * L2F_STREAM_BYTES, 0);
-    auto split = [](float w, __half& hi, __half& lo) {
+    const bool no_lo = getenv("C3R_L2F_NOLO") != nullptr;     // experiment: W2 rounded to one fp16 (the low-order images are zero)
+    auto split = [no_lo](float w, __half& hi, __half& lo) {
         hi = __float2half(w);
-        lo = __float2half(w - __half2float(hi));
+        lo = __float2half(no_lo ? 0.0f : w - __half2float(hi));
     };
     for (int dir = 0; dir < 2; ++dir)
         for (int hr = 0; hr < 2; ++hr) {
