@@ -41,7 +41,8 @@ constexpr int N_EV = 9;
 struct Slot {
     bool in_use = false;
     bool has_result = false;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;        // stage B: windows, allele table, network, result copies (high priority)
+    cudaStream_t st_a = nullptr;      // H2D copies and stage A (low priority: they fill the SMs the network passes leave idle)
     cudaEvent_t ev[N_EV] = {};
     cudaEvent_t ev_alt = nullptr;
     // inputs
@@ -95,6 +96,7 @@ struct c3r_ctx {
     NetF32Scratch nscr;
     TcNet tc;                 // tensor-core path state (nn_tc.cuh)
     uint64_t submit_seq = 0;
+    int prio_hi = 0;
     const c3r_site_filter* filter = nullptr;   // of the submit in progress
     bool tc_dirty = false;    // a tensor-core forward ran since the last device error check
     cudaEvent_t nn_done = nullptr;   // end of the last network pass: the scratch (h1, zx2, h2 ...) is shared by all tickets
@@ -157,7 +159,7 @@ template <class T> T* P(Buf& b) { return (T*)b.p; }
 // Stage A: everything up to the candidate list.  Needs only the resident inputs.
 int run_stage_a(c3r_ctx* ctx, Slot& s) {
     Dev& d = s.d;
-    cudaStream_t st = s.st;
+    cudaStream_t st = s.st_a;
     int& L = s.launches;
     // clear accumulators
     CK(cudaMemsetAsync(s.covA.p, 0, (size_t)(d.NW + 4) * 4, st));
@@ -234,8 +236,8 @@ int parse_scalars(c3r_ctx* ctx, Slot& s) {
 }
 
 int read_scalars(c3r_ctx* ctx, Slot& s) {
-    CK(cudaMemcpyAsync(s.h_scalars.p, s.scalars.p, 64, cudaMemcpyDeviceToHost, s.st));
-    CK(cudaStreamSynchronize(s.st));
+    CK(cudaMemcpyAsync(s.h_scalars.p, s.scalars.p, 64, cudaMemcpyDeviceToHost, s.st_a));
+    CK(cudaStreamSynchronize(s.st_a));                // stage A is complete: stage B (on s.st) may be queued without an event
     return parse_scalars(ctx, s);
 }
 
@@ -390,9 +392,17 @@ int c3r_create(c3r_ctx** out, int device_ordinal, const c3r_params* params) {
     if (prop.major != 10)
         return fail(ctx, C3R_ERR_CUDA, std::string("built for sm_100a only, device is ") + prop.name);
     ctx->sm_count = prop.multiProcessorCount;
+    // Two streams per ticket: the network passes (stage B) on high-priority streams, the H2D copies and integer stages
+    // of the tickets ahead (stage A) on low-priority ones - when SMs free up between the network's kernels, the next
+    // network kernel goes first and the integer kernels take what is left.  C3R_ONE_STREAM: both on one stream.
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (getenv("C3R_FLAT_PRIORITY")) prio_hi = prio_lo;
+    ctx->prio_hi = prio_hi;
     for (int i = 0; i < N_SLOTS; ++i) {
         Slot& s = ctx->slots[i];
-        CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithPriority(&s.st_a, cudaStreamNonBlocking, prio_lo));
         for (int k = 0; k < N_EV; ++k) CK(cudaEventCreate(&s.ev[k]));
         CK(cudaEventCreateWithFlags(&s.ev_alt, cudaEventDisableTiming));
         // spin-wait by default: a blocking-sync event wakes the waiting thread ~0.3 ms late (measured), which delays
@@ -437,6 +447,7 @@ void c3r_destroy(c3r_ctx* ctx) {
         if (s.ev_alt) cudaEventDestroy(s.ev_alt);
         if (s.ev_cnt) cudaEventDestroy(s.ev_cnt);
         if (s.st) cudaStreamDestroy(s.st);
+        if (s.st_a) cudaStreamDestroy(s.st_a);
     }
     release(ctx->wbuf);
     release(ctx->nn_scratch);
@@ -573,7 +584,7 @@ static int size_rows(c3r_ctx* ctx, Slot& s, const uint32_t* cigar_host) {
         const size_t need = 256 + tiles * 4 + 2 * tiles * sizeof(ScanElem) + 64;
         if (s.scan_scratch.cap < need) {
             EN(scan_scratch, need);
-            CK(cudaMemsetAsync(s.scan_scratch.p, 0, s.scan_scratch.cap, s.st));     // status words of epoch 0, ticket 0
+            CK(cudaMemsetAsync(s.scan_scratch.p, 0, s.scan_scratch.cap, s.st_a));   // status words of epoch 0, ticket 0
         }
         uint8_t* sp = (uint8_t*)s.scan_scratch.p;
         const size_t cap_tiles = (s.scan_scratch.cap - 256 - 64) / (4 + 2 * sizeof(ScanElem));
@@ -682,7 +693,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.head_tail = pr.enable_head_tail;
     d.tail = P<int32_t>(s.scalars) + 8;
 
-    cudaStream_t st = s.st;
+    cudaStream_t st = s.st_a;
     lap(0);
     CK(cudaEventRecord(s.ev[0], st));
     if (rd->n_reads > 0) {
@@ -718,7 +729,7 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     // the counts of stage A travel to the host behind it; stage B is queued when they have arrived (advance)
     if (!rc) { cudaError_t e = cudaMemcpyAsync(s.h_scalars.p, s.scalars.p, 64, cudaMemcpyDeviceToHost, st); if (e != cudaSuccess) rc = fail(ctx, C3R_ERR_CUDA, cudaGetErrorString(e)); }
     if (!rc) { cudaError_t e = cudaEventRecord(s.ev_cnt, st); if (e != cudaSuccess) rc = fail(ctx, C3R_ERR_CUDA, cudaGetErrorString(e)); }
-    if (rc) { cudaStreamSynchronize(st); s.in_use = false; return rc; }
+    if (rc) { cudaStreamSynchronize(st); cudaStreamSynchronize(s.st); s.in_use = false; return rc; }
     s.pending_b = true;
     s.order = ++ctx->submit_seq;
     *ticket = si;
@@ -753,11 +764,11 @@ static int advance(c3r_ctx* ctx, Slot& s, bool block) {
         if (!rc) rc = run_stage_a(ctx, s);
         if (!rc) rc = read_scalars(ctx, s);
     }
-    if (!rc) rc = ensure_stage_b(ctx, s);
+    if (!rc) rc = ensure_stage_b(ctx, s);             // (stage A has ended: the host has seen its counts)
     if (!rc) rc = run_stage_b(ctx, s);
     if (!rc) rc = queue_d2h(ctx, s);
     if (!rc) { cudaError_t e = cudaEventRecord(s.ev[8], s.st); if (e != cudaSuccess) rc = fail(ctx, C3R_ERR_CUDA, cudaGetErrorString(e)); }
-    if (rc) { cudaStreamSynchronize(s.st); s.deferred_rc = rc; s.deferred_err = ctx->err; }
+    if (rc) { cudaStreamSynchronize(s.st_a); cudaStreamSynchronize(s.st); s.deferred_rc = rc; s.deferred_err = ctx->err; }
     ctx->t_phase[4] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return 0;
 }
@@ -838,7 +849,7 @@ int c3r_wait(c3r_ctx* ctx, c3r_ticket ticket, c3r_result* res) {
 int c3r_release(c3r_ctx* ctx, c3r_ticket ticket) {
     if (!ctx || ticket < 0 || ticket >= N_SLOTS) return C3R_ERR_ARG;
     Slot& s = ctx->slots[ticket];
-    if (s.in_use) { cudaSetDevice(ctx->device); cudaStreamSynchronize(s.st); }
+    if (s.in_use) { cudaSetDevice(ctx->device); cudaStreamSynchronize(s.st_a); cudaStreamSynchronize(s.st); }
     s.in_use = false;
     s.pending_b = false;                             // released before its stage B was queued: nothing more to run
     s.deferred_rc = 0;
@@ -855,7 +866,7 @@ int c3r_rerun_resident(c3r_ctx* ctx, c3r_ticket ticket, float* total_ms, float* 
     if (s.deferred_rc) { ctx->err = s.deferred_err; return s.deferred_rc; }
     CK(cudaStreamSynchronize(s.st));
     s.launches = 0;
-    CK(cudaEventRecord(s.ev[0], s.st));
+    CK(cudaEventRecord(s.ev[0], s.st_a));
     int rc = run_stage_a(ctx, s);
     if (!rc) rc = read_scalars(ctx, s);
     if (!rc) rc = ensure_stage_b(ctx, s);

@@ -1354,7 +1354,9 @@ struct TcPipe {
 };
 inline int tc_pipe_init(TcPipe& p, std::string* err) {
     if (p.ok) return 0;
-    cudaError_t e = cudaStreamCreateWithFlags(&p.s2, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;                    // the network's streams are high priority (c3r_create)
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&p.s2, cudaStreamNonBlocking, getenv("C3R_FLAT_PRIORITY") ? prio_lo : prio_hi);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p.ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.h1_free, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.pass_done, cudaEventDisableTiming);
