@@ -6,10 +6,12 @@ transcriptome at 30x, one contig per GPU (weak scaling: rank r gets its own cont
 the same size, no data-path collective).  A "step" is one pass of the hot path over the
 whole contig.
 
-  value        sites/s with the flat reads already resident in HBM (c3r_rerun_resident)
-  e2e          sites/s through the public API (Engine.call_chunk) from pinned host arrays,
-               H2D and D2H inside the timed region
-  roofline     the network kernels (tensor bound) and, separately, the count kernel (HBM bound)
+  value        sites/s with the flat reads already resident in HBM (c3r_rerun_resident: one pass at a time)
+  e2e          sites/s through the public API (Engine.submit / wait, three tickets in flight) from pinned host
+               arrays, H2D and D2H of every step inside the timed region
+  roofline     the network kernels (tensor bound); roofline_count / _k1 / _k3 / _k4: the integer stages (HBM bound)
+  shard_cfg5   BASELINE.json configs[4]: the whole synthetic genome (24 contigs, 631 chunks) read from a BAM + FASTA,
+               sharded by (contig, chunk) over the ranks through run_chunks (strong scaling, host limiter reported)
   cpu_baseline the oracle port of the reference CPU pipeline on a bounded sample
 
 `--impl reference` times the oracle port (the reference is Python + samtools + TensorFlow,
