@@ -62,7 +62,7 @@ struct Slot {
     Buf scan_scratch;     // look-back scan state: ticket counters, tile status words, tile aggregates / prefixes
     ScanState scan = {};
     uint32_t scan_epoch = 0;
-    size_t cov_up_bytes = 0;
+    size_t zero_bytes = 0;            // bytes of the pool behind covA that every pass starts from zero
     // submit returns once stage A is queued; stage B (windows, alt table, network, result copies) is queued by a later
     // call into the library, when the candidate count has arrived on the host (advance())
     bool pending_b = false;
@@ -162,11 +162,8 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     cudaStream_t st = s.st_a;
     int& L = s.launches;
     // clear accumulators
-    CK(cudaMemsetAsync(s.covA.p, 0, (size_t)(d.NW + 4) * 4, st));
-    CK(cudaMemsetAsync(s.covE.p, 0, (size_t)(d.NW + 4) * 4, st));
-    CK(cudaMemsetAsync(s.cov_up.p, 0, s.cov_up_bytes, st));
+    CK(cudaMemsetAsync(s.covA.p, 0, s.zero_bytes, st));      // covA | covE | their summary levels | blockmax: one pool, one memset
     CK(cudaMemsetAsync(s.scalars.p, 0, 64, st));
-    CK(cudaMemsetAsync(s.blockmax.p, 0, (size_t)(d.n_reads / 256 + 2) * 4, st));
     CK(cudaEventRecord(s.ev[1], st));
     if (d.n_reads > 0) {
         // 8 lanes per read, a whole warp when reads carry hundreds of ops (the group walks a read's ops G at a time)
@@ -650,16 +647,18 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
 #define EN(b, bytes) if (ensure(ctx, s.b, (size_t)(bytes))) return C3R_ERR_CUDA
     EN(pos, R * 4); EN(flag, R * 2); EN(mapq, R); EN(hp, R); EN(cigar_off, (R + 1) * 4); EN(cigar, O * 4);
     EN(seq_off, (R + 1) * 8); EN(seq, rd->n_seq_bytes + 64); if (ref) { EN(ref, ref_len + 16); }
-    EN(admit, R); EN(read_end, R * 4); EN(blockmax, (R / 256 + 2) * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_info, O * 4);
+    EN(admit, R); EN(read_end, R * 4); EN(op_x, O * 4); EN(op_y, O * 4); EN(op_info, O * 4);
     // position space: buffers padded to whole tiles of PT_WORDS words (k_row_bits / k_row_rank store 16 bytes per thread);
     // the summary levels of covA and covE (mark_range) share one buffer: level l has NW / 32^l + 2 words
     const int64_t NWp = ((d.NW + PT_WORDS - 1) / PT_WORDS) * PT_WORDS + 8;
-    EN(covA, NWp * 4); EN(covE, NWp * 4); EN(rowR, NWp * 4); EN(word_base, NWp * 4);
-    EN(ptile, (NWp / PT_WORDS + 4) * 4);
     int64_t up_words[COV_UP], up_total = 0;
     { int64_t n = d.NW; for (int l = 0; l < COV_UP; ++l) { n = (n >> 5) + 2; up_words[l] = n; up_total += n; } }
-    EN(cov_up, 2 * up_total * 4);
-    s.cov_up_bytes = (size_t)(2 * up_total * 4);
+    // everything a pass needs zeroed lives in ONE pool (one memset per pass instead of four): covA, covE, the summary
+    // levels of both, blockmax
+    const int64_t pool_words = 2 * NWp + 2 * up_total + (R / 256 + 2) + 16;
+    EN(covA, pool_words * 4); EN(rowR, NWp * 4); EN(word_base, NWp * 4);
+    s.zero_bytes = (size_t)pool_words * 4;
+    EN(ptile, (NWp / PT_WORDS + 4) * 4);
     if (ref) { EN(refnib, ((ref_len + 7) / 8 + 1) * 4); }
     const c3r_site_filter* flt = ctx->filter;
     d.n_pbed = d.n_cbed = d.n_known = -1;
@@ -674,12 +673,13 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     d.seq = P<uint8_t>(s.seq); d.ref = ref ? P<uint8_t>(s.ref) : P<uint8_t>(ctx->ref_res);
     d.admit = P<uint8_t>(s.admit); d.read_end = P<int32_t>(s.read_end);
     d.op_x = P<int32_t>(s.op_x); d.op_y = P<uint32_t>(s.op_y); d.op_info = P<uint32_t>(s.op_info);
-    d.covA = P<uint32_t>(s.covA); d.covE = P<uint32_t>(s.covE); d.rowR = P<uint32_t>(s.rowR);
+    d.covA = P<uint32_t>(s.covA); d.covE = d.covA + NWp; d.rowR = P<uint32_t>(s.rowR);
     d.word_base = P<int32_t>(s.word_base);
     {
-        uint32_t* u = P<uint32_t>(s.cov_up);
+        uint32_t* u = d.covE + NWp;
         for (int l = 0; l < COV_UP; ++l) { d.upA[l] = u; u += up_words[l]; }
         for (int l = 0; l < COV_UP; ++l) { d.upE[l] = u; u += up_words[l]; }
+        d.blockmax = (int32_t*)u;
     }
     d.ptile = P<int32_t>(s.ptile); d.kctr = P<int32_t>(s.scalars) + 12;
     d.n_rows = P<int64_t>(s.scalars); d.n_cand = P<int64_t>(s.scalars) + 1; d.err = P<int32_t>(s.scalars) + 6;
@@ -687,7 +687,6 @@ static int submit_once(c3r_ctx* ctx, const c3r_reads* rd, const uint8_t* ref, in
     if (int rc0 = size_rows(ctx, s, nullptr)) return rc0;     // row space: cheap capacity bounds first
     d.refnib = ref ? P<uint32_t>(s.refnib) : P<uint32_t>(ctx->refnib_res);
     d.n_ref_words = (ref_len + 7) / 8;
-    d.blockmax = P<int32_t>(s.blockmax);
     d.pbed = P<int32_t>(s.pbed); d.cbed = P<int32_t>(s.cbed); d.known = P<int32_t>(s.known);
     d.covP = d.n_pbed >= 0 ? P<uint32_t>(s.covP) : d.covA;
     d.head_tail = pr.enable_head_tail;

@@ -1045,8 +1045,11 @@ __device__ __noinline__ bool window_printed(const uint32_t* covP, int64_t o, int
 
 constexpr int ROWS_WARPS = 8;
 constexpr int ROWS_HEAVY = 32;               // rows with more events than this are walked by the whole warp
+#ifndef C3R_ROWS_BLOCKS
+#define C3R_ROWS_BLOCKS 5
+#endif
 template <int C>
-__global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : 5) k_rows(Dev d) {
+__global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : C3R_ROWS_BLOCKS) k_rows(Dev d) {
     constexpr int NC = C == 30 ? 6 : 4;
     static_assert(ROWS_WARPS * 32 == COV_TILE, "one block per coverage tile");
     __shared__ __align__(16) int32_t stage[ROWS_WARPS][TILE_ROWS * C];
