@@ -85,8 +85,13 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
     import threading
     tls = threading.local()
     readers = []
-    # reference windows in page-locked buffers: tickets in flight (2) + being decoded (2) + loaded ahead
-    pool = PinnedPool(6 + 2 * max(1, loader_threads), chunk_size_bytes())
+    # reference windows in page-locked buffers: tickets in flight (2) + being decoded (2) + loaded ahead; the pool
+    # lives with the engine (page-locking 70 MB costs tens of milliseconds: once per process, not once per run)
+    pool = getattr(eng, "_ref_pool", None)
+    if pool is None or pool.n_bytes < chunk_size_bytes() or len(pool.ptrs) < 6 + 2 * max(1, loader_threads):
+        if pool is not None:
+            pool.close()
+        pool = eng._ref_pool = PinnedPool(6 + 2 * max(1, loader_threads), chunk_size_bytes())
 
     def reader():
         # one BAM handle per loader thread (a handle serves one fetch at a time)
@@ -126,7 +131,7 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
     # two decoder workers (the two tickets being decoded proceed side by side), each with half of the native threads
     loader, dec = ThreadPoolExecutor(max(1, loader_threads)), ThreadPoolExecutor(2)
     dec_threads = max(1, (native_threads if native_threads > 0 else len(os.sched_getaffinity(0))) // 2)
-    tm.update(load_wait=0.0, decode_wait=0.0)
+    tm.update(load_wait=0.0, decode_wait=0.0, release=0.0)
     submit_ms = []
     it = iter(mine)
     loads, decoding = deque(), deque()               # (shard, future) / (shard, ticket, future)
@@ -149,7 +154,9 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
             t = time.time()
             rows_of[j] = f.result()
             tm["decode_wait"] += time.time() - t
+            t = time.time()
             eng.release(tk)
+            tm["release"] += time.time() - t
             block = False
 
     for _ in range(2 + max(1, loader_threads)):
@@ -186,8 +193,9 @@ def run(bam_fn, ref_fn, chkpnt_fn, output, *, contigs=None, device=0, rank=0, wo
         retire(True)
     loader.shutdown()
     dec.shutdown()
-    pool.close()
     if engine is None:
+        pool.close()
+        eng._ref_pool = None
         eng.close()
     bf.close()
     for r in readers:
