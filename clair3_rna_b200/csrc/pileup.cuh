@@ -973,6 +973,7 @@ __device__ __forceinline__ void for_each_indel_allele(const Dev& d, const RowEve
             }
             const uint32_t mm = __ballot_sync(0xffffffffu, match);
             cnt += __popc(mm);
+            __syncwarp();                                    // every lane has read done[w] (keeps racecheck quiet: the ballot already orders them)
             if (lane == 0) done[w] = dw | mm;
         }
         __syncwarp();
