@@ -166,10 +166,10 @@ int run_stage_a(c3r_ctx* ctx, Slot& s) {
     CK(cudaMemsetAsync(s.scalars.p, 0, 64, st));
     CK(cudaEventRecord(s.ev[1], st));
     if (d.n_reads > 0) {
-        // 8 lanes per read, a whole warp when reads carry hundreds of ops (the group walks a read's ops G at a time)
+        // a warp per read, 8 lanes when reads carry few ops (the group walks a read's ops G at a time)
         static const int force_g = getenv("C3R_CIGAR_G") ? atoi(getenv("C3R_CIGAR_G")) : 0;
         const int64_t avg = d.n_ops / d.n_reads;
-        const int G = force_g ? force_g : avg > 96 ? 32 : 8;
+        const int G = force_g ? force_g : avg >= 16 ? 32 : 8;     // measured at config 2 (34 ops per read): 28.5 us with 32 lanes, 32.3 with 8
         if (G == 32) k_cigar<32><<<(unsigned)((d.n_reads * 32 + 255) / 256), 256, 0, st>>>(d);
         else if (G == 16) k_cigar<16><<<(unsigned)((d.n_reads * 16 + 255) / 256), 256, 0, st>>>(d);
         else k_cigar<8><<<(unsigned)((d.n_reads * 8 + 255) / 256), 256, 0, st>>>(d);

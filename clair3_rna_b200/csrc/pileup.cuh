@@ -186,11 +186,11 @@ __device__ __forceinline__ uint32_t up_full4(uint32_t* const* up, int64_t w4) {
 __device__ __forceinline__ bool up_full(uint32_t* const* up, int64_t w) { return (up_full4(up, w & ~3ll) >> (w & 3)) & 1u; }
 
 // ------------------------------------------------- K1: CIGAR geometry per read
-// G lanes per read (G = 8, or 32 when reads carry hundreds of ops): the group walks the read's ops G at a time, an
+// G lanes per read (G = 32, or 8 when reads carry few ops): the group walks the read's ops G at a time, an
 // inclusive scan inside the group (shuffles) gives every op the reference / query lengths consumed before it, and
 // the running totals carry over to the next G ops.  Per op: reference start op_x, base index op_y, op_info
-// (read ordinal, haplotype, strand, last-op flag; OP_SKIP when the read is not admitted); M/=/X/D ops mark covE,
-// the read's whole span marks covA.  Also the admit flag per read (samtools mpileup filters).
+// (read ordinal, haplotype, strand, last-op flag; OP_SKIP when the read is not admitted); the runs of M/=/X/D ops
+// between ref-skips mark covE (one interval per run), the read's whole span marks covA.  Also the admit flag per read (samtools mpileup filters).
 // No device-wide scan, no segment heads: reads are independent (this replaced a segmented look-back scan over all
 // ops that took 50 us for a million ops, most of it waiting on its own cross-block protocol).
 template <int G>
@@ -220,13 +220,33 @@ __global__ void __launch_bounds__(256) k_cigar(Dev d) {
             const uint32_t ur = __shfl_up_sync(gmask, ir, o, G), uq = __shfl_up_sync(gmask, iq, o, G);
             if (gl >= o) { ir += ur; iq += uq; }
         }
+        const int32_t ox = pos + (int32_t)(x + ir - rl);
         if (k < b) {
-            const int32_t ox = pos + (int32_t)(x + ir - rl);
             d.op_x[k] = ox;
             d.op_y[k] = y + iq - ql;
             d.op_info[k] = ok ? (info | (k + 1 == b ? 2u : 0u)) : OP_SKIP;
-            if (ok && rl && (op_is_match(op) || op == 2)) {
-                int64_t lo = (int64_t)ox - d.R0, hi = lo + rl;
+        }
+        // covE: consecutive M/=/X/D ops of a read are adjacent on the reference (insertions and clips take no
+        // reference), so the run of them between two ref-skips is ONE interval: its first lane marks it (a third to
+        // a tenth of the atomics of marking every op on its own)
+        {
+            const int sh = threadIdx.x & 31 & ~(G - 1);                          // the group's first lane in the warp
+            const bool md = ok && k < b && rl && (op_is_match(op) || op == 2);
+            const bool sk = k < b && op == 3 && len;
+            const uint32_t gm = G == 32 ? 0xffffffffu : (1u << G) - 1u;
+            const uint32_t md_mask = (__ballot_sync(gmask, md) >> sh) & gm, sk_mask = (__ballot_sync(gmask, sk) >> sh) & gm;
+            const uint32_t below = (1u << gl) - 1u;
+            const int prev_sk = 31 - __clz((sk_mask & below) | 0u) ;            // -1 when none ( __clz(0) == 32 )
+            const uint32_t seg_lo = prev_sk < 0 ? 0u : (prev_sk >= 31 ? 0xffffffffu : (2u << prev_sk) - 1u);   // lanes up to prev_sk
+            const bool first = md && (md_mask & below & ~seg_lo) == 0u;
+            const uint32_t above = gl >= 31 ? 0u : ~((2u << gl) - 1u);
+            const uint32_t nsk = sk_mask & above;
+            const uint32_t seg_hi = nsk ? ~((nsk & (0u - nsk)) - 1u) : 0u;       // lanes from the next skip on
+            const uint32_t mine = md_mask & ~below & ~seg_hi & gm;                // md lanes of my segment from me on
+            const int last = mine ? 31 - __clz(mine) : gl;
+            const int32_t end = __shfl_sync(gmask, ox + (int32_t)rl, sh + last, 32);
+            if (first) {
+                int64_t lo = (int64_t)ox - d.R0, hi = (int64_t)end - d.R0;
                 if (lo < 0) lo = 0;
                 if (hi > d.W) hi = d.W;
                 mark_range(d.covE, d.upE, lo, hi);
@@ -1325,7 +1345,6 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32, C == 30 ? 4 : C3R_ROWS_BLOCKS
 // dozen cached loads, no scan and no serial tail); a candidate's slot = that + its rank in the tile (position order).
 __global__ void __launch_bounds__(256) k_cand_emit(Dev d) {
     __shared__ int32_t wsum[8];
-    __shared__ int32_t base_s;
     const int64_t L = *d.n_rows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_ct = (L + COV_TILE - 1) / COV_TILE;
