@@ -159,3 +159,31 @@ def test_large_batch_sub_passes_equal_small_batches():
         small, _ = eng.forward(x[a:b])
         assert np.array_equal(big[a:b], small)
     eng.close()
+
+
+def test_release_before_wait_and_more_tickets_than_slots():
+    """c3r_submit_chunk only queues the position / row stages; the count-dependent stages are queued by later calls.
+    A ticket released before anyone waited for it must leave the context usable, a fifth submit with four tickets in
+    flight must be refused (not block), and tickets waited for out of order must give the right results."""
+    import numpy as np
+    import pytest as _pytest
+    from clair3_rna_b200 import weights
+    from clair3_rna_b200.engine import Engine, C3RError
+    from tests.golden import cases as golden_cases
+    batch, ref_bytes, _ = golden_cases.build("cfg1_ont_drna")
+    ref = np.frombuffer(ref_bytes, np.uint8)
+    n = len(ref_bytes)
+    eng = Engine(0, 18)
+    eng.set_weights(weights.synthetic(18, sharpen=8.0))
+    want = eng.call_chunk(batch, ref, 1, 1, n + 33)
+    t = eng.submit(batch, ref, 1, 1, n + 33)
+    eng.release(t)                                               # never waited for
+    ts = [eng.submit(batch, ref, 1, 1, n + 33) for _ in range(4)]
+    with _pytest.raises(C3RError, match="tickets in flight"):
+        eng.submit(batch, ref, 1, 1, n + 33)
+    for t in (ts[2], ts[0], ts[3], ts[1]):                       # out of submit order
+        r = eng.wait(t)
+        assert np.array_equal(r.pos, want.pos) and np.array_equal(r.probs, want.probs) and np.array_equal(r.alt_n, want.alt_n)
+    again = eng.call_chunk(batch, ref, 1, 1, n + 33)
+    assert np.array_equal(again.probs, want.probs)
+    eng.close()
