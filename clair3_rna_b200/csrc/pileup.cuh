@@ -344,17 +344,24 @@ __global__ void __launch_bounds__(256) k_row_bits(Dev d) {
     const int64_t w4 = w0 + 4 * t;
     uint32_t a[4] = {0u, 0u, 0u, 0u}, e[4] = {0u, 0u, 0u, 0u};
     if (w4 < d.NW) {                                 // the bitmaps hold NW + 4 zeroed words
-        const uint4 A = *(const uint4*)(d.covA + w4), E = *(const uint4*)(d.covE + w4);
-        const uint32_t mA = up_full4(d.upA, w4), mE = up_full4(d.upE, w4);
+        const uint4 A = *(const uint4*)(d.covA + w4);
+        const uint32_t mA = up_full4(d.upA, w4);
         a[0] = A.x; a[1] = A.y; a[2] = A.z; a[3] = A.w;
-        e[0] = E.x; e[1] = E.y; e[2] = E.z; e[3] = E.w;
+        // covE is a subset of covA (every M/D op lies inside its read's span): where no read covers anything - 98 % of
+        // a chromosome - the covE words and their summary levels need not even be read
+        // (genotyping mode marks known sites in covE whether a read covers them or not: no short cut there)
+        if ((A.x | A.y | A.z | A.w | mA) != 0u || d.n_known > 0) {
+            const uint4 E = *(const uint4*)(d.covE + w4);
+            const uint32_t mE = up_full4(d.upE, w4);
+            e[0] = E.x; e[1] = E.y; e[2] = E.z; e[3] = E.w;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (w4 + j >= d.NW) { a[j] = 0u; e[j] = 0u; continue; }
-            if ((mA >> j) & 1u) a[j] = 0xffffffffu;
-            if ((mE >> j) & 1u) e[j] = 0xffffffffu;
+            for (int j = 0; j < 4; ++j) {
+                if (w4 + j >= d.NW) { a[j] = 0u; e[j] = 0u; continue; }
+                if ((mA >> j) & 1u) a[j] = 0xffffffffu;
+                if ((mE >> j) & 1u) e[j] = 0xffffffffu;
+            }
+            if (mA) *(uint4*)(d.covA + w4) = make_uint4(a[0], a[1], a[2], a[3]);
         }
-        if (mA) *(uint4*)(d.covA + w4) = make_uint4(a[0], a[1], a[2], a[3]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) sE[1 + 4 * t + j] = e[j];
@@ -404,6 +411,11 @@ __global__ void __launch_bounds__(256) k_row_rank(Dev d) {
     const int NC = d.C == 30 ? 6 : 4;
     const int64_t w4 = (int64_t)blockIdx.x * PT_WORDS + 4 * t;
     const int32_t tile_base = d.ptile[blockIdx.x], tile_end = d.ptile[blockIdx.x + 1];
+    if (tile_end == tile_base && blockIdx.x != gridDim.x - 1 && blockIdx.x != 0) {
+        // a tile without rows (98 % of them): every word has the same rank, nothing to zero (block-uniform exit)
+        *(int4*)(d.word_base + w4) = make_int4(tile_base, tile_base, tile_base, tile_base);
+        return;
+    }
     const uint4 R = *(const uint4*)(d.rowR + w4);
     const uint32_t r[4] = {R.x, R.y, R.z, R.w};
     const int32_t c0 = __popc(r[0]), c1 = __popc(r[1]), c2 = __popc(r[2]), c3 = __popc(r[3]);
