@@ -564,7 +564,10 @@ def main():
             "vs_baseline": None, "dtype": "int32 pileup + fp16/fp32-accumulate network" if args.nn_impl == 1 else "int32+f32",
             "data": "synthetic",
             "config": {"workload": workload, "candidates_per_gpu": n_cand, "rows_per_gpu": n_rows, "channels": C,
-                       "l2_flush": "256 MiB write between timed steps", "reference": "resident in HBM (c3r_set_reference), not part of h2d", "nn_impl": args.nn_impl},
+                       "l2_flush": "256 MiB write between timed steps", "reference": "resident in HBM (c3r_set_reference), not part of h2d", "nn_impl": args.nn_impl,
+                       "timed_region": "value: the CUDA-event times of the K passes summed (%.1f ms in all, one pass per step, L2 flushed in "
+                                       "between); e2e: wall clock over K submit + wait pairs with %d tickets in flight (%.1f ms)" % (
+                                           float(t_dev.item()), E2E_DEPTH + 1, 1e3 * float(e2e_t.item()))},
             "e2e": {"value": e2e, "unit": "sites/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "tickets_in_flight": E2E_DEPTH + 1},
             "gpu_launches": int(launches),
