@@ -1356,7 +1356,11 @@ inline int tc_pipe_init(TcPipe& p, std::string* err) {
     if (p.ok) return 0;
     int prio_lo = 0, prio_hi = 0;                    // the network's streams are high priority (c3r_create)
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    cudaError_t e = cudaStreamCreateWithPriority(&p.s2, cudaStreamNonBlocking, getenv("C3R_FLAT_PRIORITY") ? prio_lo : prio_hi);
+    // the second stream (L4 + heads of the full rounds, beside LSTM2's remainder round) sits between the network's main
+    // stream and the integer stages: C3R_S2_PRIO = steps below the highest priority (default 0)
+    int s2p = prio_hi + (getenv("C3R_S2_PRIO") ? atoi(getenv("C3R_S2_PRIO")) : 0);
+    if (s2p > prio_lo) s2p = prio_lo;
+    cudaError_t e = cudaStreamCreateWithPriority(&p.s2, cudaStreamNonBlocking, getenv("C3R_FLAT_PRIORITY") ? prio_lo : s2p);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p.ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.h1_free, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p.pass_done, cudaEventDisableTiming);
